@@ -1,0 +1,287 @@
+/*
+ * vils_cabi.h — C-ABI of libvils_b200.so, the B200-native (sm_100a) hot path of a sliding-window
+ * visual-inertial-LiDAR estimator.
+ *
+ * The reference system (Stan994265/mVIL-Fusion) has no FFI boundary; the seams this library replaces
+ * are C++ call sites.  Every entry point cites the reference interface it stands in for
+ * (paths relative to the reference tree).  Plain pointers and sizes only; all pointers are HOST
+ * pointers unless the name says `_dev`.  The caller owns every host array; the library copies
+ * in (pinned staging -> HBM) and never retains a host pointer after the call returns.
+ *
+ * Error model (reference: Evaluate() always returns true, divergence is caught after the solve by
+ * Estimator::failureDetection(), vils_estimator/src/estimator.cpp:1076-1122): every function returns
+ * an int status, never aborts, and leaves the stored state unchanged on failure.
+ *
+ * Threading (reference: optimization() and processLidar() are serialised by m_estimator,
+ * vils_estimator/src/estimator_node.cpp:352-367,388-524): calls on one handle must be serialised by
+ * the caller; different handles may be used from different host threads.
+ */
+#ifndef VILS_CABI_H_
+#define VILS_CABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VILS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define VILS_OK 0
+#define VILS_ERR_BAD_ARG 1     /* null pointer, negative size, index out of range               */
+#define VILS_ERR_NO_DEVICE 2   /* no CUDA device / not sm_100 — there is NO CPU fallback         */
+#define VILS_ERR_CUDA 3        /* a CUDA runtime call failed; see vils_last_error()             */
+#define VILS_ERR_NOT_FINITE 4  /* a non-finite value appeared in the state or the cost           */
+#define VILS_ERR_CHOLESKY 5    /* reduced camera system not positive definite after damping     */
+#define VILS_ERR_CAPACITY 6    /* window/batch larger than the handle was created for           */
+
+/* ---- parameter-block ids (replace the pointer identity keys of
+ *      vils_estimator/src/factor/marginalization_factor.cpp:100-106) ------------------------ */
+#define VILS_BLK_POSE 0        /* para_Pose[k]       global 7, local 6  (estimator.h:110)        */
+#define VILS_BLK_SPEEDBIAS 1   /* para_SpeedBias[k]  global 9, local 9  (estimator.h:111)        */
+#define VILS_BLK_EXPOSE 2      /* para_Ex_Pose[0]    global 7, local 6  (estimator.h:113)        */
+#define VILS_BLK_TD 3          /* para_Td[0]         global 1, local 1  (estimator.h:115)        */
+#define VILS_BLK_ID(type, idx) (((int32_t)(type) << 16) | (int32_t)(idx))
+#define VILS_BLK_TYPE(id) ((id) >> 16)
+#define VILS_BLK_INDEX(id) ((id) & 0xffff)
+
+/* ---- solver modes -------------------------------------------------------------------------- */
+#define VILS_MODE_GN 0 /* exactly max_iters Gauss-Newton steps, Jacobi-diagonal regularised by mu   */
+#define VILS_MODE_LM 1 /* Levenberg-Marquardt trust region to convergence (<= max_iters)            */
+
+#define VILS_MARGIN_OLD 0        /* estimator.h MarginalizationFlag MARGIN_OLD                      */
+#define VILS_MARGIN_SECOND_NEW 1 /* MARGIN_SECOND_NEW                                               */
+
+/* Replaces the mutable globals of vils_estimator/src/parameters.{h,cpp} that the hot path reads. */
+typedef struct vils_config {
+  double focal_length;       /* FOCAL_LENGTH (parameters.h:11); projection sqrt_info = focal/2 (estimator.cpp:18) */
+  double gravity[3];         /* G (parameters.cpp:32,103), subtracted as a positive vector                 */
+  double tr;                 /* TR rolling-shutter read-out time (parameters.cpp:203-208)                  */
+  double row;                /* ROW image height (parameters.cpp:105)                                      */
+  double cauchy_visual;      /* CauchyLoss(1.0) on projection / ICP / LPS (estimator.cpp:1129)             */
+  double huber_lidar;        /* HuberLoss(0.1) on LiDAR edge/plane (lidar_mapping/src/localMapping.cpp:597) */
+  double rlb[9];             /* RLB row-major: p_l = RLB p_b + TLB (estimator.cpp:449-451)                 */
+  double tlb[3];             /* TLB                                                                       */
+  int32_t estimate_extrinsic; /* ESTIMATE_EXTRINSIC: 0 => para_Ex_Pose constant (estimator.cpp:1154-1158)  */
+  int32_t estimate_td;        /* ESTIMATE_TD: 1 => ProjectionTdFactor + para_Td (estimator.cpp:1162-1232)  */
+  int32_t max_kf;            /* capacity: keyframes per window (reference: WINDOW_SIZE+1 = 7)              */
+  int32_t max_feat;          /* capacity: landmarks per window (reference: NUM_OF_F = 1000)                */
+  int32_t max_proj;          /* capacity: projection factors per window                                   */
+  int32_t max_lidar;         /* capacity: plane + edge factors per window                                 */
+  int32_t device;            /* CUDA device ordinal                                                       */
+  int32_t reserved;
+} vils_config;
+
+/* Result of IntegrationBase (vils_estimator/src/factor/integration_base.h:203-220). 467 doubles. */
+typedef struct vils_preint {
+  double delta_p[3];
+  double delta_q[4];        /* x y z w */
+  double delta_v[3];
+  double lin_ba[3];         /* linearized_ba */
+  double lin_bg[3];         /* linearized_bg */
+  double sum_dt;
+  double jacobian[225];     /* 15x15 column-major (Eigen default), order O_P O_R O_V O_BA O_BG */
+  double covariance[225];   /* 15x15 column-major */
+} vils_preint;
+
+/* LidarICPConstraint after FindWindowsID (vils_estimator/src/lidar_backend.h:5-17,97-184). */
+typedef struct vils_icp {
+  double ta, tb, tc, td, ti, tj;
+  double trans_t[3];        /* lidar_trans(0:3,3) — the only part the functor reads (:152) */
+  double sqrt_info;         /* lidar_sqrt_info(0,0) (:156-158)                             */
+  int32_t kf[4];            /* id_a id_b id_c id_d                                         */
+} vils_icp;
+
+/* LidarLPSConstraint after FindNearest2ID (lidar_backend.h:19-26,35-95). */
+typedef struct vils_lps {
+  double tl, tr, tk;
+  double q[4];              /* LPSq, x y z w */
+  int32_t kf[2];            /* id_l id_r     */
+} vils_lps;
+
+/*
+ * One sliding window = what Estimator::optimization() hands to ceres::Problem between vector2double()
+ * and double2vector() (vils_estimator/src/estimator.cpp:1124-1419).  Factor data is SoA.
+ */
+typedef struct vils_window {
+  int32_t n_kf, n_feat, n_imu, n_proj, n_plane, n_edge, n_icp, n_lps;
+  /* state — para_Pose / para_SpeedBias / para_Ex_Pose / para_Feature / para_Td (estimator.h:110-116) */
+  const double* pose;          /* n_kf x 7  [px py pz qx qy qz qw]  (estimator.cpp:920-927) */
+  const double* speedbias;     /* n_kf x 9  [v ba bg]               (estimator.cpp:929-939) */
+  const double* ex_pose;       /* 7         tic, qic                 (estimator.cpp:943-950) */
+  const double* inv_depth;     /* n_feat    inverse depth            (feature_manager.cpp:195-212) */
+  const uint8_t* depth_fixed;  /* n_feat    lidar_depth_flag => constant block (estimator.cpp:1217-1221); may be NULL */
+  const uint8_t* kf_fixed;     /* n_kf      pose+speed-bias constant (zero-velocity mode, estimator.cpp:1368-1370); may be NULL */
+  double td;
+  /* IMUFactor (factor/imu_factor.h): factor k links keyframes imu_kf[k] and imu_kf[k]+1 */
+  const vils_preint* imu;      /* n_imu */
+  const int32_t* imu_kf;       /* n_imu */
+  /* ProjectionTdFactor / ProjectionFactor (factor/projection_td_factor.cpp:6-19,34-141) */
+  const double* pts_i;         /* n_proj x 3 */
+  const double* pts_j;         /* n_proj x 3 */
+  const double* vel_i;         /* n_proj x 2 */
+  const double* vel_j;         /* n_proj x 2 */
+  const double* td_i;          /* n_proj */
+  const double* td_j;          /* n_proj */
+  const double* row_i;         /* n_proj  uv.y of the observation; the library subtracts ROW/2 (:18-19) */
+  const double* row_j;         /* n_proj */
+  const int32_t* kf_i;         /* n_proj  anchor keyframe (start_frame) */
+  const int32_t* kf_j;         /* n_proj  observing keyframe            */
+  const int32_t* feat;         /* n_proj  feature_index                 */
+  /* LidarPlaneNormFactor / LidarEdgeFactor (lidar_mapping/src/lidarFactor.hpp:12-55,106-138), attached to
+   * keyframe kf through the fixed LiDAR<->body extrinsic (vils_config.rlb/tlb) */
+  const double* plane_p;       /* n_plane x 3  point in the LiDAR frame of keyframe plane_kf */
+  const double* plane_n;       /* n_plane x 3  unit normal (world)                            */
+  const double* plane_d;       /* n_plane      negative_OA_dot_norm                           */
+  const int32_t* plane_kf;     /* n_plane */
+  const double* edge_p;        /* n_edge x 3 */
+  const double* edge_a;        /* n_edge x 3   last_point_a (world) */
+  const double* edge_b;        /* n_edge x 3   last_point_b (world) */
+  const int32_t* edge_kf;      /* n_edge */
+  const vils_icp* icp;         /* n_icp (<=5,  estimator.cpp:1345) */
+  const vils_lps* lps;         /* n_lps (<=7,  estimator.cpp:1283) */
+  /* MarginalizationFactor (factor/marginalization_factor.cpp:340-400): r = r_lin + J_lin * (x [-] x0) */
+  int32_t prior_n;             /* residual count n (0 = no prior)   */
+  int32_t prior_nblk;          /* number of kept parameter blocks   */
+  const double* prior_J;       /* n x n column-major linearized_jacobians */
+  const double* prior_r;       /* n linearized_residuals                  */
+  const int32_t* prior_blk;    /* prior_nblk block ids (VILS_BLK_ID), in column order of J_lin */
+  const double* prior_x0;      /* concatenated global-size x0 snapshots (7/9/7/1 per block)   */
+} vils_window;
+
+typedef struct vils_solve_opts {
+  int32_t mode;              /* VILS_MODE_GN | VILS_MODE_LM                                      */
+  int32_t max_iters;         /* NUM_ITERATIONS (config yaml max_num_iterations, estimator.cpp:1404) */
+  double mu;                 /* GN: (H + mu*diag(H)) dx = -g ; Ceres dogleg's min_mu is 1e-8     */
+  double lm_initial_radius;  /* LM: Ceres default initial_trust_region_radius = 1e4              */
+  double function_tolerance; /* LM: Ceres default 1e-6                                           */
+  double parameter_tolerance;/* LM: Ceres default 1e-8                                           */
+  double min_relative_decrease; /* LM: Ceres default 1e-3                                        */
+} vils_solve_opts;
+
+typedef struct vils_summary {
+  int32_t status;            /* VILS_OK | VILS_ERR_NOT_FINITE | VILS_ERR_CHOLESKY                */
+  int32_t iterations;        /* linearisations performed                                         */
+  int32_t accepted;          /* steps accepted                                                   */
+  int32_t reserved;
+  double cost_initial;       /* 1/2 sum rho(|r|^2) before                                        */
+  double cost_final;         /* ... after                                                        */
+} vils_summary;
+
+/* Output of MarginalizationInfo::marginalize + getParameterBlocks (marginalization_factor.cpp:176-338). */
+typedef struct vils_prior_out {
+  int32_t n;                 /* out: residual count                                              */
+  int32_t nblk;              /* out: kept blocks                                                 */
+  int32_t m;                 /* out: marginalised dimension                                      */
+  int32_t capacity_n;        /* in : J has room for capacity_n^2, r for capacity_n, ...          */
+  double* J;                 /* n x n column-major                                               */
+  double* r;                 /* n                                                                */
+  int32_t* blk;              /* nblk ids ALREADY re-addressed to the slid window (addr_shift, estimator.cpp:1599-1611) */
+  double* x0;                /* concatenated global-size snapshots                               */
+} vils_prior_out;
+
+typedef struct vils_ba vils_ba;    /* opaque: device buffers, stream, staging */
+typedef struct vils_klt vils_klt;  /* opaque: pyramids + point buffers        */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int vils_abi_version(void);
+const char* vils_last_error(void);
+/* Fills a config with the constants of config/mynteye_leishen_indoor.yaml + parameters.h. */
+void vils_default_config(vils_config* cfg);
+void vils_default_solve_opts(vils_solve_opts* opts);
+
+/* ---- sliding-window BA: Estimator::optimization() (estimator.cpp:1124-1687) ------------------ */
+/* max_windows independent windows live on the device at once (batched mode). */
+int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out);
+void vils_ba_destroy(vils_ba* ba);
+/* Stage one window (host copy into pinned memory + index lists).  Replaces vector2double() +
+ * problem.AddResidualBlock(...) (estimator.cpp:1169-1398). */
+int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w);
+/* Host->device copy of every staged window (async on the handle's stream, then synchronised). */
+int vils_ba_upload(vils_ba* ba, int32_t n_windows);
+/* Device-only solve of slots [0, n_windows): replaces ceres::Solve (estimator.cpp:1400-1414).
+ * Reads the uploaded state, writes the solved state to a separate device buffer (idempotent). */
+int vils_ba_solve_device(vils_ba* ba, int32_t n_windows, const vils_solve_opts* opts);
+/* Device->host copy of solved states + summaries. */
+int vils_ba_download(vils_ba* ba, int32_t n_windows);
+/* upload + solve_device + download: the call a host makes per optimization(). */
+int vils_ba_solve(vils_ba* ba, int32_t n_windows, const vils_solve_opts* opts);
+/* Solved state of one slot (raw solver output, i.e. before double2vector()'s gauge re-anchoring). */
+int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* speedbias, double* ex_pose,
+                      double* inv_depth, double* td, vils_summary* summary);
+/* Estimator::double2vector() gauge re-anchoring (estimator.cpp:962-1011) applied on the host to a
+ * solved state, given the pre-solve pose of frame 0. */
+int vils_double2vector(int32_t n_kf, const double* pose0_before, double* pose, double* speedbias);
+
+/* Materialised CostFunction::Evaluate of every factor of one slot at its uploaded state, AFTER the
+ * robust corrector of ResidualBlockInfo::Evaluate (marginalization_factor.cpp:37-68):
+ *   residuals: concatenated [imu 15 each | proj 2 each | plane 1 | edge 3 | icp 3 | lps 3 | prior n]
+ *   jacobians: tangent-space blocks, row-major per factor:
+ *     imu 15x30 (pose_i sb_i pose_j sb_j) | proj 2x20 (pose_i pose_j ex lambda td) | plane 1x6 |
+ *     edge 3x6 | icp 3x24 | lps 3x12.  Either pointer may be NULL. apply_loss=0 gives raw Evaluate. */
+int vils_ba_evaluate(vils_ba* ba, int32_t slot, int32_t apply_loss, double* residuals, double* jacobians);
+/* Evaluate-only kernel over all slots, results kept on the device (HBM roofline measurement). */
+int vils_ba_evaluate_device(vils_ba* ba, int32_t n_windows, int32_t apply_loss);
+/* Reduced camera system of one slot at its uploaded state: S (D x D row-major, D = 15 n_kf + 7),
+ * g_r (D) with landmarks eliminated, no damping. Also the cost. */
+int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* cost);
+/* Marginalization (estimator.cpp:1483-1684 + marginalization_factor.cpp:110-338) of one slot at its
+ * SOLVED state. */
+int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out* out);
+/* Timing of the last vils_ba_solve_device in ms (CUDA events on the handle's stream). */
+int vils_ba_last_device_ms(vils_ba* ba, float* ms);
+/* Number of kernel launches issued by the last solve/evaluate call. */
+int vils_ba_last_launches(vils_ba* ba, int32_t* n);
+/* Factor-sharded mode (one window over several GPUs): phase A linearises this rank's factors and
+ * leaves the partial reduced system [S | g | cost] (D*D + D + 1 doubles) in a device buffer the
+ * caller all-reduces (NCCL, sum); phase B solves, updates and back-substitutes. */
+int vils_ba_sharded_buffer(vils_ba* ba, void** dev_ptr, size_t* n_doubles);
+int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration);
+int vils_ba_sharded_update(vils_ba* ba, const vils_solve_opts* opts);
+
+/* ---- IMU pre-integration: IntegrationBase::push_back/repropagate (integration_base.h:30-158) - */
+/* n_intervals independent intervals; interval k integrates samples [off[k], off[k+1]).  acc/gyr are
+ * n_samples x 3; acc0/gyr0/ba/bg are n_intervals x 3; noise = {ACC_N, GYR_N, ACC_W, GYR_W}. */
+int vils_preintegrate(int32_t n_intervals, const int32_t* off, const double* dt, const double* acc,
+                      const double* gyr, const double* acc0, const double* gyr0, const double* ba,
+                      const double* bg, const double noise[4], vils_preint* out, int32_t device);
+
+/* ---- KLT: cv::calcOpticalFlowPyrLK(prev, next, in, out, status, err, Size(21,21), 3)
+ *      (feature_tracker_/src/feature_tracker.cpp:113) ----------------------------------------- */
+int vils_klt_create(int32_t rows, int32_t cols, int32_t max_pts, int32_t win, int32_t max_level,
+                    int32_t device, vils_klt** out);
+void vils_klt_destroy(vils_klt* k);
+/* prev/next: rows x cols u8 with row stride `stride` bytes. */
+int vils_klt_track(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32_t stride,
+                   const float* prev_xy, int32_t n, float* next_xy, uint8_t* status, float* err);
+/* Device-resident variant for throughput measurement: images already uploaded by vils_klt_upload. */
+int vils_klt_upload(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32_t stride,
+                    const float* prev_xy, int32_t n);
+int vils_klt_track_device(vils_klt* k);
+int vils_klt_download(vils_klt* k, float* next_xy, uint8_t* status, float* err);
+int vils_klt_last_device_ms(vils_klt* k, float* ms);
+
+/* ---- LiDAR: PointProcessor::PointToRing stamp (lidar_compensator/src/PointProcessor.cc:127-341)
+ *      + TransformToEnd deskew (vils_estimator/src/lidar_frontend.cpp:1001-1041) --------------- */
+/* xyzi: n points, stride_floats floats apart (8 for pcl::PointXYZI: x y z pad intensity pad pad pad).
+ * In place, like the reference. */
+int vils_deskew(float* xyzi, int32_t n, int32_t stride_floats, const float q[4] /* x y z w */,
+                const float t[3], float time_factor, float min_r, float max_r, int32_t device);
+/* Ring id + relative time stamp. ring_out[i] = ring id or -1 (dropped); intensity <- int(I) + rel_time.
+ * start_ori is taken from the first kept point as in the reference. */
+int vils_stamp_rings(float* xyzi, int32_t n, int32_t stride_floats, float lower_deg, float upper_deg,
+                     int32_t n_rings, float scan_period, int32_t* ring_out, int32_t device);
+/* Fused stamp + deskew on a device-resident cloud (throughput measurement). */
+int vils_lidar_dev_alloc(int32_t n, int32_t stride_floats, int32_t device, void** handle);
+int vils_lidar_dev_upload(void* handle, const float* xyzi);
+int vils_lidar_dev_deskew(void* handle, const float q[4], const float t[3], float time_factor,
+                          float min_r, float max_r, float* ms);
+int vils_lidar_dev_download(void* handle, float* xyzi);
+void vils_lidar_dev_free(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILS_CABI_H_ */
