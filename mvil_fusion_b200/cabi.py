@@ -2,7 +2,7 @@
 
 Only struct layouts and small marshalling helpers live here; they are shared by the product binding
 (`mvil_fusion_b200.lib`, which loads libvils_b200.so) and by the test-side oracle binding
-(`tests/oracle_lib.py`), because the oracle deliberately reuses the header's POD types.
+binding in tests/, because the CPU checker deliberately reuses the header POD types.
 """
 import ctypes as C
 

@@ -1,0 +1,696 @@
+// ba_device.cuh — device side of the sliding-window solve: one CTA owns one window for the whole Gauss-Newton loop.
+//
+// Per iteration (all in one kernel, no host round trip):
+//   V  pair pass      : projection factors grouped by keyframe pair (i,j); a warp evaluates <=16 factors at a time
+//                       (ProjectionTdFactor + Cauchy corrector), stages the weighted 2x19 Jacobian rows + residual
+//                       in shared memory and accumulates the pair-local 20x20 block A^T A (direct terms, gradient);
+//                       per-factor landmark partials (C, g_l, E rows) go to the per-window scratch in L2.
+//   L  landmark reduce: one thread per landmark sums its factors' partials in a fixed order (deterministic).
+//   S  Schur SYRK     : Hv = -E diag(1/C) E^T, gv = -E g_l / C over the (6N+7)-dim visual sub-system (the only dense
+//                       contraction of the path), E streamed through shared memory in 32-landmark chunks.
+//   G  gather         : Hv + pair blocks -> tile-packed H (16x16 tiles, lower), g, diag for damping.
+//   I  IMU / LiDAR / ICP / LPS / prior contributions straight into H.
+//   C  blocked Cholesky with tile inverses, forward solve fused in as an extra row, blocked back-substitution.
+//   U  landmark back-substitution, PoseLocalParameterization::Plus.
+// No atomics anywhere: every accumulator has exactly one owner, so results are bit-reproducible run to run.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/vils_cabi.h"
+#include "ba_layout.h"
+#include "factors.cuh"
+
+namespace vb {
+
+constexpr int TB = 16;            // Cholesky tile
+constexpr int SOLVE_THREADS = 512;
+constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+constexpr int STAGE_LD = 24;      // pair-pass staging row: 19 Jacobian cols + residual + pad
+constexpr int PAIR_LD = 20;       // pair-local block: [pose_i 6 | pose_j 6 | ex 6 | td | r]
+constexpr int ECHUNK = 32;        // landmarks per Schur chunk
+constexpr int PART_LD = 16;       // per-factor landmark partial: C, g_l, e_i(6), e_ex(6), e_td, pad
+
+struct SolveParams {
+  const uint8_t* blobs; int64_t blob_stride;
+  double* scratch; ScratchLayout sl;
+  double* xout; int64_t xout_stride;
+  vils_summary* summary;
+  vf::BaCfg cfg;
+  int32_t mode, max_iters;
+  double mu, lm_radius, f_tol, p_tol, min_rel_dec;
+  int32_t Ncap, Mcap;             // capacities the shared-memory carve-up is sized for
+  int32_t h_in_smem, hv_in_smem;
+  double* lin_out;                // != null: dump [S (D x D row-major) | g (D) | cost] of the first linearisation and stop
+  int32_t slot0;                  // first slot handled by blockIdx.x == 0
+};
+
+struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
+  int xs, xc, g, dx, hd, gv, hdv, cinv, glam, red, linv, hv, uni, imu, total;
+  int ntile_rows;
+};
+
+__host__ __device__ inline int tri(int n) { return n * (n + 1) / 2; }
+
+__host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, int hv_in_smem) {
+  Smem s; int o = 0;
+  const int X = 16 * Ncap + 8 + Mcap, D = 15 * Ncap + 7, Dv = 6 * Ncap + 7, nb = (D + TB - 1) / TB, Dvp = (Dv + 3) & ~3;
+  auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+  s.xs = take(X); s.xc = take(X);
+  s.g = take(nb * TB); s.dx = take(nb * TB); s.hd = take(nb * TB);
+  s.gv = take(Dvp); s.hdv = take(Dvp);
+  s.cinv = take(Mcap); s.glam = take(Mcap);
+  s.red = take(64 + SOLVE_WARPS * 2);
+  s.linv = take(nb * TB * TB);
+  s.hv = hv_in_smem ? take(Dvp * Dvp) : -1;
+  int uni = SOLVE_WARPS * 32 * STAGE_LD;                     // pair-pass staging
+  if (ECHUNK * Dvp > uni) uni = ECHUNK * Dvp;                // Schur chunk
+  if (h_in_smem && tri(nb) * TB * TB > uni) uni = tri(nb) * TB * TB;
+  s.uni = take(uni);
+  s.imu = take(((Ncap + 1) / 2) * 466);
+  s.total = o; s.ntile_rows = nb;
+  return s;
+}
+
+// ---- tile-packed lower-triangular matrix -----------------------------------------------------------------------
+__device__ __forceinline__ int tidx(int i, int j) {  // requires i >= j
+  const int bi = i >> 4, bj = j >> 4;
+  return ((bi * (bi + 1) / 2 + bj) << 8) + ((i & 15) << 4) + (j & 15);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct Win {   // decoded blob
+  const uint8_t* base; const WinHdr* h;
+  int N, M, D, Dv, Dvp, nb;
+  __device__ const double* d(int which) const { return reinterpret_cast<const double*>(base + h->off[which]); }
+  __device__ const int32_t* i(int which) const { return reinterpret_cast<const int32_t*>(base + h->off[which]); }
+  __device__ const uint8_t* u(int which) const { return base + h->off[which]; }
+};
+
+__device__ __forceinline__ int vis2cam(int v, int N) { return v < 6 * N ? 15 * (v / 6) + v % 6 : 15 * N + (v - 6 * N); }
+
+// Block-wide sum of one double per thread, result broadcast. red: >= SOLVE_WARPS doubles of scratch.
+__device__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+  return s;
+}
+
+// =================================================================================================================
+// Projection residual only (cost evaluation): returns 1/2 rho
+// =================================================================================================================
+__device__ double proj_cost(const SolveParams& P, const Win& W, const double* x, int f) {
+  const int np = W.h->n_proj;
+  const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  double c[14];
+#pragma unroll
+  for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
+  const int i = ix[f], j = ix[np + f], rank = ix[2 * np + f];
+  const int feat = W.i(OFF_LM_FEAT)[rank];
+  double r[2];
+  vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(W.N), x[XL(W.N) + feat], x[XT(W.N)], r, nullptr);
+  double rho, w; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w);
+  return 0.5 * rho;
+}
+
+// =================================================================================================================
+// V: pair pass
+// =================================================================================================================
+__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage_all, double* scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int np = W.h->n_proj, npair = W.h->n_pair;
+  const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  const int32_t* pairs = W.i(OFF_PAIR); const int32_t* perm = W.i(OFF_PAIR_PERM);
+  const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const uint8_t* dfix = W.u(OFF_FIXED);
+  double* stage = stage_all + warp * 32 * STAGE_LD;
+  double* part = scr + P.sl.part; double* E = scr + P.sl.E; double* pairpart = scr + P.sl.pairpart;
+  const int ra = 5 * (lane >> 3), cb = 3 * (lane & 7);
+  double cost = 0;
+  for (int p = warp; p < npair; p += SOLVE_WARPS) {
+    const int start = pairs[4 * p], cnt = pairs[4 * p + 1], kfi = pairs[4 * p + 2], kfj = pairs[4 * p + 3];
+    double acc[5][3];
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) acc[a][b] = 0;
+    for (int c00 = 0; c00 < cnt; c00 += 16) {
+      const int n = min(16, cnt - c00);
+      if (lane < n) {
+        const int f = perm[start + c00 + lane];
+        double c[14];
+#pragma unroll
+        for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
+        const int rank = ix[2 * np + f];
+        const int feat = lm_feat[rank];
+        double r[2], J[40];
+        vf::proj_eval(P.cfg, c, x + XP(kfi), x + XP(kfj), x + XE(W.N), x[XL(W.N) + feat], x[XT(W.N)], r, J);
+        double rho, w; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w);
+        cost += 0.5 * rho;
+        r[0] *= w; r[1] *= w;
+#pragma unroll
+        for (int k = 0; k < 40; k++) J[k] *= w;
+        const bool fixed = dfix[feat] != 0;
+        const double jl0 = fixed ? 0.0 : J[18], jl1 = fixed ? 0.0 : J[38];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          double* row = stage + (2 * lane + a) * STAGE_LD;
+#pragma unroll
+          for (int k = 0; k < 18; k++) row[k] = J[20 * a + k];
+          row[18] = J[20 * a + 19]; row[19] = r[a];
+          row[20] = 0; row[21] = 0; row[22] = 0; row[23] = 0;
+        }
+        double* pt = part + (size_t)f * PART_LD;
+        pt[0] = jl0 * jl0 + jl1 * jl1;
+        pt[1] = jl0 * r[0] + jl1 * r[1];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          pt[2 + k] = J[k] * jl0 + J[20 + k] * jl1;              // e_i
+          pt[8 + k] = J[12 + k] * jl0 + J[32 + k] * jl1;         // e_ex
+          E[(size_t)rank * W.Dvp + 6 * kfj + k] = J[6 + k] * jl0 + J[26 + k] * jl1;   // e_j: this factor only
+        }
+        pt[14] = J[19] * jl0 + J[39] * jl1;                      // e_td
+      }
+      __syncwarp();
+      for (int row = 0; row < 2 * n; row++) {
+        const double* s = stage + row * STAGE_LD;
+        double av[5], bv[3];
+#pragma unroll
+        for (int a = 0; a < 5; a++) av[a] = s[ra + a];
+#pragma unroll
+        for (int b = 0; b < 3; b++) bv[b] = s[cb + b];
+#pragma unroll
+        for (int a = 0; a < 5; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+      }
+      __syncwarp();
+    }
+    double* out = pairpart + (size_t)p * PAIR_LD * PAIR_LD;
+#pragma unroll
+    for (int a = 0; a < 5; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+        if (cb + b < PAIR_LD) out[(ra + a) * PAIR_LD + cb + b] = acc[a][b];
+  }
+  return cost;
+}
+
+// L: per-landmark reduction of the factor partials (fixed order) -> cinv, glam, E rows (anchor / ex / td parts)
+__device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu) {
+  const int nlm = W.h->n_lm, np = W.h->n_proj;
+  const int32_t* lm_start = W.i(OFF_LM_START); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  const double* part = scr + P.sl.part; double* E = scr + P.sl.E;
+  for (int rnk = threadIdx.x; rnk < nlm; rnk += blockDim.x) {
+    double s[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) s[k] = 0;
+    const int f0 = lm_start[rnk], f1 = lm_start[rnk + 1];
+    for (int f = f0; f < f1; f++) {
+      const double* pt = part + (size_t)f * PART_LD;
+#pragma unroll
+      for (int k = 0; k < 15; k++) s[k] += pt[k];
+    }
+    const int kfi = ix[f0];
+    double* e = E + (size_t)rnk * W.Dvp;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { e[6 * kfi + k] = s[2 + k]; e[6 * W.N + k] = s[8 + k]; }
+    e[6 * W.N + 6] = s[14];
+    const double C = s[0];
+    if (C > 0.0) {   // free landmark: (C + mu clamp(C))^-1   [ceres min/max_lm_diagonal 1e-6 / 1e32, squared]
+      cinv[rnk] = 1.0 / (C + mu * fmin(fmax(C, 1e-12), 1e64));
+      glam[rnk] = s[1];
+    } else { cinv[rnk] = 0.0; glam[rnk] = 0.0; }
+  }
+}
+
+// S: Hv(lower) = -sum_f cinv_f e_f e_f^T ; gv = -sum_f cinv_f glam_f e_f.  3x3 register tiles over the lower triangle.
+__device__ void schur_syrk(const SolveParams& P, const Win& W, const double* cinv, const double* glam, double* Hv, double* gv,
+                           double* chunk, const double* scr) {
+  const int Dv = W.Dv, Dvp = W.Dvp, nlm = W.h->n_lm;
+  const int nt = (Dv + 2) / 3;                 // tiles per side
+  const int ntiles = nt * (nt + 1) / 2;
+  const double* E = scr + P.sl.E;
+  for (int tbase = 0; tbase < ntiles; tbase += blockDim.x) {
+  // tile id -> (ti >= tj)
+  int ti = -1, tj = 0;
+  double acc[3][3], gacc[3];
+  const int t = tbase + threadIdx.x;
+  if (t < ntiles) {
+    ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > t) ti--;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    tj = t - ti * (ti + 1) / 2;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) { gacc[a] = 0;
+#pragma unroll
+    for (int b = 0; b < 3; b++) acc[a][b] = 0; }
+  for (int f0 = 0; f0 < nlm; f0 += ECHUNK) {
+    const int n = min(ECHUNK, nlm - f0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) chunk[k] = E[(size_t)f0 * Dvp + k];
+    __syncthreads();
+    if (ti >= 0) {
+      for (int f = 0; f < n; f++) {
+        const double ci = cinv[f0 + f];
+        const double* e = chunk + f * Dvp;
+        double av[3], bv[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) { const int ia = 3 * ti + a; av[a] = ia < Dv ? e[ia] : 0.0; }
+#pragma unroll
+        for (int b = 0; b < 3; b++) { const int ib = 3 * tj + b; bv[b] = ib < Dv ? e[ib] * ci : 0.0; }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        if (tj == 0) {
+          const double gl = glam[f0 + f] * ci;
+#pragma unroll
+          for (int a = 0; a < 3; a++) gacc[a] = fma(av[a], gl, gacc[a]);
+        }
+      }
+    }
+  }
+  if (ti >= 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int ia = 3 * ti + a;
+      if (ia >= Dv) continue;
+#pragma unroll
+      for (int b = 0; b < 3; b++) { const int ib = 3 * tj + b; if (ib < Dv && ib <= ia) Hv[ia * Dvp + ib] = -acc[a][b]; }
+      if (tj == 0) gv[ia] = -gacc[a];
+    }
+  }
+  }
+}
+
+// G: Hv (Schur part) + pair blocks (direct part) -> H tiles (lower), g, hd.  One owner per entry.
+__device__ void gather_visual(const SolveParams& P, const Win& W, const double* Hv, const double* gv, double* H, double* g, double* hd,
+                              const double* scr) {
+  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp;
+  const int32_t* pid = W.i(OFF_PAIR_ID);
+  const double* pp = scr + P.sl.pairpart;
+  const int total = Dv * (Dv + 1) / 2 + Dv;     // lower entries + one gradient/diag task per row
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    int a, b; bool grad = false;
+    if (t < Dv) { a = t; b = t; grad = true; }
+    else {
+      const int u = t - Dv;
+      a = (int)((sqrt(8.0 * u + 1.0) - 1.0) * 0.5);
+      while (a * (a + 1) / 2 > u) a--;
+      while ((a + 1) * (a + 2) / 2 <= u) a++;
+      b = u - a * (a + 1) / 2;
+    }
+    const int p = a < 6 * N ? a / 6 : N + (a - 6 * N) / 6;       // block id: poses 0..N-1, ex = N, td = N+1
+    const int q = b < 6 * N ? b / 6 : N + (b - 6 * N) / 6;
+    const int ao = a < 6 * N ? a % 6 : (a - 6 * N) % 6, bo = b < 6 * N ? b % 6 : (b - 6 * N) % 6;
+    // local row for "a" inside pair (i,j): anchor -> 0.., observer -> 6.., ex -> 12.., td -> 18
+    double sum = 0, gsum = 0, dsum = 0;
+    auto add = [&](int pr, int la, int lb) {
+      const double* blk = pp + (size_t)pr * PAIR_LD * PAIR_LD;
+      if (grad) { gsum += blk[la * PAIR_LD + 19]; dsum += blk[la * PAIR_LD + la]; }
+      else sum += blk[la * PAIR_LD + lb];
+    };
+    const int la_sh = (p == N) ? 12 + ao : 18;   // local row if a is ex/td
+    const int lb_sh = (q == N) ? 12 + bo : 18;
+    if (p < N && q < N) {
+      if (p == q) {
+        for (int j = p + 1; j < N; j++) { const int pr = pid[p * N + j]; if (pr >= 0) add(pr, ao, bo); }
+        for (int i = 0; i < p; i++) { const int pr = pid[i * N + p]; if (pr >= 0) add(pr, 6 + ao, 6 + bo); }
+      } else {   // p > q: anchor q, observer p
+        const int pr = pid[q * N + p]; if (pr >= 0) add(pr, 6 + ao, bo);
+      }
+    } else if (p >= N && q < N) {
+      for (int j = q + 1; j < N; j++) { const int pr = pid[q * N + j]; if (pr >= 0) add(pr, la_sh, bo); }
+      for (int i = 0; i < q; i++) { const int pr = pid[i * N + q]; if (pr >= 0) add(pr, la_sh, 6 + bo); }
+    } else {     // both in ex/td: every pair
+      for (int pr = 0; pr < W.h->n_pair; pr++) add(pr, la_sh, lb_sh);
+    }
+    const int ca = vis2cam(a, N), cbm = vis2cam(b, N);
+    if (grad) { g[ca] = gv[a] + gsum; hd[ca] = dsum; }
+    else H[tidx(ca, cbm)] = Hv[a * Dvp + b] + sum;
+  }
+}
+
+// =================================================================================================================
+// I: IMU factors. One warp per factor; even keyframe index first, then odd (adjacent factors share a 15x15 block).
+// stage: 466 doubles per warp slot (J 15x30 | r 15).
+// =================================================================================================================
+__device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, double* H, double* g, double* hd, double* imu_stage,
+                           const double* scr, bool want_J) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nimu = W.h->n_imu;
+  const double* pre_all = W.d(OFF_IMU); const int32_t* kfs = W.i(OFF_IMU_KF);
+  const double* Wall = scr + P.sl.w_imu;
+  const int nslot = (P.Ncap + 1) / 2;
+  double cost = 0;
+  for (int parity = 0; parity < 2; parity++) {
+    // factors of this parity, in index order: slot s handles the s-th one (s strided by available warps)
+    int seen = 0;
+    for (int k = 0; k < nimu; k++) {
+      const int i = kfs[k];
+      if ((i & 1) != parity) continue;
+      const int s = seen++;
+      if ((s % SOLVE_WARPS) != warp) continue;     // same-parity factors <= nslot, so stage slot s is private
+      double* J = imu_stage + (s % nslot) * 466; double* r = J + 450;
+      const double* pre = pre_all + (size_t)k * 467; const double* Wk = Wall + (size_t)k * 225;
+      if (pre[16] > 10.0) continue;                                  // estimator.cpp:1182 skip if sum_dt > 10
+      for (int e = lane; e < 450; e += 32) J[e] = 0;
+      __syncwarp();
+      if (lane == 0) vf::imu_eval_raw(pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, want_J ? J : nullptr);
+      __syncwarp();
+      // r <- W r (W upper triangular), in place top-down
+      double rw = 0;
+      if (lane < 15) { for (int m = lane; m < 15; m++) rw = fma(Wk[lane * 15 + m], r[m], rw); }
+      __syncwarp();
+      if (lane < 15) { r[lane] = rw; cost += 0.5 * rw * rw; }
+      if (want_J) {
+        for (int row = 0; row < 15; row++) {                          // J <- W J in place: row `row` needs rows >= row only
+          double v = 0;
+          if (lane < 30) for (int m = row; m < 15; m++) v = fma(Wk[row * 15 + m], J[m * 30 + lane], v);
+          __syncwarp();
+          if (lane < 30) J[row * 30 + lane] = v;
+        }
+        __syncwarp();
+        const int base = 15 * i;
+        for (int e = lane; e < 465 + 30; e += 32) {
+          if (e < 465) {
+            int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            while (a * (a + 1) / 2 > e) a--;
+            while ((a + 1) * (a + 2) / 2 <= e) a++;
+            const int b = e - a * (a + 1) / 2;
+            double v = 0;
+#pragma unroll
+            for (int m = 0; m < 15; m++) v = fma(J[m * 30 + a], J[m * 30 + b], v);
+            H[tidx(base + a, base + b)] += v;
+            if (a == b) hd[base + a] += v;
+          } else {
+            const int a = e - 465;
+            double v = 0;
+#pragma unroll
+            for (int m = 0; m < 15; m++) v = fma(J[m * 30 + a], r[m], v);
+            g[base + a] += v;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (want_J) __syncthreads();
+  }
+  return cost;
+}
+
+// LiDAR plane + edge factors of one keyframe reduced by one warp (HuberLoss corrector), into the pose diagonal block.
+__device__ double lidar_pass(const SolveParams& P, const Win& W, const double* x, double* H, double* g, double* hd, bool want_J) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npl = W.h->n_plane, ned = W.h->n_edge;
+  const double* pl = W.d(OFF_PLANE); const double* ed = W.d(OFF_EDGE);
+  const int32_t* pls = W.i(OFF_PLANE_START); const int32_t* eds = W.i(OFF_EDGE_START);
+  double cost = 0;
+  for (int k = warp; k < W.N; k += SOLVE_WARPS) {
+    const double* pose = x + XP(k);
+    double A[21], gg[6];
+#pragma unroll
+    for (int e = 0; e < 21; e++) A[e] = 0;
+#pragma unroll
+    for (int e = 0; e < 6; e++) gg[e] = 0;
+    if (npl) for (int f = pls[k] + lane; f < pls[k + 1]; f += 32) {
+      const vm::v3 pb = vm::mk(pl[f], pl[(size_t)npl + f], pl[(size_t)2 * npl + f]);
+      const vm::v3 n = vm::mk(pl[(size_t)3 * npl + f], pl[(size_t)4 * npl + f], pl[(size_t)5 * npl + f]);
+      double J[6];
+      double r = vf::plane_eval(pose, pb, n, pl[(size_t)6 * npl + f], want_J ? J : nullptr);
+      double rho, w; vf::huber(P.cfg.huber_a, r * r, rho, w);
+      cost += 0.5 * rho;
+      if (want_J) {
+        r *= w;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) { J[a] *= w; }
+#pragma unroll
+        for (int a = 0; a < 6; a++) { gg[a] = fma(J[a], r, gg[a]);
+#pragma unroll
+          for (int b = 0; b <= a; b++) { A[e] = fma(J[a], J[b], A[e]); e++; } }
+      }
+    }
+    if (ned) for (int f = eds[k] + lane; f < eds[k + 1]; f += 32) {
+      const vm::v3 pb = vm::mk(ed[f], ed[(size_t)ned + f], ed[(size_t)2 * ned + f]);
+      const vm::v3 a_ = vm::mk(ed[(size_t)3 * ned + f], ed[(size_t)4 * ned + f], ed[(size_t)5 * ned + f]);
+      const vm::v3 b_ = vm::mk(ed[(size_t)6 * ned + f], ed[(size_t)7 * ned + f], ed[(size_t)8 * ned + f]);
+      double r[3], J[18];
+      vf::edge_eval(pose, pb, a_, b_, r, want_J ? J : nullptr);
+      double rho, w; vf::huber(P.cfg.huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w);
+      cost += 0.5 * rho;
+      if (want_J) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double rm = r[m] * w;
+          int e = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) { const double ja = J[m * 6 + a] * w; gg[a] = fma(ja, rm, gg[a]);
+#pragma unroll
+            for (int b = 0; b <= a; b++) { A[e] = fma(ja, J[m * 6 + b] * w, A[e]); e++; } }
+        }
+      }
+    }
+    if (want_J) {
+#pragma unroll
+      for (int e = 0; e < 21; e++) A[e] = warp_sum(A[e]);
+#pragma unroll
+      for (int e = 0; e < 6; e++) gg[e] = warp_sum(gg[e]);
+      if (lane == 0) {
+        int e = 0;
+        for (int a = 0; a < 6; a++) { g[15 * k + a] += gg[a];
+          for (int b = 0; b <= a; b++) { H[tidx(15 * k + a, 15 * k + b)] += A[e]; if (a == b) hd[15 * k + a] += A[e]; e++; } }
+      }
+    }
+  }
+  return cost;
+}
+
+// ICP (<=5) and LPS (<=7) autodiff constraints: thread 0..n evaluates into smem, then the whole block adds one factor at a time.
+__device__ double icp_lps_pass(const SolveParams& P, const Win& W, const double* x, double* H, double* g, double* hd, double* stage, bool want_J) {
+  const int nicp = W.h->n_icp, nlps = W.h->n_lps;
+  if (nicp + nlps == 0) return 0.0;
+  const double* icp = W.d(OFF_ICP); const double* lps = W.d(OFF_LPS);
+  double cost = 0;
+  // stage per factor: 76 doubles (r 3 | J 3x24 | pad)
+  const int t = threadIdx.x;
+  if (t < nicp) {
+    const double* c = icp + 14 * t; double* s = stage + 76 * t;
+    vf::icp_eval(c, x + XP((int)c[10]), x + XP((int)c[11]), x + XP((int)c[12]), x + XP((int)c[13]), s, s + 3);
+    double rho, w; vf::cauchy(P.cfg.cauchy_a, s[0] * s[0] + s[1] * s[1] + s[2] * s[2], rho, w);
+    cost += 0.5 * rho;
+    for (int k = 0; k < 75; k++) s[k] *= w;
+  } else if (t < nicp + nlps) {
+    const double* c = lps + 9 * (t - nicp); double* s = stage + 76 * t;
+    vf::lps_eval(c, x + XP((int)c[7]), x + XP((int)c[8]), s, s + 3);
+    double rho, w; vf::cauchy(P.cfg.cauchy_a, s[0] * s[0] + s[1] * s[1] + s[2] * s[2], rho, w);
+    cost += 0.5 * rho;
+    for (int k = 0; k < 39; k++) s[k] *= w;
+  }
+  if (!want_J) return cost;
+  __syncthreads();
+  for (int f = 0; f < nicp + nlps; f++) {
+    const bool is_icp = f < nicp;
+    const int nbk = is_icp ? 4 : 2, wdt = 6 * nbk;
+    const double* c = is_icp ? icp + 14 * f : lps + 9 * (f - nicp);
+    const double* s = stage + 76 * f;
+    int kf[4];
+    for (int b = 0; b < nbk; b++) kf[b] = (int)(is_icp ? c[10 + b] : c[7 + b]);
+    for (int e = t; e < wdt * wdt + wdt; e += blockDim.x) {
+      if (e < wdt * wdt) {
+        const int a = e / wdt, b = e % wdt;
+        const int ca = 15 * kf[a / 6] + a % 6, cb2 = 15 * kf[b / 6] + b % 6;
+        // the pose blocks of one constraint are distinct (ceres rejects duplicates) but not ordered: keep ca >= cb
+        if (ca < cb2) continue;
+        const double v = s[3 + a] * s[3 + b] + s[3 + wdt + a] * s[3 + wdt + b] + s[3 + 2 * wdt + a] * s[3 + 2 * wdt + b];
+        H[tidx(ca, cb2)] += v; if (ca == cb2) hd[ca] += v;
+      } else {
+        const int a = e - wdt * wdt;
+        g[15 * kf[a / 6] + a % 6] += s[3 + a] * s[0] + s[3 + wdt + a] * s[1] + s[3 + 2 * wdt + a] * s[2];
+      }
+    }
+    __syncthreads();
+  }
+  return cost;
+}
+
+// MarginalizationFactor (factor/marginalization_factor.cpp:352-400): r = r_lin + J_lin dx. A = J^T J and b0 = J^T r_lin are
+// constant across iterations and precomputed by prep_kernel, so g += b0 + A dx, H += A, cost = 1/2 |r|^2.
+__device__ double prior_pass(const SolveParams& P, const Win& W, const double* x, double* H, double* g, double* hd, double* dxp /* n doubles smem */,
+                             const double* scr, bool want_J) {
+  const int n = W.h->prior_n;
+  if (n == 0) return 0.0;
+  const int nblk = W.h->prior_nblk;
+  const int32_t* blk = W.i(OFF_PRIOR_BLK); const int32_t* col = W.i(OFF_PRIOR_COL);
+  const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J); const double* rl = W.d(OFF_PRIOR_R);
+  const double* A = scr + P.sl.priorA; const double* b0 = scr + P.sl.priorb0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
+    const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(W.N, idx) : type == VILS_BLK_EXPOSE ? x + XE(W.N) : x + XT(W.N);
+    if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) vf::prior_dx_pose(xb, x0 + xo, dxp + c0);
+    else { const int sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dxp[c0 + k] = xb[k] - x0[xo + k]; }
+  }
+  __syncthreads();
+  double cost = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = rl[i];
+    for (int j = 0; j < n; j++) r = fma(Jl[(size_t)j * n + i], dxp[j], r);
+    cost += 0.5 * r * r;
+  }
+  if (want_J) {
+    for (int e = threadIdx.x; e < n * n + n; e += blockDim.x) {
+      if (e < n * n) {
+        const int a = e / n, b = e % n;
+        const int ca = col[a], cb2 = col[b];
+        if (ca < cb2) continue;
+        H[tidx(ca, cb2)] += A[(size_t)a * n + b];
+        if (ca == cb2) hd[ca] += A[(size_t)a * n + b];
+      } else {
+        const int a = e - n * n;
+        double v = b0[a];
+        for (int j = 0; j < n; j++) v = fma(A[(size_t)a * n + j], dxp[j], v);
+        g[col[a]] += v;
+      }
+    }
+  }
+  return cost;
+}
+
+// =================================================================================================================
+// C: blocked Cholesky of the tile-packed lower matrix, with b (= -g) carried along as an extra row.
+// On exit: H holds L, linv[kb] the inverse of each diagonal tile, y = L^-1 b in `b`.  Returns false on breakdown.
+// =================================================================================================================
+__device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* flag) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int kb = 0; kb < nb; kb++) {
+    double* Akk = H + ((size_t)(tri(kb) + kb) << 8);
+    double* Li = linv + kb * 256;
+    if (warp == 0) {
+      // unblocked Cholesky of the 16x16 tile: lane i < 16 owns row i
+      for (int j = 0; j < 16; j++) {
+        double d = Akk[j * 16 + j];
+        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *flag = 1; d = 1.0; }
+        d = sqrt(d);
+        __syncwarp();
+        if (lane == j) Akk[j * 16 + j] = d;
+        if (lane > j && lane < 16) Akk[lane * 16 + j] /= d;
+        __syncwarp();
+        if (lane > j && lane < 16) { const double lij = Akk[lane * 16 + j]; for (int k = j + 1; k <= lane; k++) Akk[lane * 16 + k] -= lij * Akk[k * 16 + j]; }
+        __syncwarp();
+      }
+      // inverse of the lower-triangular tile: lane c < 16 solves L z = e_c
+      if (lane < 16) {
+        double z[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < 16; k++) if (k < i) s -= Akk[i * 16 + k] * z[k];
+          z[i] = (i >= lane) ? s / Akk[i * 16 + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) Li[i * 16 + lane] = z[i];
+      }
+    }
+    __syncthreads();
+    // panel: rows of tiles (ib, kb), ib > kb, and the b row:  X <- X Lkk^-T   (X[r][c] = sum_{m<=c} X[r][m] Linv[c][m])
+    const int nrows = (nb - kb - 1) * 16 + 1;
+    for (int rr = t; rr < nrows; rr += blockDim.x) {
+      double* row = (rr == nrows - 1) ? b + kb * 16 : H + ((size_t)(tri(kb + 1 + rr / 16) + kb) << 8) + (rr & 15) * 16;
+      double v[16], o[16];
+#pragma unroll
+      for (int m = 0; m < 16; m++) v[m] = row[m];
+#pragma unroll
+      for (int c = 0; c < 16; c++) { double s = 0;
+#pragma unroll
+        for (int m = 0; m < 16; m++) if (m <= c) s = fma(v[m], Li[c * 16 + m], s);
+        o[c] = s; }
+#pragma unroll
+      for (int c = 0; c < 16; c++) row[c] = o[c];
+    }
+    __syncthreads();
+    // trailing update: A(ib,jb) -= L(ib,kb) L(jb,kb)^T for kb < jb <= ib; b(jb) -= y(kb) L(jb,kb)^T. 4x4 register tiles.
+    const int rem = nb - kb - 1;
+    const int nitems = tri(rem) * 16 + rem;     // 16 sub-tiles per tile + one b item per tile row
+    for (int it = t; it < nitems; it += blockDim.x) {
+      if (it < tri(rem) * 16) {
+        const int tl = it >> 4, sub = it & 15;
+        int bi = (int)((sqrtf(8.0f * tl + 1.0f) - 1.0f) * 0.5f);
+        while (bi * (bi + 1) / 2 > tl) bi--;
+        while ((bi + 1) * (bi + 2) / 2 <= tl) bi++;
+        const int bj = tl - bi * (bi + 1) / 2;
+        const int ib = kb + 1 + bi, jb = kb + 1 + bj;
+        const double* Lik = H + ((size_t)(tri(ib) + kb) << 8);
+        const double* Ljk = H + ((size_t)(tri(jb) + kb) << 8);
+        double* Aij = H + ((size_t)(tri(ib) + jb) << 8);
+        const int r0 = (sub >> 2) * 4, c0 = (sub & 3) * 4;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) acc[a][c] = 0;
+#pragma unroll 4
+        for (int m = 0; m < 16; m++) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int a = 0; a < 4; a++) av[a] = Lik[(r0 + a) * 16 + m];
+#pragma unroll
+          for (int c = 0; c < 4; c++) bv[c] = Ljk[(c0 + c) * 16 + m];
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) Aij[(r0 + a) * 16 + c0 + c] -= acc[a][c];
+      } else {
+        const int jb = kb + 1 + (it - tri(rem) * 16);
+        const double* Ljk = H + ((size_t)(tri(jb) + kb) << 8);
+        const double* yk = b + kb * 16;
+        for (int c = 0; c < 16; c++) { double s = 0; for (int m = 0; m < 16; m++) s = fma(yk[m], Ljk[c * 16 + m], s); b[jb * 16 + c] -= s; }
+      }
+    }
+    __syncthreads();
+  }
+  return *flag == 0;
+}
+
+// Back-substitution L^T x = y (y in `b`, x written to `dx`), blocked with the stored tile inverses.
+__device__ void backsub_tiles(const double* H, const double* b, const double* linv, double* dx, int nb, double* tmp /*16*/) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int kb = nb - 1; kb >= 0; kb--) {
+    // tmp[c] = y[kb][c] - sum_{ib>kb} sum_r L(ib,kb)[r][c] dx[ib*16+r]     (warp w <-> column c = w)
+    for (int c = warp; c < 16; c += SOLVE_WARPS) {
+      double s = 0;
+      for (int rr = lane; rr < (nb - 1 - kb) * 16; rr += 32) {
+        const int ib = kb + 1 + rr / 16, r = rr & 15;
+        s = fma(H[((size_t)(tri(ib) + kb) << 8) + r * 16 + c], dx[ib * 16 + r], s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) tmp[c] = b[kb * 16 + c] - s;
+    }
+    __syncthreads();
+    if (t < 16) {   // dx_kb = Lkk^-T tmp : x[c] = sum_{m>=c} Linv[m][c] tmp[m]
+      const double* Li = linv + kb * 256;
+      double s = 0;
+      for (int m = t; m < 16; m++) s = fma(Li[m * 16 + t], tmp[m], s);
+      dx[kb * 16 + t] = s;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace vb

@@ -1,0 +1,851 @@
+// vils_ba.cu — sliding-window BA part of libvils_b200.so: host packer + kernels + C-ABI (include/vils_cabi.h).
+// Replaces the body of Estimator::optimization() between vector2double() and double2vector()
+// (vils_estimator/src/estimator.cpp:1124-1419) and the factor Evaluate()s it drives through ceres.
+// There is no CPU path: every entry point fails with VILS_ERR_NO_DEVICE when no sm_100 device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ba_device.cuh"
+#include "common.h"
+
+using namespace vb;
+
+// =================================================================================================================
+// kernels
+// =================================================================================================================
+__device__ __forceinline__ Win decode(const SolveParams& P, int slot) {
+  Win W; W.base = P.blobs + (size_t)slot * P.blob_stride; W.h = reinterpret_cast<const WinHdr*>(W.base);
+  W.N = W.h->n_kf; W.M = W.h->n_feat; W.D = 15 * W.N + 7; W.Dv = 6 * W.N + 7; W.Dvp = P.sl.Dv_pad; W.nb = (W.D + TB - 1) / TB;
+  return W;
+}
+
+// Once per upload: IMU sqrt_info (imu_factor.h:64 recomputes it in every Evaluate; it only depends on the
+// pre-integration), prior A = J_lin^T J_lin and b0 = J_lin^T r_lin, and the zero pattern of E.
+__global__ void prep_kernel(SolveParams P) {
+  const int slot = P.slot0 + blockIdx.x;
+  const Win W = decode(P, slot);
+  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  const double* pre = W.d(OFF_IMU);
+  if ((int)threadIdx.x < W.h->n_imu) {
+    double Wm[225];
+    if (!vf::imu_sqrt_info(pre + (size_t)threadIdx.x * 467 + 242, Wm)) for (int i = 0; i < 225; i++) Wm[i] = nan("");
+    for (int i = 0; i < 225; i++) scr[P.sl.w_imu + (size_t)threadIdx.x * 225 + i] = Wm[i];
+  }
+  const int n = W.h->prior_n;
+  const double* J = W.d(OFF_PRIOR_J); const double* r = W.d(OFF_PRIOR_R);
+  for (int e = threadIdx.x; e < n * n + n; e += blockDim.x) {
+    if (e < n * n) {
+      const int a = e / n, b = e % n; double s = 0;
+      for (int i = 0; i < n; i++) s = fma(J[(size_t)a * n + i], J[(size_t)b * n + i], s);
+      scr[P.sl.priorA + e] = s;
+    } else {
+      const int a = e - n * n; double s = 0;
+      for (int i = 0; i < n; i++) s = fma(J[(size_t)a * n + i], r[i], s);
+      scr[P.sl.priorb0 + a] = s;
+    }
+  }
+  for (int64_t e = threadIdx.x; e < (int64_t)W.h->n_lm * P.sl.Dv_pad; e += blockDim.x) scr[P.sl.E + e] = 0.0;
+}
+
+__device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
+  if (d >= W.D) return true;                      // tile padding
+  if (d >= 15 * W.N + 6) return !P.cfg.use_td;
+  if (d >= 15 * W.N) return !P.cfg.est_ex;
+  return W.u(OFF_FIXED)[W.M + d / 15] != 0;       // kf_fixed
+}
+
+// Full linearisation at state x: H (tiles, lower), g, hd and the cost (broadcast to all threads).
+__device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x, double* H, double* Hv,
+                            double mu) {
+  double* g = sm + L.g; double* hd = sm + L.hd;
+  double c = pair_pass(P, W, x, sm + L.uni, scr);
+  __syncthreads();
+  landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu);
+  for (int e = threadIdx.x; e < W.Dvp * W.Dv; e += blockDim.x) Hv[e] = 0.0;
+  __syncthreads();
+  schur_syrk(P, W, sm + L.cinv, sm + L.glam, Hv, sm + L.gv, sm + L.uni, scr);
+  __syncthreads();
+  for (int e = threadIdx.x; e < tri(W.nb) * TB * TB; e += blockDim.x) H[e] = 0.0;
+  for (int e = threadIdx.x; e < W.nb * TB; e += blockDim.x) { g[e] = 0.0; hd[e] = 0.0; }
+  __syncthreads();
+  gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr);
+  __syncthreads();
+  c += imu_pass(P, W, x, H, g, hd, sm + L.imu, scr, true);
+  c += lidar_pass(P, W, x, H, g, hd, true);
+  __syncthreads();
+  c += icp_lps_pass(P, W, x, H, g, hd, sm + L.imu, true);
+  c += prior_pass(P, W, x, H, g, hd, sm + L.dx, scr, true);
+  __syncthreads();
+  return block_sum(c, sm + L.red);
+}
+
+__device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x) {
+  double c = 0;
+  for (int f = threadIdx.x; f < W.h->n_proj; f += blockDim.x) c += proj_cost(P, W, x, f);
+  c += imu_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, scr, false);
+  c += lidar_pass(P, W, x, nullptr, nullptr, nullptr, false);
+  __syncthreads();
+  c += icp_lps_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, false);
+  c += prior_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.dx, scr, false);
+  __syncthreads();
+  return block_sum(c, sm + L.red);
+}
+
+// Constant blocks -> identity rows/cols (problem.SetParameterBlockConstant, estimator.cpp:1154-1166,1217-1221,1368-1370),
+// Levenberg/Jacobi damping d2 = mu clamp(diag), b = -g.
+__device__ void damp_and_fix(const SolveParams& P, const Win& W, double* H, double* g, const double* hd, double mu) {
+  const int Dp = W.nb * TB;
+  for (int e = threadIdx.x; e < Dp * (Dp + 1) / 2; e += blockDim.x) {
+    int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while (i * (i + 1) / 2 > e) i--;
+    while ((i + 1) * (i + 2) / 2 <= e) i++;
+    const int j = e - i * (i + 1) / 2;
+    const bool fi = cam_dim_fixed(P, W, i), fj = cam_dim_fixed(P, W, j);
+    if (i == j) {
+      if (fi) H[tidx(i, i)] = 1.0 + mu;
+      else H[tidx(i, i)] += mu * fmin(fmax(hd[i], 1e-12), 1e64);
+    } else if (fi || fj) H[tidx(i, j)] = 0.0;
+  }
+  for (int i = threadIdx.x; i < Dp; i += blockDim.x) g[i] = cam_dim_fixed(P, W, i) ? 0.0 : -g[i];
+}
+
+// dl_f = -cinv_f (g_l + E_f^T dx_v) ; lam += dl ; poses/speed-bias/ex/td (+)= dx
+__device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, double* sm, const double* scr, const double* xin, double* xout) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* dx = sm + L.dx; const double* cinv = sm + L.cinv; const double* glam = sm + L.glam;
+  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const int X = 16 * W.N + 8 + W.M;
+  if (xout != xin) { for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k]; __syncthreads(); }
+  for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
+    double s = 0;
+    for (int a = lane; a < W.Dv; a += 32) s = fma(E[(size_t)rnk * W.Dvp + a], dx[vis2cam(a, W.N)], s);
+    s = warp_sum(s);
+    if (lane == 0) xout[XL(W.N) + lm_feat[rnk]] += -cinv[rnk] * (glam[rnk] + s);
+  }
+  for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
+    if (k < W.N) {
+      vm::pose_plus(xout + XP(k), dx + 15 * k);
+      for (int i = 0; i < 9; i++) xout[XS(W.N, k) + i] += dx[15 * k + 6 + i];
+    } else {
+      vm::pose_plus(xout + XE(W.N), dx + 15 * W.N);
+      xout[XT(W.N)] += dx[15 * W.N + 6];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int chol_flag;
+  const int slot = P.slot0 + blockIdx.x;
+  const Win W = decode(P, slot);
+  const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
+  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* H = P.h_in_smem ? sm + L.uni : scr + P.sl.Hg;
+  double* Hv = P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg;
+  double* xs = sm + L.xs; double* xc = sm + L.xc;
+  const int X = 16 * W.N + 8 + W.M;
+  const double* x0 = W.d(OFF_X);
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
+  if (threadIdx.x == 0) chol_flag = 0;
+  __syncthreads();
+
+  int status = VILS_OK, iters = 0, accepted = 0;
+  double cost0 = 0, cost = 0;
+
+  if (P.lin_out) {   // vils_ba_linearize: one linearisation, fixed blocks applied, no damping
+    cost = linearize(P, W, L, sm, scr, xs, H, Hv, 0.0);
+    damp_and_fix(P, W, H, sm + L.g, sm + L.hd, 0.0);
+    __syncthreads();
+    const int D = W.D;
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; P.lin_out[e] = H[tidx(max(i, j), min(i, j))]; }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) P.lin_out[(size_t)D * D + i] = -sm[L.g + i];
+    if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = cost;
+    return;
+  }
+
+  if (P.mode == VILS_MODE_GN) {
+    for (int it = 0; it < P.max_iters; it++) {
+      cost = linearize(P, W, L, sm, scr, xs, H, Hv, P.mu);
+      if (it == 0) cost0 = cost;
+      if (!isfinite(cost)) { status = VILS_ERR_NOT_FINITE; break; }
+      damp_and_fix(P, W, H, sm + L.g, sm + L.hd, P.mu);
+      __syncthreads();
+      cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
+      if (chol_flag) { status = VILS_ERR_CHOLESKY; break; }
+      backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
+      apply_step(P, W, L, sm, scr, xs, xs);
+      iters++; accepted++;
+    }
+    if (status == VILS_OK) {
+      cost = cost_only(P, W, L, sm, scr, xs);
+      if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE;
+    }
+  } else {
+    // Levenberg-Marquardt after ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g,
+    // rho = (cost - new_cost) / model_change, accept if rho > min_relative_decrease.
+    double radius = P.lm_radius, decrease = 2.0;
+    cost = linearize(P, W, L, sm, scr, xs, H, Hv, 1.0 / radius);
+    cost0 = cost; iters = 1;
+    bool have_lin = true;
+    if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE;
+    for (int it = 0; it < P.max_iters && status == VILS_OK; it++) {
+      const double mu = 1.0 / radius;
+      if (!have_lin) { linearize(P, W, L, sm, scr, xs, H, Hv, mu); have_lin = true; }
+      damp_and_fix(P, W, H, sm + L.g, sm + L.hd, mu);
+      __syncthreads();
+      // b = -g_r is overwritten by the fused forward solve: keep a copy for the model decrease
+      double* bsave = sm + L.imu;   // ((Ncap+1)/2)*466 doubles >= nb*16
+      for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) bsave[i] = sm[L.g + i];
+      if (threadIdx.x == 0) chol_flag = 0;
+      __syncthreads();
+      cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
+      const bool ok = chol_flag == 0;
+      double rho = -1, new_cost = 0;
+      if (ok) {
+        backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
+        // With (H + D2) d = -g over the full camera + landmark system: cost - model(d) = -1/2 g^T d + 1/2 d^T D2 d, where
+        // the unreduced camera gradient is g_c = g_r + E Cd^-1 g_l  (Cd = damped landmark diagonal).
+        double p2 = 0;
+        for (int i = threadIdx.x; i < W.D; i += blockDim.x) {
+          const double d = sm[L.dx + i];
+          const double d2 = cam_dim_fixed(P, W, i) ? mu : mu * fmin(fmax(sm[L.hd + i], 1e-12), 1e64);
+          p2 += 0.5 * bsave[i] * d + 0.5 * d2 * d * d;
+        }
+        {
+          const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+          const double* E = scr + P.sl.E;
+          for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
+            double sdot = 0;
+            for (int a = lane; a < W.Dv; a += 32) sdot = fma(E[(size_t)rnk * W.Dvp + a], sm[L.dx + vis2cam(a, W.N)], sdot);
+            sdot = warp_sum(sdot);
+            if (lane == 0 && sm[L.cinv + rnk] != 0.0) {
+              const double ci = sm[L.cinv + rnk], gl = sm[L.glam + rnk];
+              const double dl = -ci * (gl + sdot);
+              const double Cd = 1.0 / ci, C = Cd / (1.0 + mu);   // exact while C sits inside the clamp range [1e-12, 1e64]
+              p2 += -0.5 * ci * gl * sdot - 0.5 * gl * dl + 0.5 * (Cd - C) * dl * dl;
+            }
+          }
+        }
+        const double model = block_sum(p2, sm + L.red);
+        apply_step(P, W, L, sm, scr, xs, xc);
+        new_cost = cost_only(P, W, L, sm, scr, xc);
+        rho = (isfinite(new_cost) && model > 0) ? (cost - new_cost) / model : -1;
+      }
+      if (ok && rho > P.min_rel_dec) {
+        double xn = 0, dn = 0;
+        for (int k = threadIdx.x; k < X; k += blockDim.x) { xn += xs[k] * xs[k]; const double dd = xc[k] - xs[k]; dn += dd * dd; }
+        xn = block_sum(xn, sm + L.red); dn = block_sum(dn, sm + L.red);
+        for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
+        __syncthreads();
+        accepted++;
+        const double t3 = 2.0 * rho - 1.0;
+        radius = fmin(radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3), 1e16); decrease = 2.0;
+        const double change = cost - new_cost; cost = new_cost;
+        if (fabs(change) / (cost + 1e-300) < P.f_tol) break;
+        if (sqrt(dn) <= P.p_tol * (sqrt(xn) + P.p_tol)) break;
+        have_lin = false;
+        if (it + 1 < P.max_iters) iters++; else break;
+      } else {
+        radius /= decrease; decrease *= 2.0;
+        if (radius < 1e-32) break;
+        have_lin = false;      // damping changed: rebuild (H is overwritten by the factorisation)
+      }
+    }
+  }
+  double* xo = P.xout + (size_t)slot * P.xout_stride;
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xs[k];
+  if (threadIdx.x == 0) {
+    vils_summary s; s.status = status; s.iterations = iters; s.accepted = accepted; s.reserved = 0; s.cost_initial = cost0; s.cost_final = cost;
+    P.summary[slot] = s;
+  }
+}
+
+// ---- materialised evaluation: one thread per factor, outputs in the caller's original factor order -----------------
+struct EvalParams {
+  SolveParams S;
+  double* r_out; double* J_out; int64_t r_stride, J_stride;   // per-slot strides (doubles)
+  int32_t apply_loss;
+};
+
+__global__ void eval_kernel(EvalParams Q) {
+  const SolveParams& P = Q.S;
+  const int slot = P.slot0 + blockIdx.y;
+  const Win W = decode(P, slot);
+  const WinHdr* h = W.h;
+  const double* x = W.d(OFF_X);
+  const double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = W.N;
+  int rbase = 0; int64_t jbase = 0;
+  if (t < h->n_imu) {
+    const int i = W.i(OFF_IMU_KF)[t];
+    double r[15], J[450], Jw[450];
+    for (int e = 0; e < 450; e++) J[e] = 0;
+    vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)t * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
+    const double* Wk = scr + P.sl.w_imu + (size_t)t * 225;
+    for (int a = 0; a < 15; a++) {
+      double s = 0; for (int m = a; m < 15; m++) s = fma(Wk[a * 15 + m], r[m], s);
+      R[15 * t + a] = s;
+      for (int c = 0; c < 30; c++) { double v = 0; for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v); Jw[a * 30 + c] = v; }
+    }
+    for (int e = 0; e < 450; e++) Jo[(size_t)450 * t + e] = Jw[e];
+    return;
+  }
+  t -= h->n_imu; rbase += 15 * h->n_imu; jbase += (int64_t)450 * h->n_imu;
+  if (t < h->n_proj) {
+    const int np = h->n_proj; const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
+    double c[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + t];
+    const int i = ix[t], j = ix[np + t], feat = W.i(OFF_LM_FEAT)[ix[2 * np + t]], orig = ix[3 * np + t];
+    double r[2], J[40];
+    vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(N), x[XL(N) + feat], x[XT(N)], r, J);
+    double w = 1.0;
+    if (Q.apply_loss) { double rho; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w); }
+    R[rbase + 2 * orig] = r[0] * w; R[rbase + 2 * orig + 1] = r[1] * w;
+    double* o = Jo + jbase + (int64_t)40 * orig;
+#pragma unroll
+    for (int e = 0; e < 40; e++) o[e] = J[e] * w;
+    return;
+  }
+  t -= h->n_proj; rbase += 2 * h->n_proj; jbase += (int64_t)40 * h->n_proj;
+  if (t < h->n_plane) {
+    const int n = h->n_plane; const double* pl = W.d(OFF_PLANE); const int32_t* ix = W.i(OFF_PLANE_IDX);
+    double J[6];
+    double r = vf::plane_eval(x + XP(ix[t]), vm::mk(pl[t], pl[(size_t)n + t], pl[(size_t)2 * n + t]),
+                              vm::mk(pl[(size_t)3 * n + t], pl[(size_t)4 * n + t], pl[(size_t)5 * n + t]), pl[(size_t)6 * n + t], J);
+    double w = 1.0;
+    if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r * r, rho, w); }
+    const int orig = ix[n + t];
+    R[rbase + orig] = r * w;
+    for (int e = 0; e < 6; e++) Jo[jbase + (int64_t)6 * orig + e] = J[e] * w;
+    return;
+  }
+  t -= h->n_plane; rbase += h->n_plane; jbase += (int64_t)6 * h->n_plane;
+  if (t < h->n_edge) {
+    const int n = h->n_edge; const double* ed = W.d(OFF_EDGE); const int32_t* ix = W.i(OFF_EDGE_IDX);
+    double r[3], J[18];
+    vf::edge_eval(x + XP(ix[t]), vm::mk(ed[t], ed[(size_t)n + t], ed[(size_t)2 * n + t]),
+                  vm::mk(ed[(size_t)3 * n + t], ed[(size_t)4 * n + t], ed[(size_t)5 * n + t]),
+                  vm::mk(ed[(size_t)6 * n + t], ed[(size_t)7 * n + t], ed[(size_t)8 * n + t]), r, J);
+    double w = 1.0;
+    if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
+    const int orig = ix[n + t];
+    for (int e = 0; e < 3; e++) R[rbase + 3 * orig + e] = r[e] * w;
+    for (int e = 0; e < 18; e++) Jo[jbase + (int64_t)18 * orig + e] = J[e] * w;
+    return;
+  }
+  t -= h->n_edge; rbase += 3 * h->n_edge; jbase += (int64_t)18 * h->n_edge;
+  if (t < h->n_icp) {
+    const double* c = W.d(OFF_ICP) + 14 * t; double r[3], J[72];
+    vf::icp_eval(c, x + XP((int)c[10]), x + XP((int)c[11]), x + XP((int)c[12]), x + XP((int)c[13]), r, J);
+    double w = 1.0;
+    if (Q.apply_loss) { double rho; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
+    for (int e = 0; e < 3; e++) R[rbase + 3 * t + e] = r[e] * w;
+    for (int e = 0; e < 72; e++) Jo[jbase + (int64_t)72 * t + e] = J[e] * w;
+    return;
+  }
+  t -= h->n_icp; rbase += 3 * h->n_icp; jbase += (int64_t)72 * h->n_icp;
+  if (t < h->n_lps) {
+    const double* c = W.d(OFF_LPS) + 9 * t; double r[3], J[36];
+    vf::lps_eval(c, x + XP((int)c[7]), x + XP((int)c[8]), r, J);
+    double w = 1.0;
+    if (Q.apply_loss) { double rho; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
+    for (int e = 0; e < 3; e++) R[rbase + 3 * t + e] = r[e] * w;
+    for (int e = 0; e < 36; e++) Jo[jbase + (int64_t)36 * t + e] = J[e] * w;
+    return;
+  }
+  t -= h->n_lps; rbase += 3 * h->n_lps;
+  if (t < h->prior_n) {   // MarginalizationFactor residual row t (marginalization_factor.cpp:364-383)
+    const int n = h->prior_n; const int32_t* blk = W.i(OFF_PRIOR_BLK);
+    const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
+    double r = W.d(OFF_PRIOR_R)[t];
+    for (int b = 0; b < h->prior_nblk; b++) {
+      const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
+      const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
+      double dx[9]; int sz;
+      if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
+      else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
+      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + t], dx[k], r);
+    }
+    R[rbase + t] = r;
+  }
+}
+
+// =================================================================================================================
+// host
+// =================================================================================================================
+struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; int bytes = 0; };
+
+struct vils_ba {
+  vils_config cfg{};
+  int max_windows = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  size_t blob_stride = 0;
+  uint8_t* h_blob = nullptr; uint8_t* d_blob = nullptr;
+  ScratchLayout sl{};
+  double* d_scratch = nullptr;
+  int64_t xstride = 0;
+  double* d_xout = nullptr; double* h_xout = nullptr;
+  vils_summary* d_sum = nullptr; vils_summary* h_sum = nullptr;
+  double* d_lin = nullptr; double* h_lin = nullptr;
+  double* d_er = nullptr; double* d_eJ = nullptr; int64_t er_stride = 0, eJ_stride = 0;
+  std::vector<SlotMeta> meta;
+  int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
+  float last_ms = 0; int last_launches = 0;
+  bool prepped = false;
+};
+
+static inline size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
+
+static size_t blob_capacity(const vils_config& c) {
+  const size_t N = c.max_kf, M = c.max_feat, Pn = c.max_proj, Ln = c.max_lidar, n = 15 * N + 7;
+  size_t b = al16(sizeof(WinHdr));
+  b += al16((16 * N + 8 + M) * 8) + al16(M + N) + al16(N * 467 * 8) + al16(N * 4);
+  b += al16(14 * Pn * 8) + al16(4 * Pn * 4) + al16((M + 1) * 4) + al16(M * 4) + al16(N * N * 4 * 4) + al16(Pn * 4) + al16(N * N * 4);
+  b += al16(7 * Ln * 8) + al16(2 * Ln * 4) + al16((N + 1) * 4) + al16(9 * Ln * 8) + al16(2 * Ln * 4) + al16((N + 1) * 4);
+  b += al16(16 * 14 * 8) + al16(16 * 9 * 8);
+  b += al16(n * n * 8) + al16(n * 8) + al16((2 * N + 2) * 9 * 8) + al16((2 * N + 2) * 16) + al16(n * 4);
+  return (b + 255) & ~size_t(255);
+}
+
+static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
+  SolveParams P{};
+  P.blobs = ba->d_blob; P.blob_stride = (int64_t)ba->blob_stride;
+  P.scratch = ba->d_scratch; P.sl = ba->sl;
+  P.xout = ba->d_xout; P.xout_stride = ba->xstride; P.summary = ba->d_sum;
+  const vils_config& c = ba->cfg;
+  P.cfg.s_info = c.focal_length / 2.0;
+  for (int i = 0; i < 3; i++) P.cfg.G[i] = c.gravity[i];
+  P.cfg.tr_over_row = c.tr / c.row; P.cfg.half_row = c.row / 2.0;
+  P.cfg.cauchy_a = c.cauchy_visual; P.cfg.huber_a = c.huber_lidar;
+  P.cfg.use_td = c.estimate_td; P.cfg.est_ex = c.estimate_extrinsic;
+  if (o) {
+    P.mode = o->mode; P.max_iters = o->max_iters; P.mu = o->mu; P.lm_radius = o->lm_initial_radius; P.f_tol = o->function_tolerance;
+    P.p_tol = o->parameter_tolerance; P.min_rel_dec = o->min_relative_decrease;
+  }
+  P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
+  P.lin_out = nullptr; P.slot0 = 0;
+  return P;
+}
+
+extern "C" {
+
+int vils_abi_version(void) { return VILS_ABI_VERSION; }
+const char* vils_last_error(void) { return vils::last_error().c_str(); }
+
+void vils_default_config(vils_config* cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->focal_length = 460.0;                                   // parameters.h:11
+  cfg->gravity[2] = 9.795;                                     // config/mynteye_leishen_indoor.yaml:102
+  cfg->tr = 0.0; cfg->row = 480.0;                             // yaml:12,118
+  cfg->cauchy_visual = 1.0; cfg->huber_lidar = 0.1;            // estimator.cpp:1129 ; localMapping.cpp:597
+  const double rli[9] = {-0.0320631, 0.000946093, -0.999485, -0.999482, -0.00274554, 0.0320604, -0.0027138, 0.999996, 0.00103363};  // yaml:43-47
+  for (int i = 0; i < 9; i++) cfg->rlb[i] = rli[i];
+  cfg->tlb[0] = 0.2; cfg->tlb[1] = -0.005; cfg->tlb[2] = -0.1;  // yaml:48-52
+  cfg->estimate_extrinsic = 1; cfg->estimate_td = 1;            // yaml:25,112
+  cfg->max_kf = 10; cfg->max_feat = 150; cfg->max_proj = 1400; cfg->max_lidar = 2000; cfg->device = 0;
+}
+
+void vils_default_solve_opts(vils_solve_opts* o) {
+  if (!o) return;
+  o->mode = VILS_MODE_GN; o->max_iters = 5; o->mu = 1e-8; o->lm_initial_radius = 1e4; o->function_tolerance = 1e-6;
+  o->parameter_tolerance = 1e-8; o->min_relative_decrease = 1e-3;
+}
+
+int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
+  if (!cfg || !out || max_windows <= 0 || cfg->max_kf < 2 || cfg->max_kf > 32 || cfg->max_feat < 0 || cfg->max_proj < 0 || cfg->max_lidar < 0)
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_create: bad argument");
+  int st = vils::require_device(cfg->device);
+  if (st) return st;
+  vils_ba* ba = new vils_ba();
+  ba->cfg = *cfg; ba->max_windows = max_windows;
+  ba->meta.resize(max_windows);
+  const int N = cfg->max_kf, M = cfg->max_feat, D = 15 * N + 7, Dv = 6 * N + 7, Dvp = (Dv + 3) & ~3, nb = (D + TB - 1) / TB;
+  ba->blob_stride = blob_capacity(*cfg);
+  // scratch layout
+  ScratchLayout& s = ba->sl; int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += (n + 1) & ~int64_t(1); return r; };
+  s.Dv_pad = Dvp;
+  s.w_imu = take((int64_t)N * 225); s.E = take((int64_t)M * Dvp); s.part = take((int64_t)cfg->max_proj * PART_LD);
+  s.pairpart = take((int64_t)N * (N - 1) / 2 * PAIR_LD * PAIR_LD); s.priorA = take((int64_t)D * D); s.priorb0 = take(D);
+  // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
+  int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  const size_t budget = (size_t)dev_smem - 1024;
+  ba->h_in_smem = 1; ba->hv_in_smem = 1;
+  if ((size_t)smem_layout(N, M, 1, 1).total * 8 > budget) { ba->h_in_smem = 0; }
+  if ((size_t)smem_layout(N, M, ba->h_in_smem, 1).total * 8 > budget) { ba->hv_in_smem = 0; }
+  ba->smem_bytes = (size_t)smem_layout(N, M, ba->h_in_smem, ba->hv_in_smem).total * 8;
+  if (ba->smem_bytes > budget) { delete ba; return vils::fail(VILS_ERR_CAPACITY, "vils_ba_create: window too large for shared memory plan"); }
+  s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TB * TB);
+  s.Hvg = ba->hv_in_smem ? 0 : take((int64_t)Dvp * Dvp);
+  s.total = o;
+  ba->xstride = 16 * N + 8 + M;
+  const int64_t n_lin = (int64_t)D * D + D + 1;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, #x); } } while (0)
+  CK(cudaStreamCreateWithFlags(&ba->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ba->ev0)); CK(cudaEventCreate(&ba->ev1));
+  CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
+  CK(cudaMalloc(&ba->d_blob, ba->blob_stride * max_windows));
+  CK(cudaMalloc(&ba->d_scratch, (size_t)s.total * 8 * max_windows));
+  CK(cudaMalloc(&ba->d_xout, (size_t)ba->xstride * 8 * max_windows));
+  CK(cudaMallocHost(&ba->h_xout, (size_t)ba->xstride * 8 * max_windows));
+  CK(cudaMalloc(&ba->d_sum, sizeof(vils_summary) * max_windows));
+  CK(cudaMallocHost(&ba->h_sum, sizeof(vils_summary) * max_windows));
+  CK(cudaMalloc(&ba->d_lin, n_lin * 8)); CK(cudaMallocHost(&ba->h_lin, n_lin * 8));
+  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+#undef CK
+  std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
+  std::memset(ba->h_sum, 0, sizeof(vils_summary) * max_windows);
+  *out = ba;
+  return VILS_OK;
+}
+
+void vils_ba_destroy(vils_ba* ba) {
+  if (!ba) return;
+  cudaSetDevice(ba->cfg.device);
+  if (ba->stream) cudaStreamSynchronize(ba->stream);
+  cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
+  cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ);
+  if (ba->ev0) cudaEventDestroy(ba->ev0);
+  if (ba->ev1) cudaEventDestroy(ba->ev1);
+  if (ba->stream) cudaStreamDestroy(ba->stream);
+  delete ba;
+}
+
+int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
+  if (!ba || !w || slot < 0 || slot >= ba->max_windows) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_window: bad slot / null");
+  const vils_config& c = ba->cfg;
+  const int N = w->n_kf, M = w->n_feat, np = w->n_proj, npl = w->n_plane, ned = w->n_edge;
+  if (N < 2 || N > c.max_kf || M < 0 || M > c.max_feat || np < 0 || np > c.max_proj || npl < 0 || ned < 0 || npl + ned > c.max_lidar ||
+      w->n_imu < 0 || w->n_imu > N - 1 + 0 || w->n_icp < 0 || w->n_icp > 16 || w->n_lps < 0 || w->n_lps > 16 || w->prior_n < 0 || w->prior_n > 15 * N + 7 ||
+      w->prior_nblk < 0 || w->prior_nblk > 2 * N + 2)
+    return vils::fail(VILS_ERR_CAPACITY, "vils_ba_set_window: window exceeds the handle's capacity");
+  if (!w->pose || !w->speedbias || !w->ex_pose || (M && !w->inv_depth) || (w->n_imu && (!w->imu || !w->imu_kf)) ||
+      (np && (!w->pts_i || !w->pts_j || !w->vel_i || !w->vel_j || !w->td_i || !w->td_j || !w->row_i || !w->row_j || !w->kf_i || !w->kf_j || !w->feat)) ||
+      (npl && (!w->plane_p || !w->plane_n || !w->plane_d || !w->plane_kf)) || (ned && (!w->edge_p || !w->edge_a || !w->edge_b || !w->edge_kf)) ||
+      (w->n_icp && !w->icp) || (w->n_lps && !w->lps) || (w->prior_n && (!w->prior_J || !w->prior_r || !w->prior_blk || !w->prior_x0)))
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_window: null array");
+  for (int k = 0; k < w->n_imu; k++) if (w->imu_kf[k] < 0 || w->imu_kf[k] + 1 >= N) return vils::fail(VILS_ERR_BAD_ARG, "imu_kf out of range");
+  for (int k = 0; k < np; k++)
+    if (w->kf_i[k] < 0 || w->kf_i[k] >= N || w->kf_j[k] < 0 || w->kf_j[k] >= N || w->kf_i[k] == w->kf_j[k] || w->feat[k] < 0 || w->feat[k] >= M)
+      return vils::fail(VILS_ERR_BAD_ARG, "projection factor index out of range");
+  for (int k = 0; k < npl; k++) if (w->plane_kf[k] < 0 || w->plane_kf[k] >= N) return vils::fail(VILS_ERR_BAD_ARG, "plane_kf out of range");
+  for (int k = 0; k < ned; k++) if (w->edge_kf[k] < 0 || w->edge_kf[k] >= N) return vils::fail(VILS_ERR_BAD_ARG, "edge_kf out of range");
+  for (int k = 0; k < w->n_icp; k++) for (int b = 0; b < 4; b++) if (w->icp[k].kf[b] < 0 || w->icp[k].kf[b] >= N) return vils::fail(VILS_ERR_BAD_ARG, "icp kf out of range");
+  for (int k = 0; k < w->n_lps; k++) for (int b = 0; b < 2; b++) if (w->lps[k].kf[b] < 0 || w->lps[k].kf[b] >= N) return vils::fail(VILS_ERR_BAD_ARG, "lps kf out of range");
+
+  // ---- orderings
+  std::vector<int> ord(np); std::iota(ord.begin(), ord.end(), 0);
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return w->feat[a] < w->feat[b]; });
+  std::vector<int> lm_start, lm_feat, rank_of(np);
+  for (int s = 0; s < np; s++) {
+    const int f = w->feat[ord[s]];
+    if (lm_feat.empty() || lm_feat.back() != f) { lm_feat.push_back(f); lm_start.push_back(s); }
+    else if (w->kf_i[ord[s]] != w->kf_i[ord[lm_start.back()]]) return vils::fail(VILS_ERR_BAD_ARG, "factors of one feature must share the anchor keyframe");
+    rank_of[s] = (int)lm_feat.size() - 1;
+  }
+  lm_start.push_back(np);
+  const int nlm = (int)lm_feat.size();
+  // pairs: landmark-sorted positions grouped by (kf_i, kf_j). The anchor may be any frame, pairs are ordered (i, j).
+  std::vector<int> pord(np); std::iota(pord.begin(), pord.end(), 0);
+  auto key = [&](int s) { return w->kf_i[ord[s]] * N + w->kf_j[ord[s]]; };
+  std::stable_sort(pord.begin(), pord.end(), [&](int a, int b) { return key(a) < key(b); });
+  std::vector<int> pairs; std::vector<int> pair_id(N * N, -1);
+  for (int s = 0; s < np; s++) {
+    const int k = key(pord[s]);
+    if (pairs.empty() || pairs[pairs.size() - 2] * N + pairs.back() != k) {
+      pair_id[k] = (int)pairs.size() / 4;
+      pairs.push_back(s); pairs.push_back(0); pairs.push_back(k / N); pairs.push_back(k % N);
+    }
+    pairs[pairs.size() - 3]++;
+  }
+  const int npair = (int)pairs.size() / 4;
+  if (npair > N * (N - 1) / 2) {
+    // the gather assumes anchor < observer (a feature's anchor is its first observation, estimator.cpp:1201-1206)
+    return vils::fail(VILS_ERR_BAD_ARG, "more keyframe pairs than N(N-1)/2: anchor must precede the observing frame");
+  }
+  for (int p = 0; p < npair; p++) if (pairs[4 * p + 2] >= pairs[4 * p + 3]) return vils::fail(VILS_ERR_BAD_ARG, "anchor keyframe must precede the observing keyframe");
+  auto sort_by_kf = [&](int n, const int32_t* kf, std::vector<int>& o, std::vector<int>& start) {
+    o.resize(n); std::iota(o.begin(), o.end(), 0);
+    std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return kf[a] < kf[b]; });
+    start.assign(N + 1, 0);
+    for (int k = 0; k < n; k++) start[kf[k] + 1]++;
+    for (int k = 0; k < N; k++) start[k + 1] += start[k];
+  };
+  std::vector<int> plo, pls, edo, eds;
+  sort_by_kf(npl, w->plane_kf, plo, pls); sort_by_kf(ned, w->edge_kf, edo, eds);
+
+  // ---- blob
+  uint8_t* base = ba->h_blob + (size_t)slot * ba->blob_stride;
+  WinHdr* h = reinterpret_cast<WinHdr*>(base);
+  std::memset(h, 0, sizeof(WinHdr));
+  h->n_kf = N; h->n_feat = M; h->n_imu = w->n_imu; h->n_proj = np; h->n_plane = npl; h->n_edge = ned; h->n_icp = w->n_icp; h->n_lps = w->n_lps;
+  h->prior_n = w->prior_n; h->prior_nblk = w->prior_nblk; h->n_lm = nlm; h->n_pair = npair;
+  size_t o = al16(sizeof(WinHdr));
+  auto place = [&](int which, size_t bytes) { h->off[which] = (int32_t)o; uint8_t* p = base + o; o += al16(bytes); return p; };
+  double* x = (double*)place(OFF_X, (size_t)(16 * N + 8 + M) * 8);
+  std::memcpy(x, w->pose, sizeof(double) * 7 * N); std::memcpy(x + 7 * N, w->speedbias, sizeof(double) * 9 * N);
+  std::memcpy(x + 16 * N, w->ex_pose, sizeof(double) * 7); x[16 * N + 7] = w->td;
+  if (M) std::memcpy(x + 16 * N + 8, w->inv_depth, sizeof(double) * M);
+  uint8_t* fx = place(OFF_FIXED, (size_t)M + N);
+  for (int f = 0; f < M; f++) fx[f] = w->depth_fixed ? w->depth_fixed[f] : 0;
+  for (int k = 0; k < N; k++) fx[M + k] = w->kf_fixed ? w->kf_fixed[k] : 0;
+  double* imu = (double*)place(OFF_IMU, (size_t)w->n_imu * 467 * 8);
+  if (w->n_imu) std::memcpy(imu, w->imu, sizeof(vils_preint) * w->n_imu);
+  int32_t* ikf = (int32_t*)place(OFF_IMU_KF, (size_t)w->n_imu * 4);
+  for (int k = 0; k < w->n_imu; k++) ikf[k] = w->imu_kf[k];
+  double* pj = (double*)place(OFF_PROJ, (size_t)14 * np * 8);
+  int32_t* pix = (int32_t*)place(OFF_PROJ_IDX, (size_t)4 * np * 4);
+  for (int s = 0; s < np; s++) {
+    const int k = ord[s];
+    const double v[14] = {w->pts_i[3 * k], w->pts_i[3 * k + 1], w->pts_i[3 * k + 2], w->pts_j[3 * k], w->pts_j[3 * k + 1], w->pts_j[3 * k + 2],
+                          w->vel_i[2 * k], w->vel_i[2 * k + 1], w->vel_j[2 * k], w->vel_j[2 * k + 1], w->td_i[k], w->td_j[k], w->row_i[k], w->row_j[k]};
+    for (int a = 0; a < 14; a++) pj[(size_t)a * np + s] = v[a];
+    pix[s] = w->kf_i[k]; pix[np + s] = w->kf_j[k]; pix[2 * np + s] = rank_of[s]; pix[3 * np + s] = k;
+  }
+  int32_t* ls = (int32_t*)place(OFF_LM_START, (size_t)(nlm + 1) * 4); for (int k = 0; k <= nlm; k++) ls[k] = lm_start[k];
+  int32_t* lf = (int32_t*)place(OFF_LM_FEAT, (size_t)nlm * 4); for (int k = 0; k < nlm; k++) lf[k] = lm_feat[k];
+  int32_t* pr = (int32_t*)place(OFF_PAIR, (size_t)npair * 16); for (int k = 0; k < 4 * npair; k++) pr[k] = pairs[k];
+  int32_t* pp = (int32_t*)place(OFF_PAIR_PERM, (size_t)np * 4); for (int k = 0; k < np; k++) pp[k] = pord[k];
+  int32_t* pi = (int32_t*)place(OFF_PAIR_ID, (size_t)N * N * 4); for (int k = 0; k < N * N; k++) pi[k] = pair_id[k];
+  // LiDAR points go to the body frame once, here: p_b = RLB^T (p_l - TLB)   (estimator.cpp:449-451)
+  auto to_body = [&](const double* p, double* out) {
+    const double d[3] = {p[0] - c.tlb[0], p[1] - c.tlb[1], p[2] - c.tlb[2]};
+    for (int a = 0; a < 3; a++) out[a] = c.rlb[0 * 3 + a] * d[0] + c.rlb[1 * 3 + a] * d[1] + c.rlb[2 * 3 + a] * d[2];
+  };
+  double* pl = (double*)place(OFF_PLANE, (size_t)7 * npl * 8);
+  int32_t* plx = (int32_t*)place(OFF_PLANE_IDX, (size_t)2 * npl * 4);
+  for (int s = 0; s < npl; s++) {
+    const int k = plo[s]; double pb[3]; to_body(w->plane_p + 3 * k, pb);
+    for (int a = 0; a < 3; a++) { pl[(size_t)a * npl + s] = pb[a]; pl[(size_t)(3 + a) * npl + s] = w->plane_n[3 * k + a]; }
+    pl[(size_t)6 * npl + s] = w->plane_d[k]; plx[s] = w->plane_kf[k]; plx[npl + s] = k;
+  }
+  int32_t* plst = (int32_t*)place(OFF_PLANE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) plst[k] = pls[k];
+  double* ed = (double*)place(OFF_EDGE, (size_t)9 * ned * 8);
+  int32_t* edx = (int32_t*)place(OFF_EDGE_IDX, (size_t)2 * ned * 4);
+  for (int s = 0; s < ned; s++) {
+    const int k = edo[s]; double pb[3]; to_body(w->edge_p + 3 * k, pb);
+    for (int a = 0; a < 3; a++) { ed[(size_t)a * ned + s] = pb[a]; ed[(size_t)(3 + a) * ned + s] = w->edge_a[3 * k + a]; ed[(size_t)(6 + a) * ned + s] = w->edge_b[3 * k + a]; }
+    edx[s] = w->edge_kf[k]; edx[ned + s] = k;
+  }
+  int32_t* edst = (int32_t*)place(OFF_EDGE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) edst[k] = eds[k];
+  double* ic = (double*)place(OFF_ICP, (size_t)w->n_icp * 14 * 8);
+  for (int k = 0; k < w->n_icp; k++) {
+    const vils_icp& q = w->icp[k]; double* d = ic + 14 * k;
+    d[0] = q.ta; d[1] = q.tb; d[2] = q.tc; d[3] = q.td; d[4] = q.ti; d[5] = q.tj; d[6] = q.trans_t[0]; d[7] = q.trans_t[1]; d[8] = q.trans_t[2]; d[9] = q.sqrt_info;
+    for (int b = 0; b < 4; b++) d[10 + b] = q.kf[b];
+  }
+  double* lp = (double*)place(OFF_LPS, (size_t)w->n_lps * 9 * 8);
+  for (int k = 0; k < w->n_lps; k++) {
+    const vils_lps& q = w->lps[k]; double* d = lp + 9 * k;
+    d[0] = q.tl; d[1] = q.tr; d[2] = q.tk; for (int a = 0; a < 4; a++) d[3 + a] = q.q[a]; d[7] = q.kf[0]; d[8] = q.kf[1];
+  }
+  const int n = w->prior_n;
+  double* PJ = (double*)place(OFF_PRIOR_J, (size_t)n * n * 8); if (n) std::memcpy(PJ, w->prior_J, sizeof(double) * n * n);
+  double* PR = (double*)place(OFF_PRIOR_R, (size_t)n * 8); if (n) std::memcpy(PR, w->prior_r, sizeof(double) * n);
+  int gs = 0, lsz = 0;
+  std::vector<int> pblk(4 * w->prior_nblk), pcol;
+  for (int b = 0; b < w->prior_nblk; b++) {
+    const int id = w->prior_blk[b], type = VILS_BLK_TYPE(id), idx = VILS_BLK_INDEX(id);
+    if (type < 0 || type > 3 || ((type == VILS_BLK_POSE || type == VILS_BLK_SPEEDBIAS) && idx >= N)) return vils::fail(VILS_ERR_BAD_ARG, "prior block id out of range");
+    const int g = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 7 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
+    const int l = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 6 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
+    const int off = type == VILS_BLK_POSE ? 15 * idx : type == VILS_BLK_SPEEDBIAS ? 15 * idx + 6 : type == VILS_BLK_EXPOSE ? 15 * N : 15 * N + 6;
+    pblk[4 * b] = type; pblk[4 * b + 1] = idx; pblk[4 * b + 2] = gs; pblk[4 * b + 3] = lsz;
+    for (int a = 0; a < l; a++) pcol.push_back(off + a);
+    gs += g; lsz += l;
+  }
+  if (lsz != n) return vils::fail(VILS_ERR_BAD_ARG, "prior_n does not match the local sizes of prior_blk");
+  double* PX = (double*)place(OFF_PRIOR_X0, (size_t)gs * 8); if (gs) std::memcpy(PX, w->prior_x0, sizeof(double) * gs);
+  int32_t* PB = (int32_t*)place(OFF_PRIOR_BLK, (size_t)4 * w->prior_nblk * 4); for (size_t k = 0; k < pblk.size(); k++) PB[k] = pblk[k];
+  int32_t* PC = (int32_t*)place(OFF_PRIOR_COL, (size_t)n * 4); for (int k = 0; k < n; k++) PC[k] = pcol[k];
+  if (o > ba->blob_stride) return vils::fail(VILS_ERR_CAPACITY, "vils_ba_set_window: blob overflow");
+  h->bytes = (int32_t)o;
+  SlotMeta& m = ba->meta[slot];
+  m.set = true; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
+  m.n_res = 15 * w->n_imu + 2 * np + npl + 3 * ned + 3 * w->n_icp + 3 * w->n_lps + n;
+  m.n_jac = (int64_t)450 * w->n_imu + (int64_t)40 * np + 6 * npl + 18 * ned + 72 * w->n_icp + 36 * w->n_lps;
+  m.items = w->n_imu + np + npl + ned + w->n_icp + w->n_lps + n;
+  return VILS_OK;
+}
+
+static int check_n(vils_ba* ba, int n, const char* who) {
+  if (!ba || n <= 0 || n > ba->max_windows) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": bad window count");
+  for (int k = 0; k < n; k++) if (!ba->meta[k].set) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": slot not set");
+  return cudaSetDevice(ba->cfg.device) == cudaSuccess ? VILS_OK : vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+}
+
+int vils_ba_upload(vils_ba* ba, int32_t n) {
+  int st = check_n(ba, n, "vils_ba_upload"); if (st) return st;
+  size_t width = 0; for (int k = 0; k < n; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
+  cudaError_t e = cudaMemcpy2DAsync(ba->d_blob, ba->blob_stride, ba->h_blob, ba->blob_stride, width, n, cudaMemcpyHostToDevice, ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "upload");
+  SolveParams P = make_params(ba, nullptr);
+  prep_kernel<<<n, 256, 0, ba->stream>>>(P);
+  e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "upload sync");
+  ba->prepped = true;
+  return VILS_OK;
+}
+
+int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
+  int st = check_n(ba, n, "vils_ba_solve_device"); if (st) return st;
+  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "solve: call vils_ba_upload first");
+  SolveParams P = make_params(ba, opts);
+  cudaEventRecord(ba->ev0, ba->stream);
+  solve_kernel<<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  cudaEventRecord(ba->ev1, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "solve_kernel");
+  cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  ba->last_launches = 1;
+  return VILS_OK;
+}
+
+int vils_ba_download(vils_ba* ba, int32_t n) {
+  int st = check_n(ba, n, "vils_ba_download"); if (st) return st;
+  cudaMemcpyAsync(ba->h_xout, ba->d_xout, (size_t)ba->xstride * 8 * n, cudaMemcpyDeviceToHost, ba->stream);
+  cudaMemcpyAsync(ba->h_sum, ba->d_sum, sizeof(vils_summary) * n, cudaMemcpyDeviceToHost, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "download");
+}
+
+int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
+  int st = vils_ba_upload(ba, n); if (st) return st;
+  st = vils_ba_solve_device(ba, n, opts); if (st) return st;
+  ba->last_launches = 2;
+  return vils_ba_download(ba, n);
+}
+
+int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* sb, double* ex, double* lam, double* td, vils_summary* sum) {
+  if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_get_state: bad slot");
+  const int N = ba->meta[slot].n_kf, M = ba->meta[slot].n_feat;
+  const double* x = ba->h_xout + (size_t)slot * ba->xstride;
+  if (pose) std::memcpy(pose, x, sizeof(double) * 7 * N);
+  if (sb) std::memcpy(sb, x + 7 * N, sizeof(double) * 9 * N);
+  if (ex) std::memcpy(ex, x + 16 * N, sizeof(double) * 7);
+  if (td) *td = x[16 * N + 7];
+  if (lam && M) std::memcpy(lam, x + 16 * N + 8, sizeof(double) * M);
+  if (sum) *sum = ba->h_sum[slot];
+  return ba->h_sum[slot].status;
+}
+
+static int ensure_eval_buffers(vils_ba* ba) {
+  if (ba->d_er) return VILS_OK;
+  const vils_config& c = ba->cfg; const int N = c.max_kf;
+  ba->er_stride = 15 * N + 2 * (int64_t)c.max_proj + 3 * (int64_t)c.max_lidar + 3 * 32 + 15 * N + 7;
+  ba->eJ_stride = 450 * (int64_t)N + 40 * (int64_t)c.max_proj + 18 * (int64_t)c.max_lidar + 72 * 16 + 36 * 16;
+  cudaError_t e = cudaMalloc(&ba->d_er, (size_t)ba->er_stride * 8 * ba->max_windows);
+  if (e == cudaSuccess) e = cudaMalloc(&ba->d_eJ, (size_t)ba->eJ_stride * 8 * ba->max_windows);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "eval buffers");
+}
+
+static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
+  int st = ensure_eval_buffers(ba); if (st) return st;
+  int items = 0; for (int k = slot0; k < slot0 + n; k++) items = std::max(items, ba->meta[k].items);
+  EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
+  Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
+  dim3 grid((items + 127) / 128, n);
+  cudaEventRecord(ba->ev0, ba->stream);
+  eval_kernel<<<grid, 128, 0, ba->stream>>>(Q);
+  cudaEventRecord(ba->ev1, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "eval_kernel");
+  cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  ba->last_launches = 1;
+  return VILS_OK;
+}
+
+int vils_ba_evaluate_device(vils_ba* ba, int32_t n, int32_t apply_loss) {
+  int st = check_n(ba, n, "vils_ba_evaluate_device"); if (st) return st;
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "evaluate: call vils_ba_upload first");
+  return launch_eval(ba, 0, n, apply_loss);
+}
+
+int vils_ba_evaluate(vils_ba* ba, int32_t slot, int32_t apply_loss, double* residuals, double* jacobians) {
+  if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_evaluate: bad slot");
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "evaluate: call vils_ba_upload first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  int st = launch_eval(ba, slot, 1, apply_loss); if (st) return st;
+  const SlotMeta& m = ba->meta[slot];
+  cudaError_t e = cudaSuccess;
+  if (residuals) e = cudaMemcpy(residuals, ba->d_er + (size_t)slot * ba->er_stride, sizeof(double) * m.n_res, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && jacobians) e = cudaMemcpy(jacobians, ba->d_eJ + (size_t)slot * ba->eJ_stride, sizeof(double) * m.n_jac, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "evaluate copy");
+}
+
+int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* cost) {
+  if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_linearize: bad slot");
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "linearize: call vils_ba_upload first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  vils_solve_opts o; vils_default_solve_opts(&o); o.mu = 0;
+  SolveParams P = make_params(ba, &o); P.slot0 = slot; P.lin_out = ba->d_lin;
+  solve_kernel<<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  const int D = 15 * ba->meta[slot].n_kf + 7;
+  cudaMemcpyAsync(ba->h_lin, ba->d_lin, ((size_t)D * D + D + 1) * 8, cudaMemcpyDeviceToHost, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "linearize");
+  if (S) std::memcpy(S, ba->h_lin, sizeof(double) * D * D);
+  if (g) std::memcpy(g, ba->h_lin + (size_t)D * D, sizeof(double) * D);
+  if (cost) *cost = ba->h_lin[(size_t)D * D + D];
+  return VILS_OK;
+}
+
+int vils_ba_last_device_ms(vils_ba* ba, float* ms) { if (!ba || !ms) return VILS_ERR_BAD_ARG; *ms = ba->last_ms; return VILS_OK; }
+int vils_ba_last_launches(vils_ba* ba, int32_t* n) { if (!ba || !n) return VILS_ERR_BAD_ARG; *n = ba->last_launches; return VILS_OK; }
+
+// Estimator::double2vector gauge re-anchoring (estimator.cpp:962-1011): host arithmetic on 7N + 9N doubles, kept on the
+// host exactly where the reference has it (it needs the pre-solve Rs[0]/Ps[0] the caller owns).
+static void q2R_h(const double* q, double R[9]) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+static void R2ypr_h(const double R[9], double ypr[3]) {   // utility.h:66-81, degrees
+  const double nx = R[0], ny = R[3], nz = R[6], ox = R[1], oy = R[4], ax = R[2], ay = R[5];
+  const double y = atan2(ny, nx), p = atan2(-nz, nx * cos(y) + ny * sin(y)), r = atan2(ax * sin(y) - ay * cos(y), -ox * sin(y) + oy * cos(y));
+  ypr[0] = y / M_PI * 180.0; ypr[1] = p / M_PI * 180.0; ypr[2] = r / M_PI * 180.0;
+}
+static void R2q_h(const double m[9], double q[4]) {   // Eigen Quaternion(Matrix3)
+  double t = m[0] + m[4] + m[8];
+  if (t > 0) { t = sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t; q[0] = (m[7] - m[5]) * t; q[1] = (m[2] - m[6]) * t; q[2] = (m[3] - m[1]) * t; }
+  else {
+    int i = 0; if (m[4] > m[0]) i = 1; if (m[8] > m[i * 4]) i = 2; const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m[i * 4] - m[j * 4] - m[k * 4] + 1.0); q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t; q[j] = (m[j * 3 + i] + m[i * 3 + j]) * t; q[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+  }
+}
+int vils_double2vector(int32_t n_kf, const double* pose0_before, double* pose, double* sb) {
+  if (n_kf <= 0 || !pose0_before || !pose || !sb) return VILS_ERR_BAD_ARG;
+  double R0[9], R00[9], y0[3], y00[3], rot[9];
+  q2R_h(pose0_before + 3, R0); q2R_h(pose + 3, R00); R2ypr_h(R0, y0); R2ypr_h(R00, y00);
+  const double yd = (y0[0] - y00[0]) / 180.0 * M_PI;
+  rot[0] = cos(yd); rot[1] = -sin(yd); rot[2] = 0; rot[3] = sin(yd); rot[4] = cos(yd); rot[5] = 0; rot[6] = 0; rot[7] = 0; rot[8] = 1;
+  if (fabs(fabs(y0[1]) - 90) < 1.0 || fabs(fabs(y00[1]) - 90) < 1.0)   // :979-988
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += R0[i * 3 + k] * R00[j * 3 + k]; rot[i * 3 + j] = s; }
+  const double P0[3] = {pose[0], pose[1], pose[2]};
+  for (int k = 0; k < n_kf; k++) {
+    double* p = pose + 7 * k; double qn[4]; const double nn = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
+    for (int a = 0; a < 4; a++) qn[a] = p[3 + a] / nn;
+    double R[9], RR[9]; q2R_h(qn, R);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int m = 0; m < 3; m++) s += rot[i * 3 + m] * R[m * 3 + j]; RR[i * 3 + j] = s; }
+    const double d[3] = {p[0] - P0[0], p[1] - P0[1], p[2] - P0[2]}; double* v = sb + 9 * k; const double v0[3] = {v[0], v[1], v[2]};
+    for (int i = 0; i < 3; i++) { p[i] = rot[i * 3] * d[0] + rot[i * 3 + 1] * d[1] + rot[i * 3 + 2] * d[2] + pose0_before[i]; v[i] = rot[i * 3] * v0[0] + rot[i * 3 + 1] * v0[1] + rot[i * 3 + 2] * v0[2]; }
+    R2q_h(RR, p + 3);
+  }
+  return VILS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+// vils_lidar.cu — LiDAR per-point path of libvils_b200.so:
+//   * stamp : PointProcessor::PointToRing (lidar_compensator/src/PointProcessor.cc:127-341) — ring id from elevation,
+//             relative time from azimuth, intensity <- int(I) + rel_time;
+//   * deskew: TransformToEnd (vils_estimator/src/lidar_frontend.cpp:1001-1041) — FP32 motion compensation to sweep end.
+// One thread per point, 16-byte vector loads/stores on the PCL PointXYZI layout (x y z pad | intensity pad pad pad).
+// Compiled with --fmad=false: the reference is plain IEEE FP32 arithmetic, and keeping every multiply/add separately
+// rounded makes the GPU result bit-identical to it wherever the transcendental calls agree (they are evaluated in FP64
+// and rounded once, i.e. correctly rounded FP32).
+#include <cmath>
+#include <cstdio>
+
+#include "common.h"
+
+namespace {
+
+struct DeskewParams { float qx, qy, qz, qw, tx, ty, tz, time_factor; double min_r, max_r; };
+
+__device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float acos_cr(float x) { return (float)acos((double)x); }
+
+// Eigen QuaternionBase::_transformVector: uv = 2 (q.vec x v); v + w uv + q.vec x uv
+__device__ __forceinline__ void rot(float qw, float qx, float qy, float qz, float& x, float& y, float& z) {
+  float ux = qy * z - qz * y, uy = qz * x - qx * z, uz = qx * y - qy * x;
+  ux += ux; uy += uy; uz += uz;
+  const float cx = qy * uz - qz * uy, cy = qz * ux - qx * uz, cz = qx * uy - qy * ux;
+  x = x + qw * ux + cx; y = y + qw * uy + cy; z = z + qw * uz + cz;
+}
+
+__device__ __forceinline__ void deskew_point(const DeskewParams& P, float& x, float& y, float& z, float& I) {
+  const double distance = (double)sqrtf(x * x + y * y);                  // :1008
+  const float s = P.time_factor * (I - (float)(int)I);                    // :1009
+  if (s < 0 || (double)s > 1.001 || distance < P.min_r || distance > P.max_r) {   // :1011
+    x = y = z = nanf(""); return;
+  }
+  x -= s * P.tx; y -= s * P.ty; z -= s * P.tz;                            // :1021-1023
+  // q_s = identity.slerp(s, q_e)  [Eigen 3.3 slerp]
+  const float d = P.qw, absD = fabsf(d);
+  float s0, s1;
+  if (absD >= 1.0f - 1.1920929e-07f) { s0 = 1.0f - s; s1 = s; }
+  else { const float th = acos_cr(absD), st = sin_cr(th); s0 = sin_cr((1.0f - s) * th) / st; s1 = sin_cr(s * th) / st; }
+  if (d < 0) s1 = -s1;
+  float w = s0 + s1 * P.qw, qx = s1 * P.qx, qy = s1 * P.qy, qz = s1 * P.qz;   // s0*(1,0,0,0) + s1*q_e
+  // conjugate().normalized()
+  qx = -qx; qy = -qy; qz = -qz;
+  const float n = sqrtf(w * w + qx * qx + qy * qy + qz * qz);
+  w /= n; qx /= n; qy /= n; qz /= n;
+  rot(w, qx, qy, qz, x, y, z);                                            // :1031
+  rot(P.qw, P.qx, P.qy, P.qz, x, y, z);                                   // :1034
+  x += P.tx; y += P.ty; z += P.tz;                                        // :1035-1037
+  I = (float)(int)I;                                                       // :1038
+}
+
+__global__ void deskew_kernel8(float4* __restrict__ pts, int n, DeskewParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = pts[2 * i], b = pts[2 * i + 1];
+  deskew_point(P, a.x, a.y, a.z, b.x);
+  pts[2 * i] = a; pts[2 * i + 1] = b;
+}
+__global__ void deskew_kernel_generic(float* __restrict__ pts, int n, int stride, DeskewParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* p = pts + (size_t)i * stride;
+  const int io = stride >= 8 ? 4 : 3;
+  float x = p[0], y = p[1], z = p[2], I = p[io];
+  deskew_point(P, x, y, z, I);
+  p[0] = x; p[1] = y; p[2] = z; p[io] = I;
+}
+
+// ---- stamp ----
+struct StampParams { float lower, factor, scan_period; int n_rings; };
+__global__ void stamp_pass1(const float* __restrict__ pts, int n, int stride, StampParams P, int* __restrict__ ring, float* __restrict__ azi, int* first_valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pts + (size_t)i * stride;
+  const float x = p[0], y = p[1], z = p[2];
+  int id = -1; float az = 0;
+  if (isfinite(x) && isfinite(y) && isfinite(z)) {                        // PointProcessor.cc:161-166
+    const float dis = sqrtf(x * x + y * y);                               // :168
+    const float ele = (float)atan2((double)z, (double)dis);               // :169 (FP32 atan2, correctly rounded)
+    az = (float)(2 * M_PI - (double)(float)atan2((double)y, (double)x)); // :170
+    if ((double)az >= 2 * M_PI) az = (float)((double)az - 2 * M_PI);      // :174-177
+    const float deg = (float)((double)ele * 180.0 / M_PI);                // RadToDeg
+    id = (int)((deg - P.lower) * P.factor + 0.5);                          // PointProcessor.h:77-81 (double 0.5 promotes)
+    if (id >= P.n_rings || id < 0) id = -1;                                // :181-184
+  }
+  ring[i] = id; azi[i] = az;
+  if (id >= 0) atomicMin(first_valid, i);                                  // :186-190 start_ori = first kept point
+}
+__global__ void stamp_pass2(float* __restrict__ pts, int n, int stride, StampParams P, const int* __restrict__ ring, const float* __restrict__ azi, const int* first_valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || ring[i] < 0) return;
+  const float start = azi[*first_valid];
+  float rel = azi[i] - start;                                              // :318
+  if (rel < 0) rel = (float)((double)rel + 2 * M_PI);                      // :319-322
+  const float rel_time = (float)((double)(P.scan_period * rel) / (2 * M_PI));   // :324
+  float* I = pts + (size_t)i * stride + (stride >= 8 ? 4 : 3);
+  *I = (float)(int)(*I) + rel_time;                                        // :331
+}
+
+struct LidarDev { float* d = nullptr; int n = 0, stride = 0, device = 0; cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; };
+
+int run_deskew(float* d, int n, int stride, const DeskewParams& P, cudaStream_t st) {
+  if (n == 0) return VILS_OK;
+  const int T = 256, B = (n + T - 1) / T;
+  if (stride == 8 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) deskew_kernel8<<<B, T, 0, st>>>(reinterpret_cast<float4*>(d), n, P);
+  else deskew_kernel_generic<<<B, T, 0, st>>>(d, n, stride, P);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "deskew launch");
+}
+
+DeskewParams mk(const float q[4], const float t[3], float tf, float mn, float mx) {
+  DeskewParams P; P.qx = q[0]; P.qy = q[1]; P.qz = q[2]; P.qw = q[3]; P.tx = t[0]; P.ty = t[1]; P.tz = t[2]; P.time_factor = tf;
+  P.min_r = (double)mn; P.max_r = (double)mx; return P;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vils_deskew(float* xyzi, int32_t n, int32_t stride, const float q[4], const float t[3], float time_factor, float min_r, float max_r, int32_t device) {
+  if (!xyzi || n < 0 || stride < 4 || !q || !t) return vils::fail(VILS_ERR_BAD_ARG, "vils_deskew: bad argument");
+  int st = vils::require_device(device); if (st) return st;
+  if (n == 0) return VILS_OK;
+  float* d = nullptr; const size_t bytes = (size_t)n * stride * sizeof(float);
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_deskew alloc");
+  e = cudaMemcpy(d, xyzi, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { st = run_deskew(d, n, stride, mk(q, t, time_factor, min_r, max_r), 0); if (st) { cudaFree(d); return st; } e = cudaMemcpy(xyzi, d, bytes, cudaMemcpyDeviceToHost); }
+  cudaFree(d);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_deskew copy");
+}
+
+int vils_stamp_rings(float* xyzi, int32_t n, int32_t stride, float lower_deg, float upper_deg, int32_t n_rings, float scan_period, int32_t* ring_out, int32_t device) {
+  if (!xyzi || !ring_out || n < 0 || stride < 4 || n_rings < 2) return vils::fail(VILS_ERR_BAD_ARG, "vils_stamp_rings: bad argument");
+  int st = vils::require_device(device); if (st) return st;
+  if (n == 0) return VILS_OK;
+  float* d = nullptr; int* ring = nullptr; float* azi = nullptr; int* first = nullptr;
+  const size_t bytes = (size_t)n * stride * sizeof(float);
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ring, sizeof(int) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&azi, sizeof(float) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&first, sizeof(int));
+  const int big = n;
+  if (e == cudaSuccess) e = cudaMemcpy(first, &big, sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d, xyzi, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    StampParams P; P.lower = lower_deg; P.factor = (n_rings - 1) / (upper_deg - lower_deg); P.scan_period = scan_period; P.n_rings = n_rings;
+    const int T = 256, B = (n + T - 1) / T;
+    stamp_pass1<<<B, T>>>(d, n, stride, P, ring, azi, first);
+    stamp_pass2<<<B, T>>>(d, n, stride, P, ring, azi, first);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(xyzi, d, bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(ring_out, ring, sizeof(int) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d); cudaFree(ring); cudaFree(azi); cudaFree(first);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_stamp_rings");
+}
+
+int vils_lidar_dev_alloc(int32_t n, int32_t stride, int32_t device, void** handle) {
+  if (!handle || n <= 0 || stride < 4) return vils::fail(VILS_ERR_BAD_ARG, "vils_lidar_dev_alloc: bad argument");
+  int st = vils::require_device(device); if (st) return st;
+  LidarDev* h = new LidarDev(); h->n = n; h->stride = stride; h->device = device;
+  cudaError_t e = cudaMalloc(&h->d, (size_t)n * stride * sizeof(float));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->e1);
+  if (e != cudaSuccess) { cudaFree(h->d); delete h; return vils::fail_cuda(e, "vils_lidar_dev_alloc"); }
+  *handle = h; return VILS_OK;
+}
+int vils_lidar_dev_upload(void* handle, const float* xyzi) {
+  LidarDev* h = static_cast<LidarDev*>(handle); if (!h || !xyzi) return vils::fail(VILS_ERR_BAD_ARG, "null");
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaMemcpyAsync(h->d, xyzi, (size_t)h->n * h->stride * sizeof(float), cudaMemcpyHostToDevice, h->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "lidar upload");
+}
+int vils_lidar_dev_deskew(void* handle, const float q[4], const float t[3], float time_factor, float min_r, float max_r, float* ms) {
+  LidarDev* h = static_cast<LidarDev*>(handle); if (!h || !q || !t) return vils::fail(VILS_ERR_BAD_ARG, "null");
+  cudaSetDevice(h->device);
+  cudaEventRecord(h->e0, h->st);
+  int st = run_deskew(h->d, h->n, h->stride, mk(q, t, time_factor, min_r, max_r), h->st); if (st) return st;
+  cudaEventRecord(h->e1, h->st);
+  cudaError_t e = cudaStreamSynchronize(h->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "deskew");
+  if (ms) cudaEventElapsedTime(ms, h->e0, h->e1);
+  return VILS_OK;
+}
+int vils_lidar_dev_download(void* handle, float* xyzi) {
+  LidarDev* h = static_cast<LidarDev*>(handle); if (!h || !xyzi) return vils::fail(VILS_ERR_BAD_ARG, "null");
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaMemcpyAsync(xyzi, h->d, (size_t)h->n * h->stride * sizeof(float), cudaMemcpyDeviceToHost, h->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "lidar download");
+}
+void vils_lidar_dev_free(void* handle) {
+  LidarDev* h = static_cast<LidarDev*>(handle); if (!h) return;
+  cudaSetDevice(h->device); cudaFree(h->d); cudaEventDestroy(h->e0); cudaEventDestroy(h->e1); cudaStreamDestroy(h->st); delete h;
+}
+
+}  // extern "C"

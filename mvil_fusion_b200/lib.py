@@ -1,0 +1,256 @@
+"""Python binding of libvils_b200.so (the C-ABI of include/vils_cabi.h) — what tests/ and bench.py call.
+
+The reference is a C++ system; its host side is mirrored in C++ (csrc/host/estimator.h, feature_tracker.h).  This
+module is the thin ctypes view of the same C-ABI used for parity tests and measurement.  It never falls back to a CPU
+implementation: if the shared library is missing or no sm_100 device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import cabi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libvils_b200.so")
+_lib = None
+
+
+class VilsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvils_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(f"{SO_PATH} is missing: run `python -m mvil_fusion_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    L.vils_last_error.restype = C.c_char_p
+    vp = C.c_void_p
+    dp, ip, up, fp = cabi.c_double_p, cabi.c_int32_p, cabi.c_uint8_p, cabi.c_float_p
+    L.vils_ba_create.argtypes = [C.POINTER(cabi.VilsConfig), C.c_int32, C.POINTER(vp)]
+    L.vils_ba_destroy.argtypes = [vp]
+    L.vils_ba_destroy.restype = None
+    L.vils_ba_set_window.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsWindow)]
+    L.vils_ba_upload.argtypes = [vp, C.c_int32]
+    L.vils_ba_solve_device.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_ba_download.argtypes = [vp, C.c_int32]
+    L.vils_ba_solve.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_ba_get_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp, C.POINTER(cabi.VilsSummary)]
+    L.vils_double2vector.argtypes = [C.c_int32, dp, dp, dp]
+    L.vils_ba_evaluate.argtypes = [vp, C.c_int32, C.c_int32, dp, dp]
+    L.vils_ba_evaluate_device.argtypes = [vp, C.c_int32, C.c_int32]
+    L.vils_ba_linearize.argtypes = [vp, C.c_int32, dp, dp, dp]
+    L.vils_ba_marginalize.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(cabi.VilsPriorOut)]
+    L.vils_ba_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_ba_last_launches.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.vils_ba_sharded_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.vils_ba_sharded_linearize.argtypes = [vp, C.c_int32]
+    L.vils_ba_sharded_update.argtypes = [vp, C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_preintegrate.argtypes = [C.c_int32, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(cabi.VilsPreint), C.c_int32]
+    L.vils_klt_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.vils_klt_destroy.argtypes = [vp]
+    L.vils_klt_destroy.restype = None
+    L.vils_klt_track.argtypes = [vp, up, up, C.c_int32, fp, C.c_int32, fp, up, fp]
+    L.vils_klt_upload.argtypes = [vp, up, up, C.c_int32, fp, C.c_int32]
+    L.vils_klt_track_device.argtypes = [vp]
+    L.vils_klt_download.argtypes = [vp, fp, up, fp]
+    L.vils_klt_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
+    L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
+    L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.vils_lidar_dev_upload.argtypes = [vp, fp]
+    L.vils_lidar_dev_deskew.argtypes = [vp, fp, fp, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    L.vils_lidar_dev_download.argtypes = [vp, fp]
+    L.vils_lidar_dev_free.argtypes = [vp]
+    L.vils_lidar_dev_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(code):
+    if code != 0:
+        raise VilsError(code, load().vils_last_error().decode())
+
+
+def _d(a):
+    return a.ctypes.data_as(cabi.c_double_p)
+
+
+class BA:
+    """One vils_ba handle: up to max_windows sliding windows resident on one GPU."""
+
+    def __init__(self, cfg=None, max_windows=1):
+        self.L = load()
+        self.cfg = cfg or cabi.default_config()
+        self.h = C.c_void_p()
+        _check(self.L.vils_ba_create(C.byref(self.cfg), max_windows, C.byref(self.h)))
+        self.max_windows = max_windows
+        self._dims = {}
+
+    def close(self):
+        if self.h:
+            self.L.vils_ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_window(self, slot, w):
+        ws, keep = cabi.window_struct(w)
+        _check(self.L.vils_ba_set_window(self.h, slot, C.byref(ws)))
+        self._dims[slot] = (ws.n_kf, ws.n_feat, cabi.residual_count(w), cabi.jacobian_count(w))
+
+    def upload(self, n):
+        _check(self.L.vils_ba_upload(self.h, n))
+
+    def solve_device(self, n, opts):
+        _check(self.L.vils_ba_solve_device(self.h, n, C.byref(opts)))
+
+    def download(self, n):
+        _check(self.L.vils_ba_download(self.h, n))
+
+    def solve(self, n, opts):
+        _check(self.L.vils_ba_solve(self.h, n, C.byref(opts)))
+
+    def get_state(self, slot):
+        N, M, _, _ = self._dims[slot]
+        pose = np.zeros((N, 7)); sb = np.zeros((N, 9)); ex = np.zeros(7); lam = np.zeros(max(M, 1)); td = C.c_double()
+        s = cabi.VilsSummary()
+        st = self.L.vils_ba_get_state(self.h, slot, _d(pose), _d(sb), _d(ex), _d(lam), C.byref(td), C.byref(s))
+        return dict(status=st, pose=pose, speedbias=sb, ex_pose=ex, inv_depth=lam[:M], td=td.value, iterations=s.iterations,
+                    accepted=s.accepted, cost_initial=s.cost_initial, cost_final=s.cost_final)
+
+    def evaluate(self, slot, apply_loss=True):
+        _, _, nr, nj = self._dims[slot]
+        r = np.zeros(nr); J = np.zeros(max(nj, 1))
+        _check(self.L.vils_ba_evaluate(self.h, slot, int(apply_loss), _d(r), _d(J)))
+        return r, J[:nj]
+
+    def evaluate_device(self, n, apply_loss=True):
+        _check(self.L.vils_ba_evaluate_device(self.h, n, int(apply_loss)))
+
+    def linearize(self, slot):
+        N = self._dims[slot][0]
+        D = 15 * N + 7
+        S = np.zeros((D, D)); g = np.zeros(D); cost = C.c_double()
+        _check(self.L.vils_ba_linearize(self.h, slot, _d(S), _d(g), C.byref(cost)))
+        return S, g, cost.value
+
+    def marginalize(self, slot, flag, capacity_n=512):
+        out = cabi.VilsPriorOut()
+        J = np.zeros(capacity_n * capacity_n); r = np.zeros(capacity_n); blk = np.zeros(80, np.int32); x0 = np.zeros(80 * 9)
+        out.capacity_n = capacity_n
+        out.J, out.r, out.x0 = _d(J), _d(r), _d(x0)
+        out.blk = blk.ctypes.data_as(cabi.c_int32_p)
+        _check(self.L.vils_ba_marginalize(self.h, slot, int(flag), C.byref(out)))
+        n, nb = out.n, out.nblk
+        gs = sum(cabi.blk_global_size(cabi.blk_type(int(b))) for b in blk[:nb])
+        return dict(n=n, m=out.m, J=J[:n * n].copy(), r=r[:n].copy(), blk=blk[:nb].copy(), x0=x0[:gs].copy())
+
+    @property
+    def last_ms(self):
+        ms = C.c_float()
+        self.L.vils_ba_last_device_ms(self.h, C.byref(ms))
+        return ms.value
+
+    @property
+    def last_launches(self):
+        n = C.c_int32()
+        self.L.vils_ba_last_launches(self.h, C.byref(n))
+        return n.value
+
+
+def double2vector(pose0_before, pose, sb):
+    pose = np.ascontiguousarray(pose, np.float64).copy(); sb = np.ascontiguousarray(sb, np.float64).copy()
+    p0 = np.ascontiguousarray(pose0_before, np.float64)
+    _check(load().vils_double2vector(int(pose.shape[0]), _d(p0), _d(pose), _d(sb)))
+    return pose, sb
+
+
+def preintegrate(off, dt, acc, gyr, acc0, gyr0, ba, bg, noise, device=0):
+    K = len(off) - 1
+    out = np.zeros((K, cabi.PREINT_DOUBLES))
+    off = np.ascontiguousarray(off, np.int32)
+    a = [np.ascontiguousarray(x, np.float64) for x in (dt, acc, gyr, acc0, gyr0, ba, bg, noise)]
+    _check(load().vils_preintegrate(K, off.ctypes.data_as(cabi.c_int32_p), *[_d(x) for x in a],
+                                    C.cast(out.ctypes.data, C.POINTER(cabi.VilsPreint)), device))
+    return out
+
+
+def deskew(xyzi, stride, q, t, time_factor, min_r, max_r, device=0):
+    a = np.ascontiguousarray(xyzi, np.float32).copy()
+    q = np.ascontiguousarray(q, np.float32); t = np.ascontiguousarray(t, np.float32)
+    fp = cabi.c_float_p
+    _check(load().vils_deskew(a.ctypes.data_as(fp), a.size // stride, stride, q.ctypes.data_as(fp), t.ctypes.data_as(fp),
+                              float(time_factor), float(min_r), float(max_r), device))
+    return a
+
+
+def stamp_rings(xyzi, stride, lower_deg=-15.0, upper_deg=15.0, n_rings=16, scan_period=0.1, device=0):
+    a = np.ascontiguousarray(xyzi, np.float32).copy()
+    n = a.size // stride
+    ring = np.zeros(n, np.int32)
+    _check(load().vils_stamp_rings(a.ctypes.data_as(cabi.c_float_p), n, stride, lower_deg, upper_deg, n_rings, scan_period,
+                                   ring.ctypes.data_as(cabi.c_int32_p), device))
+    return a, ring
+
+
+class KLT:
+    """cv::calcOpticalFlowPyrLK replacement (feature_tracker_/src/feature_tracker.cpp:113)."""
+
+    def __init__(self, rows, cols, max_pts=512, win=21, max_level=3, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        _check(self.L.vils_klt_create(rows, cols, max_pts, win, max_level, device, C.byref(self.h)))
+        self.rows, self.cols = rows, cols
+
+    def close(self):
+        if self.h:
+            self.L.vils_klt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track(self, prev, nxt, pts):
+        prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = pts.shape[0]
+        out = np.zeros((n, 2), np.float32); status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+        up, fp = cabi.c_uint8_p, cabi.c_float_p
+        _check(self.L.vils_klt_track(self.h, prev.ctypes.data_as(up), nxt.ctypes.data_as(up), prev.strides[0], pts.ctypes.data_as(fp), n,
+                                     out.ctypes.data_as(fp), status.ctypes.data_as(up), err.ctypes.data_as(fp)))
+        return out, status, err
+
+    def upload(self, prev, nxt, pts):
+        prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        self._n = pts.shape[0]
+        up, fp = cabi.c_uint8_p, cabi.c_float_p
+        _check(self.L.vils_klt_upload(self.h, prev.ctypes.data_as(up), nxt.ctypes.data_as(up), prev.strides[0], pts.ctypes.data_as(fp), self._n))
+
+    def track_device(self):
+        _check(self.L.vils_klt_track_device(self.h))
+
+    def download(self):
+        n = self._n
+        out = np.zeros((n, 2), np.float32); status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
+        _check(self.L.vils_klt_download(self.h, out.ctypes.data_as(cabi.c_float_p), status.ctypes.data_as(cabi.c_uint8_p), err.ctypes.data_as(cabi.c_float_p)))
+        return out, status, err
+
+    @property
+    def last_ms(self):
+        ms = C.c_float()
+        self.L.vils_klt_last_device_ms(self.h, C.byref(ms))
+        return ms.value
