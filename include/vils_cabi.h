@@ -234,6 +234,8 @@ int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out*
 int vils_ba_last_device_ms(vils_ba* ba, float* ms);
 /* Number of kernel launches issued by the last solve/evaluate call. */
 int vils_ba_last_launches(vils_ba* ba, int32_t* n);
+/* Bytes moved by the last vils_ba_upload (host->device) and vils_ba_download (device->host). */
+int vils_ba_last_transfer_bytes(vils_ba* ba, size_t* h2d, size_t* d2h);
 /* Factor-sharded mode (one window over several GPUs): phase A linearises this rank's factors and
  * leaves the partial reduced system [S | g | cost] (D*D + D + 1 doubles) in a device buffer the
  * caller all-reduces (NCCL, sum); phase B solves, updates and back-substitutes. */

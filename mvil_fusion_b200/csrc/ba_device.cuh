@@ -42,10 +42,11 @@ struct SolveParams {
   int32_t h_in_smem, hv_in_smem;
   double* lin_out;                // != null: dump [S (D x D row-major) | g (D) | cost] of the first linearisation and stop
   int32_t slot0;                  // first slot handled by blockIdx.x == 0
+  long long* prof;                // optional: per-phase SM cycle counters of block 0 (VILS_PROF=1)
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
-  int xs, xc, g, dx, hd, gv, hdv, cinv, glam, red, linv, hv, uni, imu, total;
+  int xs, xc, g, dx, hd, fx, gv, hdv, cinv, glam, red, linv, hv, uni, imu, total;
   int ntile_rows;
 };
 
@@ -56,7 +57,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   const int X = 16 * Ncap + 8 + Mcap, D = 15 * Ncap + 7, Dv = 6 * Ncap + 7, nb = (D + TB - 1) / TB, Dvp = (Dv + 3) & ~3;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
   s.xs = take(X); s.xc = take(X);
-  s.g = take(nb * TB); s.dx = take(nb * TB); s.hd = take(nb * TB);
+  s.g = take(nb * TB); s.dx = take(nb * TB); s.hd = take(nb * TB); s.fx = take(nb * TB / 2 + 1);
   s.gv = take(Dvp); s.hdv = take(Dvp);
   s.cinv = take(Mcap); s.glam = take(Mcap);
   s.red = take(64 + SOLVE_WARPS * 2);
@@ -366,7 +367,8 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
       if (pre[16] > 10.0) continue;                                  // estimator.cpp:1182 skip if sum_dt > 10
       for (int e = lane; e < 450; e += 32) J[e] = 0;
       __syncwarp();
-      if (lane == 0) vf::imu_eval_raw(pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, want_J ? J : nullptr);
+      if (lane < vf::IMU_PARTS && (want_J || lane == vf::IMU_PARTS - 1))
+        vf::imu_eval_part(lane, pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, J);
       __syncwarp();
       // r <- W r (W upper triangular), in place top-down
       double rw = 0;
@@ -577,27 +579,41 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
     double* Akk = H + ((size_t)(tri(kb) + kb) << 8);
     double* Li = linv + kb * 256;
     if (warp == 0) {
-      // unblocked Cholesky of the 16x16 tile: lane i < 16 owns row i
+      // 16x16 diagonal tile, register resident: lane (r = lane & 15) owns row r; pivots and column entries travel by
+      // shuffle, 1/sqrt by rsqrt (no FP64 divide on the critical path).  Lanes 16..31 mirror 0..15.
+      const int r = lane & 15;
+      double a[16], dinv_r = 1.0;
+#pragma unroll
+      for (int c = 0; c < 16; c++) a[c] = Akk[r * 16 + c];
+#pragma unroll
       for (int j = 0; j < 16; j++) {
-        double d = Akk[j * 16 + j];
-        if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) *flag = 1; d = 1.0; }
-        d = sqrt(d);
-        __syncwarp();
-        if (lane == j) Akk[j * 16 + j] = d;
-        if (lane > j && lane < 16) Akk[lane * 16 + j] /= d;
-        __syncwarp();
-        if (lane > j && lane < 16) { const double lij = Akk[lane * 16 + j]; for (int k = j + 1; k <= lane; k++) Akk[lane * 16 + k] -= lij * Akk[k * 16 + j]; }
-        __syncwarp();
+        double ajj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(ajj > 0.0) || !isfinite(ajj)) { if (lane == 0) *flag = 1; ajj = 1.0; }
+        double di = rsqrt(ajj);
+        di = di * (1.5 - 0.5 * ajj * di * di);          // one Newton step: full double accuracy
+        if (r == j) dinv_r = di;
+        a[j] = (r >= j) ? a[j] * di : 0.0;               // column j of L (diagonal: ajj / sqrt(ajj))
+#pragma unroll
+        for (int k = j + 1; k < 16; k++) {
+          const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+          if (r >= k) a[k] = fma(-a[j], lkj, a[k]);
+        }
       }
-      // inverse of the lower-triangular tile: lane c < 16 solves L z = e_c
+      if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) Akk[r * 16 + c] = a[c];
+      }
+      __syncwarp();
+      // inverse of L: lane c < 16 owns column c of X = L^-1 (forward substitution against rows of L read from the tile)
       if (lane < 16) {
         double z[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          double s = (i == lane) ? 1.0 : 0.0;
+          double sacc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-          for (int k = 0; k < 16; k++) if (k < i) s -= Akk[i * 16 + k] * z[k];
-          z[i] = (i >= lane) ? s / Akk[i * 16 + i] : 0.0;
+          for (int k = 0; k < 16; k++) if (k < i) sacc = fma(-Akk[i * 16 + k], z[k], sacc);
+          const double dii = __shfl_sync(0x0000ffffu, dinv_r, i);
+          z[i] = (i >= lane) ? sacc * dii : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < 16; i++) Li[i * 16 + lane] = z[i];
@@ -622,7 +638,7 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
     __syncthreads();
     // trailing update: A(ib,jb) -= L(ib,kb) L(jb,kb)^T for kb < jb <= ib; b(jb) -= y(kb) L(jb,kb)^T. 4x4 register tiles.
     const int rem = nb - kb - 1;
-    const int nitems = tri(rem) * 16 + rem;     // 16 sub-tiles per tile + one b item per tile row
+    const int nitems = tri(rem) * 16 + rem * 16;   // 16 sub-tiles per tile + 16 b entries per tile row
     for (int it = t; it < nitems; it += blockDim.x) {
       if (it < tri(rem) * 16) {
         const int tl = it >> 4, sub = it & 15;
@@ -657,10 +673,13 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
 #pragma unroll
           for (int c = 0; c < 4; c++) Aij[(r0 + a) * 16 + c0 + c] -= acc[a][c];
       } else {
-        const int jb = kb + 1 + (it - tri(rem) * 16);
+        const int q = it - tri(rem) * 16, jb = kb + 1 + (q >> 4), c = q & 15;
         const double* Ljk = H + ((size_t)(tri(jb) + kb) << 8);
         const double* yk = b + kb * 16;
-        for (int c = 0; c < 16; c++) { double s = 0; for (int m = 0; m < 16; m++) s = fma(yk[m], Ljk[c * 16 + m], s); b[jb * 16 + c] -= s; }
+        double sacc = 0;
+#pragma unroll
+        for (int m = 0; m < 16; m++) sacc = fma(yk[m], Ljk[c * 16 + m], sacc);
+        b[jb * 16 + c] -= sacc;
       }
     }
     __syncthreads();

@@ -193,6 +193,54 @@ VHD void imu_eval_raw(const double* pre, const double* G3, const double* pose_i,
   put33(J, 30, O_BG, 27, eye());
 }
 
+// The same arithmetic as imu_eval_raw, split into IMU_PARTS independent pieces so that the lanes of a warp can each
+// produce one 3x3 block (part 0..17) or the residual (part 18) after the shared quaternion algebra.
+constexpr int IMU_PARTS = 19;
+VHD void imu_eval_part(int part, const double* pre, const double* G3, const double* pose_i, const double* sb_i, const double* pose_j,
+                       const double* sb_j, double* r, double* J) {
+  const v3 Pi = ld3(pose_i), Pj = ld3(pose_j), Vi = ld3(sb_i), Vj = ld3(sb_j), Bgi = ld3(sb_i + 6);
+  const q4 Qi = ldq(pose_i + 3), Qj = ldq(pose_j + 3);
+  const v3 G = ld3(G3);
+  const q4 dq = ldq(pre + 3);
+  const double dt = pre[16];
+  const double* jac = pre + 17;
+  const q4 Qi_inv = qinv(Qi);
+  const m3 dq_dbg = blk_cm15(jac, O_R, O_BG);
+  const v3 th = mul(dq_dbg, Bgi - ld3(pre + 13));
+  const q4 cdq = qmul(dq, mkq(1.0, th.x * 0.5, th.y * 0.5, th.z * 0.5));
+  switch (part) {
+    case 0: put33(J, 30, O_P, 0, q2R(Qi_inv), -1.0); break;
+    case 1: put33(J, 30, O_P, 3, skew(qrot(Qi_inv, G * (0.5 * dt * dt) + Pj - Pi - Vi * dt))); break;
+    case 2: {
+      const q4 qji = qmul(qinv(Qj), Qi);
+      const m3 L = qleft33(qji), R = qright33(cdq);
+      m3 LR = mul(L, R);
+      const double lcol[3] = {qji.x, qji.y, qji.z}, rrow[3] = {-cdq.x, -cdq.y, -cdq.z};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) LR.m[i][j] += lcol[i] * rrow[j];
+      put33(J, 30, O_R, 3, LR, -1.0);
+    } break;
+    case 3: put33(J, 30, O_V, 3, skew(qrot(Qi_inv, G * dt + Vj - Vi))); break;
+    case 4: put33(J, 30, O_P, 6, q2R(Qi_inv), -dt); break;
+    case 5: put33(J, 30, O_P, 9, blk_cm15(jac, O_P, O_BA), -1.0); break;
+    case 6: put33(J, 30, O_P, 12, blk_cm15(jac, O_P, O_BG), -1.0); break;
+    case 7: put33(J, 30, O_R, 12, mul(qleft33(qmul(qmul(qinv(Qj), Qi), dq)), dq_dbg), -1.0); break;
+    case 8: put33(J, 30, O_V, 6, q2R(Qi_inv), -1.0); break;
+    case 9: put33(J, 30, O_V, 9, blk_cm15(jac, O_V, O_BA), -1.0); break;
+    case 10: put33(J, 30, O_V, 12, blk_cm15(jac, O_V, O_BG), -1.0); break;
+    case 11: put33(J, 30, O_BA, 9, eye(), -1.0); break;
+    case 12: put33(J, 30, O_BG, 12, eye(), -1.0); break;
+    case 13: put33(J, 30, O_P, 15, q2R(Qi_inv)); break;
+    case 14: put33(J, 30, O_R, 18, qleft33(qmul(qinv(cdq), qmul(Qi_inv, Qj)))); break;
+    case 15: put33(J, 30, O_V, 21, q2R(Qi_inv)); break;
+    case 16: put33(J, 30, O_BA, 24, eye()); break;
+    case 17: put33(J, 30, O_BG, 27, eye()); break;
+    default: imu_eval_raw(pre, G3, pose_i, sb_i, pose_j, sb_j, r, nullptr); break;
+  }
+}
+
 // ---- LiDAR point factors attached to keyframe k through the fixed LiDAR<->body extrinsic.
 // pb = RLB^T (p_l - TLB) is precomputed at pack time; p_w = R_k pb + P_k.
 // LidarPlaneNormFactor (lidar_mapping/src/lidarFactor.hpp:113-125): r = n . p_w + d.  J: 1 x 6.

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -59,29 +60,42 @@ __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
   return W.u(OFF_FIXED)[W.M + d / 15] != 0;       // kf_fixed
 }
 
+// Optional phase profiling (VILS_PROF=1): thread 0 of block 0 accumulates SM cycles per phase.
+#define PROF_T0() long long prof_t = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
+#define PROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - prof_t; prof_t = n_; } } while (0)
+
 // Full linearisation at state x: H (tiles, lower), g, hd and the cost (broadcast to all threads).
 __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x, double* H, double* Hv,
                             double mu) {
   double* g = sm + L.g; double* hd = sm + L.hd;
+  PROF_T0();
   double c = pair_pass(P, W, x, sm + L.uni, scr);
   __syncthreads();
+  PROF(0);
   landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu);
   for (int e = threadIdx.x; e < W.Dvp * W.Dv; e += blockDim.x) Hv[e] = 0.0;
   __syncthreads();
+  PROF(1);
   schur_syrk(P, W, sm + L.cinv, sm + L.glam, Hv, sm + L.gv, sm + L.uni, scr);
   __syncthreads();
+  PROF(2);
   for (int e = threadIdx.x; e < tri(W.nb) * TB * TB; e += blockDim.x) H[e] = 0.0;
   for (int e = threadIdx.x; e < W.nb * TB; e += blockDim.x) { g[e] = 0.0; hd[e] = 0.0; }
   __syncthreads();
   gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr);
   __syncthreads();
+  PROF(3);
   c += imu_pass(P, W, x, H, g, hd, sm + L.imu, scr, true);
+  PROF(4);
   c += lidar_pass(P, W, x, H, g, hd, true);
   __syncthreads();
+  PROF(5);
   c += icp_lps_pass(P, W, x, H, g, hd, sm + L.imu, true);
   c += prior_pass(P, W, x, H, g, hd, sm + L.dx, scr, true);
   __syncthreads();
-  return block_sum(c, sm + L.red);
+  c = block_sum(c, sm + L.red);
+  PROF(6);
+  return c;
 }
 
 __device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x) {
@@ -97,30 +111,29 @@ __device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, d
 }
 
 // Constant blocks -> identity rows/cols (problem.SetParameterBlockConstant, estimator.cpp:1154-1166,1217-1221,1368-1370),
-// Levenberg/Jacobi damping d2 = mu clamp(diag), b = -g.
-__device__ void damp_and_fix(const SolveParams& P, const Win& W, double* H, double* g, const double* hd, double mu) {
+// Levenberg/Jacobi damping d2 = mu clamp(diag), b = -g.  fx: per-dimension constant mask (tile padding included),
+// nfix: number of constant dimensions below D (0 in the common case -> no O(D^2) sweep).
+__device__ void damp_and_fix(const Win& W, double* H, double* g, const double* hd, const int* fx, int nfix, double mu) {
   const int Dp = W.nb * TB;
-  for (int e = threadIdx.x; e < Dp * (Dp + 1) / 2; e += blockDim.x) {
-    int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-    while (i * (i + 1) / 2 > e) i--;
-    while ((i + 1) * (i + 2) / 2 <= e) i++;
-    const int j = e - i * (i + 1) / 2;
-    const bool fi = cam_dim_fixed(P, W, i), fj = cam_dim_fixed(P, W, j);
-    if (i == j) {
-      if (fi) H[tidx(i, i)] = 1.0 + mu;
-      else H[tidx(i, i)] += mu * fmin(fmax(hd[i], 1e-12), 1e64);
-    } else if (fi || fj) H[tidx(i, j)] = 0.0;
+  for (int i = threadIdx.x; i < Dp; i += blockDim.x) {
+    if (fx[i]) { H[tidx(i, i)] = 1.0 + mu; g[i] = 0.0; }
+    else { H[tidx(i, i)] += mu * fmin(fmax(hd[i], 1e-12), 1e64); g[i] = -g[i]; }
   }
-  for (int i = threadIdx.x; i < Dp; i += blockDim.x) g[i] = cam_dim_fixed(P, W, i) ? 0.0 : -g[i];
+  if (nfix > 0)
+    for (int e = threadIdx.x; e < W.D * W.D; e += blockDim.x) {
+      const int i = e / W.D, j = e % W.D;
+      if (i > j && (fx[i] || fx[j])) H[tidx(i, j)] = 0.0;
+    }
 }
 
-// dl_f = -cinv_f (g_l + E_f^T dx_v) ; lam += dl ; poses/speed-bias/ex/td (+)= dx
+// dl_f = -cinv_f (g_l + E_f^T dx_v) ; lam += dl ; poses/speed-bias/ex/td (+)= dx.  xout != xin.
 __device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, double* sm, const double* scr, const double* xin, double* xout) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* dx = sm + L.dx; const double* cinv = sm + L.cinv; const double* glam = sm + L.glam;
   const double* E = scr + P.sl.E; const int32_t* lm_feat = W.i(OFF_LM_FEAT);
   const int X = 16 * W.N + 8 + W.M;
-  if (xout != xin) { for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k]; __syncthreads(); }
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
+  __syncthreads();
   for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
     double s = 0;
     for (int a = lane; a < W.Dv; a += 32) s = fma(E[(size_t)rnk * W.Dvp + a], dx[vis2cam(a, W.N)], s);
@@ -139,6 +152,9 @@ __device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, do
   __syncthreads();
 }
 
+// One CTA = one window for the whole solve.  SMEM_H: the tile-packed H and the visual sub-system Hv live in shared memory
+// (windows up to ~12 keyframes); otherwise they sit in the per-window scratch (L2).
+template <bool SMEM_H>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int chol_flag;
@@ -146,116 +162,111 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   const Win W = decode(P, slot);
   const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
   double* scr = P.scratch + (size_t)slot * P.sl.total;
-  double* H = P.h_in_smem ? sm + L.uni : scr + P.sl.Hg;
-  double* Hv = P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg;
+  double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
+  double* Hv = SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg);
   double* xs = sm + L.xs; double* xc = sm + L.xc;
+  int* fx = reinterpret_cast<int*>(sm + L.fx);
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
+  double nf = 0;
+  for (int d = threadIdx.x; d < W.nb * TB; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
   if (threadIdx.x == 0) chol_flag = 0;
+  const int nfix = (int)block_sum(nf, sm + L.red);
   __syncthreads();
 
-  int status = VILS_OK, iters = 0, accepted = 0;
-  double cost0 = 0, cost = 0;
+  const bool lm = P.mode == VILS_MODE_LM;
+  int status = VILS_OK, iters = 0, accepted = 0, trials = 0;
+  double cost0 = 0, cost = 0, radius = P.lm_radius, decrease = 2.0;
 
-  if (P.lin_out) {   // vils_ba_linearize: one linearisation, fixed blocks applied, no damping
-    cost = linearize(P, W, L, sm, scr, xs, H, Hv, 0.0);
-    damp_and_fix(P, W, H, sm + L.g, sm + L.hd, 0.0);
+  for (int it = 0;; it++) {
+    // LM follows ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g ; GN uses P.mu.
+    const double mu = P.lin_out ? 0.0 : (lm ? 1.0 / radius : P.mu);
+    const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu);
+    if (it == 0) { cost0 = c_lin; cost = c_lin; if (lm) iters = 1; }
+    if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
+    if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
+      damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, 0.0);
+      __syncthreads();
+      const int D = W.D;
+      for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; P.lin_out[e] = H[tidx(max(i, j), min(i, j))]; }
+      for (int i = threadIdx.x; i < D; i += blockDim.x) P.lin_out[(size_t)D * D + i] = -sm[L.g + i];
+      if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = c_lin;
+      return;
+    }
+    if (P.max_iters <= 0) break;
+    PROF_T0();
+    damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
+    double* bsave = sm + L.imu;   // LM: b = -g_r is overwritten by the fused forward solve; ((Ncap+1)/2)*466 doubles >= nb*16
     __syncthreads();
-    const int D = W.D;
-    for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; P.lin_out[e] = H[tidx(max(i, j), min(i, j))]; }
-    for (int i = threadIdx.x; i < D; i += blockDim.x) P.lin_out[(size_t)D * D + i] = -sm[L.g + i];
-    if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = cost;
-    return;
-  }
-
-  if (P.mode == VILS_MODE_GN) {
-    for (int it = 0; it < P.max_iters; it++) {
-      cost = linearize(P, W, L, sm, scr, xs, H, Hv, P.mu);
-      if (it == 0) cost0 = cost;
-      if (!isfinite(cost)) { status = VILS_ERR_NOT_FINITE; break; }
-      damp_and_fix(P, W, H, sm + L.g, sm + L.hd, P.mu);
-      __syncthreads();
-      cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
-      if (chol_flag) { status = VILS_ERR_CHOLESKY; break; }
+    if (lm) for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) bsave[i] = sm[L.g + i];
+    if (threadIdx.x == 0) chol_flag = 0;
+    __syncthreads();
+    PROF(7);
+    cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
+    const bool ok = chol_flag == 0;
+    PROF(8);
+    if (!ok && !lm) { status = VILS_ERR_CHOLESKY; break; }
+    const bool last = !lm && (iters + 1 >= P.max_iters);
+    double rho = -1, new_cost = 0;
+    if (ok) {
       backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
-      apply_step(P, W, L, sm, scr, xs, xs);
-      iters++; accepted++;
-    }
-    if (status == VILS_OK) {
-      cost = cost_only(P, W, L, sm, scr, xs);
-      if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE;
-    }
-  } else {
-    // Levenberg-Marquardt after ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g,
-    // rho = (cost - new_cost) / model_change, accept if rho > min_relative_decrease.
-    double radius = P.lm_radius, decrease = 2.0;
-    cost = linearize(P, W, L, sm, scr, xs, H, Hv, 1.0 / radius);
-    cost0 = cost; iters = 1;
-    bool have_lin = true;
-    if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE;
-    for (int it = 0; it < P.max_iters && status == VILS_OK; it++) {
-      const double mu = 1.0 / radius;
-      if (!have_lin) { linearize(P, W, L, sm, scr, xs, H, Hv, mu); have_lin = true; }
-      damp_and_fix(P, W, H, sm + L.g, sm + L.hd, mu);
-      __syncthreads();
-      // b = -g_r is overwritten by the fused forward solve: keep a copy for the model decrease
-      double* bsave = sm + L.imu;   // ((Ncap+1)/2)*466 doubles >= nb*16
-      for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) bsave[i] = sm[L.g + i];
-      if (threadIdx.x == 0) chol_flag = 0;
-      __syncthreads();
-      cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
-      const bool ok = chol_flag == 0;
-      double rho = -1, new_cost = 0;
-      if (ok) {
-        backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
+      PROF(9);
+      double model = 0;
+      if (lm) {
         // With (H + D2) d = -g over the full camera + landmark system: cost - model(d) = -1/2 g^T d + 1/2 d^T D2 d, where
         // the unreduced camera gradient is g_c = g_r + E Cd^-1 g_l  (Cd = damped landmark diagonal).
         double p2 = 0;
         for (int i = threadIdx.x; i < W.D; i += blockDim.x) {
           const double d = sm[L.dx + i];
-          const double d2 = cam_dim_fixed(P, W, i) ? mu : mu * fmin(fmax(sm[L.hd + i], 1e-12), 1e64);
+          const double d2 = fx[i] ? mu : mu * fmin(fmax(sm[L.hd + i], 1e-12), 1e64);
           p2 += 0.5 * bsave[i] * d + 0.5 * d2 * d * d;
         }
-        {
-          const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-          const double* E = scr + P.sl.E;
-          for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
-            double sdot = 0;
-            for (int a = lane; a < W.Dv; a += 32) sdot = fma(E[(size_t)rnk * W.Dvp + a], sm[L.dx + vis2cam(a, W.N)], sdot);
-            sdot = warp_sum(sdot);
-            if (lane == 0 && sm[L.cinv + rnk] != 0.0) {
-              const double ci = sm[L.cinv + rnk], gl = sm[L.glam + rnk];
-              const double dl = -ci * (gl + sdot);
-              const double Cd = 1.0 / ci, C = Cd / (1.0 + mu);   // exact while C sits inside the clamp range [1e-12, 1e64]
-              p2 += -0.5 * ci * gl * sdot - 0.5 * gl * dl + 0.5 * (Cd - C) * dl * dl;
-            }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const double* E = scr + P.sl.E;
+        for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
+          double sdot = 0;
+          for (int a = lane; a < W.Dv; a += 32) sdot = fma(E[(size_t)rnk * W.Dvp + a], sm[L.dx + vis2cam(a, W.N)], sdot);
+          sdot = warp_sum(sdot);
+          if (lane == 0 && sm[L.cinv + rnk] != 0.0) {
+            const double ci = sm[L.cinv + rnk], gl = sm[L.glam + rnk];
+            const double dl = -ci * (gl + sdot);
+            const double Cd = 1.0 / ci, C = Cd / (1.0 + mu);   // exact while C sits inside the clamp range [1e-12, 1e64]
+            p2 += -0.5 * ci * gl * sdot - 0.5 * gl * dl + 0.5 * (Cd - C) * dl * dl;
           }
         }
-        const double model = block_sum(p2, sm + L.red);
-        apply_step(P, W, L, sm, scr, xs, xc);
-        new_cost = cost_only(P, W, L, sm, scr, xc);
-        rho = (isfinite(new_cost) && model > 0) ? (cost - new_cost) / model : -1;
+        model = block_sum(p2, sm + L.red);
       }
-      if (ok && rho > P.min_rel_dec) {
-        double xn = 0, dn = 0;
-        for (int k = threadIdx.x; k < X; k += blockDim.x) { xn += xs[k] * xs[k]; const double dd = xc[k] - xs[k]; dn += dd * dd; }
-        xn = block_sum(xn, sm + L.red); dn = block_sum(dn, sm + L.red);
-        for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
-        __syncthreads();
-        accepted++;
-        const double t3 = 2.0 * rho - 1.0;
-        radius = fmin(radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3), 1e16); decrease = 2.0;
-        const double change = cost - new_cost; cost = new_cost;
-        if (fabs(change) / (cost + 1e-300) < P.f_tol) break;
-        if (sqrt(dn) <= P.p_tol * (sqrt(xn) + P.p_tol)) break;
-        have_lin = false;
-        if (it + 1 < P.max_iters) iters++; else break;
-      } else {
-        radius /= decrease; decrease *= 2.0;
-        if (radius < 1e-32) break;
-        have_lin = false;      // damping changed: rebuild (H is overwritten by the factorisation)
-      }
+      apply_step(P, W, L, sm, scr, xs, xc);
+      PROF(10);
+      if (lm || last) { new_cost = cost_only(P, W, L, sm, scr, xc); PROF(11); }
+      if (lm) rho = (isfinite(new_cost) && model > 0) ? (cost - new_cost) / model : -1;
+    }
+    if (!lm) {   // Gauss-Newton: every step is taken
+      for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
+      __syncthreads();
+      iters++; accepted++;
+      if (last) { cost = new_cost; if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE; break; }
+      continue;
+    }
+    trials++;
+    if (ok && rho > P.min_rel_dec) {
+      double xn = 0, dn = 0;
+      for (int k = threadIdx.x; k < X; k += blockDim.x) { xn += xs[k] * xs[k]; const double dd = xc[k] - xs[k]; dn += dd * dd; }
+      xn = block_sum(xn, sm + L.red); dn = block_sum(dn, sm + L.red);
+      for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
+      __syncthreads();
+      accepted++;
+      const double t3 = 2.0 * rho - 1.0;
+      radius = fmin(radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3), 1e16); decrease = 2.0;
+      const double change = cost - new_cost; cost = new_cost;
+      if (fabs(change) / (cost + 1e-300) < P.f_tol) break;
+      if (sqrt(dn) <= P.p_tol * (sqrt(xn) + P.p_tol)) break;
+      if (trials >= P.max_iters) break;
+      iters++;
+    } else {
+      radius /= decrease; decrease *= 2.0;
+      if (radius < 1e-32 || trials >= P.max_iters) break;
     }
   }
   double* xo = P.xout + (size_t)slot * P.xout_stride;
@@ -400,7 +411,7 @@ struct vils_ba {
   double* d_er = nullptr; double* d_eJ = nullptr; int64_t er_stride = 0, eJ_stride = 0;
   std::vector<SlotMeta> meta;
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
-  float last_ms = 0; int last_launches = 0;
+  float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
   bool prepped = false;
 };
 
@@ -433,7 +444,7 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
     P.p_tol = o->parameter_tolerance; P.min_rel_dec = o->min_relative_decrease;
   }
   P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
-  P.lin_out = nullptr; P.slot0 = 0;
+  P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr;
   return P;
 }
 
@@ -502,7 +513,8 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaMalloc(&ba->d_sum, sizeof(vils_summary) * max_windows));
   CK(cudaMallocHost(&ba->h_sum, sizeof(vils_summary) * max_windows));
   CK(cudaMalloc(&ba->d_lin, n_lin * 8)); CK(cudaMallocHost(&ba->h_lin, n_lin * 8));
-  CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
 #undef CK
   std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
   std::memset(ba->h_sum, 0, sizeof(vils_summary) * max_windows);
@@ -688,6 +700,7 @@ static int check_n(vils_ba* ba, int n, const char* who) {
 int vils_ba_upload(vils_ba* ba, int32_t n) {
   int st = check_n(ba, n, "vils_ba_upload"); if (st) return st;
   size_t width = 0; for (int k = 0; k < n; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
+  ba->last_h2d = width * n;
   cudaError_t e = cudaMemcpy2DAsync(ba->d_blob, ba->blob_stride, ba->h_blob, ba->blob_stride, width, n, cudaMemcpyHostToDevice, ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "upload");
   SolveParams P = make_params(ba, nullptr);
@@ -703,18 +716,30 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
   if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "solve: call vils_ba_upload first");
   SolveParams P = make_params(ba, opts);
+  static const bool prof = getenv("VILS_PROF") != nullptr;
+  long long* d_prof = nullptr;
+  if (prof) { cudaMalloc(&d_prof, 16 * sizeof(long long)); cudaMemset(d_prof, 0, 16 * sizeof(long long)); P.prof = d_prof; }
   cudaEventRecord(ba->ev0, ba->stream);
-  solve_kernel<<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  if (ba->h_in_smem && ba->hv_in_smem) solve_kernel<true><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  else solve_kernel<false><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "solve_kernel");
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  if (prof) {
+    long long h[16]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
+    static const char* names[12] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost"};
+    long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
+    fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
+    for (int i = 0; i < 12; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+  }
   ba->last_launches = 1;
   return VILS_OK;
 }
 
 int vils_ba_download(vils_ba* ba, int32_t n) {
   int st = check_n(ba, n, "vils_ba_download"); if (st) return st;
+  ba->last_d2h = (size_t)ba->xstride * 8 * n + sizeof(vils_summary) * n;
   cudaMemcpyAsync(ba->h_xout, ba->d_xout, (size_t)ba->xstride * 8 * n, cudaMemcpyDeviceToHost, ba->stream);
   cudaMemcpyAsync(ba->h_sum, ba->d_sum, sizeof(vils_summary) * n, cudaMemcpyDeviceToHost, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
@@ -791,7 +816,8 @@ int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* c
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   vils_solve_opts o; vils_default_solve_opts(&o); o.mu = 0;
   SolveParams P = make_params(ba, &o); P.slot0 = slot; P.lin_out = ba->d_lin;
-  solve_kernel<<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  if (ba->h_in_smem && ba->hv_in_smem) solve_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  else solve_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
   const int D = 15 * ba->meta[slot].n_kf + 7;
   cudaMemcpyAsync(ba->h_lin, ba->d_lin, ((size_t)D * D + D + 1) * 8, cudaMemcpyDeviceToHost, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
@@ -803,6 +829,7 @@ int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* c
 }
 
 int vils_ba_last_device_ms(vils_ba* ba, float* ms) { if (!ba || !ms) return VILS_ERR_BAD_ARG; *ms = ba->last_ms; return VILS_OK; }
+int vils_ba_last_transfer_bytes(vils_ba* ba, size_t* h2d, size_t* d2h) { if (!ba) return VILS_ERR_BAD_ARG; if (h2d) *h2d = ba->last_h2d; if (d2h) *d2h = ba->last_d2h; return VILS_OK; }
 int vils_ba_last_launches(vils_ba* ba, int32_t* n) { if (!ba || !n) return VILS_ERR_BAD_ARG; *n = ba->last_launches; return VILS_OK; }
 
 // Estimator::double2vector gauge re-anchoring (estimator.cpp:962-1011): host arithmetic on 7N + 9N doubles, kept on the

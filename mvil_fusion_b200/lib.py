@@ -48,6 +48,7 @@ def load():
     L.vils_ba_marginalize.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(cabi.VilsPriorOut)]
     L.vils_ba_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.vils_ba_last_launches.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.vils_ba_last_transfer_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.vils_ba_sharded_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.vils_ba_sharded_linearize.argtypes = [vp, C.c_int32]
     L.vils_ba_sharded_update.argtypes = [vp, C.POINTER(cabi.VilsSolveOpts)]
@@ -160,6 +161,12 @@ class BA:
         ms = C.c_float()
         self.L.vils_ba_last_device_ms(self.h, C.byref(ms))
         return ms.value
+
+    @property
+    def last_transfer_bytes(self):
+        a, b = C.c_size_t(), C.c_size_t()
+        self.L.vils_ba_last_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     @property
     def last_launches(self):

@@ -14,6 +14,10 @@ void hc_imu_eval_raw(const double* pre, const double* G, const double* pi, const
   for (int i = 0; i < 450; i++) J[i] = 0;
   imu_eval_raw(pre, G, pi, sbi, pj, sbj, r, J);
 }
+void hc_imu_eval_parts(const double* pre, const double* G, const double* pi, const double* sbi, const double* pj, const double* sbj, double* r, double* J) {
+  for (int i = 0; i < 450; i++) J[i] = 0;
+  for (int part = 0; part < IMU_PARTS; part++) imu_eval_part(part, pre, G, pi, sbi, pj, sbj, r, J);
+}
 double hc_plane_eval(const double* pose, const double* pb, const double* n, double d, double* J) { return plane_eval(pose, ld3(pb), ld3(n), d, J); }
 void hc_edge_eval(const double* pose, const double* pb, const double* a, const double* b, double* r, double* J) { edge_eval(pose, ld3(pb), ld3(a), ld3(b), r, J); }
 void hc_lps_eval(const double* c, const double* pa, const double* pb, double* r, double* J) { lps_eval(c, pa, pb, r, J); }

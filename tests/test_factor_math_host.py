@@ -44,6 +44,9 @@ def product_evaluate(hc, cfg, w):
         W = np.zeros((15, 15)); r = np.zeros(15); J = np.zeros((15, 30))
         assert hc.hc_imu_sqrt_info(P(pre[242:]), P(W)) == 0
         hc.hc_imu_eval_raw(P(pre), P(G), P(pose[i]), P(sb[i]), P(pose[i + 1]), P(sb[i + 1]), P(r), P(J))
+        r2 = np.zeros(15); J2 = np.zeros((15, 30))   # the lane-split variant the solve kernel uses must be identical
+        hc.hc_imu_eval_parts(P(pre), P(G), P(pose[i]), P(sb[i]), P(pose[i + 1]), P(sb[i + 1]), P(r2), P(J2))
+        assert np.array_equal(r, r2) and np.array_equal(J, J2)
         rs.append(W @ r); Js.append((W @ J).reshape(-1))
     for k in range(len(w["kf_i"])):
         i, j, f = int(w["kf_i"][k]), int(w["kf_j"][k]), int(w["feat"][k])
