@@ -23,6 +23,8 @@
 namespace vb {
 
 constexpr int TB = 16;            // Cholesky tile
+constexpr int TLD = 17;           // padded tile row stride (doubles): lanes walking rows hit distinct shared-memory banks
+constexpr int TSZ = TB * TLD + 2; // padded tile stride: neighbouring tiles start 2 doubles (4 banks) apart
 constexpr int SOLVE_THREADS = 512;
 constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
 constexpr int STAGE_LD = 24;      // pair-pass staging row: 19 Jacobian cols + residual + pad
@@ -65,7 +67,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   s.hv = hv_in_smem ? take(Dvp * Dvp) : -1;
   int uni = SOLVE_WARPS * 32 * STAGE_LD;                     // pair-pass staging
   if (ECHUNK * Dvp > uni) uni = ECHUNK * Dvp;                // Schur chunk
-  if (h_in_smem && tri(nb) * TB * TB > uni) uni = tri(nb) * TB * TB;
+  if (h_in_smem && tri(nb) * TSZ > uni) uni = tri(nb) * TSZ;
   s.uni = take(uni);
   s.imu = take(((Ncap + 1) / 2) * 466);
   s.total = o; s.ntile_rows = nb;
@@ -75,7 +77,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
 // ---- tile-packed lower-triangular matrix -----------------------------------------------------------------------
 __device__ __forceinline__ int tidx(int i, int j) {  // requires i >= j
   const int bi = i >> 4, bj = j >> 4;
-  return ((bi * (bi + 1) / 2 + bj) << 8) + ((i & 15) << 4) + (j & 15);
+  return (bi * (bi + 1) / 2 + bj) * TSZ + (i & 15) * TLD + (j & 15);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -569,22 +571,15 @@ __device__ double prior_pass(const SolveParams& P, const Win& W, const double* x
   return cost;
 }
 
-// =================================================================================================================
-// C: blocked Cholesky of the tile-packed lower matrix, with b (= -g) carried along as an extra row.
-// On exit: H holds L, linv[kb] the inverse of each diagonal tile, y = L^-1 b in `b`.  Returns false on breakdown.
-// =================================================================================================================
-__device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* flag) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int kb = 0; kb < nb; kb++) {
-    double* Akk = H + ((size_t)(tri(kb) + kb) << 8);
-    double* Li = linv + kb * 256;
-    if (warp == 0) {
+// 16x16 diagonal tile factorisation + inverse by ONE warp (own register allocation: kept out of line on purpose).
+__device__ __noinline__ void chol_diag_tile(double* Akk, double* Li, int* flag) {
+  const int lane = threadIdx.x & 31;
       // 16x16 diagonal tile, register resident: lane (r = lane & 15) owns row r; pivots and column entries travel by
       // shuffle, 1/sqrt by rsqrt (no FP64 divide on the critical path).  Lanes 16..31 mirror 0..15.
       const int r = lane & 15;
       double a[16], dinv_r = 1.0;
 #pragma unroll
-      for (int c = 0; c < 16; c++) a[c] = Akk[r * 16 + c];
+      for (int c = 0; c < 16; c++) a[c] = Akk[r * TLD + c];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         double ajj = __shfl_sync(0xffffffffu, a[j], j);
@@ -601,7 +596,7 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
       }
       if (lane < 16) {
 #pragma unroll
-        for (int c = 0; c < 16; c++) Akk[r * 16 + c] = a[c];
+        for (int c = 0; c < 16; c++) Akk[r * TLD + c] = a[c];
       }
       __syncwarp();
       // inverse of L: lane c < 16 owns column c of X = L^-1 (forward substitution against rows of L read from the tile)
@@ -611,19 +606,34 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
         for (int i = 0; i < 16; i++) {
           double sacc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-          for (int k = 0; k < 16; k++) if (k < i) sacc = fma(-Akk[i * 16 + k], z[k], sacc);
+          for (int k = 0; k < 16; k++) if (k < i) sacc = fma(-Akk[i * TLD + k], z[k], sacc);
           const double dii = __shfl_sync(0x0000ffffu, dinv_r, i);
           z[i] = (i >= lane) ? sacc * dii : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < 16; i++) Li[i * 16 + lane] = z[i];
       }
-    }
+}
+
+// =================================================================================================================
+// C: blocked Cholesky of the tile-packed lower matrix, with b (= -g) carried along as an extra row.
+// On exit: H holds L, linv[kb] the inverse of each diagonal tile, y = L^-1 b in `b`.  Returns false on breakdown.
+// =================================================================================================================
+__device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* flag, long long* prof = nullptr) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  long long pt = (prof && blockIdx.x == 0 && t == 0) ? clock64() : 0;
+#define CPROF(i) do { if (prof && blockIdx.x == 0 && t == 0) { const long long n_ = clock64(); prof[i] += n_ - pt; pt = n_; } } while (0)
+  for (int kb = 0; kb < nb; kb++) {
+    double* Akk = H + (size_t)(tri(kb) + kb) * TSZ;
+    double* Li = linv + kb * 256;
+    if (warp == 0) chol_diag_tile(Akk, Li, flag);
+    CPROF(12);
     __syncthreads();
+    CPROF(13);
     // panel: rows of tiles (ib, kb), ib > kb, and the b row:  X <- X Lkk^-T   (X[r][c] = sum_{m<=c} X[r][m] Linv[c][m])
     const int nrows = (nb - kb - 1) * 16 + 1;
     for (int rr = t; rr < nrows; rr += blockDim.x) {
-      double* row = (rr == nrows - 1) ? b + kb * 16 : H + ((size_t)(tri(kb + 1 + rr / 16) + kb) << 8) + (rr & 15) * 16;
+      double* row = (rr == nrows - 1) ? b + kb * 16 : H + (size_t)(tri(kb + 1 + rr / 16) + kb) * TSZ + (rr & 15) * TLD;
       double v[16], o[16];
 #pragma unroll
       for (int m = 0; m < 16; m++) v[m] = row[m];
@@ -636,6 +646,7 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
       for (int c = 0; c < 16; c++) row[c] = o[c];
     }
     __syncthreads();
+    CPROF(14);
     // trailing update: A(ib,jb) -= L(ib,kb) L(jb,kb)^T for kb < jb <= ib; b(jb) -= y(kb) L(jb,kb)^T. 4x4 register tiles.
     const int rem = nb - kb - 1;
     const int nitems = tri(rem) * 16 + rem * 16;   // 16 sub-tiles per tile + 16 b entries per tile row
@@ -647,9 +658,9 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
         while ((bi + 1) * (bi + 2) / 2 <= tl) bi++;
         const int bj = tl - bi * (bi + 1) / 2;
         const int ib = kb + 1 + bi, jb = kb + 1 + bj;
-        const double* Lik = H + ((size_t)(tri(ib) + kb) << 8);
-        const double* Ljk = H + ((size_t)(tri(jb) + kb) << 8);
-        double* Aij = H + ((size_t)(tri(ib) + jb) << 8);
+        const double* Lik = H + (size_t)(tri(ib) + kb) * TSZ;
+        const double* Ljk = H + (size_t)(tri(jb) + kb) * TSZ;
+        double* Aij = H + (size_t)(tri(ib) + jb) * TSZ;
         const int r0 = (sub >> 2) * 4, c0 = (sub & 3) * 4;
         double acc[4][4];
 #pragma unroll
@@ -660,9 +671,9 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
         for (int m = 0; m < 16; m++) {
           double av[4], bv[4];
 #pragma unroll
-          for (int a = 0; a < 4; a++) av[a] = Lik[(r0 + a) * 16 + m];
+          for (int a = 0; a < 4; a++) av[a] = Lik[(r0 + a) * TLD + m];
 #pragma unroll
-          for (int c = 0; c < 4; c++) bv[c] = Ljk[(c0 + c) * 16 + m];
+          for (int c = 0; c < 4; c++) bv[c] = Ljk[(c0 + c) * TLD + m];
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -671,19 +682,21 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, int nb, int* 
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-          for (int c = 0; c < 4; c++) Aij[(r0 + a) * 16 + c0 + c] -= acc[a][c];
+          for (int c = 0; c < 4; c++) Aij[(r0 + a) * TLD + c0 + c] -= acc[a][c];
       } else {
         const int q = it - tri(rem) * 16, jb = kb + 1 + (q >> 4), c = q & 15;
-        const double* Ljk = H + ((size_t)(tri(jb) + kb) << 8);
+        const double* Ljk = H + (size_t)(tri(jb) + kb) * TSZ;
         const double* yk = b + kb * 16;
         double sacc = 0;
 #pragma unroll
-        for (int m = 0; m < 16; m++) sacc = fma(yk[m], Ljk[c * 16 + m], sacc);
+        for (int m = 0; m < 16; m++) sacc = fma(yk[m], Ljk[c * TLD + m], sacc);
         b[jb * 16 + c] -= sacc;
       }
     }
     __syncthreads();
+    CPROF(15);
   }
+#undef CPROF
   return *flag == 0;
 }
 
@@ -696,7 +709,7 @@ __device__ void backsub_tiles(const double* H, const double* b, const double* li
       double s = 0;
       for (int rr = lane; rr < (nb - 1 - kb) * 16; rr += 32) {
         const int ib = kb + 1 + rr / 16, r = rr & 15;
-        s = fma(H[((size_t)(tri(ib) + kb) << 8) + r * 16 + c], dx[ib * 16 + r], s);
+        s = fma(H[(size_t)(tri(ib) + kb) * TSZ + r * TLD + c], dx[ib * 16 + r], s);
       }
       s = warp_sum(s);
       if (lane == 0) tmp[c] = b[kb * 16 + c] - s;

@@ -79,7 +79,7 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   schur_syrk(P, W, sm + L.cinv, sm + L.glam, Hv, sm + L.gv, sm + L.uni, scr);
   __syncthreads();
   PROF(2);
-  for (int e = threadIdx.x; e < tri(W.nb) * TB * TB; e += blockDim.x) H[e] = 0.0;
+  for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;
   for (int e = threadIdx.x; e < W.nb * TB; e += blockDim.x) { g[e] = 0.0; hd[e] = 0.0; }
   __syncthreads();
   gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
     if (threadIdx.x == 0) chol_flag = 0;
     __syncthreads();
     PROF(7);
-    cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag);
+    cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag, P.prof);
     const bool ok = chol_flag == 0;
     PROF(8);
     if (!ok && !lm) { status = VILS_ERR_CHOLESKY; break; }
@@ -497,7 +497,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   if ((size_t)smem_layout(N, M, ba->h_in_smem, 1).total * 8 > budget) { ba->hv_in_smem = 0; }
   ba->smem_bytes = (size_t)smem_layout(N, M, ba->h_in_smem, ba->hv_in_smem).total * 8;
   if (ba->smem_bytes > budget) { delete ba; return vils::fail(VILS_ERR_CAPACITY, "vils_ba_create: window too large for shared memory plan"); }
-  s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TB * TB);
+  s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TSZ);
   s.Hvg = ba->hv_in_smem ? 0 : take((int64_t)Dvp * Dvp);
   s.total = o;
   ba->xstride = 16 * N + 8 + M;
@@ -728,10 +728,10 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   if (prof) {
     long long h[16]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
-    static const char* names[12] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost"};
+    static const char* names[16] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:diag-wait", "  chol:panel", "  chol:trailing"};
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
-    for (int i = 0; i < 12; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+    for (int i = 0; i < 16; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
   }
   ba->last_launches = 1;
   return VILS_OK;
