@@ -94,6 +94,12 @@ struct Win {   // decoded blob
   __device__ const uint8_t* u(int which) const { return base + h->off[which]; }
 };
 
+__device__ __forceinline__ Win decode(const SolveParams& P, int slot) {
+  Win W; W.base = P.blobs + (size_t)slot * P.blob_stride; W.h = reinterpret_cast<const WinHdr*>(W.base);
+  W.N = W.h->n_kf; W.M = W.h->n_feat; W.D = 15 * W.N + 7; W.Dv = 6 * W.N + 7; W.Dvp = P.sl.Dv_pad; W.nb = (W.D + TB - 1) / TB;
+  return W;
+}
+
 __device__ __forceinline__ int vis2cam(int v, int N) { return v < 6 * N ? 15 * (v / 6) + v % 6 : 15 * N + (v - 6 * N); }
 
 // Block-wide sum of one double per thread, result broadcast. red: >= SOLVE_WARPS doubles of scratch.

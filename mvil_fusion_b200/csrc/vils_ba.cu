@@ -13,18 +13,13 @@
 
 #include "ba_device.cuh"
 #include "common.h"
+#include "margin_device.cuh"
 
 using namespace vb;
 
 // =================================================================================================================
 // kernels
 // =================================================================================================================
-__device__ __forceinline__ Win decode(const SolveParams& P, int slot) {
-  Win W; W.base = P.blobs + (size_t)slot * P.blob_stride; W.h = reinterpret_cast<const WinHdr*>(W.base);
-  W.N = W.h->n_kf; W.M = W.h->n_feat; W.D = 15 * W.N + 7; W.Dv = 6 * W.N + 7; W.Dvp = P.sl.Dv_pad; W.nb = (W.D + TB - 1) / TB;
-  return W;
-}
-
 // Once per upload: IMU sqrt_info (imu_factor.h:64 recomputes it in every Evaluate; it only depends on the
 // pre-integration), prior A = J_lin^T J_lin and b0 = J_lin^T r_lin, and the zero pattern of E.
 __global__ void prep_kernel(SolveParams P) {
@@ -413,6 +408,7 @@ struct vils_ba {
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
   float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
   bool prepped = false;
+  double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
 };
 
 static inline size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -527,7 +523,7 @@ void vils_ba_destroy(vils_ba* ba) {
   cudaSetDevice(ba->cfg.device);
   if (ba->stream) cudaStreamSynchronize(ba->stream);
   cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
-  cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ);
+  cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws);
   if (ba->ev0) cudaEventDestroy(ba->ev0);
   if (ba->ev1) cudaEventDestroy(ba->ev1);
   if (ba->stream) cudaStreamDestroy(ba->stream);
@@ -825,6 +821,53 @@ int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* c
   if (S) std::memcpy(S, ba->h_lin, sizeof(double) * D * D);
   if (g) std::memcpy(g, ba->h_lin + (size_t)D * D, sizeof(double) * D);
   if (cost) *cost = ba->h_lin[(size_t)D * D + D];
+  return VILS_OK;
+}
+
+
+// Marginalization of one slot at its SOLVED state (the last vils_ba_solve / solve_device of that slot).
+int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out* out) {
+  if (!ba || !out || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set || (flag != VILS_MARGIN_OLD && flag != VILS_MARGIN_SECOND_NEW))
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_marginalize: bad argument");
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "marginalize: solve the window first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  const vils_config& c = ba->cfg;
+  const int D = 15 * c.max_kf + 7, Tcap = D + c.max_feat;
+  if (!ba->d_mws) {
+    MargParams& q = ba->mq; int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += (n + 1) & ~int64_t(1); return r; };
+    const int64_t T2 = (int64_t)Tcap * Tcap;
+    q.oH = take(T2); q.oG = take(Tcap); q.oA = take(T2); q.oB = take(Tcap); q.oV = take(T2); q.oW = take(Tcap); q.oAinv = take(T2); q.oArm = take(T2);
+    q.oAr = take((int64_t)D * D); q.oBr = take(Tcap); q.oV2 = take(T2); q.oS = take(Tcap);
+    q.oStage = take(std::max<int64_t>((int64_t)c.max_proj * 44, 512)); q.oJout = take((int64_t)D * D); q.oRout = take(D); q.oX0 = take((2 * c.max_kf + 2) * 9);
+    ba->mws_doubles = o; ba->mi_ints = 8 + 5 * Tcap + c.max_feat + 128;
+    q.Tcap = Tcap; q.Mcap = c.max_feat;
+    cudaError_t e = cudaMalloc(&ba->d_mws, (size_t)o * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ba->d_miws, sizeof(int32_t) * ba->mi_ints);
+    if (e != cudaSuccess) return vils::fail_cuda(e, "marginalize workspace");
+    q.ws = ba->d_mws; q.iws = ba->d_miws;
+    cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
+  }
+  MargParams q = ba->mq; q.slot = slot; q.flag = flag;
+  SolveParams P = make_params(ba, nullptr);
+  cudaMemsetAsync(ba->d_miws, 0, sizeof(int32_t) * 8, ba->stream);
+  margin_kernel<<<1, SOLVE_THREADS, 16384, ba->stream>>>(P, q);
+  int32_t hdr[8];
+  cudaMemcpyAsync(hdr, ba->d_miws, sizeof(hdr), cudaMemcpyDeviceToHost, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "margin_kernel");
+  const int n = hdr[0], m = hdr[1], nb = hdr[2], nx0 = hdr[4];
+  out->n = n; out->m = m; out->nblk = nb;
+  if (n == 0) return VILS_OK;
+  if (n > out->capacity_n || !out->J || !out->r || !out->blk || !out->x0) return vils::fail(VILS_ERR_CAPACITY, "vils_ba_marginalize: output capacity too small");
+  std::vector<int32_t> blk(2 * nb);
+  const int N = ba->meta[slot].n_kf; (void)N;
+  e = cudaMemcpy(out->J, ba->d_mws + q.oJout, sizeof(double) * n * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out->r, ba->d_mws + q.oRout, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out->x0, ba->d_mws + q.oX0, sizeof(double) * nx0, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(blk.data(), ba->d_miws + 8 + 3 * Tcap + c.max_feat, sizeof(int32_t) * 2 * nb, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "marginalize copy");
+  for (int b = 0; b < nb; b++) out->blk[b] = blk[2 * b];     // ids already re-addressed to the slid window
   return VILS_OK;
 }
 
