@@ -46,6 +46,7 @@ __global__ void prep_kernel(SolveParams P) {
     }
   }
   for (int64_t e = threadIdx.x; e < (int64_t)W.h->n_lm * P.sl.Dv_pad; e += blockDim.x) scr[P.sl.E + e] = 0.0;
+  for (int e = threadIdx.x; e < PAIR_LD * PAIR_LD; e += blockDim.x) scr[P.sl.pairpart + (int64_t)(P.Ncap * (P.Ncap - 1) / 2) * PAIR_LD * PAIR_LD + e] = 0.0;
 }
 
 __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
@@ -77,10 +78,10 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;
   for (int e = threadIdx.x; e < W.nb * TB; e += blockDim.x) { g[e] = 0.0; hd[e] = 0.0; }
   __syncthreads();
-  gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr);
+  gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr, reinterpret_cast<const int*>(sm + L.pid), P.Ncap * (P.Ncap - 1) / 2);
   __syncthreads();
   PROF(3);
-  c += imu_pass(P, W, x, H, g, hd, sm + L.imu, scr, true);
+  c += imu_pass(P, W, x, H, g, hd, P.hv_in_smem ? sm + L.hv : sm + L.imu, scr, true, P.hv_in_smem != 0);
   PROF(4);
   c += lidar_pass(P, W, x, H, g, hd, true);
   __syncthreads();
@@ -96,7 +97,7 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
 __device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x) {
   double c = 0;
   for (int f = threadIdx.x; f < W.h->n_proj; f += blockDim.x) c += proj_cost(P, W, x, f);
-  c += imu_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, scr, false);
+  c += imu_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, scr, false, false);
   c += lidar_pass(P, W, x, nullptr, nullptr, nullptr, false);
   __syncthreads();
   c += icp_lps_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, false);
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
+  { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
   double nf = 0;
   for (int d = threadIdx.x; d < W.nb * TB; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
   if (threadIdx.x == 0) chol_flag = 0;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
     if (threadIdx.x == 0) chol_flag = 0;
     __syncthreads();
     PROF(7);
-    cholesky_tiles(H, sm + L.g, sm + L.linv, W.nb, &chol_flag, P.prof);
+    cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, P.prof);
     const bool ok = chol_flag == 0;
     PROF(8);
     if (!ok && !lm) { status = VILS_ERR_CHOLESKY; break; }
@@ -279,7 +281,100 @@ struct EvalParams {
   int32_t apply_loss;
 };
 
-__global__ void eval_kernel(EvalParams Q) {
+// Projection factors: one thread per factor (landmark-sorted order), results staged in shared memory and written with fully
+// coalesced 8-byte stores.  Output order inside a family is the library's SORTED order; the single-slot host API
+// un-permutes (vils_ba_evaluate), the batched device API documents it (vils_ba_evaluate_device).
+constexpr int EV_T = 128, EV_PLD = 43, EV_ELD = 21, EV_LLD = 7;
+__global__ void __launch_bounds__(EV_T, 3) eval_proj_kernel(EvalParams Q) {
+  extern __shared__ __align__(16) double st[];
+  const SolveParams& P = Q.S;
+  const int slot = P.slot0 + blockIdx.y;
+  const Win W = decode(P, slot);
+  const int np = W.h->n_proj, fbase = blockIdx.x * EV_T;
+  if (fbase >= np) return;
+  const double* x = W.d(OFF_X);
+  const int N = W.N, t = threadIdx.x, f = fbase + t;
+  if (f < np) {
+    const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
+    double c[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
+    const int i = ix[f], j = ix[np + f], feat = W.i(OFF_LM_FEAT)[ix[2 * np + f]];
+    double* o = st + t * EV_PLD;
+    vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(N), x[XL(N) + feat], x[XT(N)], o, o + 2);   // straight into the staging row
+    if (Q.apply_loss) {
+      double rho, w; vf::cauchy(P.cfg.cauchy_a, o[0] * o[0] + o[1] * o[1], rho, w);
+#pragma unroll
+      for (int e = 0; e < 42; e++) o[e] *= w;
+    }
+  }
+  __syncthreads();
+  const int cnt = min(EV_T, np - fbase);
+  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * W.h->n_imu + 2 * (size_t)fbase;
+  double* Jo = Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * W.h->n_imu + (size_t)40 * fbase;
+  for (int e = t; e < cnt * 2; e += EV_T) R[e] = st[(e >> 1) * EV_PLD + (e & 1)];
+  for (int e = t; e < cnt * 40; e += EV_T) Jo[e] = st[(e / 40) * EV_PLD + 2 + e % 40];
+}
+
+// LiDAR plane + edge factors (keyframe-sorted order): blockIdx.x < plane chunks -> planes, else edges.
+__global__ void __launch_bounds__(EV_T) eval_lidar_kernel(EvalParams Q, int plane_chunks) {
+  extern __shared__ __align__(16) double st[];
+  const SolveParams& P = Q.S;
+  const int slot = P.slot0 + blockIdx.y;
+  const Win W = decode(P, slot);
+  const WinHdr* h = W.h;
+  const double* x = W.d(OFF_X);
+  const int t = threadIdx.x;
+  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * h->n_imu + 2 * (size_t)h->n_proj;
+  double* Jo = Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * h->n_imu + (size_t)40 * h->n_proj;
+  if ((int)blockIdx.x < plane_chunks) {
+    const int n = h->n_plane, fbase = blockIdx.x * EV_T, f = fbase + t;
+    if (fbase >= n) return;
+    if (f < n) {
+      const double* pl = W.d(OFF_PLANE); const int32_t* ix = W.i(OFF_PLANE_IDX);
+      double J[6];
+      double r = vf::plane_eval(x + XP(ix[f]), vm::mk(pl[f], pl[(size_t)n + f], pl[(size_t)2 * n + f]),
+                                vm::mk(pl[(size_t)3 * n + f], pl[(size_t)4 * n + f], pl[(size_t)5 * n + f]), pl[(size_t)6 * n + f], J);
+      double w = 1.0;
+      if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r * r, rho, w); }
+      R[f] = r * w;
+#pragma unroll
+      for (int e = 0; e < 6; e++) st[t * EV_LLD + e] = J[e] * w;
+    }
+    __syncthreads();
+    const int cnt = min(EV_T, n - fbase);
+    for (int e = t; e < cnt * 6; e += EV_T) Jo[(size_t)6 * fbase + e] = st[(e / 6) * EV_LLD + e % 6];
+  } else {
+    const int n = h->n_edge, fbase = (blockIdx.x - plane_chunks) * EV_T, f = fbase + t;
+    if (fbase >= n) return;
+    R += h->n_plane; Jo += (size_t)6 * h->n_plane;
+    if (f < n) {
+      const double* ed = W.d(OFF_EDGE); const int32_t* ix = W.i(OFF_EDGE_IDX);
+      double r[3], J[18];
+      vf::edge_eval(x + XP(ix[f]), vm::mk(ed[f], ed[(size_t)n + f], ed[(size_t)2 * n + f]),
+                    vm::mk(ed[(size_t)3 * n + f], ed[(size_t)4 * n + f], ed[(size_t)5 * n + f]),
+                    vm::mk(ed[(size_t)6 * n + f], ed[(size_t)7 * n + f], ed[(size_t)8 * n + f]), r, J);
+      double w = 1.0;
+      if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
+      double* o = st + t * EV_ELD;
+#pragma unroll
+      for (int e = 0; e < 3; e++) o[e] = r[e] * w;
+#pragma unroll
+      for (int e = 0; e < 18; e++) o[3 + e] = J[e] * w;
+    }
+    __syncthreads();
+    const int cnt = min(EV_T, n - fbase);
+    for (int e = t; e < cnt * 3; e += EV_T) R[(size_t)3 * fbase + e] = st[(e / 3) * EV_ELD + e % 3];
+    for (int e = t; e < cnt * 18; e += EV_T) Jo[(size_t)18 * fbase + e] = st[(e / 18) * EV_ELD + 3 + e % 18];
+  }
+}
+
+// The few heavy factors: IMU (whitened 15x30), ICP, LPS and the prior residual. One block of 256 threads per window:
+// a warp per IMU factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30 whitening and the coalesced
+// stores by all lanes), then one thread per ICP / LPS constraint and per prior row.
+constexpr int EVS_T = 320;
+__global__ void __launch_bounds__(EVS_T) eval_small_kernel(EvalParams Q) {
+  __shared__ double sJ[EVS_T / 32][450 + 16];
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
@@ -287,68 +382,27 @@ __global__ void eval_kernel(EvalParams Q) {
   const double* x = W.d(OFF_X);
   const double* scr = P.scratch + (size_t)slot * P.sl.total;
   double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = W.N;
-  int rbase = 0; int64_t jbase = 0;
-  if (t < h->n_imu) {
-    const int i = W.i(OFF_IMU_KF)[t];
-    double r[15], J[450], Jw[450];
-    for (int e = 0; e < 450; e++) J[e] = 0;
-    vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)t * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
-    const double* Wk = scr + P.sl.w_imu + (size_t)t * 225;
-    for (int a = 0; a < 15; a++) {
-      double s = 0; for (int m = a; m < 15; m++) s = fma(Wk[a * 15 + m], r[m], s);
-      R[15 * t + a] = s;
-      for (int c = 0; c < 30; c++) { double v = 0; for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v); Jw[a * 30 + c] = v; }
+  const int N = W.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < h->n_imu; k += EVS_T / 32) {
+    double* J = sJ[warp]; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
+    const int i = W.i(OFF_IMU_KF)[k];
+    for (int e = lane; e < 450; e += 32) J[e] = 0.0;
+    __syncwarp();
+    if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
+    __syncwarp();
+    if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
+    for (int e = lane; e < 450; e += 32) {
+      const int a = e / 30, c = e % 30; double v = 0;
+      for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
+      Jo[(size_t)450 * k + e] = v;
     }
-    for (int e = 0; e < 450; e++) Jo[(size_t)450 * t + e] = Jw[e];
-    return;
+    __syncwarp();
   }
-  t -= h->n_imu; rbase += 15 * h->n_imu; jbase += (int64_t)450 * h->n_imu;
-  if (t < h->n_proj) {
-    const int np = h->n_proj; const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
-    double c[14];
-#pragma unroll
-    for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + t];
-    const int i = ix[t], j = ix[np + t], feat = W.i(OFF_LM_FEAT)[ix[2 * np + t]], orig = ix[3 * np + t];
-    double r[2], J[40];
-    vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(N), x[XL(N) + feat], x[XT(N)], r, J);
-    double w = 1.0;
-    if (Q.apply_loss) { double rho; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w); }
-    R[rbase + 2 * orig] = r[0] * w; R[rbase + 2 * orig + 1] = r[1] * w;
-    double* o = Jo + jbase + (int64_t)40 * orig;
-#pragma unroll
-    for (int e = 0; e < 40; e++) o[e] = J[e] * w;
-    return;
-  }
-  t -= h->n_proj; rbase += 2 * h->n_proj; jbase += (int64_t)40 * h->n_proj;
-  if (t < h->n_plane) {
-    const int n = h->n_plane; const double* pl = W.d(OFF_PLANE); const int32_t* ix = W.i(OFF_PLANE_IDX);
-    double J[6];
-    double r = vf::plane_eval(x + XP(ix[t]), vm::mk(pl[t], pl[(size_t)n + t], pl[(size_t)2 * n + t]),
-                              vm::mk(pl[(size_t)3 * n + t], pl[(size_t)4 * n + t], pl[(size_t)5 * n + t]), pl[(size_t)6 * n + t], J);
-    double w = 1.0;
-    if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r * r, rho, w); }
-    const int orig = ix[n + t];
-    R[rbase + orig] = r * w;
-    for (int e = 0; e < 6; e++) Jo[jbase + (int64_t)6 * orig + e] = J[e] * w;
-    return;
-  }
-  t -= h->n_plane; rbase += h->n_plane; jbase += (int64_t)6 * h->n_plane;
-  if (t < h->n_edge) {
-    const int n = h->n_edge; const double* ed = W.d(OFF_EDGE); const int32_t* ix = W.i(OFF_EDGE_IDX);
-    double r[3], J[18];
-    vf::edge_eval(x + XP(ix[t]), vm::mk(ed[t], ed[(size_t)n + t], ed[(size_t)2 * n + t]),
-                  vm::mk(ed[(size_t)3 * n + t], ed[(size_t)4 * n + t], ed[(size_t)5 * n + t]),
-                  vm::mk(ed[(size_t)6 * n + t], ed[(size_t)7 * n + t], ed[(size_t)8 * n + t]), r, J);
-    double w = 1.0;
-    if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
-    const int orig = ix[n + t];
-    for (int e = 0; e < 3; e++) R[rbase + 3 * orig + e] = r[e] * w;
-    for (int e = 0; e < 18; e++) Jo[jbase + (int64_t)18 * orig + e] = J[e] * w;
-    return;
-  }
-  t -= h->n_edge; rbase += 3 * h->n_edge; jbase += (int64_t)18 * h->n_edge;
+  int t = threadIdx.x;
+  int rbase; int64_t jbase;
+  rbase = 15 * h->n_imu + 2 * h->n_proj + h->n_plane;
+  jbase = (int64_t)450 * h->n_imu + (int64_t)40 * h->n_proj + (int64_t)6 * h->n_plane;
+  rbase += 3 * h->n_edge; jbase += (int64_t)18 * h->n_edge;
   if (t < h->n_icp) {
     const double* c = W.d(OFF_ICP) + 14 * t; double r[3], J[72];
     vf::icp_eval(c, x + XP((int)c[10]), x + XP((int)c[11]), x + XP((int)c[12]), x + XP((int)c[13]), r, J);
@@ -369,19 +423,19 @@ __global__ void eval_kernel(EvalParams Q) {
     return;
   }
   t -= h->n_lps; rbase += 3 * h->n_lps;
-  if (t < h->prior_n) {   // MarginalizationFactor residual row t (marginalization_factor.cpp:364-383)
+  for (int row = t; row >= 0 && row < h->prior_n; row += EVS_T - h->n_icp - h->n_lps) {   // MarginalizationFactor residual rows (marginalization_factor.cpp:364-383)
     const int n = h->prior_n; const int32_t* blk = W.i(OFF_PRIOR_BLK);
     const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
-    double r = W.d(OFF_PRIOR_R)[t];
+    double r = W.d(OFF_PRIOR_R)[row];
     for (int b = 0; b < h->prior_nblk; b++) {
       const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
       const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
       double dx[9]; int sz;
       if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
       else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
-      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + t], dx[k], r);
+      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + row], dx[k], r);
     }
-    R[rbase + t] = r;
+    R[rbase + row] = r;
   }
 }
 
@@ -484,7 +538,8 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   auto take = [&](int64_t n) { int64_t r = o; o += (n + 1) & ~int64_t(1); return r; };
   s.Dv_pad = Dvp;
   s.w_imu = take((int64_t)N * 225); s.E = take((int64_t)M * Dvp); s.part = take((int64_t)cfg->max_proj * PART_LD);
-  s.pairpart = take((int64_t)N * (N - 1) / 2 * PAIR_LD * PAIR_LD); s.priorA = take((int64_t)D * D); s.priorb0 = take(D);
+  s.pairpart = take(((int64_t)N * (N - 1) / 2 + 1) * PAIR_LD * PAIR_LD);   // + one all-zero block
+  s.priorA = take((int64_t)D * D); s.priorb0 = take(D);
   // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
   int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   const size_t budget = (size_t)dev_smem - 1024;
@@ -724,7 +779,7 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   if (prof) {
     long long h[16]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
-    static const char* names[16] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:diag-wait", "  chol:panel", "  chol:trailing"};
+    static const char* names[16] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA"};
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
     for (int i = 0; i < 16; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
@@ -774,17 +829,27 @@ static int ensure_eval_buffers(vils_ba* ba) {
 
 static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   int st = ensure_eval_buffers(ba); if (st) return st;
-  int items = 0; for (int k = slot0; k < slot0 + n; k++) items = std::max(items, ba->meta[k].items);
+  int np = 0, npl = 0, ned = 0, small = 0;
+  for (int k = slot0; k < slot0 + n; k++) {
+    const WinHdr* h = reinterpret_cast<const WinHdr*>(ba->h_blob + (size_t)k * ba->blob_stride);
+    np = std::max(np, h->n_proj); npl = std::max(npl, h->n_plane); ned = std::max(ned, h->n_edge);
+    small = std::max(small, h->n_imu + h->n_icp + h->n_lps + h->prior_n);
+  }
   EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
   Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
-  dim3 grid((items + 127) / 128, n);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(eval_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_T * EV_PLD * 8); attr = true; }
   cudaEventRecord(ba->ev0, ba->stream);
-  eval_kernel<<<grid, 128, 0, ba->stream>>>(Q);
+  int launches = 0;
+  if (np) { eval_proj_kernel<<<dim3((np + EV_T - 1) / EV_T, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q); launches++; }
+  const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
+  if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream>>>(Q, pc); launches++; }
+  if (small) { eval_small_kernel<<<dim3(1, n), EVS_T, 0, ba->stream>>>(Q); launches++; }
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
-  if (e != cudaSuccess) return vils::fail_cuda(e, "eval_kernel");
+  if (e != cudaSuccess) return vils::fail_cuda(e, "eval kernels");
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
-  ba->last_launches = 1;
+  ba->last_launches = launches;
   return VILS_OK;
 }
 
@@ -800,10 +865,30 @@ int vils_ba_evaluate(vils_ba* ba, int32_t slot, int32_t apply_loss, double* resi
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   int st = launch_eval(ba, slot, 1, apply_loss); if (st) return st;
   const SlotMeta& m = ba->meta[slot];
-  cudaError_t e = cudaSuccess;
-  if (residuals) e = cudaMemcpy(residuals, ba->d_er + (size_t)slot * ba->er_stride, sizeof(double) * m.n_res, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && jacobians) e = cudaMemcpy(jacobians, ba->d_eJ + (size_t)slot * ba->eJ_stride, sizeof(double) * m.n_jac, cudaMemcpyDeviceToHost);
-  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "evaluate copy");
+  // The kernels write each family in the library's sorted order; hand the caller its own factor order back.
+  std::vector<double> hr(m.n_res), hj((size_t)std::max<int64_t>(m.n_jac, 1));
+  cudaError_t e = cudaMemcpy(hr.data(), ba->d_er + (size_t)slot * ba->er_stride, sizeof(double) * m.n_res, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && m.n_jac) e = cudaMemcpy(hj.data(), ba->d_eJ + (size_t)slot * ba->eJ_stride, sizeof(double) * m.n_jac, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "evaluate copy");
+  const uint8_t* base = ba->h_blob + (size_t)slot * ba->blob_stride;
+  const WinHdr* h = reinterpret_cast<const WinHdr*>(base);
+  auto unperm = [&](int n, const int32_t* orig, int nr, int nj, size_t ro, size_t jo) {
+    std::vector<double> tr((size_t)n * nr), tj((size_t)n * nj);
+    for (int s2 = 0; s2 < n; s2++) {
+      std::copy(hr.begin() + ro + (size_t)s2 * nr, hr.begin() + ro + (size_t)(s2 + 1) * nr, tr.begin() + (size_t)orig[s2] * nr);
+      std::copy(hj.begin() + jo + (size_t)s2 * nj, hj.begin() + jo + (size_t)(s2 + 1) * nj, tj.begin() + (size_t)orig[s2] * nj);
+    }
+    std::copy(tr.begin(), tr.end(), hr.begin() + ro); std::copy(tj.begin(), tj.end(), hj.begin() + jo);
+  };
+  size_t ro = (size_t)15 * h->n_imu, jo = (size_t)450 * h->n_imu;
+  unperm(h->n_proj, reinterpret_cast<const int32_t*>(base + h->off[OFF_PROJ_IDX]) + 3 * h->n_proj, 2, 40, ro, jo);
+  ro += (size_t)2 * h->n_proj; jo += (size_t)40 * h->n_proj;
+  unperm(h->n_plane, reinterpret_cast<const int32_t*>(base + h->off[OFF_PLANE_IDX]) + h->n_plane, 1, 6, ro, jo);
+  ro += h->n_plane; jo += (size_t)6 * h->n_plane;
+  unperm(h->n_edge, reinterpret_cast<const int32_t*>(base + h->off[OFF_EDGE_IDX]) + h->n_edge, 3, 18, ro, jo);
+  if (residuals) std::copy(hr.begin(), hr.end(), residuals);
+  if (jacobians && m.n_jac) std::copy(hj.begin(), hj.begin() + m.n_jac, jacobians);
+  return VILS_OK;
 }
 
 int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* cost) {

@@ -1,0 +1,37 @@
+"""Window sharding across ranks: independent windows, no data-path collective; only the timing
+reduction (max over ranks) and the final gather of solved states cross ranks."""
+
+
+def shard_range(total, world, rank):
+    """Contiguous, balanced [lo, hi) of `total` windows for `rank` (first `total % world` ranks get one more)."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def max_over_ranks(values, device=None):
+    """Element-wise max of a list of floats over all ranks (identity when torch.distributed is not initialised)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return list(values)
+    t = torch.tensor(list(values), dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def gather_states(local_states, device=None):
+    """all_gather of per-rank (n_local, X) solved-state arrays -> list over ranks (numpy)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [np.asarray(local_states)]
+    t = torch.as_tensor(np.ascontiguousarray(local_states), dtype=torch.float64, device=device or "cpu")
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(dist.get_world_size())]
+    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    mx = int(max(int(s.item()) for s in sizes))
+    pad = torch.zeros((mx, t.shape[1]), dtype=torch.float64, device=t.device); pad[:t.shape[0]] = t
+    outs = [torch.zeros_like(pad) for _ in sizes]
+    dist.all_gather(outs, pad)
+    return [o[:int(s.item())].cpu().numpy() for o, s in zip(outs, sizes)]

@@ -194,3 +194,25 @@ def test_error_codes(lib):
     ba.set_window(0, nanw)
     ba.solve(1, cabi.default_solve_opts())
     assert ba.get_state(0)["status"] in (cabi.VILS_ERR_NOT_FINITE, cabi.VILS_ERR_CHOLESKY)
+
+
+def test_config4_large_window_global_memory_path(lib):
+    """configs[3]: 20 KF, 300 features, 5000 LiDAR factors, ICP/LPS, prior.  D = 307 does not fit shared memory, so H and
+    Hv live in the per-window L2 scratch (solve_kernel<false>)."""
+    cfg = cabi.default_config(max_kf=20, max_feat=300, max_proj=3600, max_lidar=5000)
+    w = synth.make_window(4, 0, N=20, M=300, n_lidar=5000, n_icp=3, n_lps=3)
+    assert len(w["kf_i"]) == 3333
+    ba = lib.BA(cfg, 2)
+    ba.set_window(0, w); ba.set_window(1, synth.make_window(4, 1, N=20, M=300, n_lidar=5000, n_icp=3, n_lps=3))
+    ba.upload(2)
+    S, g, cost = ba.linearize(0)
+    So, go, co = ol.linearize_window(cfg, w)
+    assert abs(cost - co) <= 1e-11 * abs(co)
+    assert np.abs(S - So).max() <= 1e-9 * np.abs(So).max()
+    opts = cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, 1e-8)
+    ba.solve(2, opts)
+    gs = ba.get_state(0)
+    o = ol.solve_window(cfg, w, opts)
+    assert gs["status"] == 0 and o["status"] == 0
+    assert abs(gs["cost_final"] - o["cost_final"]) <= 1e-7 * o["cost_final"]
+    assert helpers.rel_state_delta(gs, o) <= 1e-5
