@@ -236,12 +236,23 @@ int vils_ba_last_device_ms(vils_ba* ba, float* ms);
 int vils_ba_last_launches(vils_ba* ba, int32_t* n);
 /* Bytes moved by the last vils_ba_upload (host->device) and vils_ba_download (device->host). */
 int vils_ba_last_transfer_bytes(vils_ba* ba, size_t* h2d, size_t* d2h);
-/* Factor-sharded mode (one window over several GPUs): phase A linearises this rank's factors and
- * leaves the partial reduced system [S | g | cost] (D*D + D + 1 doubles) in a device buffer the
- * caller all-reduces (NCCL, sum); phase B solves, updates and back-substitutes. */
+/* Factor-sharded mode: ONE window over several GPUs (large windows only; at 10 keyframes the all-reduce latency is of
+ * the order of a whole single-GPU iteration).  Every rank stages in slot 0 a window with the FULL state but only ITS share
+ * of the factors (landmarks with all their projection factors by feature % G, LiDAR factors round-robin, IMU / prior /
+ * ICP / LPS on rank 0) and uploads it.  Per Gauss-Newton iteration:
+ *   vils_ba_sharded_linearize : local factors -> partial system [H (D x D row-major, no damping, constant blocks untouched)
+ *                               | g (D) | diag for damping (D) | cost] in the device buffer of vils_ba_sharded_buffer;
+ *   caller                    : all-reduce (sum) of that buffer over ranks (ncclAllReduce on the device pointer);
+ *   vils_ba_sharded_update    : damping + Cholesky + back-substitution (identical on every rank), landmark
+ *                               back-substitution and Plus for the local landmarks.
+ * Iteration 0 starts from the uploaded state; afterwards vils_ba_download / vils_ba_get_state as usual (a rank owns the
+ * inverse depths of its own landmarks; poses, speed-biases, extrinsic and td are identical on all ranks). */
 int vils_ba_sharded_buffer(vils_ba* ba, void** dev_ptr, size_t* n_doubles);
-int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration);
+int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_opts* opts);
 int vils_ba_sharded_update(vils_ba* ba, const vils_solve_opts* opts);
+/* Host-mediated access to the same buffer (tests; transports other than NCCL). */
+int vils_ba_sharded_read(vils_ba* ba, double* host);
+int vils_ba_sharded_write(vils_ba* ba, const double* host);
 
 /* ---- IMU pre-integration: IntegrationBase::push_back/repropagate (integration_base.h:30-158) - */
 /* n_intervals independent intervals; interval k integrates samples [off[k], off[k+1]).  acc/gyr are

@@ -274,6 +274,75 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   }
 }
 
+// ---- factor-sharded mode (one window over several GPUs) ------------------------------------------------
+// shard_lin_kernel: linearise THIS rank's factors at the device-resident state, leave [H (D x D) | g | hd | cost] in `buf`
+// for the caller's all-reduce.  shard_upd_kernel: reduced buffer -> damping, Cholesky, back-substitution (identical on every
+// rank), then landmark back-substitution + Plus for the local landmarks.
+template <bool SMEM_H>
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_lin_kernel(SolveParams P, double* buf, int first, double mu) {
+  extern __shared__ __align__(16) double sm[];
+  const int slot = P.slot0;
+  const Win W = decode(P, slot);
+  const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
+  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
+  double* Hv = SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg);
+  double* xs = sm + L.xs;
+  const int X = 16 * W.N + 8 + W.M, D = W.D;
+  double* xo = P.xout + (size_t)slot * P.xout_stride;
+  const double* x0 = first ? W.d(OFF_X) : xo;
+  for (int k = threadIdx.x; k < X; k += blockDim.x) { xs[k] = x0[k]; if (first) xo[k] = x0[k]; }
+  { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
+  __syncthreads();
+  const double c = linearize(P, W, L, sm, scr, xs, H, Hv, mu);
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; buf[e] = H[tidx(max(i, j), min(i, j))]; }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { buf[(size_t)D * D + i] = sm[L.g + i]; buf[(size_t)D * D + D + i] = sm[L.hd + i]; }
+  if (threadIdx.x == 0) buf[(size_t)D * D + 2 * D] = c;
+  for (int r = threadIdx.x; r < W.h->n_lm; r += blockDim.x) { scr[P.sl.lmsave + r] = sm[L.cinv + r]; scr[P.sl.lmsave + P.Mcap + r] = sm[L.glam + r]; }
+}
+
+template <bool SMEM_H>
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_upd_kernel(SolveParams P, const double* buf, double mu) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int chol_flag;
+  const int slot = P.slot0;
+  const Win W = decode(P, slot);
+  const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
+  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
+  double* xs = sm + L.xs; double* xc = sm + L.xc;
+  int* fx = reinterpret_cast<int*>(sm + L.fx);
+  const int X = 16 * W.N + 8 + W.M, D = W.D;
+  double* xo = P.xout + (size_t)slot * P.xout_stride;
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xo[k];
+  double nf = 0;
+  for (int d = threadIdx.x; d < W.nb * TB; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
+  if (threadIdx.x == 0) chol_flag = 0;
+  const int nfix = (int)block_sum(nf, sm + L.red);
+  for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;
+  for (int e = threadIdx.x; e < W.nb * TB; e += blockDim.x) { sm[L.g + e] = 0.0; sm[L.hd + e] = 0.0; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; if (i >= j) H[tidx(i, j)] = buf[e]; }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { sm[L.g + i] = buf[(size_t)D * D + i]; sm[L.hd + i] = buf[(size_t)D * D + D + i]; }
+  for (int r = threadIdx.x; r < W.h->n_lm; r += blockDim.x) { sm[L.cinv + r] = scr[P.sl.lmsave + r]; sm[L.glam + r] = scr[P.sl.lmsave + P.Mcap + r]; }
+  __syncthreads();
+  damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
+  __syncthreads();
+  cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+  int status = VILS_OK;
+  if (chol_flag) status = VILS_ERR_CHOLESKY;
+  else {
+    backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
+    apply_step(P, W, L, sm, scr, xs, xc);
+    for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xc[k];
+  }
+  if (threadIdx.x == 0) {
+    vils_summary s = P.summary[slot];
+    s.status = status; s.iterations += 1; s.accepted += (status == VILS_OK); s.cost_final = buf[(size_t)D * D + 2 * D];
+    P.summary[slot] = s;
+  }
+}
+
 // ---- materialised evaluation: one thread per factor, outputs in the caller's original factor order -----------------
 struct EvalParams {
   SolveParams S;
@@ -462,6 +531,7 @@ struct vils_ba {
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
   float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
   bool prepped = false;
+  double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
 };
 
@@ -539,7 +609,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   s.Dv_pad = Dvp;
   s.w_imu = take((int64_t)N * 225); s.E = take((int64_t)M * Dvp); s.part = take((int64_t)cfg->max_proj * PART_LD);
   s.pairpart = take(((int64_t)N * (N - 1) / 2 + 1) * PAIR_LD * PAIR_LD);   // + one all-zero block
-  s.priorA = take((int64_t)D * D); s.priorb0 = take(D);
+  s.priorA = take((int64_t)D * D); s.priorb0 = take(D); s.lmsave = take(2 * (int64_t)M);
   // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
   int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   const size_t budget = (size_t)dev_smem - 1024;
@@ -566,6 +636,10 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaMalloc(&ba->d_lin, n_lin * 8)); CK(cudaMallocHost(&ba->h_lin, n_lin * 8));
   CK(cudaFuncSetAttribute(solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
   CK(cudaFuncSetAttribute(solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(shard_lin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(shard_lin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(shard_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  CK(cudaFuncSetAttribute(shard_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
 #undef CK
   std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
   std::memset(ba->h_sum, 0, sizeof(vils_summary) * max_windows);
@@ -578,7 +652,7 @@ void vils_ba_destroy(vils_ba* ba) {
   cudaSetDevice(ba->cfg.device);
   if (ba->stream) cudaStreamSynchronize(ba->stream);
   cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
-  cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws);
+  cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws); cudaFree(ba->d_shard);
   if (ba->ev0) cudaEventDestroy(ba->ev0);
   if (ba->ev1) cudaEventDestroy(ba->ev1);
   if (ba->stream) cudaStreamDestroy(ba->stream);
@@ -954,6 +1028,66 @@ int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out*
   if (e != cudaSuccess) return vils::fail_cuda(e, "marginalize copy");
   for (int b = 0; b < nb; b++) out->blk[b] = blk[2 * b];     // ids already re-addressed to the slid window
   return VILS_OK;
+}
+
+
+// ---- factor-sharded mode ---------------------------------------------------------------------------------------------
+static int ensure_shard_buffer(vils_ba* ba) {
+  if (ba->d_shard) return VILS_OK;
+  const int D = 15 * ba->cfg.max_kf + 7;
+  ba->shard_doubles = (size_t)D * D + 2 * (size_t)D + 1;
+  cudaError_t e = cudaMalloc(&ba->d_shard, ba->shard_doubles * 8);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "sharded buffer");
+}
+int vils_ba_sharded_buffer(vils_ba* ba, void** dev_ptr, size_t* n_doubles) {
+  if (!ba || !dev_ptr || !n_doubles || !ba->meta[0].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_buffer: stage the window in slot 0 first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  int st = ensure_shard_buffer(ba); if (st) return st;
+  const int D = 15 * ba->meta[0].n_kf + 7;
+  *dev_ptr = ba->d_shard; *n_doubles = (size_t)D * D + 2 * (size_t)D + 1;
+  return VILS_OK;
+}
+int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_opts* opts) {
+  if (!ba || !opts || iteration < 0 || !ba->meta[0].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_linearize: bad argument");
+  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "sharded: call vils_ba_upload first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  int st = ensure_shard_buffer(ba); if (st) return st;
+  SolveParams P = make_params(ba, opts);
+  if (iteration == 0) cudaMemsetAsync(ba->d_sum, 0, sizeof(vils_summary), ba->stream);
+  cudaEventRecord(ba->ev0, ba->stream);
+  if (ba->h_in_smem && ba->hv_in_smem) shard_lin_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, iteration == 0, opts->mu);
+  else shard_lin_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, iteration == 0, opts->mu);
+  cudaEventRecord(ba->ev1, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);      // the caller's all-reduce runs on its own stream: hand over a finished buffer
+  if (e != cudaSuccess) return vils::fail_cuda(e, "shard_lin_kernel");
+  cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  return VILS_OK;
+}
+int vils_ba_sharded_update(vils_ba* ba, const vils_solve_opts* opts) {
+  if (!ba || !opts || !ba->d_shard) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_update: linearize first");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  SolveParams P = make_params(ba, opts);
+  cudaEventRecord(ba->ev0, ba->stream);
+  if (ba->h_in_smem && ba->hv_in_smem) shard_upd_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, opts->mu);
+  else shard_upd_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, opts->mu);
+  cudaEventRecord(ba->ev1, ba->stream);
+  cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "shard_upd_kernel");
+  cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  return VILS_OK;
+}
+// Host-mediated access to the partial system (tests, or transports other than NCCL).
+int vils_ba_sharded_read(vils_ba* ba, double* host) {
+  if (!ba || !host || !ba->d_shard) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_read");
+  const int D = 15 * ba->meta[0].n_kf + 7;
+  cudaError_t e = cudaMemcpy(host, ba->d_shard, ((size_t)D * D + 2 * D + 1) * 8, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "sharded read");
+}
+int vils_ba_sharded_write(vils_ba* ba, const double* host) {
+  if (!ba || !host || !ba->d_shard) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_write");
+  const int D = 15 * ba->meta[0].n_kf + 7;
+  cudaError_t e = cudaMemcpy(ba->d_shard, host, ((size_t)D * D + 2 * D + 1) * 8, cudaMemcpyHostToDevice);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "sharded write");
 }
 
 int vils_ba_last_device_ms(vils_ba* ba, float* ms) { if (!ba || !ms) return VILS_ERR_BAD_ARG; *ms = ba->last_ms; return VILS_OK; }

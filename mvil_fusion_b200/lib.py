@@ -50,7 +50,9 @@ def load():
     L.vils_ba_last_launches.argtypes = [vp, C.POINTER(C.c_int32)]
     L.vils_ba_last_transfer_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.vils_ba_sharded_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
-    L.vils_ba_sharded_linearize.argtypes = [vp, C.c_int32]
+    L.vils_ba_sharded_linearize.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_ba_sharded_read.argtypes = [vp, dp]
+    L.vils_ba_sharded_write.argtypes = [vp, dp]
     L.vils_ba_sharded_update.argtypes = [vp, C.POINTER(cabi.VilsSolveOpts)]
     L.vils_preintegrate.argtypes = [C.c_int32, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(cabi.VilsPreint), C.c_int32]
     L.vils_klt_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -155,6 +157,38 @@ class BA:
         n, nb = out.n, out.nblk
         gs = sum(cabi.blk_global_size(cabi.blk_type(int(b))) for b in blk[:nb])
         return dict(n=n, m=out.m, J=J[:n * n].copy(), r=r[:n].copy(), blk=blk[:nb].copy(), x0=x0[:gs].copy())
+
+    # ---- factor-sharded mode (one window over several GPUs) ----
+    def sharded_buffer(self):
+        """(device pointer, n_doubles) of the partial system [H | g | hd | cost] the caller all-reduces."""
+        ptr = C.c_void_p(); n = C.c_size_t()
+        _check(self.L.vils_ba_sharded_buffer(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def sharded_buffer_tensor(self):
+        """The same buffer as a torch CUDA tensor view (for torch.distributed.all_reduce over NCCL)."""
+        import torch
+        ptr, n = self.sharded_buffer()
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.cfg.device}")
+
+    def sharded_linearize(self, iteration, opts):
+        _check(self.L.vils_ba_sharded_linearize(self.h, iteration, C.byref(opts)))
+
+    def sharded_update(self, opts):
+        _check(self.L.vils_ba_sharded_update(self.h, C.byref(opts)))
+
+    def sharded_read(self):
+        _, n = self.sharded_buffer()
+        a = np.zeros(n)
+        _check(self.L.vils_ba_sharded_read(self.h, _d(a)))
+        return a
+
+    def sharded_write(self, a):
+        a = np.ascontiguousarray(a, np.float64)
+        _check(self.L.vils_ba_sharded_write(self.h, _d(a)))
 
     @property
     def last_ms(self):

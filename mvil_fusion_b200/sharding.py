@@ -35,3 +35,26 @@ def gather_states(local_states, device=None):
     outs = [torch.zeros_like(pad) for _ in sizes]
     dist.all_gather(outs, pad)
     return [o[:int(s.item())].cpu().numpy() for o, s in zip(outs, sizes)]
+
+
+def split_window(w, world, rank):
+    """Factor shard of ONE window for `rank`: the full state, landmarks (with all their projection
+    factors) by feature % world, LiDAR plane/edge factors round-robin, IMU / prior / ICP / LPS on rank 0 only."""
+    import numpy as np
+    out = dict(w)
+    if w.get("kf_i") is not None and len(w["kf_i"]):
+        keep = (np.asarray(w["feat"]) % world) == rank
+        for k in ["pts_i", "pts_j", "vel_i", "vel_j", "td_i", "td_j", "row_i", "row_j", "kf_i", "kf_j", "feat"]:
+            out[k] = np.asarray(w[k])[keep]
+    for fam, keys in (("plane_kf", ["plane_p", "plane_n", "plane_d", "plane_kf"]), ("edge_kf", ["edge_p", "edge_a", "edge_b", "edge_kf"])):
+        if w.get(fam) is not None and len(w[fam]):
+            keep = (np.arange(len(w[fam])) % world) == rank
+            for k in keys:
+                out[k] = np.asarray(w[k])[keep]
+    if rank != 0:
+        out["imu"] = np.asarray(w["imu"])[:0]; out["imu_kf"] = np.asarray(w["imu_kf"])[:0]
+        out["icp"], out["lps"] = [], []
+        out["prior_n"] = 0
+        for k in ["prior_J", "prior_r", "prior_blk", "prior_x0"]:
+            out.pop(k, None)
+    return out
