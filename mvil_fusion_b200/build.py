@@ -6,6 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvils_b200.so")
+HOST_OUT = os.path.join(HERE, "libvils_host.so")
 SOURCES = ["common.cu", "vils_ba.cu", "vils_lidar.cu", "vils_preint.cu", "vils_klt.cu", "vils_margin.cu"]
 # per-file extra flags: the FP32 LiDAR path must not contract a*b+c into FMA (bit parity with the reference arithmetic)
 EXTRA = {"vils_lidar.cu": ["--fmad=false"], "vils_klt.cu": ["--fmad=false"]}
@@ -17,7 +18,9 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vils_cabi.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))] + [os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))] + [os.path.join(HERE, "..", "include", "vils_cabi.h")]
+    if not os.path.exists(HOST_OUT):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -45,6 +48,9 @@ def build(force=False, verbose=False):
     if not ok:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs + ["-lcudart"])
+    # C++ host mirror of the reference's class API (Estimator / FeatureTracker), plain g++ on top of the C-ABI
+    host = os.path.join(CSRC, "host", "vils_host.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_OUT, host, "-L" + HERE, "-lvils_b200", "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 

@@ -1,0 +1,123 @@
+// vils_host.h — C++ host side above the C-ABI, mirroring the reference's class API for the hot path so that the ROS nodes
+// (estimator_node.cpp / feature_tracker_node.cpp) can keep calling the same methods:
+//   vils::Estimator::{processIMU, processImage, optimization, slideWindow}   <- vils_estimator/src/estimator.h:37-50,141
+//   vils::FeatureTracker::readImage                                          <- feature_tracker_/src/feature_tracker.h:33
+//   vils::TransformToEnd                                                     <- vils_estimator/src/lidar_frontend.h:287
+// ROS / Eigen / OpenCV types are replaced by plain structs (Header{stamp}, std::array, raw image pointers).  All heavy
+// arithmetic goes through libvils_b200.so (include/vils_cabi.h); there is no CPU implementation of it here.
+// Scope: the NON_LINEAR steady state of processImage (solveOdometry -> optimization -> slideWindow).  Initialisation
+// (initialStructure, estimator.cpp:618-871), SVD triangulation and failure-recovery reboot are "next" rows.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <deque>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "../../../include/vils_cabi.h"
+
+namespace vils {
+
+struct Header { double stamp = 0.0; };                                        // std_msgs::Header::stamp.toSec()
+typedef std::array<double, 8> Feature8;                                       // x y z u v vx vy depth (estimator_node.cpp:485-503)
+typedef std::map<int, std::vector<std::pair<int, Feature8>>> ImageFeatures;   // feature id -> [(camera id, xyz_uv_velocity_depth)]
+
+struct FeaturePerFrame { double point[3]; double uv[2]; double velocity[2]; double cur_td; double depth; };   // feature_manager.h:19-45
+struct FeaturePerId {                                                         // feature_manager.h:47-72
+  int feature_id = 0, start_frame = 0;
+  std::vector<FeaturePerFrame> feature_per_frame;
+  double estimated_depth = -1.0;
+  bool lidar_depth_flag = false;
+  int solve_flag = 0;                                                         // 0 not solved, 1 ok, 2 failed
+  int endFrame() const { return start_frame + (int)feature_per_frame.size() - 1; }
+};
+
+class Estimator {
+ public:
+  enum SolverFlag { INITIAL, NON_LINEAR };
+  enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };
+
+  // window_size = the reference's compile-time WINDOW_SIZE (parameters.h:12), a runtime value here; frames = window_size + 1
+  Estimator(const vils_config& cfg, int window_size, int num_iterations = 8);
+  ~Estimator();
+  Estimator(const Estimator&) = delete;
+  Estimator& operator=(const Estimator&) = delete;
+
+  void setParameter(const double ric_rowmajor[9], const double tic[3], double td_);          // estimator.cpp:21-33
+  void clearState();                                                                          // estimator.cpp:35-84
+  // Bootstrap for the steady state (the reference gets here through initialStructure): sets frame k and marks NON_LINEAR.
+  void setFrameState(int k, const double P[3], const double Q_xyzw[4], const double V[3], const double Ba[3], const double Bg[3]);
+
+  void processIMU(double dt, const double linear_acceleration[3], const double angular_velocity[3]);   // estimator.cpp:86-120
+  void processImage(const ImageFeatures& image, const Header& header);                                 // estimator.cpp:506-616
+  void optimization();                                                                                 // estimator.cpp:1124-1687
+  void slideWindow();                                                                                  // estimator.cpp:1689-1814
+
+  // ---- public state, reference names (estimator.h:67-121) ----
+  int WINDOW_SIZE;
+  SolverFlag solver_flag = INITIAL;
+  MarginalizationFlag marginalization_flag = MARGIN_OLD;
+  std::vector<std::array<double, 3>> Ps, Vs, Bas, Bgs;
+  std::vector<std::array<double, 4>> Qs;                 // Rs as unit quaternions x y z w
+  std::vector<Header> Headers;
+  double ric[4] = {0, 0, 0, 1}, tic[3] = {0, 0, 0};      // qic x y z w
+  double td = 0.0;
+  double g[3] = {0, 0, 9.795};
+  int frame_count = 0;
+  std::deque<FeaturePerId> feature;                       // f_manager.feature
+  double MIN_PARALLAX = 10.0 / 460.0;                     // keyframe_parallax / FOCAL_LENGTH (parameters.cpp:118-119)
+  double INIT_DEPTH = 5.0;                                // parameters.cpp:189
+  vils_summary last_summary{};
+  int last_status = VILS_OK;                              // status of the last optimization() (VILS_OK / VILS_ERR_*)
+  vils_solve_opts solve_opts{};
+
+  // what optimization() handed to the library last time (for tests / inspection)
+  int last_n_proj = 0, last_n_feat = 0, last_prior_n = 0;
+
+ private:
+  bool addFeatureCheckParallax(int frame_count_, const ImageFeatures& image, double td_);   // feature_manager.cpp:45-106
+  double compensatedParallax2(const FeaturePerId& it, int frame_count_) const;              // feature_manager.cpp:386-421
+  void removeBackShiftDepth();                                                               // feature_manager.cpp:286-344
+  void removeFront(int frame_count_);                                                        // feature_manager.cpp:364-384
+  void removeFailures();                                                                     // feature_manager.cpp:171-184
+
+  vils_config cfg_;
+  vils_ba* ba_ = nullptr;
+  bool first_imu_ = false;
+  double acc_0_[3] = {0, 0, 0}, gyr_0_[3] = {0, 0, 0};
+  // raw IMU samples per interval (dt_buf / linear_acceleration_buf / angular_velocity_buf, estimator.h:99-101); the
+  // pre-integration itself (IntegrationBase) is done on the GPU for all intervals at once in optimization()
+  struct ImuBuf { std::vector<double> dt, acc, gyr; double acc0[3], gyr0[3]; double ba[3], bg[3]; bool started = false; };
+  std::vector<ImuBuf> imu_;
+  // marginalization prior carried across frames (last_marginalization_info, estimator.h:120-121)
+  std::vector<double> prior_J_, prior_r_, prior_x0_;
+  std::vector<int32_t> prior_blk_;
+  int prior_n_ = 0;
+};
+
+// feature_tracker_/src/feature_tracker.{h,cpp}: the LK part of readImage (CLAHE, goodFeaturesToTrack, rejectWithF are "next" rows)
+class FeatureTracker {
+ public:
+  FeatureTracker(int rows, int cols, int max_cnt = 150, int device = 0);
+  ~FeatureTracker();
+  // readImage(const cv::Mat&, double): tracks cur_pts into the new image, drops lost / out-of-border points (:113-123),
+  // rotates prev/cur/forw (:160-164). New corners are supplied by the caller through addPoints (stands in for :134-158).
+  void readImage(const uint8_t* img, int stride, double cur_time);
+  void addPoints(const float* xy, int n);
+  std::vector<std::array<float, 2>> cur_pts, prev_pts;
+  std::vector<int> ids, track_cnt;
+  double cur_time = 0, prev_time = 0;
+  int last_status = VILS_OK;
+ private:
+  bool inBorder(float x, float y) const;                  // feature_tracker.cpp:13-19
+  int rows_, cols_, max_cnt_, n_id_ = 0;
+  vils_klt* klt_ = nullptr;
+  std::vector<uint8_t> cur_img_;
+  bool has_img_ = false;
+};
+
+// lidar_frontend.h:287 — in place on a PCL PointXYZI buffer (8 floats per point)
+int TransformToEnd(float* xyzi, int n_points, const float q_xyzw[4], const float t[3], float time_factor, double min_r, double max_r, int device = 0);
+
+}  // namespace vils

@@ -343,6 +343,7 @@ def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n
         w_["prior_r"] = np.zeros(7)
         w_["prior_blk"] = np.array([cabi.blk_id(cabi.VILS_BLK_EXPOSE, 0), cabi.blk_id(cabi.VILS_BLK_TD, 0)], np.int32)
         w_["prior_x0"] = np.concatenate([ex, [w_["td"]]])
+    w_["raw"] = dict(ts=ts, acc=acc_m, gyr=gyr_m, kf=kf, obs=obs, vel=vel, start=start, depth=depth, ric=ric, tic=tic)
     w_["truth"] = dict(pose=np.concatenate([Pk, Qk], 1), speedbias=np.concatenate([Vk, np.tile(ba_true, (N, 1)), np.tile(bg_true, (N, 1))], 1),
                        inv_depth=lam_true, td=cabi.TD0, t_kf=tk)
     return w_
