@@ -37,6 +37,8 @@ UNIQUE_WINDOWS = 74   # distinct seeded windows generated on the host; tiled to 
 BYTES_PER_LINEARISATION = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544 + (157 * 157 + 157) * 8
 BYTES_PER_COST_EVAL = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544
 BYTES_PER_SOLVE = 5 * BYTES_PER_LINEARISATION + BYTES_PER_COST_EVAL
+# dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel per window, from the committed ncu capture (profiles/r1_ncu_solve_kernel.txt)
+SOLVE_DRAM_TRAFFIC_PER_WINDOW = None
 # Materialised Evaluate() traffic per window (what the CPU reference moves per linearisation; §8d first table)
 BYTES_PER_EVAL_WINDOW = 906 * 460 + 9 * 6016 + 1500 * 116 + 500 * 244 + 2544
 
@@ -214,10 +216,8 @@ def main():
     sampler.stop()
     st = ba.get_state(0)
     assert st["status"] == 0, st
-    t = torch.tensor([dev_ms, wall_ms, e2e_ms, ev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, ev_ms = [float(x) for x in t.tolist()]
+    from mvil_fusion_b200.sharding import max_over_ranks
+    dev_ms, wall_ms, e2e_ms, ev_ms = max_over_ranks([dev_ms, wall_ms, e2e_ms, ev_ms], device="cuda")   # timing = max over ranks
     if rank == 0:
         peak, peak_src = read_peaks()
         total = B * args.steps * world
@@ -243,7 +243,7 @@ def main():
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": args.steps,
             "roofline": {"kernel": "solve_kernel (fused GN loop, one CTA per window)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": SOLVE_DRAM_TRAFFIC_PER_WINDOW * B if SOLVE_DRAM_TRAFFIC_PER_WINDOW else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_solve": BYTES_PER_SOLVE, "note": "latency-bound FP64 kernel; see DESIGN.md §4 and profiles/"},
             "roofline_eval": {"kernel": "eval_kernel (materialised residual+Jacobian of every factor)", "bound": "hbm", "achieved": ev_achieved, "peak": peak,
                               "unit": "GB/s", "frac": ev_achieved / peak, "ms_per_launch": ev_ms / args.steps, "algorithmic_bytes_per_window": BYTES_PER_EVAL_WINDOW},

@@ -136,7 +136,7 @@ __device__ double proj_cost(const SolveParams& P, const Win& W, const double* x,
 // =================================================================================================================
 // V: pair pass
 // =================================================================================================================
-__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr) {
+__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost) {
   // Rounds of PAIR_CHUNK factors in PAIR order: (1) one thread per factor evaluates ProjectionTdFactor + corrector and
   // stages the weighted rows [J(19) | r] in shared memory, writes the landmark partials / E row to the scratch;
   // (2) one warp per keyframe pair accumulates the pair-local 20x20 block A^T A over the staged rows of that pair
@@ -151,6 +151,12 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
   const int ra = 5 * (lane >> 3), cb = 3 * (lane & 7);
   double cost = 0;
   int p_lo = 0;                                   // first pair that may intersect the current round
+  // per-pair context (everything that only depends on the two keyframe poses and the extrinsic), once per linearisation
+  double* pctx = scr + P.sl.pairctx;
+  for (int p = threadIdx.x; p < npair; p += blockDim.x) vf::proj_pair_ctx(x + XP(pairs[4 * p + 2]), x + XP(pairs[4 * p + 3]), x + XE(W.N), pctx + (size_t)p * vf::PCTX_LD);
+  __syncthreads();
+  long long pt_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+#define PPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - pt_; pt_ = n_; } } while (0)
   for (int base = 0; base < np; base += PAIR_CHUNK) {
     const int cnt_round = min(PAIR_CHUNK, np - base);
     const int t = threadIdx.x;
@@ -163,8 +169,9 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
       const int feat = lm_feat[rank];
       double* row0 = stage + (2 * t) * STAGE_LD; double* row1 = row0 + STAGE_LD;
       double r[2], J[40];
-      vf::proj_eval(P.cfg, c, x + XP(kfi), x + XP(kfj), x + XE(W.N), x[XL(W.N) + feat], x[XT(W.N)], r, J);
-      double rho, w; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w);
+      vf::proj_eval_ctx(P.cfg, pctx + (size_t)pid[kfi * W.N + kfj] * vf::PCTX_LD, c, x[XL(W.N) + feat], x[XT(W.N)], r, J);
+      double rho, w; const double s2 = r[0] * r[0] + r[1] * r[1];
+      if (need_cost) vf::cauchy(P.cfg.cauchy_a, s2, rho, w); else { w = vf::cauchy_w(P.cfg.cauchy_a, s2); rho = s2; }   // the log is only paid when the cost is reported
       cost += 0.5 * rho;
       r[0] *= w; r[1] *= w;
 #pragma unroll
@@ -187,7 +194,9 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
       }
       pt[14] = J[19] * jl0 + J[39] * jl1;                      // e_td
     }
+    PPROF(16);
     __syncthreads();
+    PPROF(17);
     // pairs intersecting [base, base + cnt_round)
     while (p_lo < npair && pairs[4 * p_lo] + pairs[4 * p_lo + 1] <= base) p_lo++;
     for (int p = p_lo + warp; p < npair; p += SOLVE_WARPS) {
@@ -200,7 +209,7 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
 #pragma unroll
         for (int b = 0; b < 3; b++) acc[a][b] = 0;
       const double* sp = stage + (size_t)(2 * (s0 - base)) * STAGE_LD;
-#pragma unroll 2
+#pragma unroll 4
       for (int row = 0; row < 2 * (s1 - s0); row++, sp += STAGE_LD) {
         double av[5], bv[3];
 #pragma unroll
@@ -220,8 +229,11 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
         for (int b = 0; b < 3; b++)
           if (cb + b < PAIR_LD) { double* o = out + (ra + a) * PAIR_LD + cb + b; *o = first ? acc[a][b] : *o + acc[a][b]; }
     }
+    PPROF(18);
     __syncthreads();
+    PPROF(19);
   }
+#undef PPROF
   return cost;
 }
 
@@ -255,7 +267,8 @@ __device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv
 
 // S: Hv(lower) = -sum_f cinv_f e_f e_f^T ; gv = -sum_f cinv_f glam_f e_f.  3x3 register tiles over the lower triangle.
 __device__ void schur_syrk(const SolveParams& P, const Win& W, const double* cinv, const double* glam, double* Hv, double* gv,
-                           double* chunk, const double* scr) {
+                           double* chunk, const double* scr, int chunk_cap /* doubles available at `chunk` */) {
+  const int ECH = max(ECHUNK, chunk_cap / W.Dvp);     // as many landmarks per staging pass as fit (all of them for a 10-keyframe window)
   const int Dv = W.Dv, Dvp = W.Dvp, nlm = W.h->n_lm;
   const int nt = (Dv + 2) / 3;                 // tiles per side
   const int ntiles = nt * (nt + 1) / 2;
@@ -275,8 +288,8 @@ __device__ void schur_syrk(const SolveParams& P, const Win& W, const double* cin
   for (int a = 0; a < 3; a++) { gacc[a] = 0;
 #pragma unroll
     for (int b = 0; b < 3; b++) acc[a][b] = 0; }
-  for (int f0 = 0; f0 < nlm; f0 += ECHUNK) {
-    const int n = min(ECHUNK, nlm - f0);
+  for (int f0 = 0; f0 < nlm; f0 += ECH) {
+    const int n = min(ECH, nlm - f0);
     __syncthreads();
     for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) chunk[k] = E[(size_t)f0 * Dvp + k];
     __syncthreads();
@@ -392,8 +405,8 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
       const double* pre = pre_all + (size_t)k * 467; const double* Wk = Wall + (size_t)k * 225;
       for (int e = lane; e < 450; e += 32) J[e] = 0;
       __syncwarp();
-      if (lane < vf::IMU_PARTS && (want_J || lane == vf::IMU_PARTS - 1))
-        vf::imu_eval_part(lane, pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, J);
+      // one lane, straight-line: measured 4-5 k cycles; splitting the blocks over lanes with a switch DIVERGES and costs 12 k
+      if (lane == 0) vf::imu_eval_raw(pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, want_J ? J : nullptr);
       __syncwarp();
       double rw = 0;
       if (lane < 15) { for (int m = lane; m < 15; m++) rw = fma(Wk[lane * 15 + m], r[m], rw); }
@@ -468,8 +481,8 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
       if (pre[16] > 10.0) continue;                                  // estimator.cpp:1182 skip if sum_dt > 10
       for (int e = lane; e < 450; e += 32) J[e] = 0;
       __syncwarp();
-      if (lane < vf::IMU_PARTS && (want_J || lane == vf::IMU_PARTS - 1))
-        vf::imu_eval_part(lane, pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, J);
+      // one lane, straight-line: measured 4-5 k cycles; splitting the blocks over lanes with a switch DIVERGES and costs 12 k
+      if (lane == 0) vf::imu_eval_raw(pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, want_J ? J : nullptr);
       __syncwarp();
       // r <- W r (W upper triangular), in place top-down
       double rw = 0;

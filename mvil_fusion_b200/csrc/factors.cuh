@@ -24,6 +24,8 @@ struct BaCfg {
 // ---- robust losses [ceres loss_function.cc]; with rho'' <= 0 the corrector of ResidualBlockInfo::Evaluate
 // (factor/marginalization_factor.cpp:37-68, branch :49-53) is r <- sqrt(rho') r, J <- sqrt(rho') J. ----
 VHD void cauchy(double a, double s, double& rho, double& w) { const double b = a * a, sum = 1.0 + s / b; rho = b * log(sum); w = sqrt(fmax(2.2250738585072014e-308, 1.0 / sum)); }
+// weight only (no log): used when the robust cost value itself is not needed
+VHD double cauchy_w(double a, double s) { return sqrt(fmax(2.2250738585072014e-308, 1.0 / (1.0 + s / (a * a)))); }
 VHD void huber(double a, double s, double& rho, double& w) {
   const double b = a * a;
   if (s > b) { const double r = sqrt(s); rho = 2 * a * r - b; w = sqrt(fmax(2.2250738585072014e-308, a / r)); }
@@ -79,6 +81,74 @@ VHD void proj_eval(const BaCfg& cfg, const double* c, const double* pose_i, cons
     }
     Jr[18] = red[a][0] * jl.x + red[a][1] * jl.y + red[a][2] * jl.z;
     Jr[19] = cfg.use_td ? (red[a][0] * jt.x + red[a][1] * jt.y + red[a][2] * jt.z + cfg.s_info * (a == 0 ? vj.x : vj.y)) : 0.0;  // :135
+  }
+}
+
+// ---- the same factor with everything that only depends on the keyframe PAIR (i, j) and the extrinsic hoisted out.
+// In a window ~900 projection factors share ~45 (i, j) pairs, so A = ric^T Rj^T, A Ri, T = A Ri ric, ric^T (Rj^T Ri - I)
+// and the translation term of the extrinsic Jacobian are built once per pair per linearisation (proj_pair_ctx) and the
+// per-factor work drops to the point chain plus a few 2x3 * 3x3 products (proj_eval_ctx).  Same formulas as proj_eval.
+constexpr int PCTX_LD = 84;   // doubles per pair context
+// ctx: A(0) ARi(9) T(18) Aex(27) ric(36) Ri(45) Rj(54) Pi(63) Pj(66) tic(69) tex(72) [75..83 pad]
+VHD void proj_pair_ctx(const double* pose_i, const double* pose_j, const double* ex, double* ctx) {
+  const v3 Pi = ld3(pose_i), Pj = ld3(pose_j), tic = ld3(ex);
+  const m3 Ri = q2R(ldq(pose_i + 3)), Rj = q2R(ldq(pose_j + 3)), ric = q2R(ldq(ex + 3));
+  const m3 A = mulT(ric, transpose(Rj)), ARi = mul(A, Ri), T = mul(ARi, ric), Aex = mulT(ric, sub(mulT(Rj, Ri), eye()));
+  const v3 tex = mulT(ric, mulT(Rj, mul(Ri, tic) + Pi - Pj) - tic);
+  const m3* ms[7] = {&A, &ARi, &T, &Aex, &ric, &Ri, &Rj};
+  for (int k = 0; k < 7; k++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) ctx[9 * k + 3 * i + j] = ms[k]->m[i][j];
+  ctx[63] = Pi.x; ctx[64] = Pi.y; ctx[65] = Pi.z; ctx[66] = Pj.x; ctx[67] = Pj.y; ctx[68] = Pj.z;
+  ctx[69] = tic.x; ctx[70] = tic.y; ctx[71] = tic.z; ctx[72] = tex.x; ctx[73] = tex.y; ctx[74] = tex.z;
+}
+VHD m3 ldm(const double* p) { m3 r;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.m[i][j] = p[3 * i + j];
+  return r; }
+// J: 2 x 20 row-major [pose_i 6 | pose_j 6 | ex 6 | lambda | td] as proj_eval
+VHD void proj_eval_ctx(const BaCfg& cfg, const double* ctx, const double* c, double lam, double td, double* r, double* J) {
+  const m3 A = ldm(ctx), ARi = ldm(ctx + 9), T = ldm(ctx + 18), Aex = ldm(ctx + 27), ric = ldm(ctx + 36), Ri = ldm(ctx + 45), Rj = ldm(ctx + 54);
+  const v3 Pi = ld3(ctx + 63), Pj = ld3(ctx + 66), tic = ld3(ctx + 69), tex = ld3(ctx + 72);
+  v3 pi = mk(c[0], c[1], c[2]), pj = mk(c[3], c[4], c[5]);
+  const v3 vi = mk(c[6], c[7], 0.0), vj = mk(c[8], c[9], 0.0);
+  if (cfg.use_td) {
+    const double si = td - c[10] + cfg.tr_over_row * (c[12] - cfg.half_row);
+    const double sj = td - c[11] + cfg.tr_over_row * (c[13] - cfg.half_row);
+    pi = pi - vi * si; pj = pj - vj * sj;
+  }
+  const double inv_lam = 1.0 / lam;
+  const v3 pc_i = pi * inv_lam;
+  const v3 pb_i = mul(ric, pc_i) + tic;
+  const v3 pw = mul(Ri, pb_i) + Pi;
+  const v3 pb_j = mulT(Rj, pw - Pj);
+  const v3 pc_j = mulT(ric, pb_j - tic);
+  const double iz = 1.0 / pc_j.z;
+  r[0] = cfg.s_info * (pc_j.x * iz - pj.x);
+  r[1] = cfg.s_info * (pc_j.y * iz - pj.y);
+  if (!J) return;
+  const double red[2][3] = {{cfg.s_info * iz, 0.0, -cfg.s_info * pc_j.x * iz * iz}, {0.0, cfg.s_info * iz, -cfg.s_info * pc_j.y * iz * iz}};
+  const v3 Tpc = mul(T, pc_i);
+  const v3 sk = Tpc + tex;                          // skew(T pc_i) + skew(tex) = skew(T pc_i + tex)
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    double* Jr = J + 20 * a;
+    // row vectors red_a * M for the shared matrices
+    const v3 rA = mk(red[a][0] * A.m[0][0] + red[a][1] * A.m[1][0] + red[a][2] * A.m[2][0], red[a][0] * A.m[0][1] + red[a][1] * A.m[1][1] + red[a][2] * A.m[2][1], red[a][0] * A.m[0][2] + red[a][1] * A.m[1][2] + red[a][2] * A.m[2][2]);
+    const v3 rARi = mk(red[a][0] * ARi.m[0][0] + red[a][1] * ARi.m[1][0] + red[a][2] * ARi.m[2][0], red[a][0] * ARi.m[0][1] + red[a][1] * ARi.m[1][1] + red[a][2] * ARi.m[2][1], red[a][0] * ARi.m[0][2] + red[a][1] * ARi.m[1][2] + red[a][2] * ARi.m[2][2]);
+    const v3 rT = mk(red[a][0] * T.m[0][0] + red[a][1] * T.m[1][0] + red[a][2] * T.m[2][0], red[a][0] * T.m[0][1] + red[a][1] * T.m[1][1] + red[a][2] * T.m[2][1], red[a][0] * T.m[0][2] + red[a][1] * T.m[1][2] + red[a][2] * T.m[2][2]);
+    const v3 rAex = mk(red[a][0] * Aex.m[0][0] + red[a][1] * Aex.m[1][0] + red[a][2] * Aex.m[2][0], red[a][0] * Aex.m[0][1] + red[a][1] * Aex.m[1][1] + red[a][2] * Aex.m[2][1], red[a][0] * Aex.m[0][2] + red[a][1] * Aex.m[1][2] + red[a][2] * Aex.m[2][2]);
+    const v3 rricT = mk(red[a][0] * ric.m[0][0] + red[a][1] * ric.m[0][1] + red[a][2] * ric.m[0][2], red[a][0] * ric.m[1][0] + red[a][1] * ric.m[1][1] + red[a][2] * ric.m[1][2], red[a][0] * ric.m[2][0] + red[a][1] * ric.m[2][1] + red[a][2] * ric.m[2][2]);   // red_a ric^T
+    const v3 ra_ = mk(red[a][0], red[a][1], red[a][2]);
+    // u^T skew(b) = (u x b)^T
+    const v3 ji_rot = cross(rARi, pb_i) * -1.0;      // -red ARi skew(pb_i)
+    const v3 jj_rot = cross(rricT, pb_j);            //  red ric^T skew(pb_j)
+    const v3 jex_rot = cross(rT, pc_i) * -1.0 + cross(ra_, sk);
+    Jr[0] = rA.x; Jr[1] = rA.y; Jr[2] = rA.z; Jr[3] = ji_rot.x; Jr[4] = ji_rot.y; Jr[5] = ji_rot.z;
+    Jr[6] = -rA.x; Jr[7] = -rA.y; Jr[8] = -rA.z; Jr[9] = jj_rot.x; Jr[10] = jj_rot.y; Jr[11] = jj_rot.z;
+    Jr[12] = rAex.x; Jr[13] = rAex.y; Jr[14] = rAex.z; Jr[15] = jex_rot.x; Jr[16] = jex_rot.y; Jr[17] = jex_rot.z;
+    Jr[18] = -dot(rT, pi) * inv_lam * inv_lam;
+    Jr[19] = cfg.use_td ? (-dot(rT, vi) * inv_lam + cfg.s_info * (a == 0 ? vj.x : vj.y)) : 0.0;
   }
 }
 

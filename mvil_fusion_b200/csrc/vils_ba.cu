@@ -62,17 +62,17 @@ __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
 
 // Full linearisation at state x: H (tiles, lower), g, hd and the cost (broadcast to all threads).
 __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x, double* H, double* Hv,
-                            double mu) {
+                            double mu, bool need_cost = true) {
   double* g = sm + L.g; double* hd = sm + L.hd;
   PROF_T0();
-  double c = pair_pass(P, W, x, sm + L.uni, scr);
+  double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost);
   __syncthreads();
   PROF(0);
   landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu);
   for (int e = threadIdx.x; e < W.Dvp * W.Dv; e += blockDim.x) Hv[e] = 0.0;
   __syncthreads();
   PROF(1);
-  schur_syrk(P, W, sm + L.cinv, sm + L.glam, Hv, sm + L.gv, sm + L.uni, scr);
+  schur_syrk(P, W, sm + L.cinv, sm + L.glam, Hv, sm + L.gv, sm + L.uni, scr, L.hv >= 0 ? L.hv - L.uni : L.imu - L.uni);
   __syncthreads();
   PROF(2);
   for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   for (int it = 0;; it++) {
     // LM follows ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g ; GN uses P.mu.
     const double mu = P.lin_out ? 0.0 : (lm ? 1.0 / radius : P.mu);
-    const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu);
+    const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0);   // later costs come from cost_only()
     if (it == 0) { cost0 = c_lin; cost = c_lin; if (lm) iters = 1; }
     if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
     if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
@@ -516,8 +516,8 @@ struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int it
 struct vils_ba {
   vils_config cfg{};
   int max_windows = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   size_t blob_stride = 0;
   uint8_t* h_blob = nullptr; uint8_t* d_blob = nullptr;
   ScratchLayout sl{};
@@ -609,6 +609,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   s.Dv_pad = Dvp;
   s.w_imu = take((int64_t)N * 225); s.E = take((int64_t)M * Dvp); s.part = take((int64_t)cfg->max_proj * PART_LD);
   s.pairpart = take(((int64_t)N * (N - 1) / 2 + 1) * PAIR_LD * PAIR_LD);   // + one all-zero block
+  s.pairctx = take((int64_t)N * (N - 1) / 2 * vf::PCTX_LD);
   s.priorA = take((int64_t)D * D); s.priorb0 = take(D); s.lmsave = take(2 * (int64_t)M);
   // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
   int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -626,6 +627,8 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, #x); } } while (0)
   CK(cudaStreamCreateWithFlags(&ba->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ba->ev0)); CK(cudaEventCreate(&ba->ev1));
+  CK(cudaStreamCreateWithFlags(&ba->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ba->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ba->ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_scratch, (size_t)s.total * 8 * max_windows));
@@ -655,6 +658,9 @@ void vils_ba_destroy(vils_ba* ba) {
   cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws); cudaFree(ba->d_shard);
   if (ba->ev0) cudaEventDestroy(ba->ev0);
   if (ba->ev1) cudaEventDestroy(ba->ev1);
+  if (ba->ev_fork) cudaEventDestroy(ba->ev_fork);
+  if (ba->ev_join) cudaEventDestroy(ba->ev_join);
+  if (ba->stream2) cudaStreamDestroy(ba->stream2);
   if (ba->stream) cudaStreamDestroy(ba->stream);
   delete ba;
 }
@@ -843,7 +849,7 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   SolveParams P = make_params(ba, opts);
   static const bool prof = getenv("VILS_PROF") != nullptr;
   long long* d_prof = nullptr;
-  if (prof) { cudaMalloc(&d_prof, 16 * sizeof(long long)); cudaMemset(d_prof, 0, 16 * sizeof(long long)); P.prof = d_prof; }
+  if (prof) { cudaMalloc(&d_prof, 24 * sizeof(long long)); cudaMemset(d_prof, 0, 24 * sizeof(long long)); P.prof = d_prof; }
   cudaEventRecord(ba->ev0, ba->stream);
   if (ba->h_in_smem && ba->hv_in_smem) solve_kernel<true><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
   else solve_kernel<false><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
@@ -852,11 +858,11 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   if (e != cudaSuccess) return vils::fail_cuda(e, "solve_kernel");
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   if (prof) {
-    long long h[16]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
-    static const char* names[16] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA"};
+    long long h[24]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
+    static const char* names[20] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait"};
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
-    for (int i = 0; i < 16; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+    for (int i = 0; i < 20; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
   }
   ba->last_launches = 1;
   return VILS_OK;
@@ -915,10 +921,16 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   if (!attr) { cudaFuncSetAttribute(eval_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_T * EV_PLD * 8); attr = true; }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
+  // the few heavy (latency-bound) factors run on a second stream, concurrently with the two streaming kernels
+  if (small) {
+    cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
+    eval_small_kernel<<<dim3(1, n), EVS_T, 0, ba->stream2>>>(Q); launches++;
+    cudaEventRecord(ba->ev_join, ba->stream2);
+  }
   if (np) { eval_proj_kernel<<<dim3((np + EV_T - 1) / EV_T, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q); launches++; }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
   if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream>>>(Q, pc); launches++; }
-  if (small) { eval_small_kernel<<<dim3(1, n), EVS_T, 0, ba->stream>>>(Q); launches++; }
+  if (small) cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "eval kernels");

@@ -9,6 +9,12 @@ void hc_proj_eval(double s_info, double tr_over_row, double half_row, int use_td
   BaCfg cfg{}; cfg.s_info = s_info; cfg.tr_over_row = tr_over_row; cfg.half_row = half_row; cfg.use_td = use_td;
   proj_eval(cfg, c, pi, pj, ex, lam, td, r, J);
 }
+void hc_proj_eval_ctx(double s_info, double tr_over_row, double half_row, int use_td, const double* c, const double* pi,
+                      const double* pj, const double* ex, double lam, double td, double* r, double* J) {
+  BaCfg cfg{}; cfg.s_info = s_info; cfg.tr_over_row = tr_over_row; cfg.half_row = half_row; cfg.use_td = use_td;
+  double ctx[PCTX_LD]; proj_pair_ctx(pi, pj, ex, ctx);
+  proj_eval_ctx(cfg, ctx, c, lam, td, r, J);
+}
 int hc_imu_sqrt_info(const double* cov, double* W) { return imu_sqrt_info(cov, W) ? 0 : 1; }
 void hc_imu_eval_raw(const double* pre, const double* G, const double* pi, const double* sbi, const double* pj, const double* sbj, double* r, double* J) {
   for (int i = 0; i < 450; i++) J[i] = 0;

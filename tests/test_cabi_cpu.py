@@ -28,6 +28,17 @@ def test_library_exports_every_declared_symbol():
     assert L.vils_abi_version() == 1
 
 
+def test_host_mirror_library_builds_and_exports_the_reference_api():
+    from mvil_fusion_b200 import build
+    build.build()
+    H = C.CDLL(build.HOST_OUT)
+    for sym in ("vh_estimator_create", "vh_process_imu", "vh_process_image", "vh_tracker_read", "vh_transform_to_end"):
+        assert hasattr(H, sym), sym
+    hdr = open(os.path.join(ROOT, "mvil_fusion_b200", "csrc", "host", "vils_host.h")).read()
+    for name in ("processIMU", "processImage", "optimization", "slideWindow", "readImage", "TransformToEnd"):   # the reference's method names
+        assert name in hdr
+
+
 def test_struct_layouts_match_header_sizes():
     assert C.sizeof(cabi.VilsPreint) == 467 * 8
     assert C.sizeof(cabi.VilsSummary) == 32

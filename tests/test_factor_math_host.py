@@ -54,6 +54,10 @@ def product_evaluate(hc, cfg, w):
         r = np.zeros(2); J = np.zeros(40)
         hc.hc_proj_eval(C.c_double(cfg.focal_length / 2), C.c_double(cfg.tr / cfg.row), C.c_double(cfg.row / 2), int(cfg.estimate_td),
                         P(c), P(pose[i]), P(pose[j]), P(ex), C.c_double(w["inv_depth"][f]), C.c_double(w["td"]), P(r), P(J))
+        r2 = np.zeros(2); J2 = np.zeros(40)   # the pair-context variant used by the solve kernel: same formulas, re-associated
+        hc.hc_proj_eval_ctx(C.c_double(cfg.focal_length / 2), C.c_double(cfg.tr / cfg.row), C.c_double(cfg.row / 2), int(cfg.estimate_td),
+                            P(c), P(pose[i]), P(pose[j]), P(ex), C.c_double(w["inv_depth"][f]), C.c_double(w["td"]), P(r2), P(J2))
+        assert np.abs(r2 - r).max() <= 1e-11 * max(1.0, np.abs(r).max()) and np.abs(J2 - J).max() <= 1e-11 * max(1.0, np.abs(J).max())
         rs.append(r); Js.append(J)
     for k in range(len(w.get("plane_kf", []))):
         pb = np.ascontiguousarray(RLB.T @ (w["plane_p"][k] - TLB)); n = np.ascontiguousarray(w["plane_n"][k]); J = np.zeros(6)
