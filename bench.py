@@ -38,7 +38,7 @@ BYTES_PER_LINEARISATION = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544 + (
 BYTES_PER_COST_EVAL = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544
 BYTES_PER_SOLVE = 5 * BYTES_PER_LINEARISATION + BYTES_PER_COST_EVAL
 # dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel per window, from the committed ncu capture (profiles/r1_ncu_solve_kernel.txt)
-SOLVE_DRAM_TRAFFIC_PER_WINDOW = None
+SOLVE_DRAM_TRAFFIC_PER_WINDOW = 4814608   # (1.209570 + 1.640678) GB / 592 windows, ncu --set full capture of the bench command
 # Materialised Evaluate() traffic per window (what the CPU reference moves per linearisation; §8d first table)
 BYTES_PER_EVAL_WINDOW = 906 * 460 + 9 * 6016 + 1500 * 116 + 500 * 244 + 2544
 

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(EV_T) eval_lidar_kernel(EvalParams Q, int plan
 // a warp per IMU factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30 whitening and the coalesced
 // stores by all lanes), then one thread per ICP / LPS constraint and per prior row.
 constexpr int EVS_T = 320;
-__global__ void __launch_bounds__(EVS_T) eval_small_kernel(EvalParams Q) {
+__global__ void __launch_bounds__(EVS_T, 2) eval_small_kernel(EvalParams Q) {
   __shared__ double sJ[EVS_T / 32][450 + 16];
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
@@ -467,6 +467,32 @@ __global__ void __launch_bounds__(EVS_T) eval_small_kernel(EvalParams Q) {
     }
     __syncwarp();
   }
+  const int rbase = 15 * h->n_imu + 2 * h->n_proj + h->n_plane + 3 * h->n_edge + 3 * h->n_icp + 3 * h->n_lps;
+  for (int row = threadIdx.x; row < h->prior_n; row += EVS_T) {   // MarginalizationFactor residual rows (marginalization_factor.cpp:364-383)
+    const int n = h->prior_n; const int32_t* blk = W.i(OFF_PRIOR_BLK);
+    const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
+    double r = W.d(OFF_PRIOR_R)[row];
+    for (int b = 0; b < h->prior_nblk; b++) {
+      const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
+      const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
+      double dx[9]; int sz;
+      if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
+      else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
+      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + row], dx[k], r);
+    }
+    R[rbase + row] = r;
+  }
+}
+
+// ICP / LPS constraints (forward-mode duals, register hungry): their own tiny kernel so that they do not set the register
+// budget of the IMU kernel.  One thread per constraint.
+__global__ void eval_cons_kernel(EvalParams Q) {
+  const SolveParams& P = Q.S;
+  const int slot = P.slot0 + blockIdx.y;
+  const Win W = decode(P, slot);
+  const WinHdr* h = W.h;
+  const double* x = W.d(OFF_X);
+  double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
   int t = threadIdx.x;
   int rbase; int64_t jbase;
   rbase = 15 * h->n_imu + 2 * h->n_proj + h->n_plane;
@@ -490,21 +516,6 @@ __global__ void __launch_bounds__(EVS_T) eval_small_kernel(EvalParams Q) {
     for (int e = 0; e < 3; e++) R[rbase + 3 * t + e] = r[e] * w;
     for (int e = 0; e < 36; e++) Jo[jbase + (int64_t)36 * t + e] = J[e] * w;
     return;
-  }
-  t -= h->n_lps; rbase += 3 * h->n_lps;
-  for (int row = t; row >= 0 && row < h->prior_n; row += EVS_T - h->n_icp - h->n_lps) {   // MarginalizationFactor residual rows (marginalization_factor.cpp:364-383)
-    const int n = h->prior_n; const int32_t* blk = W.i(OFF_PRIOR_BLK);
-    const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
-    double r = W.d(OFF_PRIOR_R)[row];
-    for (int b = 0; b < h->prior_nblk; b++) {
-      const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
-      const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
-      double dx[9]; int sz;
-      if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
-      else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
-      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + row], dx[k], r);
-    }
-    R[rbase + row] = r;
   }
 }
 
@@ -909,11 +920,11 @@ static int ensure_eval_buffers(vils_ba* ba) {
 
 static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   int st = ensure_eval_buffers(ba); if (st) return st;
-  int np = 0, npl = 0, ned = 0, small = 0;
+  int np = 0, npl = 0, ned = 0, small = 0, cons = 0;
   for (int k = slot0; k < slot0 + n; k++) {
     const WinHdr* h = reinterpret_cast<const WinHdr*>(ba->h_blob + (size_t)k * ba->blob_stride);
     np = std::max(np, h->n_proj); npl = std::max(npl, h->n_plane); ned = std::max(ned, h->n_edge);
-    small = std::max(small, h->n_imu + h->n_icp + h->n_lps + h->prior_n);
+    small = std::max(small, h->n_imu + h->prior_n); cons = std::max(cons, h->n_icp + h->n_lps);
   }
   EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
   Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
@@ -922,15 +933,16 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
   // the few heavy (latency-bound) factors run on a second stream, concurrently with the two streaming kernels
-  if (small) {
+  if (small || cons) {
     cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
     eval_small_kernel<<<dim3(1, n), EVS_T, 0, ba->stream2>>>(Q); launches++;
+    if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
     cudaEventRecord(ba->ev_join, ba->stream2);
   }
   if (np) { eval_proj_kernel<<<dim3((np + EV_T - 1) / EV_T, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q); launches++; }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
   if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream>>>(Q, pc); launches++; }
-  if (small) cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
+  if (small || cons) cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "eval kernels");
