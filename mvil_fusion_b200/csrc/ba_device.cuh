@@ -45,6 +45,7 @@ struct SolveParams {
   int32_t h_in_smem, hv_in_smem;
   double* lin_out;                // != null: dump [S (D x D row-major) | g (D) | cost] of the first linearisation and stop
   int32_t slot0;                  // first slot handled by blockIdx.x == 0
+  int32_t do_prep;                // solve_kernel runs prep_window itself (vils_ba_solve's pipelined path)
   long long* prof;                // optional: per-phase SM cycle counters of block 0 (VILS_PROF=1)
 };
 

@@ -20,18 +20,86 @@ using namespace vb;
 // =================================================================================================================
 // kernels
 // =================================================================================================================
-// Once per upload: IMU sqrt_info (imu_factor.h:64 recomputes it in every Evaluate; it only depends on the
-// pre-integration), prior A = J_lin^T J_lin and b0 = J_lin^T r_lin, and the zero pattern of E.
-__global__ void prep_kernel(SolveParams P) {
-  const int slot = P.slot0 + blockIdx.x;
-  const Win W = decode(P, slot);
-  double* scr = P.scratch + (size_t)slot * P.sl.total;
-  const double* pre = W.d(OFF_IMU);
-  if ((int)threadIdx.x < W.h->n_imu) {
-    double Wm[225];
-    if (!vf::imu_sqrt_info(pre + (size_t)threadIdx.x * 467 + 242, Wm)) for (int i = 0; i < 225; i++) Wm[i] = nan("");
-    for (int i = 0; i < 225; i++) scr[P.sl.w_imu + (size_t)threadIdx.x * 225 + i] = Wm[i];
+// IMUFactor's sqrt_info = LLT(covariance.inverse()).matrixL().transpose() (factor/imu_factor.h:64) by ONE WARP.
+// Same elimination sequence, pivot rule and per-element operation order as the scalar vf::imu_sqrt_info (partial-pivot LU
+// inverse, then lower Cholesky), with the 15 rows / columns spread over lanes 0..14.  wk: 450 doubles of shared memory
+// private to the warp.  W: 15x15 row-major upper triangular, NaN-filled on breakdown.
+__device__ void warp_imu_sqrt_info(const double* cov, double* W, double* wk) {
+  const int lane = threadIdx.x & 31;
+  double* a = wk; double* inv = wk + 225;
+  for (int e = lane; e < 225; e += 32) a[e] = cov[(e % 15) * 15 + e / 15];   // a[i][j] = cov(i, j), column-major input
+  __syncwarp();
+  int mypiv = lane;            // lane i < 15: piv[i]
+  bool ok = true;
+  for (int k = 0; k < 15; k++) {
+    // pivot: first row >= k with the largest |a[i][k]|
+    double best = (lane >= k && lane < 15) ? fabs(a[lane * 15 + k]) : -1.0; int p = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int op = __shfl_xor_sync(0xffffffffu, p, o);
+      if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+    }
+    if (best == 0.0 || !(best == best)) { ok = false; break; }
+    if (p != k) {
+      if (lane < 15) { const double t = a[k * 15 + lane]; a[k * 15 + lane] = a[p * 15 + lane]; a[p * 15 + lane] = t; }
+      const int pk = __shfl_sync(0xffffffffu, mypiv, k), pp = __shfl_sync(0xffffffffu, mypiv, p);
+      if (lane == k) mypiv = pp; else if (lane == p) mypiv = pk;
+    }
+    __syncwarp();
+    if (lane > k && lane < 15) {
+      double* row = a + lane * 15; const double* rk = a + k * 15;
+      row[k] /= rk[k]; const double l = row[k];
+      for (int j = k + 1; j < 15; j++) row[j] -= l * rk[j];
+    }
+    __syncwarp();
   }
+  if (ok) {
+    // lane c < 15 owns column c of the inverse: forward (unit lower) then backward (upper) substitution
+    int piv[15];
+#pragma unroll
+    for (int i = 0; i < 15; i++) piv[i] = __shfl_sync(0xffffffffu, mypiv, i);
+    if (lane < 15) {
+      double x[15];
+#pragma unroll
+      for (int i = 0; i < 15; i++) x[i] = (piv[i] == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int i = 0; i < 15; i++) { double sacc = x[i];
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k < i) sacc -= a[i * 15 + k] * x[k];
+        x[i] = sacc; }
+#pragma unroll
+      for (int i = 14; i >= 0; i--) { double sacc = x[i];
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k > i) sacc -= a[i * 15 + k] * x[k];
+        x[i] = sacc / a[i * 15 + i]; }
+#pragma unroll
+      for (int i = 0; i < 15; i++) inv[i * 15 + lane] = x[i];
+    }
+    __syncwarp();
+    // lower Cholesky of inv (reads the lower triangle like Eigen's LLT): lane i owns row i
+    for (int j = 0; j < 15; j++) {
+      double d = inv[j * 15 + j];
+      for (int k = 0; k < j; k++) d -= inv[j * 15 + k] * inv[j * 15 + k];
+      if (!(d > 0.0)) { ok = false; break; }            // warp-uniform: every lane evaluates the same d
+      d = sqrt(d);
+      __syncwarp();
+      if (lane == j) inv[j * 15 + j] = d;
+      if (lane > j && lane < 15) { double sacc = inv[lane * 15 + j]; for (int k = 0; k < j; k++) sacc -= inv[lane * 15 + k] * inv[j * 15 + k]; inv[lane * 15 + j] = sacc / d; }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < 225; e += 32) { const int i = e / 15, j = e % 15; W[e] = ok ? ((j >= i) ? inv[j * 15 + i] : 0.0) : nan(""); }
+  __syncwarp();
+}
+
+// Once per upload (or at the head of a solve when SolveParams::do_prep is set): IMU sqrt_info (imu_factor.h:64 recomputes
+// it in every Evaluate; it only depends on the pre-integration), prior A = J_lin^T J_lin and b0 = J_lin^T r_lin, and the
+// zero pattern of E.  work: 450 doubles of shared memory per warp of the block.  Ends with a block barrier.
+__device__ void prep_window(const SolveParams& P, const Win& W, double* scr, double* work) {
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const double* pre = W.d(OFF_IMU);
+  for (int k = warp; k < W.h->n_imu; k += nwarp) warp_imu_sqrt_info(pre + (size_t)k * 467 + 242, scr + P.sl.w_imu + (size_t)k * 225, work + warp * 450);
   const int n = W.h->prior_n;
   const double* J = W.d(OFF_PRIOR_J); const double* r = W.d(OFF_PRIOR_R);
   for (int e = threadIdx.x; e < n * n + n; e += blockDim.x) {
@@ -47,6 +115,14 @@ __global__ void prep_kernel(SolveParams P) {
   }
   for (int64_t e = threadIdx.x; e < (int64_t)W.h->n_lm * P.sl.Dv_pad; e += blockDim.x) scr[P.sl.E + e] = 0.0;
   for (int e = threadIdx.x; e < PAIR_LD * PAIR_LD; e += blockDim.x) scr[P.sl.pairpart + (int64_t)(P.Ncap * (P.Ncap - 1) / 2) * PAIR_LD * PAIR_LD + e] = 0.0;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(SolveParams P) {
+  __shared__ double work[8 * 450];
+  const int slot = P.slot0 + blockIdx.x;
+  const Win W = decode(P, slot);
+  prep_window(P, W, P.scratch + (size_t)slot * P.sl.total, work);
 }
 
 __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
@@ -164,6 +240,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   int* fx = reinterpret_cast<int*>(sm + L.fx);
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
+  if (P.do_prep) prep_window(P, W, scr, sm + L.uni);     // vils_ba_solve: no separate prep launch in the upload -> solve chain
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
   double nf = 0;
@@ -350,26 +427,57 @@ struct EvalParams {
   int32_t apply_loss;
 };
 
-// Projection factors: one thread per factor (landmark-sorted order), results staged in shared memory and written with fully
-// coalesced 8-byte stores.  Output order inside a family is the library's SORTED order; the single-slot host API
-// un-permutes (vils_ba_evaluate), the batched device API documents it (vils_ba_evaluate_device).
+// Projection + IMU factors in ONE launch (both are register-hungry FP64 paths; fusing them lets the latency-bound IMU warps
+// fill in next to the streaming projection warps instead of serialising behind them on a second stream).
+//   blockIdx.x <  imu_blocks : one WARP per IMU factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30
+//                              whitening and the coalesced stores by all lanes);
+//   blockIdx.x >= imu_blocks : one thread per projection factor (landmark-sorted order); each warp stages its 32 rows
+//                              [r(2) | J(40)] in its own slice of shared memory (no block barrier) and writes them out as
+//                              one contiguous 10 KB segment with 16-byte stores.
+// Output order inside a family is the library's SORTED order; the single-slot host API un-permutes (vils_ba_evaluate),
+// the batched device API documents it (vils_ba_evaluate_device).
 constexpr int EV_T = 128, EV_PLD = 43, EV_ELD = 21, EV_LLD = 7;
-__global__ void __launch_bounds__(EV_T, 3) eval_proj_kernel(EvalParams Q) {
+#ifndef EV_PROJ_BLOCKS
+#define EV_PROJ_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(EV_T, EV_PROJ_BLOCKS) eval_heavy_kernel(EvalParams Q, int imu_blocks) {
   extern __shared__ __align__(16) double st[];
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
-  const int np = W.h->n_proj, fbase = blockIdx.x * EV_T;
-  if (fbase >= np) return;
+  const WinHdr* h = W.h;
   const double* x = W.d(OFF_X);
-  const int N = W.N, t = threadIdx.x, f = fbase + t;
+  const int N = W.N, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if ((int)blockIdx.x < imu_blocks) {
+    const int k = blockIdx.x * (EV_T / 32) + warp;
+    if (k >= h->n_imu) return;
+    double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
+    const double* scr = P.scratch + (size_t)slot * P.sl.total;
+    double* J = st + warp * 466; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
+    const int i = W.i(OFF_IMU_KF)[k];
+    for (int e = lane; e < 450; e += 32) J[e] = 0.0;
+    __syncwarp();
+    if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
+    __syncwarp();
+    if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
+    for (int e = lane; e < 450; e += 32) {
+      const int a = e / 30, c = e % 30; double v = 0;
+      for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
+      Jo[(size_t)450 * k + e] = v;
+    }
+    return;
+  }
+  const int np = h->n_proj, fbase = (blockIdx.x - imu_blocks) * EV_T + 32 * warp;   // first factor of this WARP
+  if (fbase >= np) return;
+  const int f = fbase + lane;
+  double* rows = st + (size_t)(32 * warp) * EV_PLD;
   if (f < np) {
     const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
     double c[14];
 #pragma unroll
     for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
     const int i = ix[f], j = ix[np + f], feat = W.i(OFF_LM_FEAT)[ix[2 * np + f]];
-    double* o = st + t * EV_PLD;
+    double* o = rows + lane * EV_PLD;
     vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(N), x[XL(N) + feat], x[XT(N)], o, o + 2);   // straight into the staging row
     if (Q.apply_loss) {
       double rho, w; vf::cauchy(P.cfg.cauchy_a, o[0] * o[0] + o[1] * o[1], rho, w);
@@ -377,12 +485,17 @@ __global__ void __launch_bounds__(EV_T, 3) eval_proj_kernel(EvalParams Q) {
       for (int e = 0; e < 42; e++) o[e] *= w;
     }
   }
-  __syncthreads();
-  const int cnt = min(EV_T, np - fbase);
-  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * W.h->n_imu + 2 * (size_t)fbase;
-  double* Jo = Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * W.h->n_imu + (size_t)40 * fbase;
-  for (int e = t; e < cnt * 2; e += EV_T) R[e] = st[(e >> 1) * EV_PLD + (e & 1)];
-  for (int e = t; e < cnt * 40; e += EV_T) Jo[e] = st[(e / 40) * EV_PLD + 2 + e % 40];
+  __syncwarp();
+  const int cnt = min(32, np - fbase);
+  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * h->n_imu + 2 * (size_t)fbase;
+  double2* Jo = reinterpret_cast<double2*>(Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * h->n_imu + (size_t)40 * fbase);   // 16-byte aligned: every term is even
+  for (int e = lane; e < cnt * 2; e += 32) R[e] = rows[(e >> 1) * EV_PLD + (e & 1)];
+#pragma unroll 4
+  for (int e = lane; e < cnt * 20; e += 32) {
+    const int fr = e / 20, c2 = e - fr * 20;
+    const double* sp = rows + fr * EV_PLD + 2 + 2 * c2;
+    Jo[e] = make_double2(sp[0], sp[1]);
+  }
 }
 
 // LiDAR plane + edge factors (keyframe-sorted order): blockIdx.x < plane chunks -> planes, else edges.
@@ -438,50 +551,30 @@ __global__ void __launch_bounds__(EV_T) eval_lidar_kernel(EvalParams Q, int plan
   }
 }
 
-// The few heavy factors: IMU (whitened 15x30), ICP, LPS and the prior residual. One block of 256 threads per window:
-// a warp per IMU factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30 whitening and the coalesced
-// stores by all lanes), then one thread per ICP / LPS constraint and per prior row.
-constexpr int EVS_T = 320;
-__global__ void __launch_bounds__(EVS_T, 2) eval_small_kernel(EvalParams Q) {
-  __shared__ double sJ[EVS_T / 32][450 + 16];
+// MarginalizationFactor residual rows (marginalization_factor.cpp:364-383): one thread per row.
+constexpr int EVS_T = 128;
+__global__ void __launch_bounds__(EVS_T) eval_prior_kernel(EvalParams Q) {
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
   const WinHdr* h = W.h;
+  const int row = blockIdx.x * EVS_T + threadIdx.x, n = h->prior_n, N = W.N;
+  if (row >= n) return;
   const double* x = W.d(OFF_X);
-  const double* scr = P.scratch + (size_t)slot * P.sl.total;
-  double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
-  const int N = W.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < h->n_imu; k += EVS_T / 32) {
-    double* J = sJ[warp]; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
-    const int i = W.i(OFF_IMU_KF)[k];
-    for (int e = lane; e < 450; e += 32) J[e] = 0.0;
-    __syncwarp();
-    if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
-    __syncwarp();
-    if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
-    for (int e = lane; e < 450; e += 32) {
-      const int a = e / 30, c = e % 30; double v = 0;
-      for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
-      Jo[(size_t)450 * k + e] = v;
-    }
-    __syncwarp();
-  }
+  double* R = Q.r_out + (size_t)slot * Q.r_stride;
   const int rbase = 15 * h->n_imu + 2 * h->n_proj + h->n_plane + 3 * h->n_edge + 3 * h->n_icp + 3 * h->n_lps;
-  for (int row = threadIdx.x; row < h->prior_n; row += EVS_T) {   // MarginalizationFactor residual rows (marginalization_factor.cpp:364-383)
-    const int n = h->prior_n; const int32_t* blk = W.i(OFF_PRIOR_BLK);
-    const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
-    double r = W.d(OFF_PRIOR_R)[row];
-    for (int b = 0; b < h->prior_nblk; b++) {
-      const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
-      const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
-      double dx[9]; int sz;
-      if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
-      else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
-      for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + row], dx[k], r);
-    }
-    R[rbase + row] = r;
+  const int32_t* blk = W.i(OFF_PRIOR_BLK);
+  const double* x0 = W.d(OFF_PRIOR_X0); const double* Jl = W.d(OFF_PRIOR_J);
+  double r = W.d(OFF_PRIOR_R)[row];
+  for (int b = 0; b < h->prior_nblk; b++) {
+    const int type = blk[4 * b], idx = blk[4 * b + 1], xo = blk[4 * b + 2], c0 = blk[4 * b + 3];
+    const double* xb = type == VILS_BLK_POSE ? x + XP(idx) : type == VILS_BLK_SPEEDBIAS ? x + XS(N, idx) : type == VILS_BLK_EXPOSE ? x + XE(N) : x + XT(N);
+    double dx[9]; int sz;
+    if (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) { vf::prior_dx_pose(xb, x0 + xo, dx); sz = 6; }
+    else { sz = type == VILS_BLK_SPEEDBIAS ? 9 : 1; for (int k = 0; k < sz; k++) dx[k] = xb[k] - x0[xo + k]; }
+    for (int k = 0; k < sz; k++) r = fma(Jl[(size_t)(c0 + k) * n + row], dx[k], r);
   }
+  R[rbase + row] = r;
 }
 
 // ICP / LPS constraints (forward-mode duals, register hungry): their own tiny kernel so that they do not set the register
@@ -528,6 +621,8 @@ struct vils_ba {
   vils_config cfg{};
   int max_windows = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // vils_ba_solve: chunked upload / solve / download pipeline
+  int n_sm = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   size_t blob_stride = 0;
   uint8_t* h_blob = nullptr; uint8_t* d_blob = nullptr;
@@ -575,7 +670,7 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
     P.p_tol = o->parameter_tolerance; P.min_rel_dec = o->min_relative_decrease;
   }
   P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
-  P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr;
+  P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr; P.do_prep = 0;
   return P;
 }
 
@@ -639,6 +734,8 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaStreamCreateWithFlags(&ba->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ba->ev0)); CK(cudaEventCreate(&ba->ev1));
   CK(cudaStreamCreateWithFlags(&ba->stream2, cudaStreamNonBlocking));
+  for (int k = 0; k < 3; k++) CK(cudaStreamCreateWithFlags(&ba->pipe[k], cudaStreamNonBlocking));
+  CK(cudaDeviceGetAttribute(&ba->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaEventCreateWithFlags(&ba->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ba->ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_blob, ba->blob_stride * max_windows));
@@ -672,6 +769,7 @@ void vils_ba_destroy(vils_ba* ba) {
   if (ba->ev_fork) cudaEventDestroy(ba->ev_fork);
   if (ba->ev_join) cudaEventDestroy(ba->ev_join);
   if (ba->stream2) cudaStreamDestroy(ba->stream2);
+  for (int k = 0; k < 3; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
   if (ba->stream) cudaStreamDestroy(ba->stream);
   delete ba;
 }
@@ -888,11 +986,41 @@ int vils_ba_download(vils_ba* ba, int32_t n) {
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "download");
 }
 
+// The call a host makes per optimization(): host buffers in, host buffers out.  Slots are processed in chunks of half
+// the SM count (one CTA per window, one CTA per SM), each chunk on one of three streams: the host->device copy of chunk
+// c+1 runs on the copy engine while chunk c is being solved, the small device->host copies ride behind each solve, and a
+// single synchronisation closes the call (a one-window call therefore pays one sync instead of three).
 int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
-  int st = vils_ba_upload(ba, n); if (st) return st;
-  st = vils_ba_solve_device(ba, n, opts); if (st) return st;
-  ba->last_launches = 2;
-  return vils_ba_download(ba, n);
+  int st = check_n(ba, n, "vils_ba_solve"); if (st) return st;
+  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
+  static const int chunk_env = getenv("VILS_CHUNK") ? atoi(getenv("VILS_CHUNK")) : 0;
+  const int chunk = chunk_env > 0 ? chunk_env : std::max(1, ba->n_sm / 2);
+  SolveParams P = make_params(ba, opts);
+  const bool both = ba->h_in_smem && ba->hv_in_smem;
+  size_t h2d = 0; int launches = 0;
+  cudaEventRecord(ba->ev_fork, ba->stream);                 // order after anything still queued on the handle's main stream
+  for (int k = 0; k < 3; k++) cudaStreamWaitEvent(ba->pipe[k], ba->ev_fork, 0);
+  for (int c0 = 0, c = 0; c0 < n; c0 += chunk, c++) {
+    const int cn = std::min(chunk, n - c0);
+    cudaStream_t s = ba->pipe[c % 3];
+    size_t width = 0; for (int k = c0; k < c0 + cn; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
+    h2d += width * cn;
+    cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
+                      cudaMemcpyHostToDevice, s);
+    P.slot0 = c0; P.do_prep = 1;
+    if (both) solve_kernel<true><<<cn, SOLVE_THREADS, ba->smem_bytes, s>>>(P);
+    else solve_kernel<false><<<cn, SOLVE_THREADS, ba->smem_bytes, s>>>(P);
+    launches += 1;
+    cudaMemcpyAsync(ba->h_xout + (size_t)c0 * ba->xstride, ba->d_xout + (size_t)c0 * ba->xstride, (size_t)ba->xstride * 8 * cn, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(ba->h_sum + c0, ba->d_sum + c0, sizeof(vils_summary) * cn, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 3; k++) { const cudaError_t ek = cudaStreamSynchronize(ba->pipe[k]); if (e == cudaSuccess) e = ek; }
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_ba_solve");
+  ba->prepped = true;
+  ba->last_h2d = h2d; ba->last_d2h = (size_t)ba->xstride * 8 * n + sizeof(vils_summary) * n;
+  ba->last_launches = launches;
+  return VILS_OK;
 }
 
 int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* sb, double* ex, double* lam, double* td, vils_summary* sum) {
@@ -920,29 +1048,28 @@ static int ensure_eval_buffers(vils_ba* ba) {
 
 static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   int st = ensure_eval_buffers(ba); if (st) return st;
-  int np = 0, npl = 0, ned = 0, small = 0, cons = 0;
+  int np = 0, npl = 0, ned = 0, nimu = 0, nprior = 0, cons = 0;
   for (int k = slot0; k < slot0 + n; k++) {
     const WinHdr* h = reinterpret_cast<const WinHdr*>(ba->h_blob + (size_t)k * ba->blob_stride);
     np = std::max(np, h->n_proj); npl = std::max(npl, h->n_plane); ned = std::max(ned, h->n_edge);
-    small = std::max(small, h->n_imu + h->prior_n); cons = std::max(cons, h->n_icp + h->n_lps);
+    nimu = std::max(nimu, h->n_imu); nprior = std::max(nprior, h->prior_n); cons = std::max(cons, h->n_icp + h->n_lps);
   }
   EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
   Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(eval_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_T * EV_PLD * 8); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(eval_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_T * EV_PLD * 8); attr = true; }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
-  // the few heavy (latency-bound) factors run on a second stream, concurrently with the two streaming kernels
-  if (small || cons) {
-    cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
-    eval_small_kernel<<<dim3(1, n), EVS_T, 0, ba->stream2>>>(Q); launches++;
-    if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
-    cudaEventRecord(ba->ev_join, ba->stream2);
-  }
-  if (np) { eval_proj_kernel<<<dim3((np + EV_T - 1) / EV_T, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q); launches++; }
+  // two streams so that the block scheduler interleaves the FP64-heavy launch (IMU + projection) with the streaming LiDAR one
+  cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
+  const int ib = (nimu + EV_T / 32 - 1) / (EV_T / 32), pb = (np + EV_T - 1) / EV_T;
+  if (ib + pb) { eval_heavy_kernel<<<dim3(ib + pb, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q, ib); launches++; }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
-  if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream>>>(Q, pc); launches++; }
-  if (small || cons) cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
+  if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q, pc); launches++; }
+  if (nprior) { eval_prior_kernel<<<dim3((nprior + EVS_T - 1) / EVS_T, n), EVS_T, 0, ba->stream2>>>(Q); launches++; }
+  if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
+  cudaEventRecord(ba->ev_join, ba->stream2);
+  cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "eval kernels");
