@@ -398,6 +398,8 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
     const int k = warp;
     const bool mine = k < nimu && pre_all[(size_t)(k < nimu ? k : 0) * 467 + 16] <= 10.0;   // estimator.cpp:1182 skip if sum_dt > 10
     double hv[16]; int i = 0;
+    long long it_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+#define IPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - it_; it_ = n_; } } while (0)
 #pragma unroll
     for (int e = 0; e < 16; e++) hv[e] = 0;
     if (mine) {
@@ -409,6 +411,7 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
       // one lane, straight-line: measured 4-5 k cycles; splitting the blocks over lanes with a switch DIVERGES and costs 12 k
       if (lane == 0) vf::imu_eval_raw(pre, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), r, want_J ? J : nullptr);
       __syncwarp();
+      IPROF(20);
       double rw = 0;
       if (lane < 15) { for (int m = lane; m < 15; m++) rw = fma(Wk[lane * 15 + m], r[m], rw); }
       __syncwarp();
@@ -425,6 +428,7 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
             J[a * 30 + lane] = v; }
         }
         __syncwarp();
+        IPROF(21);
 #pragma unroll
         for (int q = 0; q < 16; q++) {
           const int e = lane + 32 * q;
@@ -446,6 +450,7 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
         }
       }
     }
+    IPROF(22);
     if (want_J) {
       for (int parity = 0; parity < 2; parity++) {
         if (mine && (i & 1) == parity) {
@@ -466,6 +471,8 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
         __syncthreads();
       }
     }
+    IPROF(23);
+#undef IPROF
     return cost;
   }
   const int nslot = (P.Ncap + 1) / 2;

@@ -427,74 +427,132 @@ struct EvalParams {
   int32_t apply_loss;
 };
 
-// Projection + IMU factors in ONE launch (both are register-hungry FP64 paths; fusing them lets the latency-bound IMU warps
-// fill in next to the streaming projection warps instead of serialising behind them on a second stream).
-//   blockIdx.x <  imu_blocks : one WARP per IMU factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30
-//                              whitening and the coalesced stores by all lanes);
-//   blockIdx.x >= imu_blocks : one thread per projection factor (landmark-sorted order); each warp stages its 32 rows
-//                              [r(2) | J(40)] in its own slice of shared memory (no block barrier) and writes them out as
-//                              one contiguous 10 KB segment with 16-byte stores.
+// Projection factors: PERSISTENT kernel, grid = SM count x MINB blocks of 128 threads, one thread per factor, work items
+// (window, 128-factor chunk) strided over the grid.  The SoA factor tile of the NEXT item (14 constants + 3 indices per
+// factor, the 2.5 KB window state and the landmark -> feature table) is staged into shared memory with cp.async while the
+// current item is being evaluated, so the HBM latency of the dependent chain header -> {constants, indices, state} is hidden
+// behind FP64 math.  Each thread writes its corrected Jacobian row (2x20 doubles, 320 B) into its own 336-byte shared-memory
+// row with 16-byte stores (21 x 16 B row pitch: conflict-free) and hands it to the TMA engine as one bulk shared->global
+// copy (cp.async.bulk); the wait for that copy is deferred to just before the row is rewritten one item later.
 // Output order inside a family is the library's SORTED order; the single-slot host API un-permutes (vils_ba_evaluate),
 // the batched device API documents it (vils_ba_evaluate_device).
-constexpr int EV_T = 128, EV_PLD = 43, EV_ELD = 21, EV_LLD = 7;
-#ifndef EV_PROJ_BLOCKS
-#define EV_PROJ_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(EV_T, EV_PROJ_BLOCKS) eval_heavy_kernel(EvalParams Q, int imu_blocks) {
+constexpr int EV_T = 128, EV_PLD = 42, EV_ELD = 21, EV_LLD = 7;
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+struct ProjItem { const uint8_t* base; const WinHdr* h; int slot, chunk, np, N, X, n_lm; };
+__device__ __forceinline__ ProjItem proj_item(const SolveParams& P, int item, int pb) {
+  ProjItem it; it.slot = P.slot0 + item / pb; it.chunk = item % pb;
+  it.base = P.blobs + (size_t)it.slot * P.blob_stride; it.h = reinterpret_cast<const WinHdr*>(it.base);
+  it.np = it.h->n_proj; it.N = it.h->n_kf; it.X = 16 * it.N + 8 + it.h->n_feat; it.n_lm = it.h->n_lm;
+  return it;
+}
+// per-thread slots of the factor tile: c[k] at cst[k * 128 + t] (doubles), idx[k] at ist[k * 128 + t] (ints); shared part: xs, feat
+__device__ __forceinline__ void proj_prefetch(const ProjItem& it, double* cst, int32_t* ist, double* xs, int32_t* feat, int t) {
+  const int f = it.chunk * EV_T + t;
+  if (it.chunk * EV_T < it.np) {
+    const double* x = reinterpret_cast<const double*>(it.base + it.h->off[OFF_X]);
+    for (int k = t; k < it.X; k += EV_T) cp_async8(xs + k, x + k);
+    const int32_t* lf = reinterpret_cast<const int32_t*>(it.base + it.h->off[OFF_LM_FEAT]);
+    for (int k = t; k < it.n_lm; k += EV_T) cp_async4(feat + k, lf + k);
+    if (f < it.np) {
+      const double* c0 = reinterpret_cast<const double*>(it.base + it.h->off[OFF_PROJ]);
+      const int32_t* ix = reinterpret_cast<const int32_t*>(it.base + it.h->off[OFF_PROJ_IDX]);
+#pragma unroll
+      for (int k = 0; k < 14; k++) cp_async8(cst + k * EV_T + t, c0 + (size_t)k * it.np + f);
+#pragma unroll
+      for (int k = 0; k < 3; k++) cp_async4(ist + k * EV_T + t, ix + (size_t)k * it.np + f);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int MINB>
+__global__ void __launch_bounds__(EV_T, MINB) eval_proj_kernel(EvalParams Q, int n_items, int pb, int xs_doubles, int feat_ints) {
   extern __shared__ __align__(16) double st[];
+  const SolveParams& P = Q.S;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // carve-up: rows | cst | xs[2] | ist | feat[2]
+  double* rows = st; double* cst = rows + EV_T * EV_PLD; double* xsb = cst + 14 * EV_T;
+  int32_t* ist = reinterpret_cast<int32_t*>(xsb + 2 * xs_doubles); int32_t* featb = ist + 3 * EV_T;
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  const int G = gridDim.x;
+  ProjItem cur = proj_item(P, item, pb);
+  proj_prefetch(cur, cst, ist, xsb, featb, t);
+  ProjItem nx = cur;
+  if (item + G < n_items) nx = proj_item(P, item + G, pb);
+  double* row = rows + (size_t)t * EV_PLD;
+  const double* wrows = rows + (size_t)(32 * warp) * EV_PLD;       // this warp's 32 rows
+  for (int n = 0; item < n_items; n++, item += G) {
+    // the header of the item AFTER the next one is fetched now and consumed one iteration later (by its proj_prefetch)
+    ProjItem nn = nx;
+    if (item + 2 * G < n_items) nn = proj_item(P, item + 2 * G, pb);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // tile of `cur` complete and visible; previous item fully consumed
+    const double* xs = xsb + (n & 1) * xs_doubles; const int32_t* feat = featb + (n & 1) * feat_ints;
+    const int fw = cur.chunk * EV_T + 32 * warp, f = fw + lane;   // fw: first factor of this warp
+    const bool act = f < cur.np;
+    double c[14]; int i = 0, j = 0, rank = 0;
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 14; k++) c[k] = cst[k * EV_T + t];
+      i = ist[t]; j = ist[EV_T + t]; rank = ist[2 * EV_T + t];
+    }
+    if (item + G < n_items) proj_prefetch(nx, cst, ist, xsb + ((n + 1) & 1) * xs_doubles, featb + ((n + 1) & 1) * feat_ints, t);   // own slots already copied to registers
+    const int n_imu = cur.h->n_imu;
+    if (act) {
+      const int N = cur.N;
+      double r[2];
+      // J goes straight into the shared-memory row as it is produced (keeps the 40 values out of the register file)
+      vf::proj_eval_rows(P.cfg, c, vm::q2R(vm::ldq(xs + XP(i) + 3)), vm::q2R(vm::ldq(xs + XP(j) + 3)), vm::q2R(vm::ldq(xs + XE(N) + 3)), vm::ld3(xs + XP(i)),
+                         vm::ld3(xs + XP(j)), vm::ld3(xs + XE(N)), xs[XL(N) + feat[rank]], xs[XT(N)], r, row, Q.apply_loss ? P.cfg.cauchy_a : 0.0);
+      double* R = Q.r_out + (size_t)cur.slot * Q.r_stride + 15 * n_imu + 2 * (size_t)f;
+      R[0] = r[0]; R[1] = r[1];
+    }
+    __syncwarp();
+    if (fw < cur.np) {   // the warp's rows leave as one contiguous segment (<= 10 KB) of 16-byte stores
+      const int cnt = min(32, cur.np - fw);
+      double2* Jo = reinterpret_cast<double2*>(Q.J_out + (size_t)cur.slot * Q.J_stride + (size_t)450 * n_imu + (size_t)40 * fw);   // 16-byte aligned: every term is even
+#pragma unroll 4
+      for (int e = lane; e < cnt * 20; e += 32) {
+        const int fr = e / 20, c2 = e - fr * 20;
+        Jo[e] = *reinterpret_cast<const double2*>(wrows + fr * EV_PLD + 2 * c2);
+      }
+    }
+    __syncwarp();
+    cur = nx; nx = nn;
+  }
+}
+
+// IMU factors: one WARP per factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30 whitening and the
+// coalesced stores by all lanes).  Latency-bound and tiny (9 per window): launched ahead of the streaming kernels.
+constexpr int EVI_WARPS = 2;
+__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q) {
+  __shared__ double sJ[EVI_WARPS][466];
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
   const WinHdr* h = W.h;
+  const int N = W.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * EVI_WARPS + warp;
+  if (k >= h->n_imu) return;
   const double* x = W.d(OFF_X);
-  const int N = W.N, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if ((int)blockIdx.x < imu_blocks) {
-    const int k = blockIdx.x * (EV_T / 32) + warp;
-    if (k >= h->n_imu) return;
-    double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
-    const double* scr = P.scratch + (size_t)slot * P.sl.total;
-    double* J = st + warp * 466; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
-    const int i = W.i(OFF_IMU_KF)[k];
-    for (int e = lane; e < 450; e += 32) J[e] = 0.0;
-    __syncwarp();
-    if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
-    __syncwarp();
-    if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
-    for (int e = lane; e < 450; e += 32) {
-      const int a = e / 30, c = e % 30; double v = 0;
-      for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
-      Jo[(size_t)450 * k + e] = v;
-    }
-    return;
-  }
-  const int np = h->n_proj, fbase = (blockIdx.x - imu_blocks) * EV_T + 32 * warp;   // first factor of this WARP
-  if (fbase >= np) return;
-  const int f = fbase + lane;
-  double* rows = st + (size_t)(32 * warp) * EV_PLD;
-  if (f < np) {
-    const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
-    double c[14];
-#pragma unroll
-    for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
-    const int i = ix[f], j = ix[np + f], feat = W.i(OFF_LM_FEAT)[ix[2 * np + f]];
-    double* o = rows + lane * EV_PLD;
-    vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(N), x[XL(N) + feat], x[XT(N)], o, o + 2);   // straight into the staging row
-    if (Q.apply_loss) {
-      double rho, w; vf::cauchy(P.cfg.cauchy_a, o[0] * o[0] + o[1] * o[1], rho, w);
-#pragma unroll
-      for (int e = 0; e < 42; e++) o[e] *= w;
-    }
-  }
+  double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
+  const double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* J = sJ[warp]; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
+  const int i = W.i(OFF_IMU_KF)[k];
+  for (int e = lane; e < 450; e += 32) J[e] = 0.0;
   __syncwarp();
-  const int cnt = min(32, np - fbase);
-  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * h->n_imu + 2 * (size_t)fbase;
-  double2* Jo = reinterpret_cast<double2*>(Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * h->n_imu + (size_t)40 * fbase);   // 16-byte aligned: every term is even
-  for (int e = lane; e < cnt * 2; e += 32) R[e] = rows[(e >> 1) * EV_PLD + (e & 1)];
-#pragma unroll 4
-  for (int e = lane; e < cnt * 20; e += 32) {
-    const int fr = e / 20, c2 = e - fr * 20;
-    const double* sp = rows + fr * EV_PLD + 2 + 2 * c2;
-    Jo[e] = make_double2(sp[0], sp[1]);
+  if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
+  __syncwarp();
+  if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
+  for (int e = lane; e < 450; e += 32) {
+    const int a = e / 30, c = e % 30; double v = 0;
+    for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
+    Jo[(size_t)450 * k + e] = v;
   }
 }
 
@@ -968,10 +1026,10 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   if (prof) {
     long long h[24]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
-    static const char* names[20] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait"};
+    static const char* names[24] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait", "  imu:zero+raw", "  imu:whiten", "  imu:JtJ", "  imu:add"};
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
-    for (int i = 0; i < 20; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+    for (int i = 0; i < 24; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
   }
   ba->last_launches = 1;
   return VILS_OK;
@@ -1056,14 +1114,30 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   }
   EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
   Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
+  const int xs_doubles = (16 * ba->cfg.max_kf + 8 + ba->cfg.max_feat + 1) & ~1, feat_ints = (ba->cfg.max_feat + 3) & ~3;
+  const size_t proj_smem = (size_t)(EV_T * EV_PLD + 14 * EV_T + 2 * xs_doubles) * 8 + (size_t)(3 * EV_T + 2 * feat_ints) * 4;
+  static const int minb = getenv("VILS_EV_MINB") ? atoi(getenv("VILS_EV_MINB")) : 3;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(eval_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_T * EV_PLD * 8); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(eval_proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
+    cudaFuncSetAttribute(eval_proj_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
+    cudaFuncSetAttribute(eval_proj_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
+    attr = true;
+  }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
-  // two streams so that the block scheduler interleaves the FP64-heavy launch (IMU + projection) with the streaming LiDAR one
+  // the latency-bound IMU warps go first; then two streams so that the block scheduler interleaves the FP64-heavy projection
+  // launch with the streaming LiDAR one
   cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
-  const int ib = (nimu + EV_T / 32 - 1) / (EV_T / 32), pb = (np + EV_T - 1) / EV_T;
-  if (ib + pb) { eval_heavy_kernel<<<dim3(ib + pb, n), EV_T, EV_T * EV_PLD * 8, ba->stream>>>(Q, ib); launches++; }
+  if (nimu) { eval_imu_kernel<<<dim3((nimu + EVI_WARPS - 1) / EVI_WARPS, n), 32 * EVI_WARPS, 0, ba->stream>>>(Q); launches++; }
+  const int pb = (np + EV_T - 1) / EV_T;
+  if (pb) {
+    const int items = pb * n, g = std::min(items, ba->n_sm * minb);
+    if (minb == 2) eval_proj_kernel<2><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    else if (minb == 4) eval_proj_kernel<4><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    else eval_proj_kernel<3><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    launches++;
+  }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
   if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q, pc); launches++; }
   if (nprior) { eval_prior_kernel<<<dim3((nprior + EVS_T - 1) / EVS_T, n), EVS_T, 0, ba->stream2>>>(Q); launches++; }

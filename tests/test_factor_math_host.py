@@ -47,6 +47,9 @@ def product_evaluate(hc, cfg, w):
         r2 = np.zeros(15); J2 = np.zeros((15, 30))   # the lane-split variant the solve kernel uses must be identical
         hc.hc_imu_eval_parts(P(pre), P(G), P(pose[i]), P(sb[i]), P(pose[i + 1]), P(sb[i + 1]), P(r2), P(J2))
         assert np.array_equal(r, r2) and np.array_equal(J, J2)
+        r3 = np.zeros(15); J3 = np.zeros((15, 30))   # the table-assembled (warp-cooperative) variant the kernels use
+        hc.hc_imu_eval_tbl(P(pre), P(G), P(pose[i]), P(sb[i]), P(pose[i + 1]), P(sb[i + 1]), P(r3), P(J3))
+        assert np.array_equal(r, r3) and np.array_equal(J, J3)
         rs.append(W @ r); Js.append((W @ J).reshape(-1))
     for k in range(len(w["kf_i"])):
         i, j, f = int(w["kf_i"][k]), int(w["kf_j"][k]), int(w["feat"][k])
@@ -58,6 +61,15 @@ def product_evaluate(hc, cfg, w):
         hc.hc_proj_eval_ctx(C.c_double(cfg.focal_length / 2), C.c_double(cfg.tr / cfg.row), C.c_double(cfg.row / 2), int(cfg.estimate_td),
                             P(c), P(pose[i]), P(pose[j]), P(ex), C.c_double(w["inv_depth"][f]), C.c_double(w["td"]), P(r2), P(J2))
         assert np.abs(r2 - r).max() <= 1e-11 * max(1.0, np.abs(r).max()) and np.abs(J2 - J).max() <= 1e-11 * max(1.0, np.abs(J).max())
+        # the row-vector variant used by the evaluate kernel (and its folded Cauchy corrector) against the line-by-line one
+        for loss_a in (0.0, 1.0):
+            r3 = np.zeros(2); J3 = np.zeros(40); r4 = np.zeros(2); J4 = np.zeros(40)
+            args = (C.c_double(cfg.focal_length / 2), C.c_double(cfg.tr / cfg.row), C.c_double(cfg.row / 2), int(cfg.estimate_td),
+                    P(c), P(pose[i]), P(pose[j]), P(ex), C.c_double(w["inv_depth"][f]), C.c_double(w["td"]), C.c_double(loss_a))
+            hc.hc_proj_eval_rows(*args, P(r3), P(J3)); hc.hc_proj_eval_loss(*args, P(r4), P(J4))
+            wgt = 1.0 if loss_a == 0.0 else np.sqrt(1.0 / (1.0 + (r @ r) / loss_a ** 2))   # corrector of marginalization_factor.cpp:49-53
+            for rr, JJ in ((r3, J3), (r4, J4)):
+                assert np.abs(rr - wgt * r).max() <= 1e-11 * max(1.0, np.abs(r).max()) and np.abs(JJ - wgt * J).max() <= 1e-11 * max(1.0, np.abs(J).max())
         rs.append(r); Js.append(J)
     for k in range(len(w.get("plane_kf", []))):
         pb = np.ascontiguousarray(RLB.T @ (w["plane_p"][k] - TLB)); n = np.ascontiguousarray(w["plane_n"][k]); J = np.zeros(6)

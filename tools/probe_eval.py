@@ -6,5 +6,7 @@ ws = [synth.make_window(2, k) for k in range(8)]
 ba = lib.BA(cabi.default_config(), B)
 for k in range(B): ba.set_window(k, ws[k % 8])
 ba.upload(B)
-for it in range(5):
-    ba.evaluate_device(B, True); print("evaluate_device ms", ba.last_ms, "GB/s", 769448 * B / ba.last_ms / 1e6)
+best = 1e9
+for it in range(12):
+    ba.evaluate_device(B, True); best = min(best, ba.last_ms)
+print("VILS_EV_MINB", os.environ.get("VILS_EV_MINB"), "evaluate_device best ms", best, "GB/s", 769448 * B / best / 1e6, "frac", 769448 * B / best / 1e6 / 6544.3)
