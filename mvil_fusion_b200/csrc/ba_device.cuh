@@ -25,10 +25,13 @@ namespace vb {
 constexpr int TB = 16;            // Cholesky tile
 constexpr int TLD = 17;           // padded tile row stride (doubles): lanes walking rows hit distinct shared-memory banks
 constexpr int TSZ = TB * TLD + 2; // padded tile stride: neighbouring tiles start 2 doubles (4 banks) apart
-constexpr int SOLVE_THREADS = 512;
+#ifndef VILS_SOLVE_THREADS
+#define VILS_SOLVE_THREADS 512
+#endif
+constexpr int SOLVE_THREADS = VILS_SOLVE_THREADS;
 constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
 constexpr int STAGE_LD = 25;      // pair-pass staging row: 19 Jacobian cols + residual + pad (odd stride: fewer bank conflicts)
-constexpr int PAIR_CHUNK = 304;   // projection factors evaluated per round (one per thread), staged in shared memory
+constexpr int PAIR_CHUNK = 304;   // keep PAIR_WARPS below in sync   // projection factors evaluated per round (one per thread), staged in shared memory
 constexpr int PAIR_LD = 20;       // pair-local block: [pose_i 6 | pose_j 6 | ex 6 | td | r]
 constexpr int ECHUNK = 32;        // landmarks per Schur chunk
 constexpr int PART_LD = 16;       // per-factor landmark partial: C, g_l, e_i(6), e_ex(6), e_td, pad
@@ -50,7 +53,7 @@ struct SolveParams {
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
-  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, total;
+  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, total;
   int ntile_rows;
 };
 
@@ -65,6 +68,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   s.gv = take(Dvp); s.hdv = take(Dvp);
   s.cinv = take(Mcap); s.glam = take(Mcap);
   s.red = take(64 + SOLVE_WARPS * 2);
+  s.tbl = take(114);                                         // IMU Jacobian assembly table (450 x uint16)
   s.linv = take(nb * TB * TB);
   int uni = PAIR_CHUNK * 2 * STAGE_LD;                       // pair-pass staging
   if (ECHUNK * Dvp > uni) uni = ECHUNK * Dvp;                // Schur chunk
@@ -134,10 +138,142 @@ __device__ double proj_cost(const SolveParams& P, const Win& W, const double* x,
   return 0.5 * rho;
 }
 
+// IMU Jacobian assembly table (vf::imu_build_table), uploaded once per device by vils_ba_create.
+__device__ uint16_t g_imu_tbl[450];
+
+// Warp-cooperative IMUFactor::Evaluate: lane 0 does the quaternion algebra (vf::imu_core) while the other lanes fetch the
+// bias-Jacobian blocks of the pre-integration; all lanes then assemble the 15 x 30 Jacobian through the table and whiten it
+// with sqrt_info (W, upper triangular) staged in shared memory.  The independent global loads (W, table) are issued first.
+// stage (shared memory, private to the warp): J 450 | r 15 | pad | core IMU_CORE_LD | W 226.   On exit J = W J_raw, r = W r_raw.
+constexpr int IMU_SLOT = 466 + vf::IMU_CORE_LD + 226;
+constexpr int IMU_PROD_LD = 512;                  // per-factor products in the scratch: lower J^T J (465) | J^T r (30)
+constexpr int PAIR_WARPS = (304 + 31) / 32;       // warps that evaluate projection factors in a pair-pass round (PAIR_CHUNK = 304)
+__device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared memory copy of g_imu_tbl */, const double* pre, const double* Wk, const double* G,
+                                                  const double* pi, const double* sbi, const double* pj, const double* sbj, double* stage, bool want_J,
+                                                  long long* prof = nullptr) {
+  const int lane = threadIdx.x & 31;
+  long long wt_ = prof ? clock64() : 0;
+#define WPROF(i) do { if (prof) { const long long n_ = clock64(); prof[i] += n_ - wt_; wt_ = n_; } } while (0)
+  double* J = stage; double* r = stage + 450; double* core = stage + 466; double* Wsm = core + vf::IMU_CORE_LD;
+  // one coalesced pass brings everything the single-lane algebra reads from HBM/L2 into shared memory (the J area doubles
+  // as the landing zone of the pre-integration record minus its covariance): one exposed latency instead of one per use
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = lane + 32 * q; if (e < 242) J[e] = pre[e]; }
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = lane + 32 * q; if (e < 225) Wsm[e] = Wk[e]; }
+  __syncwarp();
+  if (lane == 0) vf::imu_core(J, G, pi, sbi, pj, sbj, core);
+  else for (int e = lane - 1; e < 36; e += 31) core[vf::IC_JAC + e] = vf::imu_core_jac(J, e);
+  __syncwarp();
+  WPROF(20);
+  double rw = 0;
+  if (lane < 15) {
+#pragma unroll
+    for (int m = 0; m < 15; m++) if (m >= lane) rw = fma(Wsm[lane * 15 + m], core[vf::IC_R + m], rw);
+    r[lane] = rw;
+  }
+  if (want_J) {
+#pragma unroll
+    for (int q = 0; q < 15; q++) { const int e = lane + 32 * q; if (e < 450) J[e] = vf::imu_tbl_value(tbl[e], core); }
+    __syncwarp();
+    WPROF(21);
+    if (lane < 30) {                                            // J <- W J: lane owns column `lane` (no hazards)
+      double col[15];
+#pragma unroll
+      for (int m = 0; m < 15; m++) col[m] = J[m * 30 + lane];
+#pragma unroll
+      for (int a = 0; a < 15; a++) { double v = 0;
+#pragma unroll
+        for (int m = 0; m < 15; m++) if (m >= a) v = fma(Wsm[a * 15 + m], col[m], v);
+        J[a * 30 + lane] = v; }
+    }
+  }
+  __syncwarp();
+  WPROF(22);
+#undef WPROF
+}
+
+// One warp, one IMU factor: whitened residual / Jacobian, then the 30x30 lower product J^T J and J^T r written to the
+// per-window scratch (added into H later by imu_add).  Returns this lane's share of the cost.
+__device__ double imu_factor_products(const SolveParams& P, const Win& W, const uint16_t* tbl, const double* x, int k, double* stage, double* scr) {
+  const int lane = threadIdx.x & 31;
+  const double* pre = W.d(OFF_IMU) + (size_t)k * 467; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
+  double* prod = scr + P.sl.imuprod + (size_t)k * IMU_PROD_LD;
+  if (pre[16] > 10.0) {                                      // estimator.cpp:1182 skip if sum_dt > 10
+    for (int e = lane; e < 495; e += 32) prod[e] = 0.0;
+    return 0.0;
+  }
+  const int i = W.i(OFF_IMU_KF)[k];
+  const double* J = stage; const double* r = stage + 450;
+  const bool prof_ = P.prof && blockIdx.x == 0 && threadIdx.x == 32 * PAIR_WARPS;
+  long long it_ = prof_ ? clock64() : 0;
+#define IPROF(i) do { if (prof_) { const long long n_ = clock64(); P.prof[i] += n_ - it_; it_ = n_; } } while (0)
+  warp_imu_whitened(tbl, pre, Wk, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), stage, true, prof_ ? P.prof : nullptr);
+  it_ = prof_ ? clock64() : 0;
+  const double cost = lane < 15 ? 0.5 * r[lane] * r[lane] : 0.0;
+#pragma unroll 4
+  for (int q = 0; q < 16; q++) {
+    const int e = lane + 32 * q;
+    if (e < 465) {
+      int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while (a * (a + 1) / 2 > e) a--;
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      const int b = e - a * (a + 1) / 2;
+      double v = 0;
+#pragma unroll
+      for (int m = 0; m < 15; m++) v = fma(J[m * 30 + a], J[m * 30 + b], v);
+      prod[e] = v;
+    } else if (e < 495) {
+      const int a = e - 465; double v = 0;
+#pragma unroll
+      for (int m = 0; m < 15; m++) v = fma(J[m * 30 + a], r[m], v);
+      prod[e] = v;
+    }
+  }
+  __syncwarp();
+  IPROF(23);
+#undef IPROF
+  return cost;
+}
+
+// H += the IMU products of imu_factor_products: one warp per factor, even keyframes first, then odd (adjacent factors share
+// a 15x15 block).  Ends with a block barrier.
+__device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g, double* hd, const double* scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nimu = W.h->n_imu;
+  const int32_t* kfs = W.i(OFF_IMU_KF);
+  for (int parity = 0; parity < 2; parity++) {
+    for (int k = warp; k < nimu; k += SOLVE_WARPS) {
+      const int i = kfs[k];
+      if ((i & 1) != parity) continue;
+      const double* prod = scr + P.sl.imuprod + (size_t)k * IMU_PROD_LD;
+      const int base = 15 * i;
+      double pv[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) { const int e = lane + 32 * q; pv[q] = e < 495 ? prod[e] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const int e = lane + 32 * q;
+        if (e < 465) {
+          int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+          while (a * (a + 1) / 2 > e) a--;
+          while ((a + 1) * (a + 2) / 2 <= e) a++;
+          const int b = e - a * (a + 1) / 2;
+          H[tidx(base + a, base + b)] += pv[q];
+          if (a == b) hd[base + a] += pv[q];
+        } else if (e < 495) g[base + e - 465] += pv[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // =================================================================================================================
 // V: pair pass
 // =================================================================================================================
-__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost) {
+// imu_stage != nullptr: the warps that have no projection factor in a round (PAIR_WARPS..SOLVE_WARPS-1) process the IMU
+// factors meanwhile (imu_factor_products), SOLVE_WARPS - PAIR_WARPS per round; imu_stage holds that many IMU_SLOT slots.
+__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost, double* imu_stage, const uint16_t* tbl) {
   // Rounds of PAIR_CHUNK factors in PAIR order: (1) one thread per factor evaluates ProjectionTdFactor + corrector and
   // stages the weighted rows [J(19) | r] in shared memory, writes the landmark partials / E row to the scratch;
   // (2) one warp per keyframe pair accumulates the pair-local 20x20 block A^T A over the staged rows of that pair
@@ -156,6 +292,8 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
   double* pctx = scr + P.sl.pairctx;
   for (int p = threadIdx.x; p < npair; p += blockDim.x) vf::proj_pair_ctx(x + XP(pairs[4 * p + 2]), x + XP(pairs[4 * p + 3]), x + XE(W.N), pctx + (size_t)p * vf::PCTX_LD);
   __syncthreads();
+  int imu_next = 0;
+  const int nimu = imu_stage ? W.h->n_imu : 0;
   long long pt_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 #define PPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - pt_; pt_ = n_; } } while (0)
   for (int base = 0; base < np; base += PAIR_CHUNK) {
@@ -194,7 +332,10 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
         E[(size_t)rank * W.Dvp + 6 * kfj + k] = J[6 + k] * jl0 + J[26 + k] * jl1;   // e_j: this factor only
       }
       pt[14] = J[19] * jl0 + J[39] * jl1;                      // e_td
+    } else if (warp >= PAIR_WARPS && imu_next + (warp - PAIR_WARPS) < nimu) {
+      cost += imu_factor_products(P, W, tbl, x, imu_next + (warp - PAIR_WARPS), imu_stage + (warp - PAIR_WARPS) * IMU_SLOT, scr);
     }
+    imu_next += SOLVE_WARPS - PAIR_WARPS;
     PPROF(16);
     __syncthreads();
     PPROF(17);
@@ -235,6 +376,12 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
     PPROF(19);
   }
 #undef PPROF
+  // windows with few projection rounds: the IMU factors that did not get a slot above
+  while (imu_next < nimu) {
+    if (warp >= PAIR_WARPS && imu_next + (warp - PAIR_WARPS) < nimu)
+      cost += imu_factor_products(P, W, tbl, x, imu_next + (warp - PAIR_WARPS), imu_stage + (warp - PAIR_WARPS) * IMU_SLOT, scr);
+    imu_next += SOLVE_WARPS - PAIR_WARPS;
+  }
   return cost;
 }
 

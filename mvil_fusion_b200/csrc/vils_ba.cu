@@ -141,7 +141,9 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
                             double mu, bool need_cost = true) {
   double* g = sm + L.g; double* hd = sm + L.hd;
   PROF_T0();
-  double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost);
+  // IMU factors ride on the idle warps of the pair pass when their staging fits in the (still unused) Hv region
+  const bool imu_inline = P.hv_in_smem && (SOLVE_WARPS - PAIR_WARPS) * IMU_SLOT <= W.Dvp * W.Dvp + ((P.Ncap + 1) / 2) * 466;
+  double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost, imu_inline ? sm + L.hv : nullptr, reinterpret_cast<const uint16_t*>(sm + L.tbl));
   __syncthreads();
   PROF(0);
   landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu);
@@ -157,7 +159,8 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   gather_visual(P, W, Hv, sm + L.gv, H, g, hd, scr, reinterpret_cast<const int*>(sm + L.pid), P.Ncap * (P.Ncap - 1) / 2);
   __syncthreads();
   PROF(3);
-  c += imu_pass(P, W, x, H, g, hd, P.hv_in_smem ? sm + L.hv : sm + L.imu, scr, true, P.hv_in_smem != 0);
+  if (imu_inline) imu_add(P, W, H, g, hd, scr);
+  else c += imu_pass(P, W, x, H, g, hd, P.hv_in_smem ? sm + L.hv : sm + L.imu, scr, true, P.hv_in_smem != 0);
   PROF(4);
   c += lidar_pass(P, W, x, H, g, hd, true);
   __syncthreads();
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   if (P.do_prep) prep_window(P, W, scr, sm + L.uni);     // vils_ba_solve: no separate prep launch in the upload -> solve chain
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
+  { uint16_t* tb = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tb[k] = g_imu_tbl[k]; }
   double nf = 0;
   for (int d = threadIdx.x; d < W.nb * TB; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
   if (threadIdx.x == 0) chol_flag = 0;
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_lin_kernel(SolveParams
   const double* x0 = first ? W.d(OFF_X) : xo;
   for (int k = threadIdx.x; k < X; k += blockDim.x) { xs[k] = x0[k]; if (first) xo[k] = x0[k]; }
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
+  { uint16_t* tb = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tb[k] = g_imu_tbl[k]; }
   __syncthreads();
   const double c = linearize(P, W, L, sm, scr, xs, H, Hv, mu);
   for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; buf[e] = H[tidx(max(i, j), min(i, j))]; }
@@ -527,33 +532,42 @@ __global__ void __launch_bounds__(EV_T, MINB) eval_proj_kernel(EvalParams Q, int
   }
 }
 
-// IMU factors: one WARP per factor (raw Jacobian by one lane into shared memory, the 15x15 * 15x30 whitening and the
-// coalesced stores by all lanes).  Latency-bound and tiny (9 per window): launched ahead of the streaming kernels.
+// IMU factors: one WARP per factor (factors packed across windows).  warp_imu_whitened: one coalesced pass stages the
+// pre-integration record, sqrt_info and the four state blocks in shared memory, lane 0 does the quaternion algebra, all
+// lanes assemble the 15 x 30 Jacobian through the table and whiten it; the rows then leave as coalesced stores.
+// Latency-bound and tiny (9 per window, 7 % of the bytes): launched ahead of the streaming kernels.
 constexpr int EVI_WARPS = 2;
-__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q) {
-  __shared__ double sJ[EVI_WARPS][466];
+__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q, int nimu_max, int n) {
+  __shared__ double sJ[EVI_WARPS][IMU_SLOT];
+  __shared__ double sx[EVI_WARPS][32];
+  __shared__ uint16_t stbl[450];
   const SolveParams& P = Q.S;
-  const int slot = P.slot0 + blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint16_t treg[8];                                            // table loads fly together with the header loads below
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = threadIdx.x + 32 * EVI_WARPS * q; treg[q] = e < 450 ? g_imu_tbl[e] : (uint16_t)0; }
+  const int fid = blockIdx.x * EVI_WARPS + warp;             // factors packed across windows: no half-empty blocks
+  const bool act0 = fid < nimu_max * n;
+  const int slot = P.slot0 + (act0 ? fid / nimu_max : 0), k = act0 ? fid % nimu_max : 0;
   const Win W = decode(P, slot);
-  const WinHdr* h = W.h;
-  const int N = W.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = blockIdx.x * EVI_WARPS + warp;
-  if (k >= h->n_imu) return;
-  const double* x = W.d(OFF_X);
+  const bool act = act0 && k < W.h->n_imu;
+  const int N = W.N;
+  int i = 0;
+  if (act) {   // the four state blocks of the factor, one coalesced fetch: pose_i 0..6 | pose_j 7..13 | sb_i 14..22 | sb_j 23..31
+    i = W.i(OFF_IMU_KF)[k];
+    const double* x = W.d(OFF_X);
+    sx[warp][lane] = x[lane < 14 ? XP(i) + lane : XS(N, i) + (lane - 14)];
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = threadIdx.x + 32 * EVI_WARPS * q; if (e < 450) stbl[e] = treg[q]; }
+  __syncthreads();
+  if (!act) return;
   double* R = Q.r_out + (size_t)slot * Q.r_stride; double* Jo = Q.J_out + (size_t)slot * Q.J_stride;
   const double* scr = P.scratch + (size_t)slot * P.sl.total;
-  double* J = sJ[warp]; double* r = J + 450; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
-  const int i = W.i(OFF_IMU_KF)[k];
-  for (int e = lane; e < 450; e += 32) J[e] = 0.0;
-  __syncwarp();
-  if (lane == 0) vf::imu_eval_raw(W.d(OFF_IMU) + (size_t)k * 467, P.cfg.G, x + XP(i), x + XS(N, i), x + XP(i + 1), x + XS(N, i + 1), r, J);
-  __syncwarp();
-  if (lane < 15) { double s = 0; for (int m = lane; m < 15; m++) s = fma(Wk[lane * 15 + m], r[m], s); R[15 * k + lane] = s; }
-  for (int e = lane; e < 450; e += 32) {
-    const int a = e / 30, c = e % 30; double v = 0;
-    for (int m = a; m < 15; m++) v = fma(Wk[a * 15 + m], J[m * 30 + c], v);
-    Jo[(size_t)450 * k + e] = v;
-  }
+  double* J = sJ[warp]; const double* r = J + 450; const double* xw = sx[warp];
+  warp_imu_whitened(stbl, W.d(OFF_IMU) + (size_t)k * 467, scr + P.sl.w_imu + (size_t)k * 225, P.cfg.G, xw, xw + 14, xw + 7, xw + 23, J, true);
+  if (lane < 15) R[15 * k + lane] = r[lane];
+  for (int e = lane; e < 450; e += 32) Jo[(size_t)450 * k + e] = J[e];
 }
 
 // LiDAR plane + edge factors (keyframe-sorted order): blockIdx.x < plane chunks -> planes, else edges.
@@ -774,7 +788,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   s.w_imu = take((int64_t)N * 225); s.E = take((int64_t)M * Dvp); s.part = take((int64_t)cfg->max_proj * PART_LD);
   s.pairpart = take(((int64_t)N * (N - 1) / 2 + 1) * PAIR_LD * PAIR_LD);   // + one all-zero block
   s.pairctx = take((int64_t)N * (N - 1) / 2 * vf::PCTX_LD);
-  s.priorA = take((int64_t)D * D); s.priorb0 = take(D); s.lmsave = take(2 * (int64_t)M);
+  s.priorA = take((int64_t)D * D); s.priorb0 = take(D); s.lmsave = take(2 * (int64_t)M); s.imuprod = take((int64_t)N * IMU_PROD_LD);
   // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
   int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   const size_t budget = (size_t)dev_smem - 1024;
@@ -810,6 +824,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaFuncSetAttribute(shard_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
   CK(cudaFuncSetAttribute(shard_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
 #undef CK
+  { uint16_t tbl[450]; vf::imu_build_table(tbl); cudaError_t e_ = cudaMemcpyToSymbol(g_imu_tbl, tbl, sizeof(tbl)); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, "imu table"); } }
   std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
   std::memset(ba->h_sum, 0, sizeof(vils_summary) * max_windows);
   *out = ba;
@@ -1026,7 +1041,7 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   if (prof) {
     long long h[24]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
-    static const char* names[24] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait", "  imu:zero+raw", "  imu:whiten", "  imu:JtJ", "  imu:add"};
+    static const char* names[24] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait", "  imu:loads+core", "  imu:assemble", "  imu:whiten", "  imu:JtJ+store"};
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
     for (int i = 0; i < 24; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
@@ -1126,10 +1141,12 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
-  // the latency-bound IMU warps go first; then two streams so that the block scheduler interleaves the FP64-heavy projection
-  // launch with the streaming LiDAR one
+  // Two streams: the latency-bound IMU warps and then the persistent projection kernel on one, the streaming LiDAR / prior /
+  // constraint kernels on the other.
   cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
-  if (nimu) { eval_imu_kernel<<<dim3((nimu + EVI_WARPS - 1) / EVI_WARPS, n), 32 * EVI_WARPS, 0, ba->stream>>>(Q); launches++; }
+  if (nimu) {
+    eval_imu_kernel<<<(nimu * n + EVI_WARPS - 1) / EVI_WARPS, 32 * EVI_WARPS, 0, ba->stream>>>(Q, nimu, n); launches++;
+  }
   const int pb = (np + EV_T - 1) / EV_T;
   if (pb) {
     const int items = pb * n, g = std::min(items, ba->n_sm * minb);

@@ -12,7 +12,7 @@ import numpy as np
 from . import cabi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libvils_b200.so")
+SO_PATH = os.environ.get("VILS_SO") or os.path.join(HERE, "libvils_b200.so")   # VILS_SO: experiment builds (tools/ only)
 _lib = None
 
 
