@@ -38,7 +38,7 @@ BYTES_PER_LINEARISATION = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544 + (
 BYTES_PER_COST_EVAL = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544
 BYTES_PER_SOLVE = 5 * BYTES_PER_LINEARISATION + BYTES_PER_COST_EVAL
 # dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel per window, from the committed ncu capture (profiles/r1_ncu_solve_kernel.txt)
-SOLVE_DRAM_TRAFFIC_PER_WINDOW = 4814608   # (1.209570 + 1.640678) GB / 592 windows, ncu --set full capture of the bench command
+SOLVE_DRAM_TRAFFIC_PER_WINDOW = 5265906   # (335.82 + 443.53) MB / 148 windows, ncu --set full capture of solve_kernel (profiles/r1_ncu_solve_s3.txt)
 # Materialised Evaluate() traffic per window (what the CPU reference moves per linearisation; §8d first table)
 BYTES_PER_EVAL_WINDOW = 906 * 460 + 9 * 6016 + 1500 * 116 + 500 * 244 + 2544
 
@@ -221,9 +221,10 @@ def main():
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        ba.solve(B, opts)                 # pinned staging -> H2D -> prep + solve kernels -> D2H of states + summaries
+        ba.solve(B, opts)                 # pinned staging -> chunked H2D | solve kernels | D2H of states + summaries, pipelined on 3 streams
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e0)
+    e2e_launches = ba.last_launches
     # ---- Jacobian evaluation kernel (materialised Evaluate of every factor), the HBM-roofline kernel north_star names
     for _ in range(3):
         ba.evaluate_device(B, True)
@@ -257,12 +258,13 @@ def main():
                        "l2_policy": "inputs larger than L2 (592 window blobs x 281 KB = 166 MB per GPU, each step re-reads all of them)",
                        "solver": "GN x5, mu=1e-8 Jacobi damping, Cauchy(1) visual, Huber(0.1) LiDAR", "host_pack_ms_per_window": pack_ms,
                        "wall_ms_per_step": wall_ms / args.steps},
-            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "launches_per_step": e2e_launches, "pipeline": "chunks of n_sm/2 windows round-robin on 3 streams: H2D | solve_kernel (prep folded in) | D2H"},
             "gpu_launches": args.steps,
             "roofline": {"kernel": "solve_kernel (fused GN loop, one CTA per window)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": SOLVE_DRAM_TRAFFIC_PER_WINDOW * B if SOLVE_DRAM_TRAFFIC_PER_WINDOW else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_solve": BYTES_PER_SOLVE, "note": "latency-bound FP64 kernel; see DESIGN.md §4 and profiles/"},
-            "roofline_eval": {"kernel": "eval_kernel (materialised residual+Jacobian of every factor)", "bound": "hbm", "achieved": ev_achieved, "peak": peak,
+            "roofline_eval": {"kernel": "eval_imu + eval_proj + eval_lidar + eval_prior kernels (materialised residual+Jacobian of every factor)", "bound": "hbm", "achieved": ev_achieved, "peak": peak,
                               "unit": "GB/s", "frac": ev_achieved / peak, "ms_per_launch": ev_ms / args.steps, "algorithmic_bytes_per_window": BYTES_PER_EVAL_WINDOW},
             "cpu_baseline": {"value": tot / T, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{tot} GN-5 solves of the same config-2 windows by oracle/ (CPU restatement) on {cores} threads"},
