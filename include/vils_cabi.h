@@ -276,6 +276,30 @@ int vils_klt_track_device(vils_klt* k);
 int vils_klt_download(vils_klt* k, float* next_xy, uint8_t* status, float* err);
 int vils_klt_last_device_ms(vils_klt* k, float* ms);
 
+/* ---- the rest of FeatureTracker::readImage around the LK call (feature_tracker_/src/feature_tracker.cpp:81-167) ---------------
+ * One handle per camera stream: device images, mask, score map, candidate list. */
+typedef struct vils_frontend vils_frontend;
+int vils_frontend_create(int32_t rows, int32_t cols, int32_t max_pts, int32_t device, vils_frontend** out);
+void vils_frontend_destroy(vils_frontend* f);
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply(src, dst)  (feature_tracker.cpp:87-93; reference: 3.0, 8 x 8). */
+int vils_clahe(vils_frontend* f, const uint8_t* src, int32_t stride, double clip_limit, int32_t tiles_x, int32_t tiles_y,
+               uint8_t* dst, int32_t dst_stride);
+/* FeatureTracker::setMask (:36-69): visit points in descending track_cnt, keep a point if its pixel is still unmasked, then blank a
+ * filled disc of `radius` (MIN_DIST) around it exactly as cv::circle(mask, p, radius, 0, -1) rasterises it.  keep_idx[0..*n_keep) are the
+ * surviving input indices in pick order.  The mask stays on the device for vils_good_features. */
+int vils_set_mask(vils_frontend* f, const float* xy, const int32_t* track_cnt, int32_t n, int32_t radius, int32_t* keep_idx, int32_t* n_keep);
+int vils_get_mask(vils_frontend* f, uint8_t* mask, int32_t stride);
+/* cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_distance, mask) as called at :149 (min-eigenvalue score, blockSize 3,
+ * Sobel 3).  use_mask: 0 none, 1 the mask of the last vils_set_mask.  xy_out needs room for max_corners points (x, y). */
+int vils_good_features(vils_frontend* f, const uint8_t* img, int32_t stride, int32_t max_corners, double quality, double min_distance,
+                       int32_t use_mask, float* xy_out, int32_t* n_out);
+int vils_frontend_get_eig(vils_frontend* f, float* eig /* rows x cols */);
+/* PinholeCamera::liftProjective (camera_model/src/camera_models/PinholeCamera.cc:450-510, recursive distortion model, 8 iterations) for
+ * n pixel positions; cam = {fx, fy, cx, cy, k1, k2, p1, p2}; rays = n x 3 (mx_u, my_u, 1) — what undistortedPoints() (:258-306) and
+ * rejectWithF() (:169-202) consume. */
+int vils_lift_projective(vils_frontend* f, const double cam[8], const float* uv, int32_t n, double* rays);
+int vils_frontend_last_device_ms(vils_frontend* f, float* ms);
+
 /* ---- LiDAR: PointProcessor::PointToRing stamp (lidar_compensator/src/PointProcessor.cc:127-341)
  *      + TransformToEnd deskew (vils_estimator/src/lidar_frontend.cpp:1001-1041) --------------- */
 /* xyzi: n points, stride_floats floats apart (8 for pcl::PointXYZI: x y z pad intensity pad pad pad).

@@ -286,9 +286,10 @@ void Estimator::slideWindow() {
 // ---- FeatureTracker ------------------------------------------------------------------------------------------------
 FeatureTracker::FeatureTracker(int rows, int cols, int max_cnt, int device) : rows_(rows), cols_(cols), max_cnt_(max_cnt) {
   last_status = vils_klt_create(rows, cols, std::max(4 * max_cnt, 64), 21, 3, device, &klt_);
+  if (last_status == VILS_OK) last_status = vils_frontend_create(rows, cols, std::max(4 * max_cnt, 64), device, &fe_);
   cur_img_.resize((size_t)rows * cols);
 }
-FeatureTracker::~FeatureTracker() { vils_klt_destroy(klt_); }
+FeatureTracker::~FeatureTracker() { vils_klt_destroy(klt_); vils_frontend_destroy(fe_); }
 bool FeatureTracker::inBorder(float x, float y) const {
   const int B = 1; const int ix = (int)std::lround(x), iy = (int)std::lround(y);   // BORDER_SIZE = 1, cvRound
   return B <= ix && ix < cols_ - B && B <= iy && iy < rows_ - B;
@@ -296,10 +297,21 @@ bool FeatureTracker::inBorder(float x, float y) const {
 void FeatureTracker::addPoints(const float* xy, int n) {
   for (int k = 0; k < n && (int)cur_pts.size() < max_cnt_; k++) { cur_pts.push_back({xy[2 * k], xy[2 * k + 1]}); ids.push_back(n_id_++); track_cnt.push_back(1); }
 }
+bool FeatureTracker::updateID(unsigned int i) {
+  if (i >= ids.size()) return false;
+  if (ids[i] == -1) ids[i] = n_id_++;
+  return true;
+}
 void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
   prev_time = cur_time; cur_time = t;
   std::vector<uint8_t> forw_img((size_t)rows_ * cols_);                      // compact copy (cv::Mat::step may exceed cols)
-  for (int y = 0; y < rows_; y++) std::memcpy(forw_img.data() + (size_t)y * cols_, img + (size_t)y * stride, cols_);
+  if (EQUALIZE) {                                                             // cv::createCLAHE(3.0, Size(8, 8))->apply (:87-93)
+    last_status = vils_clahe(fe_, img, stride, 3.0, 8, 8, forw_img.data(), cols_);
+    if (last_status != VILS_OK) return;
+  } else {
+    for (int y = 0; y < rows_; y++) std::memcpy(forw_img.data() + (size_t)y * cols_, img + (size_t)y * stride, cols_);
+  }
+  std::vector<std::array<float, 2>> forw_pts;
   if (has_img_ && !cur_pts.empty()) {
     const int n = (int)cur_pts.size();
     std::vector<std::array<float, 2>> forw(n); std::vector<uint8_t> status(n); std::vector<float> err(n);
@@ -308,12 +320,57 @@ void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
     for (int i = 0; i < n; i++) if (status[i] && !inBorder(forw[i][0], forw[i][1])) status[i] = 0;        // :115-117
     prev_pts = cur_pts;
     size_t j = 0;                                                                                          // reduceVector (:21-34)
-    for (int i = 0; i < n; i++) if (status[i]) { prev_pts[j] = prev_pts[i]; forw[j] = forw[i]; ids[j] = ids[i]; track_cnt[j] = track_cnt[i] + 1; j++; }
+    for (int i = 0; i < n; i++) if (status[i]) { prev_pts[j] = prev_pts[i]; forw[j] = forw[i]; ids[j] = ids[i]; track_cnt[j] = track_cnt[i] + 1; j++; }   // + n++ (:127-128)
     prev_pts.resize(j); forw.resize(j); ids.resize(j); track_cnt.resize(j);
-    cur_pts = forw;
+    forw_pts = forw;
+  } else {
+    for (auto& c : track_cnt) c++;                                            // :127-128 also runs when nothing was tracked
+    forw_pts = cur_pts;
   }
-  cur_img_.swap(forw_img);                                                   // cur_img = forw_img (:160-164)
+  if (PUB_THIS_FRAME) {
+    // rejectWithF() (:131) is not built, see the class comment.  setMask (:36-69): long-tracked points first, MIN_DIST discs
+    const int n = (int)forw_pts.size();
+    std::vector<int32_t> keep(std::max(n, 1)), cnt32(track_cnt.begin(), track_cnt.end()); int32_t nk = 0;
+    last_status = vils_set_mask(fe_, n ? &forw_pts[0][0] : nullptr, cnt32.data(), n, MIN_DIST, keep.data(), &nk);
+    if (last_status != VILS_OK) return;
+    std::vector<std::array<float, 2>> fp(nk); std::vector<int> id2(nk), tc2(nk);
+    for (int k = 0; k < nk; k++) { fp[k] = forw_pts[keep[k]]; id2[k] = ids[keep[k]]; tc2[k] = track_cnt[keep[k]]; }
+    forw_pts.swap(fp); ids.swap(id2); track_cnt.swap(tc2);
+    const int n_max_cnt = max_cnt_ - (int)forw_pts.size();                    // :139-151
+    if (n_max_cnt > 0) {
+      std::vector<float> n_pts(2 * (size_t)n_max_cnt); int32_t nn = 0;
+      last_status = vils_good_features(fe_, forw_img.data(), cols_, n_max_cnt, 0.01, (double)MIN_DIST, 1, n_pts.data(), &nn);
+      if (last_status != VILS_OK) return;
+      for (int k = 0; k < nn; k++) { forw_pts.push_back({n_pts[2 * k], n_pts[2 * k + 1]}); ids.push_back(-1); track_cnt.push_back(1); }   // addPoints (:71-79)
+    }
+  }
+  cur_pts = forw_pts;
+  cur_img_.swap(forw_img);                                                   // prev = cur, cur = forw (:160-164)
   has_img_ = true;
+  undistortedPoints();
+}
+void FeatureTracker::undistortedPoints() {
+  const int n = (int)cur_pts.size();
+  cur_un_pts.assign(n, {0.f, 0.f}); pts_velocity.assign(n, {0.f, 0.f});
+  std::map<int, std::array<float, 2>> cur_map;
+  if (n) {
+    std::vector<double> rays(3 * (size_t)n);
+    last_status = vils_lift_projective(fe_, cam, &cur_pts[0][0], n, rays.data());   // m_camera->liftProjective (:266-268)
+    if (last_status != VILS_OK) return;
+    for (int i = 0; i < n; i++) {
+      cur_un_pts[i] = {(float)(rays[3 * i] / rays[3 * i + 2]), (float)(rays[3 * i + 1] / rays[3 * i + 2])};
+      cur_map.insert({ids[i], cur_un_pts[i]});                                 // std::map::insert keeps the FIRST entry of a duplicated id (-1)
+    }
+  }
+  if (!prev_un_pts_map_.empty()) {                                            // :274-299
+    const double dt = cur_time - prev_time;
+    for (int i = 0; i < n; i++) {
+      if (ids[i] == -1) continue;
+      auto it = prev_un_pts_map_.find(ids[i]);
+      if (it != prev_un_pts_map_.end()) pts_velocity[i] = {(float)((cur_un_pts[i][0] - it->second[0]) / dt), (float)((cur_un_pts[i][1] - it->second[1]) / dt)};
+    }
+  }
+  prev_un_pts_map_ = cur_map;
 }
 
 int TransformToEnd(float* xyzi, int n, const float q[4], const float t[3], float time_factor, double min_r, double max_r, int device) {
@@ -358,6 +415,16 @@ int vh_tracker_read(void* p, const uint8_t* img, int stride, double t) { auto* f
 int vh_tracker_get(void* p, float* xy, int* ids, int* cnt, int cap) {
   auto* f = static_cast<vils::FeatureTracker*>(p); const int n = std::min<int>(cap, (int)f->cur_pts.size());
   for (int k = 0; k < n; k++) { xy[2 * k] = f->cur_pts[k][0]; xy[2 * k + 1] = f->cur_pts[k][1]; ids[k] = f->ids[k]; cnt[k] = f->track_cnt[k]; }
+  return n;
+}
+void vh_tracker_config(void* p, int equalize, int pub, int min_dist, const double* cam) {
+  auto* f = static_cast<vils::FeatureTracker*>(p); f->EQUALIZE = equalize != 0; f->PUB_THIS_FRAME = pub != 0; f->MIN_DIST = min_dist;
+  if (cam) for (int k = 0; k < 8; k++) f->cam[k] = cam[k];
+}
+void vh_tracker_update_ids(void* p) { auto* f = static_cast<vils::FeatureTracker*>(p); for (unsigned int i = 0; f->updateID(i); i++) {} }   // feature_tracker_node.cpp:120-128
+int vh_tracker_get_un(void* p, float* un_xy, float* vel, int cap) {
+  auto* f = static_cast<vils::FeatureTracker*>(p); const int n = std::min<int>(cap, (int)f->cur_un_pts.size());
+  for (int k = 0; k < n; k++) { un_xy[2 * k] = f->cur_un_pts[k][0]; un_xy[2 * k + 1] = f->cur_un_pts[k][1]; vel[2 * k] = f->pts_velocity[k][0]; vel[2 * k + 1] = f->pts_velocity[k][1]; }
   return n;
 }
 int vh_transform_to_end(float* xyzi, int n, const float* q, const float* t, float tf, double mn, double mx) { return vils::TransformToEnd(xyzi, n, q, t, tf, mn, mx, 0); }

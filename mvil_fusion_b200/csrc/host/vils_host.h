@@ -96,16 +96,24 @@ class Estimator {
   int prior_n_ = 0;
 };
 
-// feature_tracker_/src/feature_tracker.{h,cpp}: the LK part of readImage (CLAHE, goodFeaturesToTrack, rejectWithF are "next" rows)
+// feature_tracker_/src/feature_tracker.{h,cpp}.  readImage = CLAHE (EQUALIZE) -> calcOpticalFlowPyrLK -> border check / reduceVector ->
+// [PUB_THIS_FRAME: setMask -> goodFeaturesToTrack -> addPoints] -> undistortedPoints (liftProjective + velocities), every image-sized or
+// per-point step on the device through the C-ABI (vils_clahe / vils_klt_* / vils_set_mask / vils_good_features / vils_lift_projective).
+// Not built: rejectWithF (cv::findFundamentalMat RANSAC, :169-202) — the outlier gate is left to the caller.
 class FeatureTracker {
  public:
   FeatureTracker(int rows, int cols, int max_cnt = 150, int device = 0);
   ~FeatureTracker();
-  // readImage(const cv::Mat&, double): tracks cur_pts into the new image, drops lost / out-of-border points (:113-123),
-  // rotates prev/cur/forw (:160-164). New corners are supplied by the caller through addPoints (stands in for :134-158).
   void readImage(const uint8_t* img, int stride, double cur_time);
+  // Caller-supplied corners (ids assigned immediately); the detection path of readImage uses ids = -1 + updateID like the reference.
   void addPoints(const float* xy, int n);
-  std::vector<std::array<float, 2>> cur_pts, prev_pts;
+  bool updateID(unsigned int i);                            // feature_tracker.cpp:204-214
+  void undistortedPoints();                                 // :258-306
+  // parameters.h / config yaml of the reference
+  bool EQUALIZE = false, PUB_THIS_FRAME = false;
+  int MIN_DIST = 30;
+  double cam[8] = {356.37000498, 354.92225534, 326.87903275, 250.93806883, -0.29326213, 0.07505211, 0.0002761, -0.00026777};
+  std::vector<std::array<float, 2>> cur_pts, prev_pts, cur_un_pts, pts_velocity;
   std::vector<int> ids, track_cnt;
   double cur_time = 0, prev_time = 0;
   int last_status = VILS_OK;
@@ -113,7 +121,9 @@ class FeatureTracker {
   bool inBorder(float x, float y) const;                  // feature_tracker.cpp:13-19
   int rows_, cols_, max_cnt_, n_id_ = 0;
   vils_klt* klt_ = nullptr;
+  vils_frontend* fe_ = nullptr;
   std::vector<uint8_t> cur_img_;
+  std::map<int, std::array<float, 2>> prev_un_pts_map_;
   bool has_img_ = false;
 };
 

@@ -1,0 +1,451 @@
+// vils_frontend.cu — the rest of FeatureTracker::readImage around the LK call (feature_tracker_/src/feature_tracker.cpp:81-167):
+//   CLAHE(3.0, 8x8)            :87-93   -> vils_clahe            (u8, bit-exact integer histograms / LUTs, FP32 bilinear blend)
+//   setMask()                   :36-69   -> vils_set_mask         (track-count ordered greedy pick on the host, disc raster on the device)
+//   goodFeaturesToTrack(...)    :149     -> vils_good_features    (min-eigenvalue map, masked max, 3x3 non-max suppression, sort on
+//                                                                 the device; the inherently sequential min-distance pick on the host)
+//   undistortedPoints()         :258-306 -> vils_lift_projective  (PinholeCamera::liftProjective, camera_model/.../PinholeCamera.cc:450-510)
+// Third-party algorithms restated from OpenCV 4.x (imgproc/src/clahe.cpp, featureselect.cpp, corner.cpp, drawing.cpp); the executable
+// oracle in tests/ is cv2 4.13 itself.  Compiled with --fmad=false: the FP32 blend of CLAHE follows OpenCV's operation order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/vils_cabi.h"
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// CLAHE (OpenCV clahe.cpp: CLAHE_CalcLut_Body + CLAHE_Interpolation_Body), 8-bit
+// ---------------------------------------------------------------------------------------------------------------------------------
+// One CTA per tile: 256-bin histogram in shared memory (integer atomics: exact), clip + redistribute, cumulative LUT.
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, int rows, int cols, int stride, int tiles_x, int tile_w, int tile_h,
+                                                        int clip_limit, float lut_scale, uint8_t* __restrict__ lut) {
+  __shared__ int hist[256];
+  __shared__ int red[256];
+  const int t = threadIdx.x, tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  hist[t] = 0;
+  __syncthreads();
+  // the image is virtually extended by BORDER_REFLECT_101 to a multiple of the tile grid (clahe.cpp: copyMakeBorder)
+  for (int p = t; p < tile_w * tile_h; p += 256) {
+    const int y = reflect101(ty * tile_h + p / tile_w, rows), x = reflect101(tx * tile_w + p % tile_w, cols);
+    atomicAdd(&hist[src[(size_t)y * stride + x]], 1);
+  }
+  __syncthreads();
+  if (clip_limit > 0) {
+    int h = hist[t];
+    red[t] = h > clip_limit ? h - clip_limit : 0;
+    if (h > clip_limit) h = clip_limit;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+    const int clipped = red[0];
+    const int batch = clipped / 256; int residual = clipped - batch * 256;
+    h += batch;
+    if (residual != 0) {
+      const int step = max(256 / residual, 1);
+      // for (i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++
+      if (t % step == 0 && t / step < residual) h++;
+    }
+    __syncthreads();
+    hist[t] = h;
+  }
+  __syncthreads();
+  // inclusive prefix sum (Hillis-Steele on 256 ints)
+  red[t] = hist[t];
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) { const int v = t >= o ? red[t - o] : 0; __syncthreads(); red[t] += v; __syncthreads(); }
+  const float v = (float)red[t] * lut_scale;
+  int r = __float2int_rn(v);                                  // saturate_cast<uchar>(float) = cvRound, saturated
+  lut[(size_t)blockIdx.x * 256 + t] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void clahe_apply_kernel(const uint8_t* __restrict__ src, int rows, int cols, int stride, int tiles_x, int tiles_y, float inv_tw, float inv_th,
+                                   const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dst_stride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  const float tyf = y * inv_th - 0.5f, txf = x * inv_tw - 0.5f;
+  int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
+  int ty2 = ty1 + 1, tx2 = tx1 + 1;
+  const float ya = tyf - ty1, ya1 = 1.0f - ya, xa = txf - tx1, xa1 = 1.0f - xa;
+  ty1 = max(ty1, 0); ty2 = min(ty2, tiles_y - 1); tx1 = max(tx1, 0); tx2 = min(tx2, tiles_x - 1);
+  const int v = src[(size_t)y * stride + x];
+  const uint8_t* l1 = lut + (size_t)ty1 * tiles_x * 256; const uint8_t* l2 = lut + (size_t)ty2 * tiles_x * 256;
+  const float res = (l1[tx1 * 256 + v] * xa1 + l1[tx2 * 256 + v] * xa) * ya1 + (l2[tx1 * 256 + v] * xa1 + l2[tx2 * 256 + v] * xa) * ya;
+  dst[(size_t)y * dst_stride + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// goodFeaturesToTrack (featureselect.cpp) on cornerMinEigenVal (corner.cpp), blockSize 3, Sobel 3
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int ET_X = 32, ET_Y = 16;   // output tile; the 8-bit input tile with a 2-pixel halo is staged in shared memory
+__global__ void __launch_bounds__(ET_X * ET_Y) min_eig_kernel(const uint8_t* __restrict__ src, int rows, int cols, int stride, float* __restrict__ eig) {
+  __shared__ uint8_t tile[ET_Y + 4][ET_X + 4];
+  __shared__ float cxx[ET_Y + 2][ET_X + 2], cxy[ET_Y + 2][ET_X + 2], cyy[ET_Y + 2][ET_X + 2];
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * ET_X + tx;
+  const int x0 = blockIdx.x * ET_X, y0 = blockIdx.y * ET_Y;
+  for (int p = t; p < (ET_Y + 4) * (ET_X + 4); p += ET_X * ET_Y) {
+    const int ly = p / (ET_X + 4), lx = p % (ET_X + 4);
+    // derivative taps reflect at the IMAGE border (BORDER_REFLECT_101 of Sobel); the covariance box filter reflects again below
+    tile[ly][lx] = src[(size_t)reflect101(y0 + ly - 2, rows) * stride + reflect101(x0 + lx - 2, cols)];
+  }
+  __syncthreads();
+  const float scale = (float)(1.0 / (4.0 * 3.0) * (1.0 / 255.0));   // corner.cpp: 1 / (2^(ksize-1) * block_size), * 1/255 for 8-bit input
+  for (int p = t; p < (ET_Y + 2) * (ET_X + 2); p += ET_X * ET_Y) {
+    const int ly = p / (ET_X + 2), lx = p % (ET_X + 2);
+    // covariance sample at image position (y0 + ly - 1, x0 + lx - 1); outside the image the box filter's REFLECT_101 applies to the
+    // covariance image itself, i.e. the sample is the one of the mirrored position
+    const int gy = reflect101(y0 + ly - 1, rows), gx = reflect101(x0 + lx - 1, cols);
+    const int cy = gy - y0 + 2, cx = gx - x0 + 2;
+    float dx, dy;
+    if (cy >= 1 && cy < ET_Y + 3 && cx >= 1 && cx < ET_X + 3) {
+      const int a00 = tile[cy - 1][cx - 1], a01 = tile[cy - 1][cx], a02 = tile[cy - 1][cx + 1], a10 = tile[cy][cx - 1], a12 = tile[cy][cx + 1],
+                a20 = tile[cy + 1][cx - 1], a21 = tile[cy + 1][cx], a22 = tile[cy + 1][cx + 1];
+      dx = (float)((a02 - a00) + 2 * (a12 - a10) + (a22 - a20)) * scale;
+      dy = (float)((a20 - a00) + 2 * (a21 - a01) + (a22 - a02)) * scale;
+    } else {   // mirrored position fell outside the staged tile (only for images narrower than the halo): read from global memory
+      int a[3][3];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = src[(size_t)reflect101(gy + i - 1, rows) * stride + reflect101(gx + j - 1, cols)];
+      dx = (float)((a[0][2] - a[0][0]) + 2 * (a[1][2] - a[1][0]) + (a[2][2] - a[2][0])) * scale;
+      dy = (float)((a[2][0] - a[0][0]) + 2 * (a[2][1] - a[0][1]) + (a[2][2] - a[0][2])) * scale;
+    }
+    cxx[ly][lx] = dx * dx; cxy[ly][lx] = dx * dy; cyy[ly][lx] = dy * dy;
+  }
+  __syncthreads();
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= cols || y >= rows) return;
+  float s[3];
+  {
+    float (*c[3])[ET_X + 2] = {cxx, cxy, cyy};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float r0 = (c[k][ty][tx] + c[k][ty][tx + 1]) + c[k][ty][tx + 2];
+      const float r1 = (c[k][ty + 1][tx] + c[k][ty + 1][tx + 1]) + c[k][ty + 1][tx + 2];
+      const float r2 = (c[k][ty + 2][tx] + c[k][ty + 2][tx + 1]) + c[k][ty + 2][tx + 2];
+      s[k] = (r0 + r1) + r2;
+    }
+  }
+  const float a = s[0] * 0.5f, b = s[1], c2 = s[2] * 0.5f;
+  eig[(size_t)y * cols + x] = (a + c2) - sqrtf((a - c2) * (a - c2) + b * b);   // calcMinEigenVal
+}
+
+// minMaxLoc(eig, 0, &maxVal, 0, 0, mask): the minimum eigenvalue of the best corner is positive, so the IEEE bit pattern orders
+__global__ void masked_max_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ mask, int n, unsigned int* out) {
+  unsigned int m = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = eig[i];
+    if (v > 0.0f && (!mask || mask[i])) m = max(m, __float_as_uint(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// threshold(TOZERO) + dilate 3x3 + "val != 0 && val == dilated && mask" over the interior (y, x in 1..n-2)
+__global__ void candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ mask, int rows, int cols, const unsigned int* maxbits, float quality,
+                                  unsigned long long* cand, unsigned int* count, unsigned int cap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
+  const float thr = (float)((double)__uint_as_float(*maxbits) * (double)quality);   // threshold(eig, eig, maxVal*qualityLevel, ...): double product
+  const float v = eig[(size_t)y * cols + x];
+  if (!(v > thr) || (mask && !mask[(size_t)y * cols + x])) return;
+  float m = v;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) m = fmaxf(m, eig[(size_t)(y + dy) * cols + x + dx]);
+  if (v != m) return;
+  const unsigned int k = atomicAdd(count, 1u);
+  // sort key, descending: value first, then the address (greaterThanPtr: equal values -> higher address first)
+  if (k < cap) cand[k] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * cols + x);
+}
+
+// Single-CTA bitonic sort (descending) of n_pad = 2^k 64-bit keys in global memory; candidates are a few thousand at most.
+__global__ void __launch_bounds__(1024) sort_desc_kernel(unsigned long long* keys, const unsigned int* count, unsigned int cap) {
+  unsigned int n = min(*count, cap), np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (unsigned int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  for (unsigned int k = 2; k <= np2; k <<= 1)
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const unsigned int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) { keys[i] = b; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// setMask(): filled cv::circle(mask, p, radius, 0, -1) for every kept point. hw[d] = half-width of the rasterised disc at row offset d.
+__global__ void mask_discs_kernel(uint8_t* mask, int rows, int cols, const int* __restrict__ centers, int n, int radius, const int* __restrict__ hw) {
+  const int k = blockIdx.x;
+  if (k >= n) return;
+  const int cx = centers[2 * k], cy = centers[2 * k + 1], side = 2 * radius + 1;
+  for (int p = threadIdx.x; p < side * side; p += blockDim.x) {
+    const int dy = p / side - radius, dx = p % side - radius;
+    const int y = cy + dy, x = cx + dx;
+    if (y < 0 || y >= rows || x < 0 || x >= cols) continue;
+    if (abs(dx) <= hw[abs(dy)]) mask[(size_t)y * cols + x] = 0;
+  }
+}
+
+// PinholeCamera::liftProjective (PinholeCamera.cc:450-510) with the recursive distortion model (n = 8), ::distortion (:646-662)
+__global__ void lift_kernel(const float* __restrict__ uv, int n, double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2,
+                            int no_distortion, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double inv_K11 = 1.0 / fx, inv_K13 = -cx / fx, inv_K22 = 1.0 / fy, inv_K23 = -cy / fy;
+  const double mx_d = inv_K11 * (double)uv[2 * i] + inv_K13, my_d = inv_K22 * (double)uv[2 * i + 1] + inv_K23;
+  double mx_u = mx_d, my_u = my_d;
+  if (!no_distortion) {
+    double ux = mx_d, uy = my_d;
+    for (int it = 0; it < 8; it++) {
+      const double mx2 = ux * ux, my2 = uy * uy, mxy = ux * uy, rho2 = mx2 + my2, rad = k1 * rho2 + k2 * rho2 * rho2;
+      const double dux = ux * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2), duy = uy * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2);
+      ux = mx_d - dux; uy = my_d - duy;
+    }
+    mx_u = ux; my_u = uy;
+  }
+  out[3 * i] = mx_u; out[3 * i + 1] = my_u; out[3 * i + 2] = 1.0;
+}
+
+// Integer midpoint circle of OpenCV's Circle() (drawing.cpp), fill = 1: half-width of the filled disc per row offset.
+void disc_half_widths(int radius, std::vector<int>& hw) {
+  hw.assign(radius + 1, -1);
+  int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  while (dx >= dy) {
+    hw[dy] = std::max(hw[dy], dx);   // rows center.y +- dy span +-dx
+    hw[dx] = std::max(hw[dx], dy);   // rows center.y +- dx span +-dy
+    dy++; err += plus; plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask; dx += mask; minus -= mask & 2;
+  }
+}
+inline int cv_round(double v) { return (int)std::nearbyint(v); }   // cvRound: round half to even (default FP environment)
+
+}  // namespace
+
+struct vils_frontend {
+  int rows = 0, cols = 0, device = 0, max_pts = 0;
+  cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  uint8_t* d_src = nullptr; uint8_t* d_dst = nullptr; uint8_t* d_lut = nullptr; uint8_t* d_mask = nullptr; uint8_t* h_img = nullptr;
+  float* d_eig = nullptr; unsigned long long* d_cand = nullptr; unsigned long long* h_cand = nullptr; unsigned int* d_cnt = nullptr; unsigned int* h_cnt = nullptr;
+  int* d_centers = nullptr; int* d_hw = nullptr; float* d_uv = nullptr; double* d_ray = nullptr;
+  unsigned int cand_cap = 0; int hw_radius = -1;
+  bool mask_valid = false;
+  float last_ms = 0;
+};
+
+extern "C" {
+
+int vils_frontend_create(int32_t rows, int32_t cols, int32_t max_pts, int32_t device, vils_frontend** out) {
+  if (!out || rows < 8 || cols < 8 || max_pts <= 0) return vils::fail(VILS_ERR_BAD_ARG, "vils_frontend_create: bad argument");
+  int st = vils::require_device(device); if (st) return st;
+  vils_frontend* f = new vils_frontend(); f->rows = rows; f->cols = cols; f->device = device; f->max_pts = max_pts;
+  const size_t px = (size_t)rows * cols;
+  f->cand_cap = 1u << 16;
+  cudaError_t e = cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&f->e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&f->e1);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_src, px);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_dst, px);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_mask, px);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_lut, 256 * 64 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_eig, px * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cand, sizeof(unsigned long long) * f->cand_cap);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cnt, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_centers, sizeof(int) * 2 * max_pts);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_hw, sizeof(int) * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_uv, sizeof(float) * 2 * max_pts);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_ray, sizeof(double) * 3 * max_pts);
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_img, px);
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_cand, sizeof(unsigned long long) * f->cand_cap);
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_cnt, 2 * sizeof(unsigned int));
+  if (e != cudaSuccess) { vils_frontend_destroy(f); return vils::fail_cuda(e, "vils_frontend_create"); }
+  *out = f; return VILS_OK;
+}
+
+void vils_frontend_destroy(vils_frontend* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->st) cudaStreamSynchronize(f->st);
+  cudaFree(f->d_src); cudaFree(f->d_dst); cudaFree(f->d_mask); cudaFree(f->d_lut); cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_cnt);
+  cudaFree(f->d_centers); cudaFree(f->d_hw); cudaFree(f->d_uv); cudaFree(f->d_ray); cudaFreeHost(f->h_img); cudaFreeHost(f->h_cand); cudaFreeHost(f->h_cnt);
+  if (f->e0) cudaEventDestroy(f->e0);
+  if (f->e1) cudaEventDestroy(f->e1);
+  if (f->st) cudaStreamDestroy(f->st);
+  delete f;
+}
+
+static int fe_upload(vils_frontend* f, const uint8_t* img, int stride, uint8_t* dst) {
+  for (int y = 0; y < f->rows; y++) memcpy(f->h_img + (size_t)y * f->cols, img + (size_t)y * stride, f->cols);
+  cudaError_t e = cudaMemcpyAsync(dst, f->h_img, (size_t)f->rows * f->cols, cudaMemcpyHostToDevice, f->st);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "frontend upload");
+}
+
+int vils_clahe(vils_frontend* f, const uint8_t* src, int32_t stride, double clip_limit, int32_t tiles_x, int32_t tiles_y, uint8_t* dst, int32_t dst_stride) {
+  if (!f || !src || !dst || stride < f->cols || dst_stride < f->cols || tiles_x <= 0 || tiles_y <= 0 || tiles_x * tiles_y > 256)
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_clahe: bad argument");
+  cudaSetDevice(f->device);
+  int st = fe_upload(f, src, stride, f->d_src); if (st) return st;
+  const int rows = f->rows, cols = f->cols;
+  // clahe.cpp: tiles cover the image extended to a multiple of the grid
+  const int ext_w = cols % tiles_x == 0 ? cols : cols + (tiles_x - cols % tiles_x), ext_h = rows % tiles_y == 0 ? rows : rows + (tiles_y - rows % tiles_y);
+  const int tw = ext_w / tiles_x, th = ext_h / tiles_y, area = tw * th;
+  int clip = 0;
+  if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = std::max(clip, 1); }
+  const float lut_scale = (float)255 / area;
+  cudaEventRecord(f->e0, f->st);
+  clahe_lut_kernel<<<tiles_x * tiles_y, 256, 0, f->st>>>(f->d_src, rows, cols, cols, tiles_x, tw, th, clip, lut_scale, f->d_lut);
+  dim3 B(32, 8), G((cols + 31) / 32, (rows + 7) / 8);
+  clahe_apply_kernel<<<G, B, 0, f->st>>>(f->d_src, rows, cols, cols, tiles_x, tiles_y, 1.0f / tw, 1.0f / th, f->d_lut, f->d_dst, cols);
+  cudaEventRecord(f->e1, f->st);
+  cudaMemcpyAsync(f->h_img, f->d_dst, (size_t)rows * cols, cudaMemcpyDeviceToHost, f->st);
+  cudaError_t e = cudaStreamSynchronize(f->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_clahe");
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  for (int y = 0; y < rows; y++) memcpy(dst + (size_t)y * dst_stride, f->h_img + (size_t)y * cols, cols);
+  return VILS_OK;
+}
+
+// FeatureTracker::setMask (:36-69): points in descending track_cnt order; a point survives if its pixel is still unmasked, then blanks a disc
+// of `radius` around itself.  keep_idx receives the surviving indices (in pick order).  The device mask is kept for vils_good_features.
+int vils_set_mask(vils_frontend* f, const float* xy, const int32_t* track_cnt, int32_t n, int32_t radius, int32_t* keep_idx, int32_t* n_keep) {
+  if (!f || n < 0 || n > f->max_pts || (n && (!xy || !track_cnt)) || radius < 0 || radius > 1000 || !keep_idx || !n_keep)
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_set_mask: bad argument");
+  cudaSetDevice(f->device);
+  std::vector<int> hw; disc_half_widths(radius, hw);
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return track_cnt[a] > track_cnt[b]; });
+  std::vector<int> centers; centers.reserve(2 * n);
+  int nk = 0;
+  for (int oi = 0; oi < n; oi++) {
+    const int i = order[oi];
+    const int px = cv_round(xy[2 * i]), py = cv_round(xy[2 * i + 1]);   // mask.at<uchar>(Point2f) / cv::circle(Point2f): saturate_cast<int>
+    bool masked = px < 0 || py < 0 || px >= f->cols || py >= f->rows;   // the reference would read out of bounds; such points are dropped before (inBorder)
+    for (size_t k = 0; !masked && k < centers.size(); k += 2) {
+      const int dx = std::abs(px - centers[k]), dy = std::abs(py - centers[k + 1]);
+      if (dy <= radius && dx <= hw[dy]) masked = true;
+    }
+    if (masked) continue;
+    keep_idx[nk++] = i; centers.push_back(px); centers.push_back(py);
+  }
+  *n_keep = nk;
+  cudaMemsetAsync(f->d_mask, 255, (size_t)f->rows * f->cols, f->st);
+  if (nk) {
+    cudaMemcpyAsync(f->d_centers, centers.data(), sizeof(int) * 2 * nk, cudaMemcpyHostToDevice, f->st);
+    cudaMemcpyAsync(f->d_hw, hw.data(), sizeof(int) * (radius + 1), cudaMemcpyHostToDevice, f->st);
+    mask_discs_kernel<<<nk, 256, 0, f->st>>>(f->d_mask, f->rows, f->cols, f->d_centers, nk, radius, f->d_hw);
+  }
+  cudaError_t e = cudaStreamSynchronize(f->st);   // centers / hw are stack-lifetime host buffers
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_set_mask");
+  f->mask_valid = true;
+  return VILS_OK;
+}
+
+int vils_get_mask(vils_frontend* f, uint8_t* mask, int32_t stride) {
+  if (!f || !mask || stride < f->cols || !f->mask_valid) return vils::fail(VILS_ERR_BAD_ARG, "vils_get_mask: no mask");
+  cudaSetDevice(f->device);
+  cudaMemcpyAsync(f->h_img, f->d_mask, (size_t)f->rows * f->cols, cudaMemcpyDeviceToHost, f->st);
+  cudaError_t e = cudaStreamSynchronize(f->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_get_mask");
+  for (int y = 0; y < f->rows; y++) memcpy(mask + (size_t)y * stride, f->h_img + (size_t)y * f->cols, f->cols);
+  return VILS_OK;
+}
+
+// cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_distance, mask) with the defaults of the call site (:149): blockSize 3,
+// Sobel 3, min-eigenvalue score.  use_mask: 0 = no mask, 1 = the device mask left by vils_set_mask.
+int vils_good_features(vils_frontend* f, const uint8_t* img, int32_t stride, int32_t max_corners, double quality, double min_distance, int32_t use_mask,
+                       float* xy_out, int32_t* n_out) {
+  if (!f || !img || stride < f->cols || !xy_out || !n_out || quality <= 0 || min_distance < 0 || (use_mask && !f->mask_valid))
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_good_features: bad argument");
+  cudaSetDevice(f->device);
+  *n_out = 0;
+  if (max_corners == 0) return VILS_OK;
+  int st = fe_upload(f, img, stride, f->d_src); if (st) return st;
+  const int rows = f->rows, cols = f->cols;
+  const uint8_t* mask = use_mask ? f->d_mask : nullptr;
+  cudaEventRecord(f->e0, f->st);
+  cudaMemsetAsync(f->d_cnt, 0, 2 * sizeof(unsigned int), f->st);
+  min_eig_kernel<<<dim3((cols + ET_X - 1) / ET_X, (rows + ET_Y - 1) / ET_Y), dim3(ET_X, ET_Y), 0, f->st>>>(f->d_src, rows, cols, cols, f->d_eig);
+  masked_max_kernel<<<148 * 2, 256, 0, f->st>>>(f->d_eig, mask, rows * cols, f->d_cnt + 1);
+  candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, f->st>>>(f->d_eig, mask, rows, cols, f->d_cnt + 1, (float)quality, f->d_cand, f->d_cnt,
+                                                                                        f->cand_cap);
+  sort_desc_kernel<<<1, 1024, 0, f->st>>>(f->d_cand, f->d_cnt, f->cand_cap);
+  cudaEventRecord(f->e1, f->st);
+  cudaMemcpyAsync(f->h_cnt, f->d_cnt, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, f->st);
+  cudaError_t e = cudaStreamSynchronize(f->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features");
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  const unsigned int total = std::min(f->h_cnt[0], f->cand_cap);
+  if (total == 0) return VILS_OK;
+  e = cudaMemcpy(f->h_cand, f->d_cand, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features copy");
+  // the greedy minimum-distance pick (featureselect.cpp: grid of cell_size = round(minDistance), 3x3 cell neighbourhood) is sequential by
+  // construction; it runs over at most a few thousand sorted candidates on the host, where the reference has it
+  int n = 0;
+  if (min_distance >= 1) {
+    const int cell = cv_round(min_distance), gw = (cols + cell - 1) / cell, gh = (rows + cell - 1) / cell;
+    std::vector<std::vector<std::pair<int, int>>> grid((size_t)gw * gh);
+    const double md2 = min_distance * min_distance;
+    for (unsigned int i = 0; i < total; i++) {
+      const int ofs = (int)(f->h_cand[i] & 0xffffffffu), y = ofs / cols, x = ofs % cols;
+      const int xc = x / cell, yc = y / cell;
+      const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
+      bool good = true;
+      for (int yy = y1; yy <= y2 && good; yy++)
+        for (int xx = x1; xx <= x2 && good; xx++)
+          for (const auto& p : grid[(size_t)yy * gw + xx]) {
+            const float dx = (float)(x - p.first), dy = (float)(y - p.second);
+            if (dx * dx + dy * dy < md2) { good = false; break; }
+          }
+      if (!good) continue;
+      grid[(size_t)yc * gw + xc].push_back({x, y});
+      xy_out[2 * n] = (float)x; xy_out[2 * n + 1] = (float)y; n++;
+      if (max_corners > 0 && n == max_corners) break;
+    }
+  } else {
+    for (unsigned int i = 0; i < total; i++) {
+      const int ofs = (int)(f->h_cand[i] & 0xffffffffu);
+      xy_out[2 * n] = (float)(ofs % cols); xy_out[2 * n + 1] = (float)(ofs / cols); n++;
+      if (max_corners > 0 && n == max_corners) break;
+    }
+  }
+  *n_out = n;
+  return VILS_OK;
+}
+
+// Device-side min-eigenvalue map of the last vils_good_features call (tests / diagnostics).
+int vils_frontend_get_eig(vils_frontend* f, float* eig) {
+  if (!f || !eig) return vils::fail(VILS_ERR_BAD_ARG, "vils_frontend_get_eig");
+  cudaSetDevice(f->device);
+  cudaError_t e = cudaMemcpy(eig, f->d_eig, sizeof(float) * (size_t)f->rows * f->cols, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_frontend_get_eig");
+}
+
+// PinholeCamera::liftProjective for n pixel positions: rays[3n] = (mx_u, my_u, 1).  cam = {fx, fy, cx, cy, k1, k2, p1, p2}.
+int vils_lift_projective(vils_frontend* f, const double cam[8], const float* uv, int32_t n, double* rays) {
+  if (!f || !cam || n < 0 || n > f->max_pts || (n && (!uv || !rays))) return vils::fail(VILS_ERR_BAD_ARG, "vils_lift_projective: bad argument");
+  if (n == 0) return VILS_OK;
+  cudaSetDevice(f->device);
+  cudaMemcpyAsync(f->d_uv, uv, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, f->st);
+  const int nodist = cam[4] == 0.0 && cam[5] == 0.0 && cam[6] == 0.0 && cam[7] == 0.0;   // m_noDistortion (PinholeCamera.cc:296-306)
+  lift_kernel<<<(n + 127) / 128, 128, 0, f->st>>>(f->d_uv, n, cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6], cam[7], nodist, f->d_ray);
+  cudaMemcpyAsync(rays, f->d_ray, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, f->st);
+  cudaError_t e = cudaStreamSynchronize(f->st);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_lift_projective");
+}
+
+int vils_frontend_last_device_ms(vils_frontend* f, float* ms) { if (!f || !ms) return VILS_ERR_BAD_ARG; *ms = f->last_ms; return VILS_OK; }
+
+}  // extern "C"

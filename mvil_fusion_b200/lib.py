@@ -63,6 +63,16 @@ def load():
     L.vils_klt_track_device.argtypes = [vp]
     L.vils_klt_download.argtypes = [vp, fp, up, fp]
     L.vils_klt_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_frontend_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.vils_frontend_destroy.argtypes = [vp]
+    L.vils_frontend_destroy.restype = None
+    L.vils_clahe.argtypes = [vp, up, C.c_int32, C.c_double, C.c_int32, C.c_int32, up, C.c_int32]
+    L.vils_set_mask.argtypes = [vp, fp, ip, C.c_int32, C.c_int32, ip, ip]
+    L.vils_get_mask.argtypes = [vp, up, C.c_int32]
+    L.vils_good_features.argtypes = [vp, up, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, fp, ip]
+    L.vils_frontend_get_eig.argtypes = [vp, fp]
+    L.vils_lift_projective.argtypes = [vp, dp, fp, C.c_int32, dp]
+    L.vils_frontend_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -295,3 +305,61 @@ class KLT:
         ms = C.c_float()
         self.L.vils_klt_last_device_ms(self.h, C.byref(ms))
         return ms.value
+
+
+class Frontend:
+    """vils_frontend handle: CLAHE, setMask, goodFeaturesToTrack, liftProjective (the rest of FeatureTracker::readImage)."""
+
+    def __init__(self, rows, cols, max_pts=1024, device=0):
+        self.L = load(); self.rows, self.cols, self.max_pts = rows, cols, max_pts
+        self.h = C.c_void_p()
+        _check(self.L.vils_frontend_create(rows, cols, max_pts, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.vils_frontend_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clahe(self, img, clip=3.0, tiles=(8, 8)):
+        img = np.ascontiguousarray(img, np.uint8); out = np.zeros_like(img)
+        _check(self.L.vils_clahe(self.h, img.ctypes.data_as(cabi.c_uint8_p), img.strides[0], clip, tiles[0], tiles[1], out.ctypes.data_as(cabi.c_uint8_p), out.strides[0]))
+        return out
+
+    def set_mask(self, xy, track_cnt, radius):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); tc = np.ascontiguousarray(track_cnt, np.int32)
+        keep = np.zeros(max(len(xy), 1), np.int32); nk = C.c_int32()
+        _check(self.L.vils_set_mask(self.h, xy.ctypes.data_as(cabi.c_float_p), tc.ctypes.data_as(cabi.c_int32_p), len(xy), radius,
+                                    keep.ctypes.data_as(cabi.c_int32_p), C.cast(C.byref(nk), cabi.c_int32_p)))
+        return keep[:nk.value]
+
+    def get_mask(self):
+        m = np.zeros((self.rows, self.cols), np.uint8)
+        _check(self.L.vils_get_mask(self.h, m.ctypes.data_as(cabi.c_uint8_p), m.strides[0]))
+        return m
+
+    def good_features(self, img, max_corners, quality, min_distance, use_mask=False):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros((max(max_corners, 1), 2), np.float32); n = C.c_int32()
+        _check(self.L.vils_good_features(self.h, img.ctypes.data_as(cabi.c_uint8_p), img.strides[0], max_corners, quality, min_distance, int(use_mask),
+                                         out.ctypes.data_as(cabi.c_float_p), C.cast(C.byref(n), cabi.c_int32_p)))
+        return out[:n.value].copy()
+
+    def eig(self):
+        e = np.zeros((self.rows, self.cols), np.float32)
+        _check(self.L.vils_frontend_get_eig(self.h, e.ctypes.data_as(cabi.c_float_p)))
+        return e
+
+    def lift_projective(self, cam, uv):
+        cam = np.ascontiguousarray(cam, np.float64); uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        rays = np.zeros((len(uv), 3))
+        _check(self.L.vils_lift_projective(self.h, _d(cam), uv.ctypes.data_as(cabi.c_float_p), len(uv), _d(rays)))
+        return rays
+
+    @property
+    def last_ms(self):
+        ms = C.c_float(); self.L.vils_frontend_last_device_ms(self.h, C.byref(ms)); return ms.value

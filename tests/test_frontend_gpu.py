@@ -1,0 +1,138 @@
+"""The rest of FeatureTracker::readImage around the LK call (feature_tracker_/src/feature_tracker.cpp:81-167) on the GPU, against the very
+functions the reference calls: cv2.createCLAHE(3.0, (8, 8)), cv2.circle-based setMask, cv2.goodFeaturesToTrack(img, N, 0.01, 30, mask)
+(OpenCV 4.13.0), and a numpy restatement of PinholeCamera::liftProjective (camera_model/src/camera_models/PinholeCamera.cc:450-510,646-662).
+Bars: CLAHE and the mask bit-exact; corners identical to OpenCV's list up to score ties (>= 97 % identical positions, same order on the
+common prefix); min-eigenvalue map within 1e-6 of its maximum; lifted rays within 1e-14."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+CAM = np.array([356.37000498, 354.92225534, 326.87903275, 250.93806883, -0.29326213, 0.07505211, 0.0002761, -0.00026777])   # config/mynteye_leishen_indoor.yaml:13-22
+
+
+def texture(seed, rows=480, cols=640):
+    rng = np.random.default_rng(seed)
+    img = cv2.GaussianBlur(rng.uniform(0, 255, (rows, cols)).astype(np.float32), (0, 0), 2.0)
+    return cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+
+
+def lift_oracle(cam, uv):
+    """PinholeCamera::liftProjective, recursive distortion model (n = 8), FP64."""
+    fx, fy, cx, cy, k1, k2, p1, p2 = cam
+    out = np.zeros((len(uv), 3))
+    for i, (u, v) in enumerate(np.asarray(uv, np.float64)):
+        mx_d = (1.0 / fx) * u + (-cx / fx); my_d = (1.0 / fy) * v + (-cy / fy)
+        ux, uy = mx_d, my_d
+        for _ in range(8):
+            mx2, my2, mxy = ux * ux, uy * uy, ux * uy
+            rho2 = mx2 + my2; rad = k1 * rho2 + k2 * rho2 * rho2
+            dux = ux * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2); duy = uy * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2)
+            ux, uy = mx_d - dux, my_d - duy
+        out[i] = (ux, uy, 1.0)
+    return out
+
+
+@pytest.mark.parametrize("seed,shape", [(1, (480, 640)), (2, (480, 640)), (3, (240, 320)), (4, (100, 150))])
+def test_clahe_bit_exact(seed, shape):
+    from mvil_fusion_b200 import lib
+    img = texture(seed, *shape)
+    if seed == 2:
+        img = (img // 3 + 40).astype(np.uint8)     # low-contrast input: heavy clipping / redistribution
+    ref = cv2.createCLAHE(3.0, (8, 8)).apply(img)
+    f = lib.Frontend(*shape)
+    out = f.clahe(img, 3.0, (8, 8))
+    assert np.array_equal(out, ref), np.abs(out.astype(int) - ref.astype(int)).max()
+    f.close()
+
+
+def test_lift_projective_matches_reference_formula():
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(7)
+    uv = np.stack([rng.uniform(0, 640, 300), rng.uniform(0, 480, 300)], 1).astype(np.float32)
+    f = lib.Frontend(480, 640, 512)
+    rays = f.lift_projective(CAM, uv)
+    ref = lift_oracle(CAM, uv)
+    assert np.abs(rays - ref).max() <= 1e-14
+    # independent check: OpenCV's iterative undistortPoints agrees near the centre (it iterates differently, so only ~1e-6)
+    K = np.array([[CAM[0], 0, CAM[2]], [0, CAM[1], CAM[3]], [0, 0, 1]])
+    und = cv2.undistortPoints(uv.reshape(-1, 1, 2).astype(np.float64), K, CAM[4:8]).reshape(-1, 2)
+    central = np.hypot(uv[:, 0] - CAM[2], uv[:, 1] - CAM[3]) < 150
+    assert np.abs(rays[central, :2] - und[central]).max() < 1e-4
+    nod = f.lift_projective(np.r_[CAM[:4], 0, 0, 0, 0], uv)
+    assert np.allclose(nod[:, 0], (uv[:, 0].astype(np.float64) - CAM[2]) / CAM[0], atol=1e-14)
+    assert f.lift_projective(CAM, np.zeros((0, 2), np.float32)).shape == (0, 3)
+    f.close()
+
+
+def ref_set_mask(pts, cnt, rows, cols, radius):
+    """FeatureTracker::setMask (:36-69) with cv2.circle; ties in track_cnt keep input order (std::sort leaves them unspecified)."""
+    mask = np.full((rows, cols), 255, np.uint8)
+    order = sorted(range(len(pts)), key=lambda i: -cnt[i])
+    keep = []
+    for i in order:
+        px, py = int(np.rint(pts[i][0])), int(np.rint(pts[i][1]))
+        if mask[py, px] == 255:
+            keep.append(i)
+            cv2.circle(mask, (px, py), radius, 0, -1)
+    return keep, mask
+
+
+@pytest.mark.parametrize("radius", [30, 7, 1])
+def test_set_mask_matches_cv_circle(radius):
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(11)
+    pts = np.stack([rng.uniform(1, 638, 200), rng.uniform(1, 478, 200)], 1).astype(np.float32)
+    pts[:6] = [[1.2, 1.4], [638.4, 477.6], [320.5, 240.5], [321.5, 241.5], [5.0, 470.0], [630.0, 3.0]]
+    cnt = rng.integers(1, 30, 200).astype(np.int32)
+    f = lib.Frontend(480, 640, 512)
+    keep = f.set_mask(pts, cnt, radius)
+    kref, mref = ref_set_mask(pts, cnt, 480, 640, radius)
+    assert list(keep) == kref
+    assert np.array_equal(f.get_mask(), mref)
+    f.close()
+
+
+@pytest.mark.parametrize("seed,with_mask", [(1, False), (2, True), (3, False), (5, True)])
+def test_good_features_matches_opencv(seed, with_mask):
+    from mvil_fusion_b200 import lib
+    img = cv2.createCLAHE(3.0, (8, 8)).apply(texture(seed))
+    f = lib.Frontend(480, 640, 512)
+    mask = None
+    if with_mask:
+        rng = np.random.default_rng(seed)
+        old = np.stack([rng.uniform(5, 634, 60), rng.uniform(5, 474, 60)], 1).astype(np.float32)
+        keep = f.set_mask(old, np.ones(60, np.int32), 30)
+        _, mask = ref_set_mask(old, np.ones(60, np.int32), 480, 640, 30)
+        assert len(keep) > 20
+    ref = cv2.goodFeaturesToTrack(img, 150, 0.01, 30, mask=mask)
+    ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+    out = f.good_features(img, 150, 0.01, 30.0, use_mask=with_mask)
+    eref = cv2.cornerMinEigenVal(img, 3, ksize=3)
+    e = f.eig()
+    assert np.abs(e - eref).max() <= 1e-6 * eref.max()      # same formula; OpenCV's SIMD summation order of the 3x3 box differs in the last bits (cancellation in a+c-sqrt)
+    sref = {tuple(p) for p in ref.astype(int)}; sout = {tuple(p) for p in out.astype(int)}
+    assert len(out) >= 0.97 * len(ref) and len(sref & sout) >= 0.97 * len(sref), (len(ref), len(out), len(sref & sout))
+    assert (out == np.floor(out)).all()
+    # pairwise minimum distance and mask are honoured exactly
+    d = np.linalg.norm(out[:, None] - out[None], axis=2) + 1e9 * np.eye(len(out))
+    assert d.min() >= 30.0
+    if with_mask:
+        assert all(mask[int(y), int(x)] == 255 for x, y in out)
+    # the strongest corners come out in OpenCV's order
+    k = min(20, len(ref), len(out))
+    assert np.array_equal(out[:k], ref[:k])
+    f.close()
+
+
+def test_good_features_small_and_flat():
+    from mvil_fusion_b200 import lib
+    f = lib.Frontend(64, 80, 64)
+    flat = np.full((64, 80), 77, np.uint8)
+    assert len(f.good_features(flat, 10, 0.01, 5.0)) == 0
+    img = texture(9, 64, 80)
+    ref = cv2.goodFeaturesToTrack(img, 10, 0.01, 5).reshape(-1, 2)
+    out = f.good_features(img, 10, 0.01, 5.0)
+    assert len({tuple(p) for p in ref.astype(int)} & {tuple(p) for p in out.astype(int)}) >= len(ref) - 1
+    f.close()

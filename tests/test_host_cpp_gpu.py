@@ -38,6 +38,9 @@ def host():
     H.vh_tracker_add.argtypes = [C.c_void_p, cabi.c_float_p, C.c_int]; H.vh_tracker_add.restype = None
     H.vh_tracker_read.argtypes = [C.c_void_p, cabi.c_uint8_p, C.c_int, C.c_double]
     H.vh_tracker_get.argtypes = [C.c_void_p, cabi.c_float_p, cabi.c_int32_p, cabi.c_int32_p, C.c_int]
+    H.vh_tracker_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, cabi.c_double_p]; H.vh_tracker_config.restype = None
+    H.vh_tracker_update_ids.argtypes = [C.c_void_p]; H.vh_tracker_update_ids.restype = None
+    H.vh_tracker_get_un.argtypes = [C.c_void_p, cabi.c_float_p, cabi.c_float_p, C.c_int]
     H.vh_transform_to_end.argtypes = [cabi.c_float_p, C.c_int, cabi.c_float_p, cabi.c_float_p, C.c_float, C.c_double, C.c_double]
     return H
 
@@ -143,3 +146,76 @@ def test_feature_tracker_cpp_and_transform_to_end(host):
     got = cloud.copy()
     assert host.vh_transform_to_end(got.ctypes.data_as(cabi.c_float_p), 500, q.ctypes.data_as(cabi.c_float_p), t.ctypes.data_as(cabi.c_float_p), 10.0, 0.5, 70.0) == 0
     assert np.allclose(got, exp, rtol=2e-6, atol=1e-6, equal_nan=True)
+
+
+def test_feature_tracker_full_read_image_sequence(host):
+    """vils::FeatureTracker::readImage with EQUALIZE + PUB_THIS_FRAME over a 4-frame sequence against an emulation of
+    feature_tracker.cpp:81-167 built from the OpenCV calls the reference makes (CLAHE, calcOpticalFlowPyrLK, circle mask,
+    goodFeaturesToTrack) and the liftProjective restatement; rejectWithF is left out on both sides."""
+    cv2 = pytest.importorskip("cv2")
+    from test_frontend_gpu import texture, ref_set_mask, lift_oracle, CAM
+    rows, cols, MAX_CNT, MIN_DIST = 480, 640, 150, 30
+    base = texture(21)
+    frames = []
+    for k in range(4):
+        M = cv2.getRotationMatrix2D((cols / 2, rows / 2), 0.4 * k, 1.0); M[:, 2] += (3.7 * k, -2.1 * k)
+        frames.append(cv2.warpAffine(base, M, (cols, rows), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101))
+    # ---- emulation of the reference
+    clahe = cv2.createCLAHE(3.0, (8, 8))
+    st = dict(cur_img=None, cur_pts=np.zeros((0, 2), np.float32), ids=[], cnt=[], prev_map={}, n_id=0, t=0.0)
+    ref_out = []
+    for k, raw in enumerate(frames):
+        t = 0.1 * k
+        img = clahe.apply(raw)
+        forw = np.zeros((0, 2), np.float32)
+        if len(st["cur_pts"]):
+            f2, status, _ = cv2.calcOpticalFlowPyrLK(st["cur_img"], img, st["cur_pts"].reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+            f2 = f2.reshape(-1, 2); status = status.reshape(-1).astype(bool)
+            inb = (np.rint(f2[:, 0]) >= 1) & (np.rint(f2[:, 0]) < cols - 1) & (np.rint(f2[:, 1]) >= 1) & (np.rint(f2[:, 1]) < rows - 1)
+            keep = status & inb
+            forw = f2[keep]; st["ids"] = [i for i, k2 in zip(st["ids"], keep) if k2]; st["cnt"] = [c for c, k2 in zip(st["cnt"], keep) if k2]
+        st["cnt"] = [c + 1 for c in st["cnt"]]
+        kept, mask = ref_set_mask(forw, st["cnt"], rows, cols, MIN_DIST)
+        forw = forw[kept] if len(kept) else np.zeros((0, 2), np.float32)
+        st["ids"] = [st["ids"][i] for i in kept]; st["cnt"] = [st["cnt"][i] for i in kept]
+        n_max = MAX_CNT - len(forw)
+        if n_max > 0:
+            npts = cv2.goodFeaturesToTrack(img, n_max, 0.01, MIN_DIST, mask=mask)
+            npts = np.zeros((0, 2), np.float32) if npts is None else npts.reshape(-1, 2)
+            forw = np.concatenate([forw, npts]).astype(np.float32); st["ids"] += [-1] * len(npts); st["cnt"] += [1] * len(npts)
+        un = lift_oracle(CAM, forw)[:, :2].astype(np.float32) if len(forw) else np.zeros((0, 2), np.float32)
+        vel = np.zeros_like(un)
+        if st["prev_map"]:
+            for i, fid in enumerate(st["ids"]):
+                if fid != -1 and fid in st["prev_map"]:
+                    vel[i] = ((un[i].astype(np.float64) - st["prev_map"][fid]) / (t - st["t"])).astype(np.float32)
+        cur_map = {}
+        for i, fid in enumerate(st["ids"]):
+            cur_map.setdefault(fid, un[i].astype(np.float64))
+        st.update(cur_img=img, cur_pts=forw, prev_map=cur_map, t=t)
+        for i in range(len(st["ids"])):                      # updateID loop of feature_tracker_node.cpp:120-128
+            if st["ids"][i] == -1:
+                st["ids"][i] = st["n_id"]; st["n_id"] += 1
+        ref_out.append((forw.copy(), list(st["ids"]), list(st["cnt"]), un.copy(), vel.copy()))
+    # ---- the C++ host mirror
+    ft = host.vh_tracker_create(rows, cols, MAX_CNT, 0)
+    host.vh_tracker_config(ft, 1, 1, MIN_DIST, d(CAM))
+    for k, raw in enumerate(frames):
+        assert host.vh_tracker_read(ft, np.ascontiguousarray(raw).ctypes.data_as(cabi.c_uint8_p), cols, 0.1 * k) == 0
+        xy = np.zeros((400, 2), np.float32); ids = np.zeros(400, np.int32); cnt = np.zeros(400, np.int32); un = np.zeros((400, 2), np.float32); vel = np.zeros((400, 2), np.float32)
+        host.vh_tracker_update_ids(ft)
+        n = host.vh_tracker_get(ft, xy.ctypes.data_as(cabi.c_float_p), ids.ctypes.data_as(cabi.c_int32_p), cnt.ctypes.data_as(cabi.c_int32_p), 400)
+        assert host.vh_tracker_get_un(ft, un.ctypes.data_as(cabi.c_float_p), vel.ctypes.data_as(cabi.c_float_p), 400) == n
+        rxy, rids, rcnt, run, rvel = ref_out[k]
+        assert abs(n - len(rxy)) <= 2, (k, n, len(rxy))
+        got = {int(i): j for j, i in enumerate(ids[:n])}
+        common = [(j, got[i]) for j, i in enumerate(rids) if i in got]
+        assert len(common) >= 0.97 * len(rids), (k, len(common), len(rids))
+        jr = np.array([a for a, _ in common]); jg = np.array([b for _, b in common])
+        assert np.abs(xy[jg] - rxy[jr]).max() <= 0.05, k
+        assert np.array_equal(cnt[jg], np.array(rcnt)[jr]), k
+        assert np.abs(un[jg] - run[jr]).max() <= 2e-4, k
+        if k > 0:
+            assert np.abs(vel[jg] - rvel[jr]).max() <= 5e-3, k       # 0.05 px / 356 px focal / 0.1 s
+            assert (cnt[:n] > 1).sum() > 100                        # the sequence really is being tracked
+    host.vh_tracker_destroy(ft)
