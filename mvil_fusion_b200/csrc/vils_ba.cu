@@ -537,7 +537,13 @@ __global__ void __launch_bounds__(EV_T, MINB) eval_proj_kernel(EvalParams Q, int
 // lanes assemble the 15 x 30 Jacobian through the table and whiten it; the rows then leave as coalesced stores.
 // Latency-bound and tiny (9 per window, 7 % of the bytes): launched ahead of the streaming kernels.
 constexpr int EVI_WARPS = 2;
-__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q, int nimu_max, int n) {
+__device__ void eval_prior_row(const EvalParams& Q, int slot, int row);
+__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q, int nimu_max, int n, int imu_blocks, int prior_bpw) {
+  if ((int)blockIdx.x >= imu_blocks) {   // CTAs past the IMU factors: prior residual rows, prior_bpw CTAs per window
+    const int b = blockIdx.x - imu_blocks;
+    eval_prior_row(Q, Q.S.slot0 + b / prior_bpw, (b % prior_bpw) * 32 * EVI_WARPS + threadIdx.x);
+    return;
+  }
   __shared__ double sJ[EVI_WARPS][IMU_SLOT];
   __shared__ double sx[EVI_WARPS][32];
   __shared__ uint16_t stbl[450];
@@ -570,67 +576,67 @@ __global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams 
   for (int e = lane; e < 450; e += 32) Jo[(size_t)450 * k + e] = J[e];
 }
 
-// LiDAR plane + edge factors (keyframe-sorted order): blockIdx.x < plane chunks -> planes, else edges.
-__global__ void __launch_bounds__(EV_T) eval_lidar_kernel(EvalParams Q, int plane_chunks) {
+// LiDAR plane and edge factors (keyframe-sorted order), one thread per factor, results staged per warp in shared memory and
+// written as contiguous 16-byte stores.  EDGE = false: LidarPlaneNormFactor (1 + 1x6), 7 KB of staging per CTA so that the SM
+// runs at full occupancy; EDGE = true: LidarEdgeFactor (3 + 3x6).
+template <bool EDGE>
+__global__ void __launch_bounds__(EV_T, EDGE ? 6 : 8) eval_lidar_kernel(EvalParams Q) {
   extern __shared__ __align__(16) double st[];
+  constexpr int LD = EDGE ? EV_ELD : EV_LLD, NJ = EDGE ? 18 : 6;
   const SolveParams& P = Q.S;
   const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
   const WinHdr* h = W.h;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = EDGE ? h->n_edge : h->n_plane, fw = blockIdx.x * EV_T + 32 * warp, f = fw + lane;   // fw: first factor of this warp
+  if (fw >= n) return;
   const double* x = W.d(OFF_X);
-  const int t = threadIdx.x;
-  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * h->n_imu + 2 * (size_t)h->n_proj;
-  double* Jo = Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * h->n_imu + (size_t)40 * h->n_proj;
-  if ((int)blockIdx.x < plane_chunks) {
-    const int n = h->n_plane, fbase = blockIdx.x * EV_T, f = fbase + t;
-    if (fbase >= n) return;
-    if (f < n) {
-      const double* pl = W.d(OFF_PLANE); const int32_t* ix = W.i(OFF_PLANE_IDX);
+  double* R = Q.r_out + (size_t)slot * Q.r_stride + 15 * h->n_imu + 2 * (size_t)h->n_proj + (EDGE ? h->n_plane : 0);
+  double* Jo = Q.J_out + (size_t)slot * Q.J_stride + (size_t)450 * h->n_imu + (size_t)40 * h->n_proj + (EDGE ? (size_t)6 * h->n_plane : 0);
+  double* rows = st + (size_t)(32 * warp) * LD;
+  if (f < n) {
+    const double* c = W.d(EDGE ? OFF_EDGE : OFF_PLANE); const int32_t* ix = W.i(EDGE ? OFF_EDGE_IDX : OFF_PLANE_IDX);
+    double* o = rows + lane * LD;
+    if (!EDGE) {
       double J[6];
-      double r = vf::plane_eval(x + XP(ix[f]), vm::mk(pl[f], pl[(size_t)n + f], pl[(size_t)2 * n + f]),
-                                vm::mk(pl[(size_t)3 * n + f], pl[(size_t)4 * n + f], pl[(size_t)5 * n + f]), pl[(size_t)6 * n + f], J);
+      const double r = vf::plane_eval(x + XP(ix[f]), vm::mk(c[f], c[(size_t)n + f], c[(size_t)2 * n + f]),
+                                      vm::mk(c[(size_t)3 * n + f], c[(size_t)4 * n + f], c[(size_t)5 * n + f]), c[(size_t)6 * n + f], J);
       double w = 1.0;
       if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r * r, rho, w); }
       R[f] = r * w;
 #pragma unroll
-      for (int e = 0; e < 6; e++) st[t * EV_LLD + e] = J[e] * w;
-    }
-    __syncthreads();
-    const int cnt = min(EV_T, n - fbase);
-    for (int e = t; e < cnt * 6; e += EV_T) Jo[(size_t)6 * fbase + e] = st[(e / 6) * EV_LLD + e % 6];
-  } else {
-    const int n = h->n_edge, fbase = (blockIdx.x - plane_chunks) * EV_T, f = fbase + t;
-    if (fbase >= n) return;
-    R += h->n_plane; Jo += (size_t)6 * h->n_plane;
-    if (f < n) {
-      const double* ed = W.d(OFF_EDGE); const int32_t* ix = W.i(OFF_EDGE_IDX);
+      for (int e = 0; e < 6; e++) o[e] = J[e] * w;
+    } else {
       double r[3], J[18];
-      vf::edge_eval(x + XP(ix[f]), vm::mk(ed[f], ed[(size_t)n + f], ed[(size_t)2 * n + f]),
-                    vm::mk(ed[(size_t)3 * n + f], ed[(size_t)4 * n + f], ed[(size_t)5 * n + f]),
-                    vm::mk(ed[(size_t)6 * n + f], ed[(size_t)7 * n + f], ed[(size_t)8 * n + f]), r, J);
+      vf::edge_eval(x + XP(ix[f]), vm::mk(c[f], c[(size_t)n + f], c[(size_t)2 * n + f]),
+                    vm::mk(c[(size_t)3 * n + f], c[(size_t)4 * n + f], c[(size_t)5 * n + f]),
+                    vm::mk(c[(size_t)6 * n + f], c[(size_t)7 * n + f], c[(size_t)8 * n + f]), r, J);
       double w = 1.0;
       if (Q.apply_loss) { double rho; vf::huber(P.cfg.huber_a, r[0] * r[0] + r[1] * r[1] + r[2] * r[2], rho, w); }
-      double* o = st + t * EV_ELD;
 #pragma unroll
-      for (int e = 0; e < 3; e++) o[e] = r[e] * w;
+      for (int e = 0; e < 18; e++) o[e] = J[e] * w;
 #pragma unroll
-      for (int e = 0; e < 18; e++) o[3 + e] = J[e] * w;
+      for (int e = 0; e < 3; e++) o[18 + e] = r[e] * w;
     }
-    __syncthreads();
-    const int cnt = min(EV_T, n - fbase);
-    for (int e = t; e < cnt * 3; e += EV_T) R[(size_t)3 * fbase + e] = st[(e / 3) * EV_ELD + e % 3];
-    for (int e = t; e < cnt * 18; e += EV_T) Jo[(size_t)18 * fbase + e] = st[(e / 18) * EV_ELD + 3 + e % 18];
+  }
+  __syncwarp();
+  const int cnt = min(32, n - fw);
+  if (EDGE) for (int e = lane; e < cnt * 3; e += 32) R[(size_t)3 * fw + e] = rows[(e / 3) * LD + 18 + e % 3];
+  double2* J2 = reinterpret_cast<double2*>(Jo + (size_t)NJ * fw);     // 16-byte aligned: every term of the offset is even
+  for (int e = lane; e < cnt * (NJ / 2); e += 32) {
+    const int fr = e / (NJ / 2), c2 = e - fr * (NJ / 2);
+    const double* sp = rows + fr * LD + 2 * c2;
+    J2[e] = make_double2(sp[0], sp[1]);
   }
 }
 
-// MarginalizationFactor residual rows (marginalization_factor.cpp:364-383): one thread per row.
-constexpr int EVS_T = 128;
-__global__ void __launch_bounds__(EVS_T) eval_prior_kernel(EvalParams Q) {
+// MarginalizationFactor residual rows (marginalization_factor.cpp:364-383): one thread per row.  Runs as extra CTAs of the IMU
+// launch (both are tiny and latency-bound; a launch of its own would cost more than the work).
+__device__ void eval_prior_row(const EvalParams& Q, int slot, int row) {
   const SolveParams& P = Q.S;
-  const int slot = P.slot0 + blockIdx.y;
   const Win W = decode(P, slot);
   const WinHdr* h = W.h;
-  const int row = blockIdx.x * EVS_T + threadIdx.x, n = h->prior_n, N = W.N;
+  const int n = h->prior_n, N = W.N;
   if (row >= n) return;
   const double* x = W.d(OFF_X);
   double* R = Q.r_out + (size_t)slot * Q.r_stride;
@@ -1144,8 +1150,9 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   // Two streams: the latency-bound IMU warps and then the persistent projection kernel on one, the streaming LiDAR / prior /
   // constraint kernels on the other.
   cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
-  if (nimu) {
-    eval_imu_kernel<<<(nimu * n + EVI_WARPS - 1) / EVI_WARPS, 32 * EVI_WARPS, 0, ba->stream>>>(Q, nimu, n); launches++;
+  if (nimu || nprior) {
+    const int ib = (nimu * n + EVI_WARPS - 1) / EVI_WARPS, pbw = (nprior + 32 * EVI_WARPS - 1) / (32 * EVI_WARPS);
+    eval_imu_kernel<<<ib + pbw * n, 32 * EVI_WARPS, 0, ba->stream>>>(Q, std::max(nimu, 1), n, ib, std::max(pbw, 1)); launches++;
   }
   const int pb = (np + EV_T - 1) / EV_T;
   if (pb) {
@@ -1156,8 +1163,8 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
     launches++;
   }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
-  if (pc + ec) { eval_lidar_kernel<<<dim3(pc + ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q, pc); launches++; }
-  if (nprior) { eval_prior_kernel<<<dim3((nprior + EVS_T - 1) / EVS_T, n), EVS_T, 0, ba->stream2>>>(Q); launches++; }
+  if (pc) { eval_lidar_kernel<false><<<dim3(pc, n), EV_T, EV_T * EV_LLD * 8, ba->stream2>>>(Q); launches++; }
+  if (ec) { eval_lidar_kernel<true><<<dim3(ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q); launches++; }
   if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
   cudaEventRecord(ba->ev_join, ba->stream2);
   cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
