@@ -298,6 +298,10 @@ int vils_frontend_get_eig(vils_frontend* f, float* eig /* rows x cols */);
  * n pixel positions; cam = {fx, fy, cx, cy, k1, k2, p1, p2}; rays = n x 3 (mx_u, my_u, 1) — what undistortedPoints() (:258-306) and
  * rejectWithF() (:169-202) consume. */
 int vils_lift_projective(vils_frontend* f, const double cam[8], const float* uv, int32_t n, double* rays);
+/* cv::findFundamentalMat(pts1, pts2, cv::FM_RANSAC, threshold, 0.99, status) as called by rejectWithF (:169-202) on the virtual-pinhole
+ * points (FOCAL_LENGTH * ray + (COL/2, ROW/2)).  Deterministic 1024-hypothesis RANSAC, OpenCV's symmetric epipolar distance.
+ * F (may be NULL): the winning fundamental matrix, row-major. */
+int vils_reject_with_f(vils_frontend* f, const float* pts1, const float* pts2, int32_t n, double threshold, uint8_t* status, double* F);
 int vils_frontend_last_device_ms(vils_frontend* f, float* ms);
 
 /* ---- LiDAR: PointProcessor::PointToRing stamp (lidar_compensator/src/PointProcessor.cc:127-341)

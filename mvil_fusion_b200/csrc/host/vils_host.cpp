@@ -328,7 +328,8 @@ void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
     forw_pts = cur_pts;
   }
   if (PUB_THIS_FRAME) {
-    // rejectWithF() (:131) is not built, see the class comment.  setMask (:36-69): long-tracked points first, MIN_DIST discs
+    if (REJECT_WITH_F && has_img_) { rejectWithF(forw_pts); if (last_status != VILS_OK) return; }   // :131
+    // setMask (:36-69): long-tracked points first, MIN_DIST discs
     const int n = (int)forw_pts.size();
     std::vector<int32_t> keep(std::max(n, 1)), cnt32(track_cnt.begin(), track_cnt.end()); int32_t nk = 0;
     last_status = vils_set_mask(fe_, n ? &forw_pts[0][0] : nullptr, cnt32.data(), n, MIN_DIST, keep.data(), &nk);
@@ -348,6 +349,25 @@ void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
   cur_img_.swap(forw_img);                                                   // prev = cur, cur = forw (:160-164)
   has_img_ = true;
   undistortedPoints();
+}
+void FeatureTracker::rejectWithF(std::vector<std::array<float, 2>>& forw_pts) {
+  const int n = (int)forw_pts.size();
+  if (n < 8 || (int)prev_pts.size() != n) return;                            // :171 (prev_pts here = the reference's cur_pts after reduceVector)
+  std::vector<double> r1(3 * (size_t)n), r2(3 * (size_t)n);
+  last_status = vils_lift_projective(fe_, cam, &prev_pts[0][0], n, r1.data());
+  if (last_status == VILS_OK) last_status = vils_lift_projective(fe_, cam, &forw_pts[0][0], n, r2.data());
+  if (last_status != VILS_OK) return;
+  std::vector<std::array<float, 2>> u1(n), u2(n);
+  for (int i = 0; i < n; i++) {                                               // :176-188 virtual pinhole with FOCAL_LENGTH
+    u1[i] = {(float)(FOCAL_LENGTH * r1[3 * i] / r1[3 * i + 2] + cols_ / 2.0), (float)(FOCAL_LENGTH * r1[3 * i + 1] / r1[3 * i + 2] + rows_ / 2.0)};
+    u2[i] = {(float)(FOCAL_LENGTH * r2[3 * i] / r2[3 * i + 2] + cols_ / 2.0), (float)(FOCAL_LENGTH * r2[3 * i + 1] / r2[3 * i + 2] + rows_ / 2.0)};
+  }
+  std::vector<uint8_t> status(n);
+  last_status = vils_reject_with_f(fe_, &u1[0][0], &u2[0][0], n, F_THRESHOLD, status.data(), nullptr);
+  if (last_status != VILS_OK) return;
+  size_t j = 0;                                                               // reduceVector x6 (:193-198)
+  for (int i = 0; i < n; i++) if (status[i]) { prev_pts[j] = prev_pts[i]; forw_pts[j] = forw_pts[i]; ids[j] = ids[i]; track_cnt[j] = track_cnt[i]; j++; }
+  prev_pts.resize(j); forw_pts.resize(j); ids.resize(j); track_cnt.resize(j);
 }
 void FeatureTracker::undistortedPoints() {
   const int n = (int)cur_pts.size();
@@ -418,7 +438,7 @@ int vh_tracker_get(void* p, float* xy, int* ids, int* cnt, int cap) {
   return n;
 }
 void vh_tracker_config(void* p, int equalize, int pub, int min_dist, const double* cam) {
-  auto* f = static_cast<vils::FeatureTracker*>(p); f->EQUALIZE = equalize != 0; f->PUB_THIS_FRAME = pub != 0; f->MIN_DIST = min_dist;
+  auto* f = static_cast<vils::FeatureTracker*>(p); f->EQUALIZE = equalize != 0; f->PUB_THIS_FRAME = (pub & 1) != 0; f->REJECT_WITH_F = (pub & 2) != 0; f->MIN_DIST = min_dist;
   if (cam) for (int k = 0; k < 8; k++) f->cam[k] = cam[k];
 }
 void vh_tracker_update_ids(void* p) { auto* f = static_cast<vils::FeatureTracker*>(p); for (unsigned int i = 0; f->updateID(i); i++) {} }   // feature_tracker_node.cpp:120-128

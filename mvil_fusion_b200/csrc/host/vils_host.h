@@ -99,7 +99,7 @@ class Estimator {
 // feature_tracker_/src/feature_tracker.{h,cpp}.  readImage = CLAHE (EQUALIZE) -> calcOpticalFlowPyrLK -> border check / reduceVector ->
 // [PUB_THIS_FRAME: setMask -> goodFeaturesToTrack -> addPoints] -> undistortedPoints (liftProjective + velocities), every image-sized or
 // per-point step on the device through the C-ABI (vils_clahe / vils_klt_* / vils_set_mask / vils_good_features / vils_lift_projective).
-// Not built: rejectWithF (cv::findFundamentalMat RANSAC, :169-202) — the outlier gate is left to the caller.
+// rejectWithF (:169-202) runs on the device as well (vils_reject_with_f: deterministic RANSAC, OpenCV's epipolar distance).
 class FeatureTracker {
  public:
   FeatureTracker(int rows, int cols, int max_cnt = 150, int device = 0);
@@ -109,6 +109,9 @@ class FeatureTracker {
   void addPoints(const float* xy, int n);
   bool updateID(unsigned int i);                            // feature_tracker.cpp:204-214
   void undistortedPoints();                                 // :258-306
+  void rejectWithF(std::vector<std::array<float, 2>>& forw_pts);   // :169-202
+  double FOCAL_LENGTH = 460.0, F_THRESHOLD = 1.0;            // parameters.h:11, yaml F_threshold
+  bool REJECT_WITH_F = true;
   // parameters.h / config yaml of the reference
   bool EQUALIZE = false, PUB_THIS_FRAME = false;
   int MIN_DIST = 30;

@@ -218,6 +218,95 @@ __global__ void lift_kernel(const float* __restrict__ uv, int n, double fx, doub
   out[3 * i] = mx_u; out[3 * i + 1] = my_u; out[3 * i + 2] = 1.0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// rejectWithF (feature_tracker.cpp:169-202): cv::findFundamentalMat(un_cur, un_forw, FM_RANSAC, F_THRESHOLD, 0.99, status).
+// RANSAC with ONE THREAD PER HYPOTHESIS (1024 = OpenCV's maxIters rounded up, no early exit so the result is deterministic):
+// 8 distinct correspondences -> normalised 8-point system (Hartley normalisation from all points) -> null vector by full-pivot
+// Gauss-Jordan -> F in pixel units -> inlier count with OpenCV's symmetric epipolar distance (fundam.cpp computeError:
+// max(d(x2, F x1)^2, d(x1, F^T x2)^2) <= threshold^2).  The best hypothesis classifies the points.  OpenCV draws 7-point samples from
+// its own RNG, so the masks agree on clear inliers / outliers, not bit for bit (see tests).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int RANSAC_H = 1024;
+__device__ __forceinline__ unsigned int rng_next(unsigned int& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+__device__ __forceinline__ double epi_err(const double* F, double x1, double y1, double x2, double y2) {
+  const double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1.0 / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+  const double a2 = F[0] * x2 + F[3] * y2 + F[6], b2 = F[1] * x2 + F[4] * y2 + F[7], c2 = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1.0 / (a2 * a2 + b2 * b2), d1 = x1 * a2 + y1 * b2 + c2;
+  return fmax(d1 * d1 * s1, d2 * d2 * s2);
+}
+__global__ void __launch_bounds__(RANSAC_H) ransac_f_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int n, double thresh2, unsigned int seed,
+                                                            uint8_t* __restrict__ status, int* __restrict__ info, double* __restrict__ F_out) {
+  extern __shared__ double sm[];                 // x1[n] y1[n] x2[n] y2[n]
+  __shared__ double nrm[6];                      // cx1 cy1 s1 cx2 cy2 s2
+  __shared__ int cnt[RANSAC_H];
+  __shared__ double Fbest[9];
+  double* X1 = sm; double* Y1 = sm + n; double* X2 = sm + 2 * n; double* Y2 = sm + 3 * n;
+  const int t = threadIdx.x;
+  for (int i = t; i < n; i += RANSAC_H) { X1[i] = p1[2 * i]; Y1[i] = p1[2 * i + 1]; X2[i] = p2[2 * i]; Y2[i] = p2[2 * i + 1]; }
+  __syncthreads();
+  if (t < 2) {                                   // Hartley normalisation: centroid, mean distance sqrt(2)
+    const double* X = t ? X2 : X1; const double* Y = t ? Y2 : Y1;
+    double cx = 0, cy = 0;
+    for (int i = 0; i < n; i++) { cx += X[i]; cy += Y[i]; }
+    cx /= n; cy /= n;
+    double d = 0;
+    for (int i = 0; i < n; i++) d += sqrt((X[i] - cx) * (X[i] - cx) + (Y[i] - cy) * (Y[i] - cy));
+    nrm[3 * t] = cx; nrm[3 * t + 1] = cy; nrm[3 * t + 2] = d > 0 ? sqrt(2.0) * n / d : 1.0;
+  }
+  __syncthreads();
+  // ---- hypothesis t
+  int my = 0; double F[9];
+  {
+    unsigned int s = seed * 2654435761u + 0x9e3779b9u * (t + 1); rng_next(s); rng_next(s);
+    int idx[8];
+    for (int k = 0; k < 8; k++) {
+      int c; bool dup;
+      do { c = (int)(rng_next(s) % (unsigned int)n); dup = false; for (int j = 0; j < k; j++) dup |= idx[j] == c; } while (dup);
+      idx[k] = c;
+    }
+    double A[8][9]; int perm[9];
+    const double c1x = nrm[0], c1y = nrm[1], s1 = nrm[2], c2x = nrm[3], c2y = nrm[4], s2 = nrm[5];
+    for (int k = 0; k < 8; k++) {
+      const double x1 = (X1[idx[k]] - c1x) * s1, y1 = (Y1[idx[k]] - c1y) * s1, x2 = (X2[idx[k]] - c2x) * s2, y2 = (Y2[idx[k]] - c2y) * s2;
+      A[k][0] = x2 * x1; A[k][1] = x2 * y1; A[k][2] = x2; A[k][3] = y2 * x1; A[k][4] = y2 * y1; A[k][5] = y2; A[k][6] = x1; A[k][7] = y1; A[k][8] = 1.0;
+    }
+    for (int j = 0; j < 9; j++) perm[j] = j;
+    bool ok = true;
+    for (int k = 0; k < 8 && ok; k++) {          // full-pivot Gauss-Jordan: A -> [I | c] in permuted columns
+      int pi = k, pj = k; double best = 0;
+      for (int i = k; i < 8; i++) for (int j = k; j < 9; j++) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pi = i; pj = j; }
+      if (best < 1e-10) { ok = false; break; }
+      if (pi != k) for (int j = 0; j < 9; j++) { const double v = A[k][j]; A[k][j] = A[pi][j]; A[pi][j] = v; }
+      if (pj != k) { for (int i = 0; i < 8; i++) { const double v = A[i][k]; A[i][k] = A[i][pj]; A[i][pj] = v; } const int v = perm[k]; perm[k] = perm[pj]; perm[pj] = v; }
+      const double inv = 1.0 / A[k][k];
+      for (int j = 0; j < 9; j++) A[k][j] *= inv;
+      for (int i = 0; i < 8; i++) if (i != k) { const double f = A[i][k]; if (f != 0.0) for (int j = 0; j < 9; j++) A[i][j] -= f * A[k][j]; }
+    }
+    if (ok) {
+      double f[9];
+      f[perm[8]] = 1.0;
+      for (int k = 0; k < 8; k++) f[perm[k]] = -A[k][8];
+      // F = T2^T Fn T1 with T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+      double G[9];                               // Fn T1
+      for (int r = 0; r < 3; r++) { G[3 * r] = f[3 * r] * s1; G[3 * r + 1] = f[3 * r + 1] * s1; G[3 * r + 2] = f[3 * r + 2] - s1 * (f[3 * r] * c1x + f[3 * r + 1] * c1y); }
+      for (int c = 0; c < 3; c++) { F[c] = s2 * G[c]; F[3 + c] = s2 * G[3 + c]; F[6 + c] = G[6 + c] - s2 * (c2x * G[c] + c2y * G[3 + c]); }
+      double nf = 0; for (int k = 0; k < 9; k++) nf += F[k] * F[k];
+      nf = 1.0 / sqrt(nf); for (int k = 0; k < 9; k++) F[k] *= nf;
+      for (int i = 0; i < n; i++) my += epi_err(F, X1[i], Y1[i], X2[i], Y2[i]) <= thresh2;
+    }
+  }
+  cnt[t] = my;
+  __syncthreads();
+  __shared__ int best_t;
+  if (t == 0) { int b = 0; for (int h = 1; h < RANSAC_H; h++) if (cnt[h] > cnt[b]) b = h; best_t = b; info[0] = cnt[b]; info[1] = b; }
+  __syncthreads();
+  if (t == best_t) for (int k = 0; k < 9; k++) { Fbest[k] = F[k]; F_out[k] = F[k]; }
+  __syncthreads();
+  const bool none = cnt[best_t] < 8;
+  for (int i = t; i < n; i += RANSAC_H) status[i] = none ? 0 : (epi_err(Fbest, X1[i], Y1[i], X2[i], Y2[i]) <= thresh2);
+}
+
 // Integer midpoint circle of OpenCV's Circle() (drawing.cpp), fill = 1: half-width of the filled disc per row offset.
 void disc_half_widths(int radius, std::vector<int>& hw) {
   hw.assign(radius + 1, -1);
@@ -444,6 +533,33 @@ int vils_lift_projective(vils_frontend* f, const double cam[8], const float* uv,
   cudaMemcpyAsync(rays, f->d_ray, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, f->st);
   cudaError_t e = cudaStreamSynchronize(f->st);
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_lift_projective");
+}
+
+// cv::findFundamentalMat(pts1, pts2, cv::FM_RANSAC, threshold, 0.99, status) as used by rejectWithF (:191): status[i] = 1 for inliers.
+// n < 8 leaves every point in (the reference only calls it with >= 8 points, :171).  F (may be NULL) receives the winning 3x3, row-major.
+int vils_reject_with_f(vils_frontend* f, const float* pts1, const float* pts2, int32_t n, double threshold, uint8_t* status, double* F) {
+  if (!f || n < 0 || n > f->max_pts || (n && (!pts1 || !pts2 || !status)) || threshold <= 0) return vils::fail(VILS_ERR_BAD_ARG, "vils_reject_with_f: bad argument");
+  if (n < 8) { for (int i = 0; i < n; i++) status[i] = 1; return VILS_OK; }
+  cudaSetDevice(f->device);
+  // scratch: reuse the candidate buffer (>= 512 KB): pts1 | pts2 | status | info | F
+  float* d1 = reinterpret_cast<float*>(f->d_cand); float* d2 = d1 + 2 * n;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(d2 + 2 * n); int* dinfo = reinterpret_cast<int*>(dst + ((n + 15) & ~15)); double* dF = reinterpret_cast<double*>(dinfo + 4);
+  cudaMemcpyAsync(d1, pts1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, f->st);
+  cudaMemcpyAsync(d2, pts2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, f->st);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(ransac_f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+  if ((size_t)n * 32 > 64 * 1024) return vils::fail(VILS_ERR_CAPACITY, "vils_reject_with_f: too many points");
+  cudaEventRecord(f->e0, f->st);
+  ransac_f_kernel<<<1, RANSAC_H, (size_t)n * 32, f->st>>>(d1, d2, n, threshold * threshold, 12345u, dst, dinfo, dF);
+  cudaEventRecord(f->e1, f->st);
+  cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, f->st);
+  double hF[9];
+  cudaMemcpyAsync(hF, dF, sizeof(hF), cudaMemcpyDeviceToHost, f->st);
+  cudaError_t e = cudaStreamSynchronize(f->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_reject_with_f");
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  if (F) memcpy(F, hF, sizeof(hF));
+  return VILS_OK;
 }
 
 int vils_frontend_last_device_ms(vils_frontend* f, float* ms) { if (!f || !ms) return VILS_ERR_BAD_ARG; *ms = f->last_ms; return VILS_OK; }

@@ -73,6 +73,7 @@ def load():
     L.vils_frontend_get_eig.argtypes = [vp, fp]
     L.vils_lift_projective.argtypes = [vp, dp, fp, C.c_int32, dp]
     L.vils_frontend_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_reject_with_f.argtypes = [vp, fp, fp, C.c_int32, C.c_double, up, dp]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -359,6 +360,13 @@ class Frontend:
         rays = np.zeros((len(uv), 3))
         _check(self.L.vils_lift_projective(self.h, _d(cam), uv.ctypes.data_as(cabi.c_float_p), len(uv), _d(rays)))
         return rays
+
+    def reject_with_f(self, p1, p2, threshold=1.0):
+        p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2); p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+        st = np.zeros(max(len(p1), 1), np.uint8); F = np.zeros(9)
+        _check(self.L.vils_reject_with_f(self.h, p1.ctypes.data_as(cabi.c_float_p), p2.ctypes.data_as(cabi.c_float_p), len(p1), threshold,
+                                         st.ctypes.data_as(cabi.c_uint8_p), _d(F)))
+        return st[:len(p1)].astype(bool), F.reshape(3, 3)
 
     @property
     def last_ms(self):

@@ -136,3 +136,47 @@ def test_good_features_small_and_flat():
     out = f.good_features(img, 10, 0.01, 5.0)
     assert len({tuple(p) for p in ref.astype(int)} & {tuple(p) for p in out.astype(int)}) >= len(ref) - 1
     f.close()
+
+
+def two_view(seed, n=150, outlier_frac=0.2, noise=0.1):
+    """Static scene seen from two poses of a virtual pinhole (f = 460, centre of a 640 x 480 image): what rejectWithF feeds to RANSAC."""
+    rng = np.random.default_rng(seed)
+    X = np.stack([rng.uniform(-6, 6, n), rng.uniform(-4, 4, n), rng.uniform(4, 20, n)], 1)
+    ang = rng.normal(0, 0.03, 3); t = rng.normal(0, 0.25, 3)
+    R, _ = cv2.Rodrigues(ang)
+    K = np.array([[460.0, 0, 320], [0, 460.0, 240], [0, 0, 1]])
+    p1 = (K @ X.T).T; p1 = p1[:, :2] / p1[:, 2:]
+    X2 = (R @ X.T).T + t
+    p2 = (K @ X2.T).T; p2 = p2[:, :2] / p2[:, 2:]
+    p1 += rng.normal(0, noise, p1.shape); p2 += rng.normal(0, noise, p2.shape)
+    out = rng.random(n) < outlier_frac
+    p2[out] += rng.uniform(-60, 60, (out.sum(), 2)) + np.sign(rng.normal(size=(out.sum(), 2))) * 8
+    return p1.astype(np.float32), p2.astype(np.float32), out
+
+
+@pytest.mark.parametrize("seed,noise,agree", [(1, 0.1, 0.9), (2, 0.1, 0.9), (3, 0.1, 0.9), (4, 0.3, 0.8)])
+def test_reject_with_f_matches_opencv_ransac(seed, noise, agree):
+    """cv::findFundamentalMat(..., FM_RANSAC, 1.0, 0.99, status) (feature_tracker.cpp:191).  OpenCV's sampling is random (7-point sets from
+    its own RNG), so the bar is agreement of the masks, not identity: with 0.1 px noise (labels unambiguous at the 1 px gate) >= 90 % of the
+    points get the same label (OpenCV stops at 0.99 confidence and may miss true inliers), >= 97 % of the TRUE inliers are kept; with 0.3 px noise borderline points may flip (>= 80 %).  Gross outliers are rejected, OpenCV's inliers kept."""
+    from mvil_fusion_b200 import lib
+    p1, p2, is_out = two_view(seed, noise=noise)
+    Fcv, mcv = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+    mcv = mcv.reshape(-1).astype(bool)
+    f = lib.Frontend(480, 640, 512)
+    st, F = f.reject_with_f(p1, p2, 1.0)
+    assert (st == mcv).mean() >= agree, ((st == mcv).mean(), st.sum(), mcv.sum())
+    assert st[is_out].mean() <= 0.25                     # gross outliers go (one that lands within 1 px of its epipolar line is a legitimate inlier)
+    if noise <= 0.1:
+        assert st[~is_out].mean() >= 0.97                # true inliers stay
+    assert st[mcv].mean() >= (0.9 if noise <= 0.1 else 0.8)   # OpenCV's inliers stay
+    # the returned F really is the epipolar geometry of the kept points (symmetric epipolar distance <= 1 px, as computeError defines it)
+    h1 = np.c_[p1, np.ones(len(p1))].astype(np.float64); h2 = np.c_[p2, np.ones(len(p2))].astype(np.float64)
+    l2 = h1 @ F.T; l1 = h2 @ F
+    d2 = (np.sum(h2 * l2, 1) ** 2) / (l2[:, 0] ** 2 + l2[:, 1] ** 2); d1 = (np.sum(h1 * l1, 1) ** 2) / (l1[:, 0] ** 2 + l1[:, 1] ** 2)
+    assert np.array_equal(np.maximum(d1, d2) <= 1.0, st)
+    st2, _ = f.reject_with_f(p1, p2, 1.0)
+    assert np.array_equal(st, st2)                        # deterministic
+    few, _ = f.reject_with_f(p1[:5], p2[:5], 1.0)
+    assert few.all()
+    f.close()

@@ -219,3 +219,13 @@ def test_feature_tracker_full_read_image_sequence(host):
             assert np.abs(vel[jg] - rvel[jr]).max() <= 5e-3, k       # 0.05 px / 356 px focal / 0.1 s
             assert (cnt[:n] > 1).sum() > 100                        # the sequence really is being tracked
     host.vh_tracker_destroy(ft)
+    # with rejectWithF switched on (bit 1) the clean sequence keeps (almost) all of its tracks
+    ft = host.vh_tracker_create(rows, cols, MAX_CNT, 0)
+    host.vh_tracker_config(ft, 1, 3, MIN_DIST, d(CAM))
+    for k, raw in enumerate(frames):
+        assert host.vh_tracker_read(ft, np.ascontiguousarray(raw).ctypes.data_as(cabi.c_uint8_p), cols, 0.1 * k) == 0
+        host.vh_tracker_update_ids(ft)
+    xy = np.zeros((400, 2), np.float32); ids = np.zeros(400, np.int32); cnt = np.zeros(400, np.int32)
+    n = host.vh_tracker_get(ft, xy.ctypes.data_as(cabi.c_float_p), ids.ctypes.data_as(cabi.c_int32_p), cnt.ctypes.data_as(cabi.c_int32_p), 400)
+    assert (cnt[:n] == 4).sum() >= 0.85 * (np.array(ref_out[-1][2]) == 4).sum()
+    host.vh_tracker_destroy(ft)
