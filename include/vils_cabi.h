@@ -304,6 +304,12 @@ int vils_lift_projective(vils_frontend* f, const double cam[8], const float* uv,
 int vils_reject_with_f(vils_frontend* f, const float* pts1, const float* pts2, int32_t n, double threshold, uint8_t* status, double* F);
 int vils_frontend_last_device_ms(vils_frontend* f, float* ms);
 
+/* ---- FeatureManager::triangulate (vils_estimator/src/feature_manager.cpp:214-268): batched DLT + SVD, one feature per thread.
+ * Feature f is observed in keyframes start[f], start[f]+1, ... with bearing points pts[off[f]..off[f+1]) (x y z); Ps n_kf x 3, Rs n_kf x 9
+ * row-major, tic 3, ric 9 row-major.  depth[f] = svd_V[2]/svd_V[3] (INIT_DEPTH when negative, :262-266). */
+int vils_triangulate(int32_t n_feat, const int32_t* start, const int32_t* off, const double* pts, int32_t n_kf, const double* Ps,
+                     const double* Rs, const double tic[3], const double ric[9], double init_depth, double* depth, int32_t device);
+
 /* ---- LiDAR: PointProcessor::PointToRing stamp (lidar_compensator/src/PointProcessor.cc:127-341)
  *      + TransformToEnd deskew (vils_estimator/src/lidar_frontend.cpp:1001-1041) --------------- */
 /* xyzi: n points, stride_floats floats apart (8 for pcl::PointXYZI: x y z pad intensity pad pad pad).

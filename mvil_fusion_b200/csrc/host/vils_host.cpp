@@ -124,9 +124,39 @@ void Estimator::processImage(const ImageFeatures& image, const Header& header) {
     return;
   }
   if (frame_count < WINDOW_SIZE) { frame_count++; return; }
-  optimization();                 // solveOdometry (:903-914) without SVD triangulation: depths come from LiDAR / INIT_DEPTH / previous solves
+  if (TRIANGULATE) { triangulate(); if (last_status != VILS_OK) return; }   // solveOdometry (:903-914)
+  optimization();
   if (last_status == VILS_OK) removeFailures();
   slideWindow();
+}
+
+// FeatureManager::triangulate (feature_manager.cpp:214-268): every feature that enters the solve and has no depth yet gets the DLT / SVD
+// depth in its anchor camera, all of them in one batched device call.
+void Estimator::triangulate() {
+  std::vector<FeaturePerId*> todo; std::vector<int32_t> start, off{0}; std::vector<double> pts;
+  for (auto& it : feature) {
+    const int used_num = (int)it.feature_per_frame.size();
+    if (!(used_num >= 2 && it.start_frame < WINDOW_SIZE - 2)) continue;
+    if (it.estimated_depth > 0) continue;                                      // depth is available, skip (trust the first estimate)
+    todo.push_back(&it); start.push_back(it.start_frame);
+    for (const auto& fpf : it.feature_per_frame) { pts.push_back(fpf.point[0]); pts.push_back(fpf.point[1]); pts.push_back(fpf.point[2]); }
+    off.push_back((int32_t)(pts.size() / 3));
+  }
+  last_status = VILS_OK;
+  if (todo.empty()) return;
+  const int F = WINDOW_SIZE + 1;
+  auto q2R = [](const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+  };
+  std::vector<double> P(3 * (size_t)F), R(9 * (size_t)F), depth(todo.size()); double Ric[9];
+  for (int k = 0; k < F; k++) { for (int a = 0; a < 3; a++) P[3 * k + a] = Ps[k][a]; q2R(Qs[k].data(), &R[9 * k]); }
+  q2R(ric, Ric);
+  last_status = vils_triangulate((int)todo.size(), start.data(), off.data(), pts.data(), F, P.data(), R.data(), tic, Ric, INIT_DEPTH, depth.data(), cfg_.device);
+  if (last_status != VILS_OK) return;
+  for (size_t k = 0; k < todo.size(); k++) todo[k]->estimated_depth = depth[k];
 }
 
 void Estimator::removeFailures() {

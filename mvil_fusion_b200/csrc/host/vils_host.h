@@ -53,6 +53,8 @@ class Estimator {
   void processImage(const ImageFeatures& image, const Header& header);                                 // estimator.cpp:506-616
   void optimization();                                                                                 // estimator.cpp:1124-1687
   void slideWindow();                                                                                  // estimator.cpp:1689-1814
+  void triangulate();                                          // f_manager.triangulate(Ps, tic, ric) in solveOdometry (estimator.cpp:903-914)
+  bool TRIANGULATE = true;
 
   // ---- public state, reference names (estimator.h:67-121) ----
   int WINDOW_SIZE;

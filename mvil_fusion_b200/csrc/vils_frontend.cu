@@ -307,6 +307,68 @@ __global__ void __launch_bounds__(RANSAC_H) ransac_f_kernel(const float* __restr
   for (int i = t; i < n; i += RANSAC_H) status[i] = none ? 0 : (epi_err(Fbest, X1[i], Y1[i], X2[i], Y2[i]) <= thresh2);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// FeatureManager::triangulate (vils_estimator/src/feature_manager.cpp:214-268): per feature, the 2L x 4 DLT matrix of its L observations
+// relative to the anchor camera, right singular vector of the smallest singular value (Eigen::JacobiSVD in the reference), depth =
+// V[2] / V[3].  One thread per feature: one-sided (Hestenes) Jacobi SVD — the same rotation family as Eigen's two-sided Jacobi and, like
+// it, accurate to the conditioning of A (no A^T A squaring).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int TRI_MAX_OBS = 32;
+__global__ void triangulate_kernel(int n_feat, const int32_t* __restrict__ start, const int32_t* __restrict__ off, const double* __restrict__ pts,
+                                   int n_kf, const double* __restrict__ Ps, const double* __restrict__ Rs, const double* __restrict__ ex /* tic(3) ric(9) */,
+                                   double init_depth, double* __restrict__ depth) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_feat) return;
+  const int L = min(off[f + 1] - off[f], TRI_MAX_OBS), i0 = start[f];
+  double A[2 * TRI_MAX_OBS][4], V[4][4];
+  const double* tic = ex; const double* ric = ex + 3;
+  auto cam = [&](int k, double R[9], double t[3]) {          // R = Rs[k] ric, t = Ps[k] + Rs[k] tic
+    const double* Rk = Rs + 9 * k;
+    for (int a = 0; a < 3; a++) {
+      t[a] = Ps[3 * k + a] + Rk[3 * a] * tic[0] + Rk[3 * a + 1] * tic[1] + Rk[3 * a + 2] * tic[2];
+      for (int b = 0; b < 3; b++) R[3 * a + b] = Rk[3 * a] * ric[b] + Rk[3 * a + 1] * ric[3 + b] + Rk[3 * a + 2] * ric[6 + b];
+    }
+  };
+  double R0[9], t0[3]; cam(min(i0, n_kf - 1), R0, t0);
+  for (int j = 0; j < L; j++) {
+    double R1[9], t1[3]; cam(min(i0 + j, n_kf - 1), R1, t1);
+    // R = R0^T R1, t = R0^T (t1 - t0);  P = [R^T | -R^T t]
+    double R[9], t[3], P[3][4];
+    for (int a = 0; a < 3; a++) {
+      t[a] = R0[a] * (t1[0] - t0[0]) + R0[3 + a] * (t1[1] - t0[1]) + R0[6 + a] * (t1[2] - t0[2]);
+      for (int b = 0; b < 3; b++) R[3 * a + b] = R0[a] * R1[b] + R0[3 + a] * R1[3 + b] + R0[6 + a] * R1[6 + b];
+    }
+    for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) P[a][b] = R[3 * b + a]; P[a][3] = -(R[a] * t[0] + R[3 + a] * t[1] + R[6 + a] * t[2]); }
+    const double* p = pts + 3 * (size_t)(off[f] + j);
+    const double inv = 1.0 / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    const double fx = p[0] * inv, fy = p[1] * inv, fz = p[2] * inv;   // it_per_frame.point.normalized()
+    for (int c = 0; c < 4; c++) { A[2 * j][c] = fx * P[2][c] - fz * P[0][c]; A[2 * j + 1][c] = fy * P[2][c] - fz * P[1][c]; }
+  }
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) V[a][b] = a == b ? 1.0 : 0.0;
+  const int m = 2 * L;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    double offn = 0;
+    for (int p = 0; p < 3; p++)
+      for (int q = p + 1; q < 4; q++) {
+        double app = 0, aqq = 0, apq = 0;
+        for (int r = 0; r < m; r++) { app += A[r][p] * A[r][p]; aqq += A[r][q] * A[r][q]; apq += A[r][p] * A[r][q]; }
+        if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-17 * sqrt(app * aqq)) continue;
+        offn = fmax(offn, fabs(apq) / sqrt(app * aqq));
+        const double zeta = (aqq - app) / (2.0 * apq);
+        const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tt * tt), s_ = c * tt;
+        for (int r = 0; r < m; r++) { const double x = A[r][p], y = A[r][q]; A[r][p] = c * x - s_ * y; A[r][q] = s_ * x + c * y; }
+        for (int r = 0; r < 4; r++) { const double x = V[r][p], y = V[r][q]; V[r][p] = c * x - s_ * y; V[r][q] = s_ * x + c * y; }
+      }
+    if (offn < 1e-15) break;
+  }
+  int best = 0; double bn = 1e300;
+  for (int c = 0; c < 4; c++) { double nn = 0; for (int r = 0; r < m; r++) nn += A[r][c] * A[r][c]; if (nn < bn) { bn = nn; best = c; } }
+  double d = V[2][best] / V[3][best];
+  if (!(d >= 0)) d = init_depth;                              // triangulation failed (:262-266; NaN also lands here)
+  depth[f] = d;
+}
+
 // Integer midpoint circle of OpenCV's Circle() (drawing.cpp), fill = 1: half-width of the filled disc per row offset.
 void disc_half_widths(int radius, std::vector<int>& hw) {
   hw.assign(radius + 1, -1);
@@ -560,6 +622,35 @@ int vils_reject_with_f(vils_frontend* f, const float* pts1, const float* pts2, i
   cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
   if (F) memcpy(F, hF, sizeof(hF));
   return VILS_OK;
+}
+
+// FeatureManager::triangulate for n_feat features: feature f has observations pts[off[f]..off[f+1]) (x y z, un-normalised) in keyframes
+// start[f], start[f]+1, ...;  Ps (n_kf x 3), Rs (n_kf x 9 row-major), tic(3), ric (9 row-major).  depth[f] = svd_V[2] / svd_V[3], or
+// init_depth when negative.  The caller keeps the reference's gating (used_num >= 2, start_frame < WINDOW_SIZE - 2, depth not yet known).
+int vils_triangulate(int32_t n_feat, const int32_t* start, const int32_t* off, const double* pts, int32_t n_kf, const double* Ps, const double* Rs,
+                     const double tic[3], const double ric[9], double init_depth, double* depth, int32_t device) {
+  if (n_feat < 0 || n_kf <= 0 || (n_feat && (!start || !off || !pts || !depth)) || !Ps || !Rs || !tic || !ric) return vils::fail(VILS_ERR_BAD_ARG, "vils_triangulate: bad argument");
+  if (n_feat == 0) return VILS_OK;
+  for (int f = 0; f < n_feat; f++) if (start[f] < 0 || off[f + 1] < off[f] || start[f] + (off[f + 1] - off[f]) > n_kf) return vils::fail(VILS_ERR_BAD_ARG, "vils_triangulate: observation outside the window");
+  int st = vils::require_device(device); if (st) return st;
+  const int n_obs = off[n_feat];
+  const size_t bytes = sizeof(int32_t) * (2 * (size_t)n_feat + 1) + sizeof(double) * (3 * (size_t)n_obs + 12 * (size_t)n_kf + 12 + n_feat) + 64;
+  uint8_t* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_triangulate alloc");
+  std::vector<double> hd(3 * (size_t)n_obs + 12 * (size_t)n_kf + 12);
+  memcpy(hd.data(), pts, sizeof(double) * 3 * n_obs); memcpy(hd.data() + 3 * n_obs, Ps, sizeof(double) * 3 * n_kf);
+  memcpy(hd.data() + 3 * n_obs + 3 * n_kf, Rs, sizeof(double) * 9 * n_kf);
+  memcpy(hd.data() + 3 * n_obs + 12 * n_kf, tic, sizeof(double) * 3); memcpy(hd.data() + 3 * n_obs + 12 * n_kf + 3, ric, sizeof(double) * 9);
+  double* dd = reinterpret_cast<double*>(d); double* ddepth = dd + hd.size();
+  int32_t* di = reinterpret_cast<int32_t*>(ddepth + n_feat);
+  cudaMemcpy(dd, hd.data(), sizeof(double) * hd.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(di, start, sizeof(int32_t) * n_feat, cudaMemcpyHostToDevice);
+  cudaMemcpy(di + n_feat, off, sizeof(int32_t) * (n_feat + 1), cudaMemcpyHostToDevice);
+  triangulate_kernel<<<(n_feat + 63) / 64, 64>>>(n_feat, di, di + n_feat, dd, n_kf, dd + 3 * n_obs, dd + 3 * n_obs + 3 * n_kf, dd + 3 * n_obs + 12 * n_kf, init_depth, ddepth);
+  e = cudaMemcpy(depth, ddepth, sizeof(double) * n_feat, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_triangulate");
 }
 
 int vils_frontend_last_device_ms(vils_frontend* f, float* ms) { if (!f || !ms) return VILS_ERR_BAD_ARG; *ms = f->last_ms; return VILS_OK; }

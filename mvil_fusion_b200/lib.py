@@ -74,6 +74,7 @@ def load():
     L.vils_lift_projective.argtypes = [vp, dp, fp, C.c_int32, dp]
     L.vils_frontend_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.vils_reject_with_f.argtypes = [vp, fp, fp, C.c_int32, C.c_double, up, dp]
+    L.vils_triangulate.argtypes = [C.c_int32, ip, ip, dp, C.c_int32, dp, dp, dp, dp, C.c_double, dp, C.c_int32]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -306,6 +307,15 @@ class KLT:
         ms = C.c_float()
         self.L.vils_klt_last_device_ms(self.h, C.byref(ms))
         return ms.value
+
+
+def triangulate(start, off, pts, Ps, Rs, tic, ric, init_depth=5.0, device=0):
+    start = np.ascontiguousarray(start, np.int32); off = np.ascontiguousarray(off, np.int32); pts = np.ascontiguousarray(pts, np.float64)
+    Ps = np.ascontiguousarray(Ps, np.float64); Rs = np.ascontiguousarray(Rs, np.float64); tic = np.ascontiguousarray(tic, np.float64); ric = np.ascontiguousarray(ric, np.float64)
+    depth = np.zeros(max(len(start), 1))
+    ip = cabi.c_int32_p
+    _check(load().vils_triangulate(len(start), start.ctypes.data_as(ip), off.ctypes.data_as(ip), _d(pts), len(Ps), _d(Ps), _d(Rs), _d(tic), _d(ric), init_depth, _d(depth), device))
+    return depth[:len(start)]
 
 
 class Frontend:

