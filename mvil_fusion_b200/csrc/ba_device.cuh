@@ -53,7 +53,7 @@ struct SolveParams {
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
-  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, total;
+  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, rot, total;
   int ntile_rows;
 };
 
@@ -69,6 +69,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   s.cinv = take(Mcap); s.glam = take(Mcap);
   s.red = take(64 + SOLVE_WARPS * 2);
   s.tbl = take(114);                                         // IMU Jacobian assembly table (450 x uint16)
+  s.rot = take((Ncap + 1) * 9);                              // rotation matrices of the keyframes + ric (pair pass)
   s.linv = take(nb * TB * TB);
   int uni = PAIR_CHUNK * 2 * STAGE_LD;                       // pair-pass staging
   if (ECHUNK * Dvp > uni) uni = ECHUNK * Dvp;                // Schur chunk
@@ -173,8 +174,8 @@ __device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared 
     r[lane] = rw;
   }
   if (want_J) {
-#pragma unroll
-    for (int q = 0; q < 15; q++) { const int e = lane + 32 * q; if (e < 450) J[e] = vf::imu_tbl_value(tbl[e], core); }
+#pragma unroll 1
+    for (int e = lane; e < 450; e += 32) J[e] = vf::imu_tbl_value(tbl[e], core);     // rolled on purpose: a lone warp is instruction-fetch bound
     __syncwarp();
     WPROF(21);
     if (lane < 30) {                                            // J <- W J: lane owns column `lane` (no hazards)
@@ -273,7 +274,7 @@ __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g
 // =================================================================================================================
 // imu_stage != nullptr: the warps that have no projection factor in a round (PAIR_WARPS..SOLVE_WARPS-1) process the IMU
 // factors meanwhile (imu_factor_products), SOLVE_WARPS - PAIR_WARPS per round; imu_stage holds that many IMU_SLOT slots.
-__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost, double* imu_stage, const uint16_t* tbl) {
+__device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost, double* imu_stage, const uint16_t* tbl, double* rot /* (N + 1) x 9 doubles of shared memory */) {
   // Rounds of PAIR_CHUNK factors in PAIR order: (1) one thread per factor evaluates ProjectionTdFactor + corrector and
   // stages the weighted rows [J(19) | r] in shared memory, writes the landmark partials / E row to the scratch;
   // (2) one warp per keyframe pair accumulates the pair-local 20x20 block A^T A over the staged rows of that pair
@@ -289,8 +290,14 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
   double cost = 0;
   int p_lo = 0;                                   // first pair that may intersect the current round
   // per-pair context (everything that only depends on the two keyframe poses and the extrinsic), once per linearisation
-  double* pctx = scr + P.sl.pairctx;
-  for (int p = threadIdx.x; p < npair; p += blockDim.x) vf::proj_pair_ctx(x + XP(pairs[4 * p + 2]), x + XP(pairs[4 * p + 3]), x + XE(W.N), pctx + (size_t)p * vf::PCTX_LD);
+  // rotation table (shared memory): R_k of every keyframe, then ric — all a projection factor needs besides the positions in x
+  for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
+    const vm::m3 R = vm::q2R(vm::ldq((k < W.N ? x + XP(k) : x + XE(W.N)) + 3));
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) rot[9 * k + 3 * a + b] = R.m[a][b];
+  }
   __syncthreads();
   int imu_next = 0;
   const int nimu = imu_stage ? W.h->n_imu : 0;
@@ -308,7 +315,8 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
       const int feat = lm_feat[rank];
       double* row0 = stage + (2 * t) * STAGE_LD; double* row1 = row0 + STAGE_LD;
       double r[2], J[40];
-      vf::proj_eval_ctx(P.cfg, pctx + (size_t)pid[kfi * W.N + kfj] * vf::PCTX_LD, c, x[XL(W.N) + feat], x[XT(W.N)], r, J);
+      vf::proj_eval_rows(P.cfg, c, vf::ldm(rot + 9 * kfi), vf::ldm(rot + 9 * kfj), vf::ldm(rot + 9 * W.N), vm::ld3(x + XP(kfi)), vm::ld3(x + XP(kfj)), vm::ld3(x + XE(W.N)),
+                         x[XL(W.N) + feat], x[XT(W.N)], r, J);
       double rho, w; const double s2 = r[0] * r[0] + r[1] * r[1];
       if (need_cost) vf::cauchy(P.cfg.cauchy_a, s2, rho, w); else { w = vf::cauchy_w(P.cfg.cauchy_a, s2); rho = s2; }   // the log is only paid when the cost is reported
       cost += 0.5 * rho;
