@@ -149,6 +149,7 @@ __device__ uint16_t g_imu_tbl[450];
 constexpr int IMU_SLOT = 466 + vf::IMU_CORE_LD + 226;
 constexpr int IMU_PROD_LD = 512;                  // per-factor products in the scratch: lower J^T J (465) | J^T r (30)
 constexpr int PAIR_WARPS = (304 + 31) / 32;       // warps that evaluate projection factors in a pair-pass round (PAIR_CHUNK = 304)
+constexpr int IMU_IDLE = SOLVE_WARPS - PAIR_WARPS;   // warps free for IMU stages in every round
 __device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared memory copy of g_imu_tbl */, const double* pre, const double* Wk, const double* G,
                                                   const double* pi, const double* sbi, const double* pj, const double* sbj, double* stage, bool want_J,
                                                   long long* prof = nullptr) {
@@ -194,24 +195,61 @@ __device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared 
 #undef WPROF
 }
 
-// One warp, one IMU factor: whitened residual / Jacobian, then the 30x30 lower product J^T J and J^T r written to the
-// per-window scratch (added into H later by imu_add).  Returns this lane's share of the cost.
-__device__ double imu_factor_products(const SolveParams& P, const Win& W, const uint16_t* tbl, const double* x, int k, double* stage, double* scr) {
+// The IMU factor of the solve kernel in two warp-level stages, so that each fits inside one round of the pair pass (a lone warp next
+// to FP64-busy ones is slow: the whole chain takes ~1.6 rounds).  slot (shared memory, one per FACTOR, kept between the stages):
+// J 450 | r 15 | pad | work 226 (stage R: core, stage P: sqrt_info).
+constexpr int IMU_SLOT2 = 466 + 226;
+// Stage R: stage the pre-integration record, quaternion algebra by lane 0, assemble the raw 15 x 30 Jacobian.
+__device__ void imu_stage_R(const SolveParams& P, const Win& W, const uint16_t* tbl, const double* x, int k, double* slot) {
   const int lane = threadIdx.x & 31;
-  const double* pre = W.d(OFF_IMU) + (size_t)k * 467; const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
-  double* prod = scr + P.sl.imuprod + (size_t)k * IMU_PROD_LD;
-  if (pre[16] > 10.0) {                                      // estimator.cpp:1182 skip if sum_dt > 10
-    for (int e = lane; e < 495; e += 32) prod[e] = 0.0;
-    return 0.0;
+  const double* pre = W.d(OFF_IMU) + (size_t)k * 467;
+  double* J = slot; double* r = slot + 450; double* core = slot + 466;
+  if (pre[16] > 10.0) {                                      // estimator.cpp:1182 skip if sum_dt > 10: the factor contributes nothing
+    for (int e = lane; e < 466; e += 32) slot[e] = 0.0;
+    __syncwarp();
+    return;
   }
   const int i = W.i(OFF_IMU_KF)[k];
-  const double* J = stage; const double* r = stage + 450;
-  const bool prof_ = P.prof && blockIdx.x == 0 && threadIdx.x == 32 * PAIR_WARPS;
-  long long it_ = prof_ ? clock64() : 0;
-#define IPROF(i) do { if (prof_) { const long long n_ = clock64(); P.prof[i] += n_ - it_; it_ = n_; } } while (0)
-  warp_imu_whitened(tbl, pre, Wk, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), stage, true, prof_ ? P.prof : nullptr);
-  it_ = prof_ ? clock64() : 0;
-  const double cost = lane < 15 ? 0.5 * r[lane] * r[lane] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = lane + 32 * q; if (e < 242) J[e] = pre[e]; }   // landing zone of the record (no covariance)
+  __syncwarp();
+  if (lane == 0) vf::imu_core(J, P.cfg.G, x + XP(i), x + XS(W.N, i), x + XP(i + 1), x + XS(W.N, i + 1), core);
+  else for (int e = lane - 1; e < 36; e += 31) core[vf::IC_JAC + e] = vf::imu_core_jac(J, e);
+  __syncwarp();
+  if (lane < 15) r[lane] = core[vf::IC_R + lane];
+#pragma unroll 1
+  for (int e = lane; e < 450; e += 32) J[e] = vf::imu_tbl_value(tbl[e], core);     // rolled on purpose: a lone warp is instruction-fetch bound
+  __syncwarp();
+}
+// Stage P: whiten with sqrt_info (staged over the dead core area), then the 30x30 lower product J^T J and J^T r into the per-window
+// scratch (added into H later by imu_add).  Returns this lane's share of the cost.
+__device__ double imu_stage_P(const SolveParams& P, const Win& W, int k, double* slot, double* scr) {
+  const int lane = threadIdx.x & 31;
+  double* J = slot; double* r = slot + 450; double* Wsm = slot + 466;
+  const double* Wk = scr + P.sl.w_imu + (size_t)k * 225;
+  double* prod = scr + P.sl.imuprod + (size_t)k * IMU_PROD_LD;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { const int e = lane + 32 * q; if (e < 225) Wsm[e] = Wk[e]; }
+  __syncwarp();
+  double rw = 0;
+  if (lane < 15) {
+#pragma unroll
+    for (int m = 0; m < 15; m++) if (m >= lane) rw = fma(Wsm[lane * 15 + m], r[m], rw);
+  }
+  __syncwarp();
+  if (lane < 15) r[lane] = rw;
+  if (lane < 30) {                                            // J <- W J: lane owns column `lane` (no hazards)
+    double col[15];
+#pragma unroll
+    for (int m = 0; m < 15; m++) col[m] = J[m * 30 + lane];
+#pragma unroll
+    for (int a = 0; a < 15; a++) { double v = 0;
+#pragma unroll
+      for (int m = 0; m < 15; m++) if (m >= a) v = fma(Wsm[a * 15 + m], col[m], v);
+      J[a * 30 + lane] = v; }
+  }
+  __syncwarp();
+  const double cost = lane < 15 ? 0.5 * rw * rw : 0.0;
 #pragma unroll 4
   for (int q = 0; q < 16; q++) {
     const int e = lane + 32 * q;
@@ -232,12 +270,10 @@ __device__ double imu_factor_products(const SolveParams& P, const Win& W, const 
     }
   }
   __syncwarp();
-  IPROF(23);
-#undef IPROF
   return cost;
 }
 
-// H += the IMU products of imu_factor_products: one warp per factor, even keyframes first, then odd (adjacent factors share
+// H += the IMU products of imu_stage_P: one warp per factor, even keyframes first, then odd (adjacent factors share
 // a 15x15 block).  Ends with a block barrier.
 __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g, double* hd, const double* scr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -273,7 +309,7 @@ __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g
 // V: pair pass
 // =================================================================================================================
 // imu_stage != nullptr: the warps that have no projection factor in a round (PAIR_WARPS..SOLVE_WARPS-1) process the IMU
-// factors meanwhile (imu_factor_products), SOLVE_WARPS - PAIR_WARPS per round; imu_stage holds that many IMU_SLOT slots.
+// factors meanwhile, one stage (imu_stage_R / imu_stage_P) per warp per round; imu_stage holds n_imu slots of IMU_SLOT2 doubles.
 __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, const int* pid, bool need_cost, double* imu_stage, const uint16_t* tbl, double* rot /* (N + 1) x 9 doubles of shared memory */) {
   // Rounds of PAIR_CHUNK factors in PAIR order: (1) one thread per factor evaluates ProjectionTdFactor + corrector and
   // stages the weighted rows [J(19) | r] in shared memory, writes the landmark partials / E row to the scratch;
@@ -299,7 +335,7 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
       for (int b = 0; b < 3; b++) rot[9 * k + 3 * a + b] = R.m[a][b];
   }
   __syncthreads();
-  int imu_next = 0;
+  int imu_R = 0, imu_P = 0;                      // raw stages started / product stages started (block-uniform)
   const int nimu = imu_stage ? W.h->n_imu : 0;
   long long pt_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 #define PPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - pt_; pt_ = n_; } } while (0)
@@ -340,10 +376,13 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
         E[(size_t)rank * W.Dvp + 6 * kfj + k] = J[6 + k] * jl0 + J[26 + k] * jl1;   // e_j: this factor only
       }
       pt[14] = J[19] * jl0 + J[39] * jl1;                      // e_td
-    } else if (warp >= PAIR_WARPS && imu_next + (warp - PAIR_WARPS) < nimu) {
-      cost += imu_factor_products(P, W, tbl, x, imu_next + (warp - PAIR_WARPS), imu_stage + (warp - PAIR_WARPS) * IMU_SLOT, scr);
+    } else if (warp >= PAIR_WARPS) {
+      // idle warps: new raw stages first (so that no stage is left for after the last round), products of completed raws next
+      const int w = warp - PAIR_WARPS, nR = min(nimu - imu_R, IMU_IDLE), nP = min(IMU_IDLE - nR, imu_R - imu_P);
+      if (w < nR) imu_stage_R(P, W, tbl, x, imu_R + w, imu_stage + (imu_R + w) * IMU_SLOT2);
+      else if (w - nR < nP) cost += imu_stage_P(P, W, imu_P + w - nR, imu_stage + (imu_P + w - nR) * IMU_SLOT2, scr);
     }
-    imu_next += SOLVE_WARPS - PAIR_WARPS;
+    { const int nR = min(nimu - imu_R, IMU_IDLE), nP = min(IMU_IDLE - nR, imu_R - imu_P); imu_P += nP; imu_R += nR; }
     PPROF(16);
     __syncthreads();
     PPROF(17);
@@ -384,11 +423,16 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
     PPROF(19);
   }
 #undef PPROF
-  // windows with few projection rounds: the IMU factors that did not get a slot above
-  while (imu_next < nimu) {
-    if (warp >= PAIR_WARPS && imu_next + (warp - PAIR_WARPS) < nimu)
-      cost += imu_factor_products(P, W, tbl, x, imu_next + (warp - PAIR_WARPS), imu_stage + (warp - PAIR_WARPS) * IMU_SLOT, scr);
-    imu_next += SOLVE_WARPS - PAIR_WARPS;
+  // stages that did not fit into the projection rounds (few projection factors, or more than two rounds' worth of IMU factors)
+  while (imu_P < nimu) {
+    const int nR = min(nimu - imu_R, IMU_IDLE), nP = min(IMU_IDLE - nR, imu_R - imu_P);
+    if (warp >= PAIR_WARPS) {
+      const int w = warp - PAIR_WARPS;
+      if (w < nR) imu_stage_R(P, W, tbl, x, imu_R + w, imu_stage + (imu_R + w) * IMU_SLOT2);
+      else if (w - nR < nP) cost += imu_stage_P(P, W, imu_P + w - nR, imu_stage + (imu_P + w - nR) * IMU_SLOT2, scr);
+    }
+    imu_P += nP; imu_R += nR;
+    __syncthreads();
   }
   return cost;
 }

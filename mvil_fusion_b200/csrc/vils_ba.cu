@@ -142,7 +142,7 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   double* g = sm + L.g; double* hd = sm + L.hd;
   PROF_T0();
   // IMU factors ride on the idle warps of the pair pass when their staging fits in the (still unused) Hv region
-  const bool imu_inline = P.hv_in_smem && (SOLVE_WARPS - PAIR_WARPS) * IMU_SLOT <= W.Dvp * W.Dvp + ((P.Ncap + 1) / 2) * 466;
+  const bool imu_inline = P.hv_in_smem && W.h->n_imu * IMU_SLOT2 <= W.Dvp * W.Dvp + ((P.Ncap + 1) / 2) * 466;
   double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost, imu_inline ? sm + L.hv : nullptr, reinterpret_cast<const uint16_t*>(sm + L.tbl), sm + L.rot);
   __syncthreads();
   PROF(0);
