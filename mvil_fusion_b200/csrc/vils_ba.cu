@@ -442,6 +442,9 @@ struct EvalParams {
 // Output order inside a family is the library's SORTED order; the single-slot host API un-permutes (vils_ba_evaluate),
 // the batched device API documents it (vils_ba_evaluate_device).
 constexpr int EV_T = 128, EV_PLD = 42, EV_ELD = 21, EV_LLD = 7;
+#ifndef EVP_T
+#define EVP_T 128    // projection kernel CTA size (96-thread CTAs at 4 per SM balance the 906-factor window better but measured 7 % slower)
+#endif
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
@@ -457,31 +460,31 @@ __device__ __forceinline__ ProjItem proj_item(const SolveParams& P, int item, in
 }
 // per-thread slots of the factor tile: c[k] at cst[k * 128 + t] (doubles), idx[k] at ist[k * 128 + t] (ints); shared part: xs, feat
 __device__ __forceinline__ void proj_prefetch(const ProjItem& it, double* cst, int32_t* ist, double* xs, int32_t* feat, int t) {
-  const int f = it.chunk * EV_T + t;
-  if (it.chunk * EV_T < it.np) {
+  const int f = it.chunk * EVP_T + t;
+  if (it.chunk * EVP_T < it.np) {
     const double* x = reinterpret_cast<const double*>(it.base + it.h->off[OFF_X]);
-    for (int k = t; k < it.X; k += EV_T) cp_async8(xs + k, x + k);
+    for (int k = t; k < it.X; k += EVP_T) cp_async8(xs + k, x + k);
     const int32_t* lf = reinterpret_cast<const int32_t*>(it.base + it.h->off[OFF_LM_FEAT]);
-    for (int k = t; k < it.n_lm; k += EV_T) cp_async4(feat + k, lf + k);
+    for (int k = t; k < it.n_lm; k += EVP_T) cp_async4(feat + k, lf + k);
     if (f < it.np) {
       const double* c0 = reinterpret_cast<const double*>(it.base + it.h->off[OFF_PROJ]);
       const int32_t* ix = reinterpret_cast<const int32_t*>(it.base + it.h->off[OFF_PROJ_IDX]);
 #pragma unroll
-      for (int k = 0; k < 14; k++) cp_async8(cst + k * EV_T + t, c0 + (size_t)k * it.np + f);
+      for (int k = 0; k < 14; k++) cp_async8(cst + k * EVP_T + t, c0 + (size_t)k * it.np + f);
 #pragma unroll
-      for (int k = 0; k < 3; k++) cp_async4(ist + k * EV_T + t, ix + (size_t)k * it.np + f);
+      for (int k = 0; k < 3; k++) cp_async4(ist + k * EVP_T + t, ix + (size_t)k * it.np + f);
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 template <int MINB>
-__global__ void __launch_bounds__(EV_T, MINB) eval_proj_kernel(EvalParams Q, int n_items, int pb, int xs_doubles, int feat_ints) {
+__global__ void __launch_bounds__(EVP_T, MINB) eval_proj_kernel(EvalParams Q, int n_items, int pb, int xs_doubles, int feat_ints) {
   extern __shared__ __align__(16) double st[];
   const SolveParams& P = Q.S;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   // carve-up: rows | cst | xs[2] | ist | feat[2]
-  double* rows = st; double* cst = rows + EV_T * EV_PLD; double* xsb = cst + 14 * EV_T;
-  int32_t* ist = reinterpret_cast<int32_t*>(xsb + 2 * xs_doubles); int32_t* featb = ist + 3 * EV_T;
+  double* rows = st; double* cst = rows + EVP_T * EV_PLD; double* xsb = cst + 14 * EVP_T;
+  int32_t* ist = reinterpret_cast<int32_t*>(xsb + 2 * xs_doubles); int32_t* featb = ist + 3 * EVP_T;
   int item = blockIdx.x;
   if (item >= n_items) return;
   const int G = gridDim.x;
@@ -498,13 +501,13 @@ __global__ void __launch_bounds__(EV_T, MINB) eval_proj_kernel(EvalParams Q, int
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                            // tile of `cur` complete and visible; previous item fully consumed
     const double* xs = xsb + (n & 1) * xs_doubles; const int32_t* feat = featb + (n & 1) * feat_ints;
-    const int fw = cur.chunk * EV_T + 32 * warp, f = fw + lane;   // fw: first factor of this warp
+    const int fw = cur.chunk * EVP_T + 32 * warp, f = fw + lane;   // fw: first factor of this warp
     const bool act = f < cur.np;
     double c[14]; int i = 0, j = 0, rank = 0;
     if (act) {
 #pragma unroll
-      for (int k = 0; k < 14; k++) c[k] = cst[k * EV_T + t];
-      i = ist[t]; j = ist[EV_T + t]; rank = ist[2 * EV_T + t];
+      for (int k = 0; k < 14; k++) c[k] = cst[k * EVP_T + t];
+      i = ist[t]; j = ist[EVP_T + t]; rank = ist[2 * EVP_T + t];
     }
     if (item + G < n_items) proj_prefetch(nx, cst, ist, xsb + ((n + 1) & 1) * xs_doubles, featb + ((n + 1) & 1) * feat_ints, t);   // own slots already copied to registers
     const int n_imu = cur.h->n_imu;
@@ -1136,7 +1139,7 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   EvalParams Q{}; Q.S = make_params(ba, nullptr); Q.S.slot0 = slot0;
   Q.r_out = ba->d_er; Q.J_out = ba->d_eJ; Q.r_stride = ba->er_stride; Q.J_stride = ba->eJ_stride; Q.apply_loss = apply_loss;
   const int xs_doubles = (16 * ba->cfg.max_kf + 8 + ba->cfg.max_feat + 1) & ~1, feat_ints = (ba->cfg.max_feat + 3) & ~3;
-  const size_t proj_smem = (size_t)(EV_T * EV_PLD + 14 * EV_T + 2 * xs_doubles) * 8 + (size_t)(3 * EV_T + 2 * feat_ints) * 4;
+  const size_t proj_smem = (size_t)(EVP_T * EV_PLD + 14 * EVP_T + 2 * xs_doubles) * 8 + (size_t)(3 * EVP_T + 2 * feat_ints) * 4;
   static const int minb = getenv("VILS_EV_MINB") ? atoi(getenv("VILS_EV_MINB")) : 3;
   static bool attr = false;
   if (!attr) {
@@ -1154,12 +1157,12 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
     const int ib = (nimu * n + EVI_WARPS - 1) / EVI_WARPS, pbw = (nprior + 32 * EVI_WARPS - 1) / (32 * EVI_WARPS);
     eval_imu_kernel<<<ib + pbw * n, 32 * EVI_WARPS, 0, ba->stream>>>(Q, std::max(nimu, 1), n, ib, std::max(pbw, 1)); launches++;
   }
-  const int pb = (np + EV_T - 1) / EV_T;
+  const int pb = (np + EVP_T - 1) / EVP_T;
   if (pb) {
     const int items = pb * n, g = std::min(items, ba->n_sm * minb);
-    if (minb == 2) eval_proj_kernel<2><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
-    else if (minb == 4) eval_proj_kernel<4><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
-    else eval_proj_kernel<3><<<g, EV_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    if (minb == 2) eval_proj_kernel<2><<<g, EVP_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    else if (minb == 4) eval_proj_kernel<4><<<g, EVP_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
+    else eval_proj_kernel<3><<<g, EVP_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
     launches++;
   }
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
