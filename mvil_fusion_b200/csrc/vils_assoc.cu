@@ -1,0 +1,210 @@
+// vils_assoc.cu — scan-to-map association: the producer of the LiDAR edge / plane factor arrays (SURVEY.md §8f-3 i).
+// Reference: lidar_mapping/src/localMapping.cpp:611-766 — for every corner point: pointAssociateToMap, 5-NN in the corner map
+// (pcl::KdTreeFLANN), if the 5th neighbour is within 1 m: mean + 3x3 scatter, SelfAdjointEigenSolver, line if l2 > 3 l1, end points
+// a, b = centre +- 0.1 direction (:626-667); for every surface point: 10-NN, the 5 with the closest intensity, colPivHouseholderQr plane
+// fit A n = -1, plane valid if every neighbour is within 0.2 m of it (:675-747).  The outputs are exactly the arrays
+// vils_window.edge_{p,a,b} / plane_{p,n,d} take.
+// Version 1 searches the map exhaustively: one warp per query point, 8 queries per CTA; the map streams through shared memory in
+// 2048-point tiles shared by the CTA, every lane keeps its K best in registers, then a K-round shuffle merge.  Exact, like the kd-tree
+// (ties broken by the smaller map index).  A uniform grid over the map is the obvious next step for maps beyond ~100 k points.
+#include <cmath>
+#include <cstring>
+
+#include "../../include/vils_cabi.h"
+#include "common.h"
+
+namespace {
+
+constexpr int KMAX = 10;
+constexpr int ASSOC_TILE = 2048;   // map points per shared-memory tile (32 KB)
+
+struct Knn { float d[KMAX]; int i[KMAX]; };
+
+template <int K>
+__device__ __forceinline__ void knn_insert(Knn& h, float d, int idx) {
+  if (!(d < h.d[K - 1] || (d == h.d[K - 1] && idx < h.i[K - 1]))) return;
+  h.d[K - 1] = d; h.i[K - 1] = idx;
+#pragma unroll
+  for (int k = K - 1; k > 0; k--) {
+    const bool sw = h.d[k] < h.d[k - 1] || (h.d[k] == h.d[k - 1] && h.i[k] < h.i[k - 1]);
+    if (sw) { const float td = h.d[k]; h.d[k] = h.d[k - 1]; h.d[k - 1] = td; const int ti = h.i[k]; h.i[k] = h.i[k - 1]; h.i[k - 1] = ti; }
+  }
+}
+
+// 3x3 symmetric eigen-decomposition (cyclic Jacobi, FP64): w ascending like Eigen::SelfAdjointEigenSolver, V columns = eigenvectors
+__device__ void eig3(double A[3][3], double w[3], double V[3][3]) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300 || off <= 1e-17 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; k++) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; k++) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+      }
+  }
+  for (int k = 0; k < 3; k++) w[k] = A[k][k];
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2 - a; b++)
+      if (w[b] > w[b + 1]) { const double t = w[b]; w[b] = w[b + 1]; w[b + 1] = t; for (int k = 0; k < 3; k++) { const double v = V[k][b]; V[k][b] = V[k][b + 1]; V[k][b + 1] = v; } }
+}
+
+// least squares A n = b (5 x 3) by Householder QR, FP64
+__device__ void lstsq53(double A[5][3], double b[5], double n[3]) {
+  for (int k = 0; k < 3; k++) {
+    double nr = 0; for (int i = k; i < 5; i++) nr += A[i][k] * A[i][k];
+    nr = sqrt(nr);
+    if (nr == 0) continue;
+    const double alpha = A[k][k] > 0 ? -nr : nr;
+    double v[5]; double vn = 0;
+    for (int i = k; i < 5; i++) { v[i] = A[i][k]; if (i == k) v[i] -= alpha; vn += v[i] * v[i]; }
+    if (vn == 0) continue;
+    for (int j = k; j < 3; j++) { double s = 0; for (int i = k; i < 5; i++) s += v[i] * A[i][j]; s *= 2.0 / vn; for (int i = k; i < 5; i++) A[i][j] -= s * v[i]; }
+    { double s = 0; for (int i = k; i < 5; i++) s += v[i] * b[i]; s *= 2.0 / vn; for (int i = k; i < 5; i++) b[i] -= s * v[i]; }
+  }
+  for (int k = 2; k >= 0; k--) { double s = b[k]; for (int j = k + 1; j < 3; j++) s -= A[k][j] * n[j]; n[k] = s / A[k][k]; }
+}
+
+// mode 0: corner (K = 5, line), mode 1: surface (K = 10 -> 5 by intensity, plane).  out: 10 doubles per query
+//   corner: p(3) a(3) b(3) -      surface: p(3) n(3) d - - -
+template <int K>
+__global__ void __launch_bounds__(256) associate_kernel(const float4* __restrict__ map, int n_map, const float4* __restrict__ scan, int n_scan, const double* __restrict__ qt,
+                                                        int mode, double* __restrict__ out, uint8_t* __restrict__ valid, int32_t* __restrict__ nn_out) {
+  __shared__ float4 tile[ASSOC_TILE];
+  const int lane = threadIdx.x & 31, qi0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool active = qi0 < n_scan;
+  const int qi = active ? qi0 : n_scan - 1;
+  const float4 po = scan[qi];
+  // pointAssociateToMap (:170-179): FP64 rotation, result stored in a float point
+  const double qx = qt[0], qy = qt[1], qz = qt[2], qw = qt[3];
+  const double px = po.x, py = po.y, pz = po.z;
+  const double tx2 = 2.0 * (qy * pz - qz * py), ty2 = 2.0 * (qz * px - qx * pz), tz2 = 2.0 * (qx * py - qy * px);
+  const float sx = (float)(px + qw * tx2 + (qy * tz2 - qz * ty2) + qt[4]), sy = (float)(py + qw * ty2 + (qz * tx2 - qx * tz2) + qt[5]),
+              sz = (float)(pz + qw * tz2 + (qx * ty2 - qy * tx2) + qt[6]);
+  Knn h;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) { h.d[k] = 3.0e38f; h.i[k] = 0x7fffffff; }
+  // the map streams through shared memory in tiles shared by the CTA's warps (8 queries per tile load: L2 traffic / 8)
+  for (int base = 0; base < n_map; base += ASSOC_TILE) {
+    const int cnt = min(ASSOC_TILE, n_map - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) tile[j] = map[base + j];
+    __syncthreads();
+    if (active)
+      for (int j = lane; j < cnt; j += 32) {
+        const float4 m = tile[j];
+        const float dx = m.x - sx, dy = m.y - sy, dz = m.z - sz;
+        knn_insert<K>(h, dx * dx + dy * dy + dz * dz, base + j);
+      }
+  }
+  if (!active) return;
+  // K-round merge: every round the lane whose head is the global minimum pops it
+  float nd[K]; int ni[K];
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    float bd = h.d[0]; int bi = h.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    nd[r] = bd; ni[r] = bi;
+    if (h.i[0] == bi && h.d[0] == bd) {
+#pragma unroll
+      for (int k = 0; k < K - 1; k++) { h.d[k] = h.d[k + 1]; h.i[k] = h.i[k + 1]; }
+      h.d[K - 1] = 3.0e38f; h.i[K - 1] = 0x7fffffff;
+    }
+  }
+  if (lane != 0) return;
+  double* o = out + (size_t)qi * 10;
+  o[0] = px; o[1] = py; o[2] = pz;
+  for (int k = 3; k < 10; k++) o[k] = 0.0;
+  uint8_t ok = 0;
+  int sel[5];
+  if (n_map >= K && nd[4] < 1.0f) {
+    if (mode == 0) {
+      for (int j = 0; j < 5; j++) sel[j] = ni[j];
+      double c[3] = {0, 0, 0}, P5[5][3];
+      for (int j = 0; j < 5; j++) { const float4 m = map[sel[j]]; P5[j][0] = m.x; P5[j][1] = m.y; P5[j][2] = m.z; c[0] += m.x; c[1] += m.y; c[2] += m.z; }
+      c[0] /= 5.0; c[1] /= 5.0; c[2] /= 5.0;
+      double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int j = 0; j < 5; j++) { const double d0 = P5[j][0] - c[0], d1 = P5[j][1] - c[1], d2 = P5[j][2] - c[2]; const double d[3] = {d0, d1, d2}; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[a][b] += d[a] * d[b]; }
+      double w[3], V[3][3]; eig3(C, w, V);
+      if (w[2] > 3 * w[1]) {
+        ok = 1;
+        for (int a = 0; a < 3; a++) { o[3 + a] = 0.1 * V[a][2] + c[a]; o[6 + a] = -0.1 * V[a][2] + c[a]; }
+      }
+    } else {
+      // the 5 of the 10 neighbours whose intensity is closest to the point's (std::sort of pair<float diff, index>, :680-692)
+      float df[K]; int id[K];
+      for (int j = 0; j < K; j++) { df[j] = fabsf(map[ni[j]].w - po.w); id[j] = ni[j]; }
+      for (int a = 1; a < K; a++) { const float d = df[a]; const int ii = id[a]; int b = a - 1; while (b >= 0 && (df[b] > d || (df[b] == d && id[b] > ii))) { df[b + 1] = df[b]; id[b + 1] = id[b]; b--; } df[b + 1] = d; id[b + 1] = ii; }
+      for (int j = 0; j < 5; j++) sel[j] = id[j];
+      double A[5][3], A0[5][3], b[5], n[3] = {0, 0, 0};
+      for (int j = 0; j < 5; j++) { const float4 m = map[sel[j]]; A[j][0] = A0[j][0] = m.x; A[j][1] = A0[j][1] = m.y; A[j][2] = A0[j][2] = m.z; b[j] = -1.0; }
+      lstsq53(A, b, n);
+      const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      const double d = 1.0 / nn; n[0] /= nn; n[1] /= nn; n[2] /= nn;
+      ok = 1;
+      for (int j = 0; j < 5; j++) if (fabs(n[0] * A0[j][0] + n[1] * A0[j][1] + n[2] * A0[j][2] + d) > 0.2) { ok = 0; break; }
+      if (!(nn > 0) || !isfinite(d)) ok = 0;
+      if (ok) { o[3] = n[0]; o[4] = n[1]; o[5] = n[2]; o[6] = d; }
+    }
+  } else {
+    for (int j = 0; j < 5; j++) sel[j] = K > j ? ni[j] : -1;
+  }
+  valid[qi] = ok;
+  if (nn_out) for (int j = 0; j < 5; j++) nn_out[(size_t)qi * 5 + j] = sel[j];
+}
+
+}  // namespace
+
+extern "C" {
+
+// Scan-to-map association (localMapping.cpp:611-766).  map / scan: PCL-style x y z intensity as 4 packed floats per point (HOST pointers);
+// q_w_curr (x y z w), t_w_curr: the current scan-to-map pose.  mode 0: corner points -> LidarEdgeFactor inputs, out[i] = p(3) a(3) b(3) -;
+// mode 1: surface points -> LidarPlaneNormFactor inputs, out[i] = p(3) n(3) d - - -.  valid[i] = 1 where the reference adds a residual
+// block.  nn_idx (may be NULL): the 5 map indices used per point.  ms (may be NULL): device time of the kernel.
+int vils_lidar_associate(const float* map_xyzi, int32_t n_map, const float* scan_xyzi, int32_t n_scan, const double q_w_curr[4], const double t_w_curr[3],
+                         int32_t mode, double* out, uint8_t* valid, int32_t* nn_idx, float* ms, int32_t device) {
+  if (n_map < 0 || n_scan < 0 || (n_map && !map_xyzi) || (n_scan && (!scan_xyzi || !out || !valid)) || !q_w_curr || !t_w_curr || (mode != 0 && mode != 1))
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_lidar_associate: bad argument");
+  if (n_scan == 0) return VILS_OK;
+  int st = vils::require_device(device); if (st) return st;
+  float4* d_map = nullptr; float4* d_scan = nullptr; double* d_qt = nullptr; double* d_out = nullptr; uint8_t* d_valid = nullptr; int32_t* d_nn = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_map, sizeof(float4) * (size_t)(n_map > 0 ? n_map : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_scan, sizeof(float4) * (size_t)n_scan);
+  if (e == cudaSuccess) e = cudaMalloc(&d_qt, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * 10 * (size_t)n_scan);
+  if (e == cudaSuccess) e = cudaMalloc(&d_valid, (size_t)n_scan);
+  if (e == cudaSuccess) e = cudaMalloc(&d_nn, sizeof(int32_t) * 5 * (size_t)n_scan);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) {
+    double qt[8] = {q_w_curr[0], q_w_curr[1], q_w_curr[2], q_w_curr[3], t_w_curr[0], t_w_curr[1], t_w_curr[2], 0.0};
+    if (n_map) cudaMemcpy(d_map, map_xyzi, sizeof(float4) * (size_t)n_map, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_scan, scan_xyzi, sizeof(float4) * (size_t)n_scan, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_qt, qt, sizeof(qt), cudaMemcpyHostToDevice);
+    cudaEventRecord(e0);
+    const int warps = 8, grid = (n_scan + warps - 1) / warps;
+    if (mode == 0) associate_kernel<5><<<grid, 32 * warps>>>(d_map, n_map, d_scan, n_scan, d_qt, 0, d_out, d_valid, d_nn);
+    else associate_kernel<10><<<grid, 32 * warps>>>(d_map, n_map, d_scan, n_scan, d_qt, 1, d_out, d_valid, d_nn);
+    cudaEventRecord(e1);
+    e = cudaMemcpy(out, d_out, sizeof(double) * 10 * (size_t)n_scan, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(valid, d_valid, (size_t)n_scan, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && nn_idx) e = cudaMemcpy(nn_idx, d_nn, sizeof(int32_t) * 5 * (size_t)n_scan, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ms) cudaEventElapsedTime(ms, e0, e1);
+  }
+  cudaFree(d_map); cudaFree(d_scan); cudaFree(d_qt); cudaFree(d_out); cudaFree(d_valid); cudaFree(d_nn);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_lidar_associate");
+}
+
+}  // extern "C"

@@ -75,6 +75,7 @@ def load():
     L.vils_frontend_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.vils_reject_with_f.argtypes = [vp, fp, fp, C.c_int32, C.c_double, up, dp]
     L.vils_triangulate.argtypes = [C.c_int32, ip, ip, dp, C.c_int32, dp, dp, dp, dp, C.c_double, dp, C.c_int32]
+    L.vils_lidar_associate.argtypes = [fp, C.c_int32, fp, C.c_int32, dp, dp, C.c_int32, dp, up, ip, C.POINTER(C.c_float), C.c_int32]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -316,6 +317,17 @@ def triangulate(start, off, pts, Ps, Rs, tic, ric, init_depth=5.0, device=0):
     ip = cabi.c_int32_p
     _check(load().vils_triangulate(len(start), start.ctypes.data_as(ip), off.ctypes.data_as(ip), _d(pts), len(Ps), _d(Ps), _d(Rs), _d(tic), _d(ric), init_depth, _d(depth), device))
     return depth[:len(start)]
+
+
+def lidar_associate(map_xyzi, scan_xyzi, q, t, mode, device=0):
+    """vils_lidar_associate: returns (out n x 10, valid n, nn n x 5, device_ms)."""
+    m = np.ascontiguousarray(map_xyzi, np.float32).reshape(-1, 4); s = np.ascontiguousarray(scan_xyzi, np.float32).reshape(-1, 4)
+    q = np.ascontiguousarray(q, np.float64); t = np.ascontiguousarray(t, np.float64)
+    out = np.zeros((max(len(s), 1), 10)); valid = np.zeros(max(len(s), 1), np.uint8); nn = np.zeros((max(len(s), 1), 5), np.int32); ms = C.c_float()
+    fp = cabi.c_float_p
+    _check(load().vils_lidar_associate(m.ctypes.data_as(fp), len(m), s.ctypes.data_as(fp), len(s), _d(q), _d(t), mode, _d(out),
+                                       valid.ctypes.data_as(cabi.c_uint8_p), nn.ctypes.data_as(cabi.c_int32_p), C.byref(ms), device))
+    return out[:len(s)], valid[:len(s)].astype(bool), nn[:len(s)], ms.value
 
 
 class Frontend:
