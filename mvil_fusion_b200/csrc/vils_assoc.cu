@@ -6,7 +6,8 @@
 // vils_window.edge_{p,a,b} / plane_{p,n,d} take.
 // Version 1 searches the map exhaustively: one warp per query point, 8 queries per CTA; the map streams through shared memory in
 // 2048-point tiles shared by the CTA, every lane keeps its K best in registers, then a K-round shuffle merge.  Exact, like the kd-tree
-// (ties broken by the smaller map index).  A uniform grid over the map is the obvious next step for maps beyond ~100 k points.
+// (ties broken by the smaller map index); after every tile the warp tightens a shared threshold to its current K-th best, so that almost
+// every later point fails one compare.  A uniform grid over the map is the obvious next step for maps beyond ~100 k points.
 #include <cmath>
 #include <cstring>
 
@@ -33,40 +34,53 @@ __device__ __forceinline__ void knn_insert(Knn& h, float d, int idx) {
 
 // 3x3 symmetric eigen-decomposition (cyclic Jacobi, FP64): w ascending like Eigen::SelfAdjointEigenSolver, V columns = eigenvectors
 __device__ void eig3(double A[3][3], double w[3], double V[3][3]) {
+  #pragma unroll
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 30; sweep++) {
     const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
     if (off < 1e-300 || off <= 1e-17 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+    #pragma unroll
     for (int p = 0; p < 2; p++)
+      #pragma unroll
       for (int q = p + 1; q < 3; q++) {
         if (fabs(A[p][q]) < 1e-300) continue;
         const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
         const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        #pragma unroll
         for (int k = 0; k < 3; k++) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+        #pragma unroll
         for (int k = 0; k < 3; k++) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+        #pragma unroll
         for (int k = 0; k < 3; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
       }
   }
+  #pragma unroll
   for (int k = 0; k < 3; k++) w[k] = A[k][k];
+  #pragma unroll
   for (int a = 0; a < 2; a++)
+    #pragma unroll
     for (int b = 0; b < 2 - a; b++)
       if (w[b] > w[b + 1]) { const double t = w[b]; w[b] = w[b + 1]; w[b + 1] = t; for (int k = 0; k < 3; k++) { const double v = V[k][b]; V[k][b] = V[k][b + 1]; V[k][b + 1] = v; } }
 }
 
 // least squares A n = b (5 x 3) by Householder QR, FP64
 __device__ void lstsq53(double A[5][3], double b[5], double n[3]) {
+  #pragma unroll
   for (int k = 0; k < 3; k++) {
     double nr = 0; for (int i = k; i < 5; i++) nr += A[i][k] * A[i][k];
     nr = sqrt(nr);
     if (nr == 0) continue;
     const double alpha = A[k][k] > 0 ? -nr : nr;
     double v[5]; double vn = 0;
+    #pragma unroll
     for (int i = k; i < 5; i++) { v[i] = A[i][k]; if (i == k) v[i] -= alpha; vn += v[i] * v[i]; }
     if (vn == 0) continue;
+    #pragma unroll
     for (int j = k; j < 3; j++) { double s = 0; for (int i = k; i < 5; i++) s += v[i] * A[i][j]; s *= 2.0 / vn; for (int i = k; i < 5; i++) A[i][j] -= s * v[i]; }
     { double s = 0; for (int i = k; i < 5; i++) s += v[i] * b[i]; s *= 2.0 / vn; for (int i = k; i < 5; i++) b[i] -= s * v[i]; }
   }
+  #pragma unroll
   for (int k = 2; k >= 0; k--) { double s = b[k]; for (int j = k + 1; j < 3; j++) s -= A[k][j] * n[j]; n[k] = s / A[k][k]; }
 }
 
@@ -89,18 +103,41 @@ __global__ void __launch_bounds__(256) associate_kernel(const float4* __restrict
   Knn h;
 #pragma unroll
   for (int k = 0; k < KMAX; k++) { h.d[k] = 3.0e38f; h.i[k] = 0x7fffffff; }
+  float T = 3.0e38f;
   // the map streams through shared memory in tiles shared by the CTA's warps (8 queries per tile load: L2 traffic / 8)
   for (int base = 0; base < n_map; base += ASSOC_TILE) {
     const int cnt = min(ASSOC_TILE, n_map - base);
     __syncthreads();
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) tile[j] = map[base + j];
     __syncthreads();
-    if (active)
+    if (active) {
       for (int j = lane; j < cnt; j += 32) {
         const float4 m = tile[j];
         const float dx = m.x - sx, dy = m.y - sy, dz = m.z - sz;
-        knn_insert<K>(h, dx * dx + dy * dy + dz * dz, base + j);
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d <= T) knn_insert<K>(h, d, base + j);           // T: the warp's current K-th best; almost every point fails this one compare
       }
+      // tighten T to the K-th smallest over all lanes' lists (non-destructive K-round merge on a copy): per-lane lists alone give a
+      // threshold 32x looser in quantile, and any lane that inserts makes the whole warp pay the insertion
+      Knn hc = h;
+      float kth = 3.0e38f;
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        float bd = hc.d[0]; int bi = hc.i[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        kth = bd;
+        if (hc.i[0] == bi && hc.d[0] == bd) {
+#pragma unroll
+          for (int k = 0; k < K - 1; k++) { hc.d[k] = hc.d[k + 1]; hc.i[k] = hc.i[k + 1]; }
+          hc.d[K - 1] = 3.0e38f; hc.i[K - 1] = 0x7fffffff;
+        }
+      }
+      T = kth;
+    }
   }
   if (!active) return;
   // K-round merge: every round the lane whose head is the global minimum pops it
