@@ -717,7 +717,7 @@ struct vils_ba {
   std::vector<SlotMeta> meta;
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
   float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
-  bool prepped = false;
+  bool prepped = false, eval_attr_set = false;
   double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
 };
@@ -1141,12 +1141,11 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   const int xs_doubles = (16 * ba->cfg.max_kf + 8 + ba->cfg.max_feat + 1) & ~1, feat_ints = (ba->cfg.max_feat + 3) & ~3;
   const size_t proj_smem = (size_t)(EVP_T * EV_PLD + 14 * EVP_T + 2 * xs_doubles) * 8 + (size_t)(3 * EVP_T + 2 * feat_ints) * 4;
   static const int minb = getenv("VILS_EV_MINB") ? atoi(getenv("VILS_EV_MINB")) : 3;
-  static bool attr = false;
-  if (!attr) {
+  if (!ba->eval_attr_set) {   // per handle, i.e. per device: function attributes belong to the device the handle lives on
     cudaFuncSetAttribute(eval_proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
     cudaFuncSetAttribute(eval_proj_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
     cudaFuncSetAttribute(eval_proj_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
-    attr = true;
+    ba->eval_attr_set = true;
   }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;

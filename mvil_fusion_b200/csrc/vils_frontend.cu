@@ -608,8 +608,7 @@ int vils_reject_with_f(vils_frontend* f, const float* pts1, const float* pts2, i
   uint8_t* dst = reinterpret_cast<uint8_t*>(d2 + 2 * n); int* dinfo = reinterpret_cast<int*>(dst + ((n + 15) & ~15)); double* dF = reinterpret_cast<double*>(dinfo + 4);
   cudaMemcpyAsync(d1, pts1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, f->st);
   cudaMemcpyAsync(d2, pts2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, f->st);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(ransac_f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+  cudaFuncSetAttribute(ransac_f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);   // per device; a few microseconds
   if ((size_t)n * 32 > 64 * 1024) return vils::fail(VILS_ERR_CAPACITY, "vils_reject_with_f: too many points");
   cudaEventRecord(f->e0, f->st);
   ransac_f_kernel<<<1, RANSAC_H, (size_t)n * 32, f->st>>>(d1, d2, n, threshold * threshold, 12345u, dst, dinfo, dF);
