@@ -901,6 +901,7 @@ __device__ __noinline__ void chol_diag_factor(double* Akk, double* dinv, int* fl
   double* dst = Akk + r * TLD;
 #pragma unroll
   for (int c = 0; c < 16; c++) a[c] = dst[c];
+  __syncwarp();                                      // every lane has its row before the first column is written back
   const double* col = Akk;                           // &A[j][j]
   bool bad = false;
   // A single warp issues ~1 instruction per 4 cycles on this dependent chain, so the body is kept to the bare minimum:
@@ -911,7 +912,7 @@ __device__ __noinline__ void chol_diag_factor(double* Akk, double* dinv, int* fl
     bad |= !(ajj > 0.0);                             // also catches NaN
     const double di = rsqrt(ajj);
     const double a0 = a[0] * di;                     // L[r][j] (rows r < j: don't-care)
-    dst[j] = a0;
+    if (lane < 16) dst[j] = a0;                      // lanes 16..31 hold the same value: one writer per address (racecheck-clean)
     if (lane == j) dinv[j] = di;
     __syncwarp();
 #pragma unroll
