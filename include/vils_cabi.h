@@ -337,6 +337,13 @@ int vils_lidar_associate(const float* map_xyzi, int32_t n_map, const float* scan
                          const double t_w_curr[3], int32_t mode, double* out /* n_scan x 10 */, uint8_t* valid, int32_t* nn_idx,
                          float* device_ms, int32_t device);
 
+/* ---- DepthRegister::get_depth (feature_tracker_/src/feature_tracker.h:98-343): LiDAR depth of the tracked features (the 8th feature
+ * channel; depth > 0 makes the landmark's inverse depth a constant block, estimator.cpp:1217-1221).  cloud: n x (x y z intensity) in the
+ * world frame; T1, T2: the two 3x4 row-major float transforms applied in sequence (:129-139); num_bins = 360; feat: m x (x, y, 1)
+ * undistorted features; depth[i] = depth along the camera z axis or -1. */
+int vils_depth_register(const float* cloud_xyzi, int32_t n, const float T1[12], const float T2[12], int32_t num_bins,
+                        const float* feat_xyz, int32_t m, float* depth, float* device_ms, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 // 2048-point tiles shared by the CTA, every lane keeps its K best in registers, then a K-round shuffle merge.  Exact, like the kd-tree
 // (ties broken by the smaller map index); after every tile the warp tightens a shared threshold to its current K-th best, so that almost
 // every later point fails one compare.  A uniform grid over the map is the obvious next step for maps beyond ~100 k points.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -199,9 +200,147 @@ __global__ void __launch_bounds__(256) associate_kernel(const float4* __restrict
   if (nn_out) for (int j = 0; j < 5; j++) nn_out[(size_t)qi * 5 + j] = sel[j];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// DepthRegister::get_depth (feature_tracker_/src/feature_tracker.h:98-343): LiDAR depth for the tracked features — the producer of the
+// 8th feature channel (depth > 0 => lidar_depth_flag => constant inverse depth in the window solve, estimator.cpp:1217-1221).
+//   A  depth_bin_kernel   : cloud -> camera-aligned LiDAR frame (two float affine transforms, as pcl::transformPointCloud applies them),
+//                           view filter, 0.5 degree range image; the CLOSEST point of every bin wins (:143-168), here by a 64-bit atomicMin on
+//                           (range bits, point index) — same winner as the sequential `dist < rangeImage` scan, ties to the first point.
+//   B  depth_compact_kernel: occupied bins -> dense list of unit-sphere points with their range (:241-250)
+//   C  depth_feature_kernel: per feature (one warp) the 3 nearest unit-sphere points (:258-262, exhaustive instead of a kd-tree), distance
+//                           gate, range spread <= 2 m, depth = mean range * feature.x, kept if > 3 m (:263-337)
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 affine(const float* T, float4 p) {   // row-major 3x4
+  return make_float4(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7], T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11], p.w);
+}
+__global__ void depth_bin_kernel(const float4* __restrict__ cloud, int n, const float* __restrict__ T /* two 3x4 */, int nb, unsigned long long* __restrict__ bins,
+                                 float4* __restrict__ local) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = affine(T + 12, affine(T, cloud[i]));
+  local[i] = p;
+  if (p.x < 0 || fabsf(p.y / p.x) > 10 || fabsf(p.z / p.x) > 10) return;
+  const float bin_res = 180.0f / (float)nb;
+  const float row_angle = (float)((double)atan2f(p.z, sqrtf(p.x * p.x + p.y * p.y)) * 180.0 / M_PI + 90.0);
+  const int row_id = (int)roundf(row_angle / bin_res);
+  const float col_angle = (float)((double)atan2f(p.x, p.y) * 180.0 / M_PI);
+  const int col_id = (int)roundf(col_angle / bin_res);
+  if (row_id < 0 || row_id >= nb || col_id < 0 || col_id >= nb) return;
+  const float dist = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+  atomicMin(&bins[(size_t)row_id * nb + col_id], ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned int)i);
+}
+__global__ void depth_compact_kernel(const unsigned long long* __restrict__ bins, int nbins, const float4* __restrict__ local, float4* __restrict__ sphere, int* __restrict__ count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const unsigned long long v = bins[b];
+  if (v == ~0ull) return;
+  float4 p = local[(unsigned int)(v & 0xffffffffu)];
+  const float range = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+  p.x /= range; p.y /= range; p.z /= range; p.w = range;
+  sphere[atomicAdd(count, 1)] = p;
+}
+__global__ void __launch_bounds__(256) depth_feature_kernel(const float4* __restrict__ sphere, const int* __restrict__ count, const float* __restrict__ feat, int m, int nb,
+                                                            float* __restrict__ depth) {
+  __shared__ float4 tile[ASSOC_TILE];
+  const int lane = threadIdx.x & 31, fi0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool active = fi0 < m;
+  const int fi = active ? fi0 : m - 1, n = *count;
+  // feature on the unit sphere, camera -> LiDAR axis convention (:226-238)
+  float fx = feat[3 * fi], fy = feat[3 * fi + 1], fz = feat[3 * fi + 2];
+  const float nn = sqrtf(fx * fx + fy * fy + fz * fz); fx /= nn; fy /= nn; fz /= nn;
+  const float px = fz, py = -fx, pz = -fy;
+  Knn h;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) { h.d[k] = 3.0e38f; h.i[k] = 0x7fffffff; }
+  for (int base = 0; base < n; base += ASSOC_TILE) {
+    const int cnt = min(ASSOC_TILE, n - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) tile[j] = sphere[base + j];
+    __syncthreads();
+    if (active)
+      for (int j = lane; j < cnt; j += 32) {
+        const float4 q = tile[j];
+        const float dx = q.x - px, dy = q.y - py, dz = q.z - pz;
+        knn_insert<3>(h, dx * dx + dy * dy + dz * dz, base + j);
+      }
+  }
+  if (!active) return;
+  float nd[3]; int ni[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    float bd = h.d[0]; int bi = h.i[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    nd[r] = bd; ni[r] = bi;
+    if (h.i[0] == bi && h.d[0] == bd) { h.d[0] = h.d[1]; h.i[0] = h.i[1]; h.d[1] = h.d[2]; h.i[1] = h.i[2]; h.d[2] = 3.0e38f; h.i[2] = 0x7fffffff; }
+  }
+  if (lane != 0) return;
+  float out = -1.0f;
+  const float bin_res = 180.0f / (float)nb;
+  const float thr = (float)pow(sin((double)bin_res / 180.0 * M_PI) * 5.0, 2);
+  if (n >= 10 && ni[2] != 0x7fffffff && nd[2] < thr) {
+    const float r1 = sphere[ni[0]].w, r2 = sphere[ni[1]].w, r3 = sphere[ni[2]].w;
+    const float mn = fminf(r1, fminf(r2, r3)), mx = fmaxf(r1, fmaxf(r2, r3));
+    if (!(mx - mn > 2)) {
+      const float s_ = (r1 + r2 + r3) / 3;
+      const float d = px * s_;                       // depth for the z-normalised feature (LiDAR x = camera z)
+      if (d > 3.0f) out = d;
+    }
+  }
+  depth[fi] = out;
+}
+
 }  // namespace
 
 extern "C" {
+
+// DepthRegister::get_depth (feature_tracker_/src/feature_tracker.h:98-343).  cloud: n points x y z intensity (4 packed floats) of the
+// stacked depth cloud in the world frame; T1, T2: the two 3x4 row-major float affine transforms the reference applies one after the
+// other (transNow.inverse(), then Tlc_ * TransFormLC.inverse());  feat: m undistorted features (x, y, 1);  depth[i] = LiDAR depth of
+// feature i along the camera z axis, or -1.  num_bins = 360 in the reference.
+int vils_depth_register(const float* cloud_xyzi, int32_t n, const float T1[12], const float T2[12], int32_t num_bins, const float* feat_xyz, int32_t m,
+                        float* depth, float* ms, int32_t device) {
+  if (n < 0 || m < 0 || (n && !cloud_xyzi) || !T1 || !T2 || num_bins <= 0 || num_bins > 4096 || (m && (!feat_xyz || !depth))) return vils::fail(VILS_ERR_BAD_ARG, "vils_depth_register: bad argument");
+  for (int i = 0; i < m; i++) depth[i] = -1.0f;
+  if (m == 0 || n == 0) return VILS_OK;
+  int st = vils::require_device(device); if (st) return st;
+  const size_t nbins = (size_t)num_bins * num_bins;
+  float4* d_cloud = nullptr; float4* d_local = nullptr; float4* d_sphere = nullptr; unsigned long long* d_bins = nullptr; float* d_T = nullptr; float* d_feat = nullptr; float* d_depth = nullptr; int* d_cnt = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_cloud, sizeof(float4) * (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_local, sizeof(float4) * (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_sphere, sizeof(float4) * std::min(nbins, (size_t)n));
+  if (e == cudaSuccess) e = cudaMalloc(&d_bins, sizeof(unsigned long long) * nbins);
+  if (e == cudaSuccess) e = cudaMalloc(&d_T, sizeof(float) * 24);
+  if (e == cudaSuccess) e = cudaMalloc(&d_feat, sizeof(float) * 3 * (size_t)m);
+  if (e == cudaSuccess) e = cudaMalloc(&d_depth, sizeof(float) * (size_t)m);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(int));
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) {
+    float T[24]; memcpy(T, T1, sizeof(float) * 12); memcpy(T + 12, T2, sizeof(float) * 12);
+    cudaMemcpy(d_cloud, cloud_xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_T, T, sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_feat, feat_xyz, sizeof(float) * 3 * (size_t)m, cudaMemcpyHostToDevice);
+    cudaEventRecord(e0);
+    cudaMemsetAsync(d_bins, 0xff, sizeof(unsigned long long) * nbins);
+    cudaMemsetAsync(d_cnt, 0, sizeof(int));
+    depth_bin_kernel<<<(n + 255) / 256, 256>>>(d_cloud, n, d_T, num_bins, d_bins, d_local);
+    depth_compact_kernel<<<(int)((nbins + 255) / 256), 256>>>(d_bins, (int)nbins, d_local, d_sphere, d_cnt);
+    depth_feature_kernel<<<(m + 7) / 8, 256>>>(d_sphere, d_cnt, d_feat, m, num_bins, d_depth);
+    cudaEventRecord(e1);
+    e = cudaMemcpy(depth, d_depth, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ms) cudaEventElapsedTime(ms, e0, e1);
+  }
+  cudaFree(d_cloud); cudaFree(d_local); cudaFree(d_sphere); cudaFree(d_bins); cudaFree(d_T); cudaFree(d_feat); cudaFree(d_depth); cudaFree(d_cnt);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_depth_register");
+}
+
 
 // Scan-to-map association (localMapping.cpp:611-766).  map / scan: PCL-style x y z intensity as 4 packed floats per point (HOST pointers);
 // q_w_curr (x y z w), t_w_curr: the current scan-to-map pose.  mode 0: corner points -> LidarEdgeFactor inputs, out[i] = p(3) a(3) b(3) -;

@@ -76,6 +76,7 @@ def load():
     L.vils_reject_with_f.argtypes = [vp, fp, fp, C.c_int32, C.c_double, up, dp]
     L.vils_triangulate.argtypes = [C.c_int32, ip, ip, dp, C.c_int32, dp, dp, dp, dp, C.c_double, dp, C.c_int32]
     L.vils_lidar_associate.argtypes = [fp, C.c_int32, fp, C.c_int32, dp, dp, C.c_int32, dp, up, ip, C.POINTER(C.c_float), C.c_int32]
+    L.vils_depth_register.argtypes = [fp, C.c_int32, fp, fp, C.c_int32, fp, C.c_int32, fp, C.POINTER(C.c_float), C.c_int32]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -328,6 +329,17 @@ def lidar_associate(map_xyzi, scan_xyzi, q, t, mode, device=0):
     _check(load().vils_lidar_associate(m.ctypes.data_as(fp), len(m), s.ctypes.data_as(fp), len(s), _d(q), _d(t), mode, _d(out),
                                        valid.ctypes.data_as(cabi.c_uint8_p), nn.ctypes.data_as(cabi.c_int32_p), C.byref(ms), device))
     return out[:len(s)], valid[:len(s)].astype(bool), nn[:len(s)], ms.value
+
+
+def depth_register(cloud_xyzi, T1, T2, feat_xyz, num_bins=360, device=0):
+    """vils_depth_register: returns (depth m, device_ms)."""
+    c = np.ascontiguousarray(cloud_xyzi, np.float32).reshape(-1, 4); f = np.ascontiguousarray(feat_xyz, np.float32).reshape(-1, 3)
+    T1 = np.ascontiguousarray(T1, np.float32).reshape(-1)[:12].copy(); T2 = np.ascontiguousarray(T2, np.float32).reshape(-1)[:12].copy()
+    depth = np.zeros(max(len(f), 1), np.float32); ms = C.c_float()
+    fp = cabi.c_float_p
+    _check(load().vils_depth_register(c.ctypes.data_as(fp), len(c), T1.ctypes.data_as(fp), T2.ctypes.data_as(fp), num_bins, f.ctypes.data_as(fp), len(f),
+                                      depth.ctypes.data_as(fp), C.byref(ms), device))
+    return depth[:len(f)], ms.value
 
 
 class Frontend:

@@ -114,3 +114,73 @@ def test_associate_edge_cases():
     assert not valid.any()
     out, valid, nn, _ = lib.lidar_associate(mp, np.zeros((0, 4), np.float32), q, t, 1)
     assert out.shape == (0, 10)
+
+
+def depth_oracle(cloud, T1, T2, feat, nb=360):
+    """numpy restatement of DepthRegister::get_depth (feature_tracker_/src/feature_tracker.h:129-343), float32 where the reference is."""
+    f32 = np.float32
+    def aff(T, p):
+        T = T.astype(f32)
+        return np.stack([((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3] for r in range(3)], 1).astype(f32)
+    p = aff(T2, aff(T1, cloud[:, :3].astype(f32)))
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        keep = ~((x < 0) | (np.abs(y / x) > 10) | (np.abs(z / x) > 10))
+    bin_res = f32(180.0) / f32(nb)
+    row_angle = (np.arctan2(z, np.sqrt(x * x + y * y).astype(f32)).astype(f32).astype(np.float64) * 180.0 / np.pi + 90.0).astype(f32)
+    col_angle = (np.arctan2(x, y).astype(f32).astype(np.float64) * 180.0 / np.pi).astype(f32)
+    def cround(v):
+        fl = np.floor(v); return np.where(v - fl >= 0.5, fl + 1, fl).astype(np.int64)
+    with np.errstate(invalid="ignore"):
+        row = cround((row_angle / bin_res).astype(f32)); col = cround((col_angle / bin_res).astype(f32))
+    keep &= (row >= 0) & (row < nb) & (col >= 0) & (col < nb)
+    dist = np.sqrt(x * x + y * y + z * z).astype(f32)
+    best = {}
+    for i in np.nonzero(keep)[0]:
+        k = (row[i], col[i])
+        if k not in best or dist[i] < dist[best[k]]:
+            best[k] = i
+    idx = np.array([best[k] for k in sorted(best)], np.int64)
+    depth = np.full(len(feat), -1.0, f32)
+    if len(idx) < 10:
+        return depth
+    sel = p[idx]; rng_ = np.sqrt((sel * sel).sum(1)).astype(f32)
+    sph = (sel / rng_[:, None]).astype(f32)
+    fv = feat.astype(f32); fv = (fv / np.sqrt((fv * fv).sum(1))[:, None]).astype(f32)
+    q = np.stack([fv[:, 2], -fv[:, 0], -fv[:, 1]], 1)
+    tree = scipy_spatial.cKDTree(sph.astype(np.float64))
+    d, nn = tree.query(q.astype(np.float64), k=3)
+    thr = f32(np.power(np.sin(float(bin_res) / 180.0 * np.pi) * 5.0, 2))
+    for i in range(len(feat)):
+        if f32(d[i, 2] ** 2) < thr:
+            r = rng_[nn[i]]
+            if not (r.max() - r.min() > 2):
+                dep = q[i, 0] * ((r[0] + r[1] + r[2]) / f32(3))
+                if dep > 3.0:
+                    depth[i] = dep
+    return depth
+
+
+def test_depth_register_matches_restatement():
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(77)
+    _, surf = room_map(rng, 4000, 120000)                       # walls of a 16 x 12 x 3 m room, world frame
+    cloud = surf.copy(); cloud[:, 2] -= 1.2                     # sensor 1.2 m above the floor
+    import cv2
+    R1, _ = cv2.Rodrigues(np.array([0.02, -0.01, 0.3])); t1 = np.array([0.5, -0.3, 0.1])
+    T1 = np.c_[R1.T, -R1.T @ t1]                                # transNow.inverse()
+    R2, _ = cv2.Rodrigues(np.array([0.01, 0.02, -0.015])); T2 = np.c_[R2, np.array([0.05, 0.0, -0.08])]
+    feat = np.stack([rng.uniform(-0.9, 0.9, 150), rng.uniform(-0.65, 0.65, 150), np.ones(150)], 1)
+    depth, ms = lib.depth_register(cloud, T1, T2, feat, 360)
+    ref = depth_oracle(cloud, T1, T2, feat, 360)
+    same = ((depth < 0) == (ref < 0))
+    assert same.mean() >= 0.98, same.mean()
+    both = (depth > 0) & (ref > 0)
+    assert both.sum() > 60                                      # most features get a LiDAR depth in this scene
+    rel = np.abs(depth[both] - ref[both]) / ref[both]
+    assert (rel <= 1e-5).mean() >= 0.98 and np.median(rel) <= 1e-6
+    # few points / no points: nothing is assigned
+    d2, _ = lib.depth_register(cloud[:5], T1, T2, feat, 360)
+    assert (d2 == -1).all()
+    d3, _ = lib.depth_register(np.zeros((0, 4), np.float32), T1, T2, feat, 360)
+    assert (d3 == -1).all()
