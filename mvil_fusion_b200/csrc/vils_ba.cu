@@ -702,7 +702,8 @@ struct vils_ba {
   vils_config cfg{};
   int max_windows = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // vils_ba_solve: chunked upload / solve / download pipeline
+  static constexpr int NPIPE = 8;
+  cudaStream_t pipe[NPIPE] = {};                        // vils_ba_solve: chunked upload / solve / download pipeline
   int n_sm = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   size_t blob_stride = 0;
@@ -815,7 +816,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaStreamCreateWithFlags(&ba->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ba->ev0)); CK(cudaEventCreate(&ba->ev1));
   CK(cudaStreamCreateWithFlags(&ba->stream2, cudaStreamNonBlocking));
-  for (int k = 0; k < 3; k++) CK(cudaStreamCreateWithFlags(&ba->pipe[k], cudaStreamNonBlocking));
+  for (int k = 0; k < vils_ba::NPIPE; k++) CK(cudaStreamCreateWithFlags(&ba->pipe[k], cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ba->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaEventCreateWithFlags(&ba->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ba->ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
@@ -851,7 +852,7 @@ void vils_ba_destroy(vils_ba* ba) {
   if (ba->ev_fork) cudaEventDestroy(ba->ev_fork);
   if (ba->ev_join) cudaEventDestroy(ba->ev_join);
   if (ba->stream2) cudaStreamDestroy(ba->stream2);
-  for (int k = 0; k < 3; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
+  for (int k = 0; k < vils_ba::NPIPE; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
   if (ba->stream) cudaStreamDestroy(ba->stream);
   delete ba;
 }
@@ -1076,15 +1077,18 @@ int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   int st = check_n(ba, n, "vils_ba_solve"); if (st) return st;
   if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
   static const int chunk_env = getenv("VILS_CHUNK") ? atoi(getenv("VILS_CHUNK")) : 0;
+  static const int ns_env = getenv("VILS_STREAMS") ? atoi(getenv("VILS_STREAMS")) : 0;
   const int chunk = chunk_env > 0 ? chunk_env : std::max(1, ba->n_sm / 2);
+  // enough streams that the chunks in flight can cover every SM (one CTA per window, one CTA per SM) plus one chunk being copied
+  const int NS = std::min<int>(vils_ba::NPIPE, ns_env > 0 ? ns_env : std::max(3, (ba->n_sm + chunk - 1) / chunk + 1));
   SolveParams P = make_params(ba, opts);
   const bool both = ba->h_in_smem && ba->hv_in_smem;
   size_t h2d = 0; int launches = 0;
   cudaEventRecord(ba->ev_fork, ba->stream);                 // order after anything still queued on the handle's main stream
-  for (int k = 0; k < 3; k++) cudaStreamWaitEvent(ba->pipe[k], ba->ev_fork, 0);
+  for (int k = 0; k < NS; k++) cudaStreamWaitEvent(ba->pipe[k], ba->ev_fork, 0);
   for (int c0 = 0, c = 0; c0 < n; c0 += chunk, c++) {
     const int cn = std::min(chunk, n - c0);
-    cudaStream_t s = ba->pipe[c % 3];
+    cudaStream_t s = ba->pipe[c % NS];
     size_t width = 0; for (int k = c0; k < c0 + cn; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
     h2d += width * cn;
     cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
@@ -1097,7 +1101,7 @@ int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
     cudaMemcpyAsync(ba->h_sum + c0, ba->d_sum + c0, sizeof(vils_summary) * cn, cudaMemcpyDeviceToHost, s);
   }
   cudaError_t e = cudaSuccess;
-  for (int k = 0; k < 3; k++) { const cudaError_t ek = cudaStreamSynchronize(ba->pipe[k]); if (e == cudaSuccess) e = ek; }
+  for (int k = 0; k < NS; k++) { const cudaError_t ek = cudaStreamSynchronize(ba->pipe[k]); if (e == cudaSuccess) e = ek; }
   if (e != cudaSuccess) return vils::fail_cuda(e, "vils_ba_solve");
   ba->prepped = true;
   ba->last_h2d = h2d; ba->last_d2h = (size_t)ba->xstride * 8 * n + sizeof(vils_summary) * n;
