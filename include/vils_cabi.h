@@ -320,6 +320,10 @@ int vils_deskew(float* xyzi, int32_t n, int32_t stride_floats, const float q[4] 
  * start_ori is taken from the first kept point as in the reference. */
 int vils_stamp_rings(float* xyzi, int32_t n, int32_t stride_floats, float lower_deg, float upper_deg,
                      int32_t n_rings, float scan_period, int32_t* ring_out, int32_t device);
+/* PointProcessor::PointToRing complete (PointProcessor.cc:106-341): stamp + the ring-major re-ordering of :114-117.  out (capacity n points):
+ * the kept points, ring 0 first, scan order inside a ring; ring_start[n_rings + 1].  The input is not modified. */
+int vils_point_to_ring(const float* xyzi, int32_t n, int32_t stride_floats, float lower_deg, float upper_deg, int32_t n_rings,
+                       float scan_period, float* out, int32_t* ring_start, int32_t device);
 /* Fused stamp + deskew on a device-resident cloud (throughput measurement). */
 int vils_lidar_dev_alloc(int32_t n, int32_t stride_floats, int32_t device, void** handle);
 int vils_lidar_dev_upload(void* handle, const float* xyzi);

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <vector>
+
 #include "common.h"
 
 namespace {
@@ -129,6 +131,85 @@ int vils_deskew(float* xyzi, int32_t n, int32_t stride, const float q[4], const 
   if (e == cudaSuccess) { st = run_deskew(d, n, stride, mk(q, t, time_factor, min_r, max_r), 0); if (st) { cudaFree(d); return st; } e = cudaMemcpy(xyzi, d, bytes, cudaMemcpyDeviceToHost); }
   cudaFree(d);
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_deskew copy");
+}
+
+}  // extern "C" (reopened below)
+
+// PointProcessor::PointToRing() (lidar_compensator/src/PointProcessor.cc:106-125): cloud_in_rings_ = ring 0 points, then ring 1, ... each in
+// scan order.  One CTA per ring walks the cloud in order; a block-wide exclusive scan of "ring == r" gives every kept point its stable
+// position inside the ring, the ring's base comes from a histogram.
+__global__ void ring_hist_kernel(const int* __restrict__ ring, int n, int n_rings, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ring[i] >= 0 && ring[i] < n_rings) atomicAdd(&count[ring[i]], 1);
+}
+__global__ void __launch_bounds__(1024) ring_scatter_kernel(const float* __restrict__ pts, const int* __restrict__ ring, int n, int stride, const int* __restrict__ start,
+                                                           float* __restrict__ out) {
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) base_s = start[r];
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + t;
+    const bool mine = i < n && ring[i] == r;
+    const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+    const int within = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; w++) { const int v = wsum[w]; if (w < warp) before += v; total += v; }
+    if (mine) {
+      const size_t dst = (size_t)(base_s + before + within) * stride, src = (size_t)i * stride;
+      for (int k = 0; k < stride; k++) out[dst + k] = pts[src + k];
+    }
+    __syncthreads();
+    if (t == 0) base_s += total;
+    __syncthreads();
+  }
+}
+
+extern "C" {
+
+// PointProcessor::PointToRing (PointProcessor.cc:106-341) complete: stamp (ring id + relative time in the intensity) and the ring-major
+// re-ordering.  out: the kept points, ring 0 first (n_kept x stride floats, capacity n); ring_start[n_rings + 1]: first point of every
+// ring in `out`.  The input cloud is not modified.
+int vils_point_to_ring(const float* xyzi, int32_t n, int32_t stride, float lower_deg, float upper_deg, int32_t n_rings, float scan_period, float* out,
+                       int32_t* ring_start, int32_t device) {
+  if (!xyzi || !out || !ring_start || n < 0 || stride < 4 || n_rings < 2 || n_rings > 1024) return vils::fail(VILS_ERR_BAD_ARG, "vils_point_to_ring: bad argument");
+  int st = vils::require_device(device); if (st) return st;
+  for (int r = 0; r <= n_rings; r++) ring_start[r] = 0;
+  if (n == 0) return VILS_OK;
+  float* d = nullptr; float* dout = nullptr; int* ring = nullptr; float* azi = nullptr; int* first = nullptr; int* cnt = nullptr;
+  const size_t bytes = (size_t)n * stride * sizeof(float);
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ring, sizeof(int) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&azi, sizeof(float) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&first, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&cnt, sizeof(int) * (n_rings + 1));
+  const int big = n;
+  if (e == cudaSuccess) e = cudaMemcpy(first, &big, sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d, xyzi, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(cnt, 0, sizeof(int) * (n_rings + 1));
+  std::vector<int> hc(n_rings + 1, 0);
+  if (e == cudaSuccess) {
+    StampParams P; P.lower = lower_deg; P.factor = (n_rings - 1) / (upper_deg - lower_deg); P.scan_period = scan_period; P.n_rings = n_rings;
+    const int T = 256, B = (n + T - 1) / T;
+    stamp_pass1<<<B, T>>>(d, n, stride, P, ring, azi, first);
+    stamp_pass2<<<B, T>>>(d, n, stride, P, ring, azi, first);
+    ring_hist_kernel<<<B, T>>>(ring, n, n_rings, cnt);
+    e = cudaMemcpy(hc.data(), cnt, sizeof(int) * n_rings, cudaMemcpyDeviceToHost);
+  }
+  if (e == cudaSuccess) {
+    int acc = 0;
+    for (int r = 0; r < n_rings; r++) { ring_start[r] = acc; acc += hc[r]; }
+    ring_start[n_rings] = acc;
+    e = cudaMemcpy(cnt, ring_start, sizeof(int) * (n_rings + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { ring_scatter_kernel<<<n_rings, 1024>>>(d, ring, n, stride, cnt, dout); e = cudaGetLastError(); }
+    if (e == cudaSuccess && acc > 0) e = cudaMemcpy(out, dout, (size_t)acc * stride * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d); cudaFree(dout); cudaFree(ring); cudaFree(azi); cudaFree(first); cudaFree(cnt);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_point_to_ring");
 }
 
 int vils_stamp_rings(float* xyzi, int32_t n, int32_t stride, float lower_deg, float upper_deg, int32_t n_rings, float scan_period, int32_t* ring_out, int32_t device) {

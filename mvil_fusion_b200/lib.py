@@ -79,6 +79,7 @@ def load():
     L.vils_depth_register.argtypes = [fp, C.c_int32, fp, fp, C.c_int32, fp, C.c_int32, fp, C.POINTER(C.c_float), C.c_int32]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
+    L.vils_point_to_ring.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, fp, ip, C.c_int32]
     L.vils_lidar_dev_alloc.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.vils_lidar_dev_upload.argtypes = [vp, fp]
     L.vils_lidar_dev_deskew.argtypes = [vp, fp, fp, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
@@ -256,6 +257,16 @@ def stamp_rings(xyzi, stride, lower_deg=-15.0, upper_deg=15.0, n_rings=16, scan_
     _check(load().vils_stamp_rings(a.ctypes.data_as(cabi.c_float_p), n, stride, lower_deg, upper_deg, n_rings, scan_period,
                                    ring.ctypes.data_as(cabi.c_int32_p), device))
     return a, ring
+
+
+def point_to_ring(xyzi, stride, lower_deg=-15.0, upper_deg=15.0, n_rings=16, scan_period=0.1, device=0):
+    """vils_point_to_ring: returns (ring-major cloud of the kept points, ring_start[n_rings + 1])."""
+    a = np.ascontiguousarray(xyzi, np.float32)
+    n = a.size // stride
+    out = np.zeros((max(n, 1), stride), np.float32); start = np.zeros(n_rings + 1, np.int32)
+    _check(load().vils_point_to_ring(a.ctypes.data_as(cabi.c_float_p), n, stride, lower_deg, upper_deg, n_rings, scan_period,
+                                     out.ctypes.data_as(cabi.c_float_p), start.ctypes.data_as(cabi.c_int32_p), device))
+    return out[:start[-1]], start
 
 
 class KLT:

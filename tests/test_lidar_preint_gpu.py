@@ -78,3 +78,21 @@ def test_preintegration_three_way():
     for other in (gpu, npy):
         scale = np.maximum(np.abs(ref), 1e-12)
         assert (np.abs(other - ref) / np.maximum(scale, np.abs(ref).max(axis=0) * 1e-3)).max() < 1e-9
+
+
+@pytest.mark.parametrize("stride", [8, 4])
+def test_point_to_ring_is_the_stable_ring_major_order(stride):
+    """PointProcessor::PointToRing() (PointProcessor.cc:106-125): cloud_in_rings_ = the kept points of ring 0 in scan order, then ring 1, ...
+    vils_point_to_ring must equal a stable sort by ring id of the stamped cloud (index work: exact)."""
+    from mvil_fusion_b200 import lib
+    pts = make_cloud(29000, 5, stride)
+    sg, rg = lib.stamp_rings(pts, stride)
+    out, start = lib.point_to_ring(pts, stride)
+    keep = np.nonzero(rg >= 0)[0]
+    order = keep[np.argsort(rg[keep], kind="stable")]
+    exp = sg.reshape(-1, stride)[order]
+    assert start[-1] == len(keep) and len(out) == len(keep)
+    assert np.array_equal(np.diff(start), np.bincount(rg[keep], minlength=16))
+    assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+    o0, s0 = lib.point_to_ring(np.zeros((0, stride), np.float32), stride)
+    assert len(o0) == 0 and s0[-1] == 0
