@@ -906,6 +906,8 @@ __device__ __noinline__ void chol_diag_factor(double* Akk, double* dinv, int* fl
   bool bad = false;
   // A single warp issues ~1 instruction per 4 cycles on this dependent chain, so the body is kept to the bare minimum:
   // no index clamping (rows past the tile are don't-care reads inside the same buffer), one pointer bump per column.
+  // (Software-pipelining the pivot chain — broadcasting lane j+1's own next pivot and issuing its rsqrt before the shared-memory
+  // round trip — was measured: no change, the trailing update of phase B is just as long.)
 #pragma unroll 1
   for (int j = 0; j < 16; j++) {
     const double ajj = __shfl_sync(0xffffffffu, a[0], j);
@@ -1026,9 +1028,11 @@ __device__ bool cholesky_tiles(double* H, double* b, double* linv, double* dinv,
     // Phase B: warp 0 factors the next diagonal tile, everyone else updates the remaining tiles (jb >= kb+2).
     if (warp == dw) {
       chol_diag_factor(H + (size_t)(tri(kb + 1) + kb + 1) * TSZ, dinv + (kb + 1) * 16, flag);
-    } else {
-      const int ntl = tri(rem - 1) * 16;
-      for (int it = t; it < ntl; it += blockDim.x - 32) {
+    } else if ((warp & 3) != (dw & 3)) {
+      // the three warps that share the diagonal warp's SM sub-partition sit this phase out: a lone dependent chain next to
+      // DFMA-saturating warps on the same scheduler runs several times slower, and the diagonal tile is the critical path
+      const int ntl = tri(rem - 1) * 16, tu = (warp - (warp >> 2)) * 32 + lane;
+      for (int it = tu; it < ntl; it += (SOLVE_WARPS - SOLVE_WARPS / 4) * 32) {
         const int tl = it >> 4;
         int bi = (int)((sqrtf(8.0f * tl + 1.0f) - 1.0f) * 0.5f);
         while (bi * (bi + 1) / 2 > tl) bi--;
