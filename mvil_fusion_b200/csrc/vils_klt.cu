@@ -237,7 +237,7 @@ int vils_klt_create(int32_t rows, int32_t cols, int32_t max_pts, int32_t win, in
   if (e == cudaSuccess) e = cudaMalloc(&k->d_next_pts, sizeof(float2) * max_pts);
   if (e == cudaSuccess) e = cudaMalloc(&k->d_status, max_pts);
   if (e == cudaSuccess) e = cudaMalloc(&k->d_err, sizeof(float) * max_pts);
-  if (e == cudaSuccess) e = cudaMallocHost(&k->h_stage, (size_t)2 * rows * cols + (size_t)max_pts * 16);
+  if (e == cudaSuccess) e = cudaMallocHost(&k->h_stage, (((size_t)2 * rows * cols + 15) & ~(size_t)15) + (size_t)max_pts * 16);
   if (e != cudaSuccess) { vils_klt_destroy(k); return vils::fail_cuda(e, "vils_klt_create"); }
   *out = k; return VILS_OK;
 }
@@ -262,7 +262,7 @@ int vils_klt_upload(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32
     memcpy(k->h_stage + (size_t)y * k->cols, prev + (size_t)y * stride, k->cols);
     memcpy(k->h_stage + px + (size_t)y * k->cols, next + (size_t)y * stride, k->cols);
   }
-  float* hp = reinterpret_cast<float*>(k->h_stage + 2 * px);
+  float* hp = reinterpret_cast<float*>(k->h_stage + ((2 * px + 15) & ~(size_t)15));
   if (n) memcpy(hp, prev_xy, sizeof(float) * 2 * n);
   cudaMemcpyAsync(k->prev.img[0], k->h_stage, px, cudaMemcpyHostToDevice, k->st);
   cudaMemcpyAsync(k->next.img[0], k->h_stage + px, px, cudaMemcpyHostToDevice, k->st);
@@ -295,11 +295,41 @@ int vils_klt_download(vils_klt* k, float* next_xy, uint8_t* status, float* err) 
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_klt_download");
 }
 
+// The call readImage makes: host buffers in, host buffers out.  Everything is queued on the handle's stream and closed by ONE
+// synchronisation (copies in, pyramids, derivatives, tracking, copies out through pinned staging).
 int vils_klt_track(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32_t stride, const float* prev_xy, int32_t n, float* next_xy,
                    uint8_t* status, float* err) {
-  int st = vils_klt_upload(k, prev, next, stride, prev_xy, n); if (st) return st;
-  st = vils_klt_track_device(k); if (st) return st;
-  return vils_klt_download(k, next_xy, status, err);
+  if (!k || !prev || !next || stride < k->cols || n < 0 || n > k->max_pts || (n && !prev_xy)) return vils::fail(VILS_ERR_BAD_ARG, "vils_klt_track: bad argument");
+  cudaSetDevice(k->device);
+  const size_t px = (size_t)k->rows * k->cols;
+  for (int y = 0; y < k->rows; y++) {   // compact into pinned staging (drops the row padding)
+    memcpy(k->h_stage + (size_t)y * k->cols, prev + (size_t)y * stride, k->cols);
+    memcpy(k->h_stage + px + (size_t)y * k->cols, next + (size_t)y * stride, k->cols);
+  }
+  float* hp = reinterpret_cast<float*>(k->h_stage + ((2 * px + 15) & ~(size_t)15));   // max_pts x 16 bytes: [xy in / xy out (8) | err (4) | status (1)]
+  if (n) memcpy(hp, prev_xy, sizeof(float) * 2 * n);
+  cudaMemcpyAsync(k->prev.img[0], k->h_stage, px, cudaMemcpyHostToDevice, k->st);
+  cudaMemcpyAsync(k->next.img[0], k->h_stage + px, px, cudaMemcpyHostToDevice, k->st);
+  if (n) cudaMemcpyAsync(k->d_prev_pts, hp, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, k->st);
+  k->n = n;
+  cudaEventRecord(k->e0, k->st);
+  int st = klt_build_and_track(k); if (st) return st;
+  cudaEventRecord(k->e1, k->st);
+  float* h_err = hp + 2 * (size_t)k->max_pts; uint8_t* h_st = reinterpret_cast<uint8_t*>(h_err + k->max_pts);
+  if (n) {
+    cudaMemcpyAsync(hp, k->d_next_pts, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, k->st);
+    cudaMemcpyAsync(h_err, k->d_err, sizeof(float) * n, cudaMemcpyDeviceToHost, k->st);
+    cudaMemcpyAsync(h_st, k->d_status, n, cudaMemcpyDeviceToHost, k->st);
+  }
+  cudaError_t e = cudaStreamSynchronize(k->st);
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_klt_track");
+  cudaEventElapsedTime(&k->last_ms, k->e0, k->e1);
+  if (n) {
+    if (next_xy) memcpy(next_xy, hp, sizeof(float) * 2 * n);
+    if (err) memcpy(err, h_err, sizeof(float) * n);
+    if (status) memcpy(status, h_st, n);
+  }
+  return VILS_OK;
 }
 
 int vils_klt_last_device_ms(vils_klt* k, float* ms) { if (!k || !ms) return VILS_ERR_BAD_ARG; *ms = k->last_ms; return VILS_OK; }
