@@ -185,9 +185,10 @@ struct vils_klt {
   uint8_t* h_stage = nullptr;   // pinned staging for the two images
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   float last_ms = 0; int n = 0;
+  cudaGraphExec_t graph_exec = nullptr; bool graph_failed = false;
 };
 
-static int klt_build_and_track(vils_klt* k) {
+static void klt_launch_pyramids(vils_klt* k) {
   dim3 B(32, 8);
   for (int img = 0; img < 2; img++) {
     Pyr& P = img ? k->next : k->prev;
@@ -200,6 +201,23 @@ static int klt_build_and_track(vils_klt* k) {
     dim3 G((k->prev.w[l] + B.x - 1) / B.x, (k->prev.h[l] + B.y - 1) / B.y);
     scharr_kernel<<<G, B, 0, k->st>>>(k->prev.img[l], k->prev.w[l], k->prev.h[l], k->prev.der[l]);
   }
+}
+
+static int klt_build_and_track(vils_klt* k) {
+  // the 2 x (levels - 1) pyrDown and the `levels` Scharr launches have fixed arguments for the life of the handle: they are captured
+  // once into a CUDA graph (10 launches -> 1 for 640x480, a launch-bound stretch at this image size); the tracking kernel, whose grid
+  // is the number of points of the call, follows as a normal launch
+  if (!k->graph_exec && !k->graph_failed) {
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(k->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      klt_launch_pyramids(k);
+      if (cudaStreamEndCapture(k->st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&k->graph_exec, g, 0) != cudaSuccess) { k->graph_exec = nullptr; k->graph_failed = true; }
+      if (g) cudaGraphDestroy(g);
+    } else k->graph_failed = true;
+    cudaGetLastError();
+  }
+  if (k->graph_exec) cudaGraphLaunch(k->graph_exec, k->st);
+  else klt_launch_pyramids(k);
   if (k->n > 0) {
     TrackParams T; T.prev = k->prev; T.next = k->next; T.prev_pts = k->d_prev_pts; T.next_pts = k->d_next_pts; T.status = k->d_status; T.err = k->d_err;
     T.n = k->n; T.levels = k->levels; T.win = k->win; T.min_eig = 1e-4f; T.max_iter = 30; T.eps2 = 0.01 * 0.01;   // criteria.epsilon *= criteria.epsilon (double)
@@ -246,6 +264,7 @@ void vils_klt_destroy(vils_klt* k) {
   if (!k) return;
   cudaSetDevice(k->device);
   if (k->st) cudaStreamSynchronize(k->st);
+  if (k->graph_exec) cudaGraphExecDestroy(k->graph_exec);
   for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(k->prev.img[l]); cudaFree(k->next.img[l]); cudaFree(k->prev.der[l]); }
   cudaFree(k->d_prev_pts); cudaFree(k->d_next_pts); cudaFree(k->d_status); cudaFree(k->d_err); cudaFreeHost(k->h_stage);
   if (k->e0) cudaEventDestroy(k->e0);
