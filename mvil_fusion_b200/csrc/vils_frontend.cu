@@ -148,7 +148,7 @@ __global__ void masked_max_kernel(const float* __restrict__ eig, const uint8_t* 
 
 // threshold(TOZERO) + dilate 3x3 + "val != 0 && val == dilated && mask" over the interior (y, x in 1..n-2)
 __global__ void candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ mask, int rows, int cols, const unsigned int* maxbits, float quality,
-                                  unsigned long long* cand, unsigned int* count, unsigned int cap) {
+                                  unsigned long long* cand, unsigned int* count, unsigned int cap, unsigned int* hist) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
   const float thr = (float)((double)__uint_as_float(*maxbits) * (double)quality);   // threshold(eig, eig, maxVal*qualityLevel, ...): double product
@@ -162,7 +162,63 @@ __global__ void candidates_kernel(const float* __restrict__ eig, const uint8_t* 
   if (v != m) return;
   const unsigned int k = atomicAdd(count, 1u);
   // sort key, descending: value first, then the address (greaterThanPtr: equal values -> higher address first)
-  if (k < cap) cand[k] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * cols + x);
+  if (k < cap) { cand[k] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * cols + x); atomicAdd(&hist[__float_as_uint(v) >> 20], 1u); }
+}
+
+// Top-K selection for the greedy pick (it consumes the candidates in descending order and stops after max_corners accepts, i.e. long
+// before the end of the list): one CTA finds, from the 4096-bin histogram of the keys' top 12 bits (sign, exponent, 3 mantissa bits), the
+// bin down to which at least `want` candidates lie, compacts those candidates into shared memory, sorts them there (bitonic, <= 8192
+// keys) and writes them out.  info[2] = number of sorted keys written (0 = does not fit: caller falls back to the full sort).
+constexpr unsigned int TOPK_SMEM = 8192;
+__global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ hist, unsigned int want,
+                                                         unsigned int cap, unsigned long long* __restrict__ top, unsigned int* __restrict__ info) {
+  extern __shared__ unsigned long long sk[];
+  __shared__ unsigned int cut_bin, n_sel;
+  const unsigned int n = min(info[0], cap), t = threadIdx.x;
+  __shared__ unsigned int part[1024];
+  {
+    // suffix sums over the 4096 bins (4 per thread): the cut is the highest bin b with  sum_{bins >= b} >= want
+    unsigned int hb[4]; unsigned int mine = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) { hb[b] = hist[4 * t + b]; mine += hb[b]; }
+    part[t] = mine;
+    if (t == 0) { cut_bin = 0; n_sel = 0; }
+    __syncthreads();
+    for (unsigned int o = 1; o < 1024; o <<= 1) { const unsigned int v = t + o < 1024 ? part[t + o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
+    const unsigned int all = part[0];
+    unsigned int acc = part[t] - mine;                      // candidates in the bins above this thread's four
+#pragma unroll
+    for (int b = 3; b >= 0; b--) {
+      const unsigned int before = acc; acc += hb[b];
+      if (before < want && acc >= want) { cut_bin = 4 * t + b; info[3] = acc; }
+    }
+    if (t == 0 && all < want) info[3] = all;                // fewer candidates than wanted: take them all (cut_bin = 0)
+  }
+  __syncthreads();
+  const unsigned int total_sel = info[3];
+  if (total_sel > TOPK_SMEM) { if (t == 0) info[2] = 0; return; }
+  unsigned int np2 = 1; while (np2 < total_sel) np2 <<= 1;
+  for (unsigned int i = t; i < np2; i += blockDim.x) sk[i] = 0ull;
+  __syncthreads();
+  for (unsigned int i = t; i < n; i += blockDim.x) {
+    const unsigned long long k = cand[i];
+    if ((unsigned int)(k >> 52) >= cut_bin) sk[atomicAdd(&n_sel, 1u)] = k;
+  }
+  __syncthreads();
+  for (unsigned int k = 2; k <= np2; k <<= 1)
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = t; i < np2; i += blockDim.x) {
+        const unsigned int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = sk[i], b = sk[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) { sk[i] = b; sk[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (unsigned int i = t; i < total_sel; i += blockDim.x) top[i] = sk[i];
+  if (t == 0) info[2] = total_sel;
 }
 
 // Single-CTA bitonic sort (descending) of n_pad = 2^k 64-bit keys in global memory; candidates are a few thousand at most.
@@ -389,7 +445,7 @@ struct vils_frontend {
   int rows = 0, cols = 0, device = 0, max_pts = 0;
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   uint8_t* d_src = nullptr; uint8_t* d_dst = nullptr; uint8_t* d_lut = nullptr; uint8_t* d_mask = nullptr; uint8_t* h_img = nullptr;
-  float* d_eig = nullptr; unsigned long long* d_cand = nullptr; unsigned long long* h_cand = nullptr; unsigned int* d_cnt = nullptr; unsigned int* h_cnt = nullptr;
+  float* d_eig = nullptr; unsigned long long* d_cand = nullptr; unsigned long long* h_cand = nullptr; unsigned int* d_cnt = nullptr; unsigned int* h_cnt = nullptr; unsigned int* d_hist = nullptr; unsigned long long* d_top = nullptr;
   int* d_centers = nullptr; int* d_hw = nullptr; float* d_uv = nullptr; double* d_ray = nullptr;
   unsigned int cand_cap = 0; int hw_radius = -1;
   bool mask_valid = false;
@@ -413,14 +469,17 @@ int vils_frontend_create(int32_t rows, int32_t cols, int32_t max_pts, int32_t de
   if (e == cudaSuccess) e = cudaMalloc(&f->d_lut, 256 * 64 * 4);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_eig, px * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&f->d_cand, sizeof(unsigned long long) * f->cand_cap);
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_cnt, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cnt, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_hist, 4096 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_top, TOPK_SMEM * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TOPK_SMEM * sizeof(unsigned long long)));
   if (e == cudaSuccess) e = cudaMalloc(&f->d_centers, sizeof(int) * 2 * max_pts);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_hw, sizeof(int) * 1024);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_uv, sizeof(float) * 2 * max_pts);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_ray, sizeof(double) * 3 * max_pts);
   if (e == cudaSuccess) e = cudaMallocHost(&f->h_img, px);
   if (e == cudaSuccess) e = cudaMallocHost(&f->h_cand, sizeof(unsigned long long) * f->cand_cap);
-  if (e == cudaSuccess) e = cudaMallocHost(&f->h_cnt, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_cnt, 4 * sizeof(unsigned int));
   if (e != cudaSuccess) { vils_frontend_destroy(f); return vils::fail_cuda(e, "vils_frontend_create"); }
   *out = f; return VILS_OK;
 }
@@ -429,7 +488,7 @@ void vils_frontend_destroy(vils_frontend* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   if (f->st) cudaStreamSynchronize(f->st);
-  cudaFree(f->d_src); cudaFree(f->d_dst); cudaFree(f->d_mask); cudaFree(f->d_lut); cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_cnt);
+  cudaFree(f->d_src); cudaFree(f->d_dst); cudaFree(f->d_mask); cudaFree(f->d_lut); cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_cnt); cudaFree(f->d_hist); cudaFree(f->d_top);
   cudaFree(f->d_centers); cudaFree(f->d_hw); cudaFree(f->d_uv); cudaFree(f->d_ray); cudaFreeHost(f->h_img); cudaFreeHost(f->h_cand); cudaFreeHost(f->h_cnt);
   if (f->e0) cudaEventDestroy(f->e0);
   if (f->e1) cudaEventDestroy(f->e1);
@@ -527,50 +586,69 @@ int vils_good_features(vils_frontend* f, const uint8_t* img, int32_t stride, int
   const int rows = f->rows, cols = f->cols;
   const uint8_t* mask = use_mask ? f->d_mask : nullptr;
   cudaEventRecord(f->e0, f->st);
-  cudaMemsetAsync(f->d_cnt, 0, 2 * sizeof(unsigned int), f->st);
+  cudaMemsetAsync(f->d_cnt, 0, 4 * sizeof(unsigned int), f->st);
+  cudaMemsetAsync(f->d_hist, 0, 4096 * sizeof(unsigned int), f->st);
   min_eig_kernel<<<dim3((cols + ET_X - 1) / ET_X, (rows + ET_Y - 1) / ET_Y), dim3(ET_X, ET_Y), 0, f->st>>>(f->d_src, rows, cols, cols, f->d_eig);
   masked_max_kernel<<<148 * 2, 256, 0, f->st>>>(f->d_eig, mask, rows * cols, f->d_cnt + 1);
   candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, f->st>>>(f->d_eig, mask, rows, cols, f->d_cnt + 1, (float)quality, f->d_cand, f->d_cnt,
-                                                                                        f->cand_cap);
-  sort_desc_kernel<<<1, 1024, 0, f->st>>>(f->d_cand, f->d_cnt, f->cand_cap);
+                                                                                        f->cand_cap, f->d_hist);
+  // the greedy pick below stops after max_corners accepts: sort only the strongest few thousand candidates (all of them if max_corners <= 0)
+  const unsigned int want = max_corners > 0 ? (unsigned int)std::min<long long>(TOPK_SMEM / 2, 16LL * max_corners + 256) : TOPK_SMEM + 1;
+  topk_sort_kernel<<<1, 1024, TOPK_SMEM * sizeof(unsigned long long), f->st>>>(f->d_cand, f->d_hist, want, f->cand_cap, f->d_top, f->d_cnt);
   cudaEventRecord(f->e1, f->st);
-  cudaMemcpyAsync(f->h_cnt, f->d_cnt, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, f->st);
+  cudaMemcpyAsync(f->h_cnt, f->d_cnt, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, f->st);
   cudaError_t e = cudaStreamSynchronize(f->st);
   if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features");
   cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
   const unsigned int total = std::min(f->h_cnt[0], f->cand_cap);
   if (total == 0) return VILS_OK;
-  e = cudaMemcpy(f->h_cand, f->d_cand, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features copy");
   // the greedy minimum-distance pick (featureselect.cpp: grid of cell_size = round(minDistance), 3x3 cell neighbourhood) is sequential by
-  // construction; it runs over at most a few thousand sorted candidates on the host, where the reference has it
+  // construction; it runs over the sorted candidates on the host, where the reference has it.  Returns true when it ran out of candidates.
+  auto pick = [&](unsigned int count, int& n) -> bool {
+    n = 0;
+    if (min_distance >= 1) {
+      const int cell = cv_round(min_distance), gw = (cols + cell - 1) / cell, gh = (rows + cell - 1) / cell;
+      std::vector<std::vector<std::pair<int, int>>> grid((size_t)gw * gh);
+      const double md2 = min_distance * min_distance;
+      for (unsigned int i = 0; i < count; i++) {
+        const int ofs = (int)(f->h_cand[i] & 0xffffffffu), y = ofs / cols, x = ofs % cols;
+        const int xc = x / cell, yc = y / cell;
+        const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
+        bool good = true;
+        for (int yy = y1; yy <= y2 && good; yy++)
+          for (int xx = x1; xx <= x2 && good; xx++)
+            for (const auto& p : grid[(size_t)yy * gw + xx]) {
+              const float dx = (float)(x - p.first), dy = (float)(y - p.second);
+              if (dx * dx + dy * dy < md2) { good = false; break; }
+            }
+        if (!good) continue;
+        grid[(size_t)yc * gw + xc].push_back({x, y});
+        xy_out[2 * n] = (float)x; xy_out[2 * n + 1] = (float)y; n++;
+        if (max_corners > 0 && n == max_corners) return false;
+      }
+    } else {
+      for (unsigned int i = 0; i < count; i++) {
+        const int ofs = (int)(f->h_cand[i] & 0xffffffffu);
+        xy_out[2 * n] = (float)(ofs % cols); xy_out[2 * n + 1] = (float)(ofs / cols); n++;
+        if (max_corners > 0 && n == max_corners) return false;
+      }
+    }
+    return true;
+  };
   int n = 0;
-  if (min_distance >= 1) {
-    const int cell = cv_round(min_distance), gw = (cols + cell - 1) / cell, gh = (rows + cell - 1) / cell;
-    std::vector<std::vector<std::pair<int, int>>> grid((size_t)gw * gh);
-    const double md2 = min_distance * min_distance;
-    for (unsigned int i = 0; i < total; i++) {
-      const int ofs = (int)(f->h_cand[i] & 0xffffffffu), y = ofs / cols, x = ofs % cols;
-      const int xc = x / cell, yc = y / cell;
-      const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
-      bool good = true;
-      for (int yy = y1; yy <= y2 && good; yy++)
-        for (int xx = x1; xx <= x2 && good; xx++)
-          for (const auto& p : grid[(size_t)yy * gw + xx]) {
-            const float dx = (float)(x - p.first), dy = (float)(y - p.second);
-            if (dx * dx + dy * dy < md2) { good = false; break; }
-          }
-      if (!good) continue;
-      grid[(size_t)yc * gw + xc].push_back({x, y});
-      xy_out[2 * n] = (float)x; xy_out[2 * n + 1] = (float)y; n++;
-      if (max_corners > 0 && n == max_corners) break;
-    }
-  } else {
-    for (unsigned int i = 0; i < total; i++) {
-      const int ofs = (int)(f->h_cand[i] & 0xffffffffu);
-      xy_out[2 * n] = (float)(ofs % cols); xy_out[2 * n + 1] = (float)(ofs / cols); n++;
-      if (max_corners > 0 && n == max_corners) break;
-    }
+  const unsigned int ntop = f->h_cnt[2];
+  bool exhausted = true;
+  if (ntop > 0) {
+    e = cudaMemcpy(f->h_cand, f->d_top, sizeof(unsigned long long) * ntop, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features copy");
+    exhausted = pick(ntop, n);
+  }
+  if (exhausted && ntop < total) {   // rare: the strongest candidates were not enough (or did not fit shared memory): sort everything
+    sort_desc_kernel<<<1, 1024, 0, f->st>>>(f->d_cand, f->d_cnt, f->cand_cap);
+    e = cudaMemcpyAsync(f->h_cand, f->d_cand, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost, f->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f->st);
+    if (e != cudaSuccess) return vils::fail_cuda(e, "vils_good_features full sort");
+    pick(total, n);
   }
   *n_out = n;
   return VILS_OK;

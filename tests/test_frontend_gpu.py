@@ -229,3 +229,18 @@ def test_triangulate_matches_svd_restatement():
     assert np.median(np.abs(out[good] - np.array(truth)) / np.array(truth)) < 0.05      # and it is the right depth
     assert out[120] == 5.0 or abs(out[120] - ref[120]) <= 1e-6 * abs(ref[120])          # degenerate: INIT_DEPTH or the same null vector
     assert lib.triangulate([], [0], np.zeros((0, 3)), Ps, Rs.reshape(N, 9), tic, ric.reshape(9)).shape == (0,)
+
+
+def test_good_features_many_corners_takes_the_full_sort_path():
+    """More corners than the top-K pre-selection holds (the greedy pick runs out of sorted candidates): the library falls back to sorting
+    every candidate; the result must still be OpenCV's."""
+    from mvil_fusion_b200 import lib
+    img = cv2.createCLAHE(3.0, (8, 8)).apply(texture(12))
+    f = lib.Frontend(480, 640, 512)
+    ref = cv2.goodFeaturesToTrack(img, 6000, 0.01, 3).reshape(-1, 2)
+    out = f.good_features(img, 6000, 0.01, 3.0)
+    assert len(ref) > 4500                                              # really beyond the pre-selection
+    sref = {tuple(p) for p in ref.astype(int)}; sout = {tuple(p) for p in out.astype(int)}
+    assert abs(len(out) - len(ref)) <= 0.02 * len(ref) and len(sref & sout) >= 0.97 * len(sref)
+    assert np.array_equal(out[:50], ref[:50])
+    f.close()
