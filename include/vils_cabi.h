@@ -348,6 +348,47 @@ int vils_lidar_associate(const float* map_xyzi, int32_t n_map, const float* scan
 int vils_depth_register(const float* cloud_xyzi, int32_t n, const float T1[12], const float T2[12], int32_t num_bins,
                         const float* feat_xyz, int32_t m, float* depth, float* device_ms, int32_t device);
 
+/* ---- voxelised GICP scan matching: the producer of the LidarICPConstraint measurement (estimator.cpp:263-303 -> fast_gicp::FastVGICP;
+ * algorithm: fast_gicp/gicp/impl/{fast_gicp_impl.hpp:240-298, fast_vgicp_impl.hpp:76-203, lsq_registration_impl.hpp:52-166},
+ * fast_gicp/gicp/fast_vgicp_voxel.hpp:109-170, fast_gicp/so3/so3.hpp:56-76).  Clouds: x y z intensity, 4 packed floats per point, HOST
+ * pointers.  Transforms: row-major 4 x 4 doubles mapping source coordinates into the target frame.  Tangent order of H, b: rotation(3),
+ * translation(3), left perturbation, as in LsqRegistration. */
+typedef struct {
+  double resolution;              /* voxel edge; FastVGICP default 1.0, the estimator uses 0.5 (estimator.cpp:270) */
+  double rotation_epsilon;        /* 2e-3  */
+  double transformation_epsilon;  /* 5e-4  */
+  double lm_init_lambda_factor;   /* 1e-9  */
+  int32_t k_correspondences;      /* 20 (the only supported value: the reference never changes FastGICP's default) */
+  int32_t neighbor_search;        /* 1 | 7 | 27 = NeighborSearchMethod::DIRECT1 / 7 / 27 (default DIRECT1) */
+  int32_t max_iterations;         /* 64 */
+  int32_t lm_max_iterations;      /* 10 */
+  int32_t compute_fitness;        /* 1: also pcl::Registration::getFitnessScore() of the result */
+  int32_t reserved;
+} vils_vgicp_opts;
+typedef struct {
+  double T[16];                   /* final transformation (double; the reference stores its float cast) */
+  double H[36];                   /* getFinalHessian(): H of the last accepted step, identity if none */
+  double error;                   /* error sum at the final pose (correspondences of the last linearize) */
+  double fitness;                 /* mean squared nearest-neighbour distance after alignment, -1 if not computed */
+  int32_t iterations;             /* nr_iterations_ */
+  int32_t converged;              /* hasConverged() */
+  int32_t n_corr;                 /* correspondences of the last linearize */
+  int32_t n_voxels;               /* voxels of the target map */
+  int32_t n_linearize;            /* linearize launches */
+  float elapsed_ms;               /* after the upload of the clouds to the last kernel, host LM steps included */
+} vils_vgicp_result;
+void vils_vgicp_default_opts(vils_vgicp_opts* opts);
+/* FastGICP::calculate_covariances (PLANE regularisation): cov6 = n x (xx xy xz yy yz zz); nn_idx (may be NULL) = n x 20, nearest first. */
+int vils_vgicp_covariances(const float* xyzi, int32_t n, double* cov6, int32_t* nn_idx, int32_t device);
+/* One FastVGICP::linearize at T: H (6 x 6 row-major), b (6), *error = sum of w e^T M e.  voxels (may be NULL, capacity n_tgt x 10): the
+ * target voxel map, mean(3) cov6(6) num_points at the index of each voxel's first point, zero rows elsewhere. */
+int vils_vgicp_linearize(const float* src_xyzi, int32_t n_src, const float* tgt_xyzi, int32_t n_tgt, const double T[16],
+                         const vils_vgicp_opts* opts, double* H, double* b, double* error, int32_t* n_corr, int32_t* n_voxels,
+                         double* voxels, int32_t device);
+/* FastVGICP::align(guess) + getFitnessScore().  guess may be NULL (identity). */
+int vils_vgicp_align(const float* src_xyzi, int32_t n_src, const float* tgt_xyzi, int32_t n_tgt, const double guess[16],
+                     const vils_vgicp_opts* opts, vils_vgicp_result* result, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif

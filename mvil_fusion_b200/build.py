@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvils_b200.so")
 HOST_OUT = os.path.join(HERE, "libvils_host.so")
-SOURCES = ["common.cu", "vils_ba.cu", "vils_lidar.cu", "vils_preint.cu", "vils_klt.cu", "vils_frontend.cu", "vils_assoc.cu"]
+SOURCES = ["common.cu", "vils_ba.cu", "vils_lidar.cu", "vils_preint.cu", "vils_klt.cu", "vils_frontend.cu", "vils_assoc.cu", "vils_vgicp.cu"]
 # per-file extra flags: the FP32 LiDAR path must not contract a*b+c into FMA (bit parity with the reference arithmetic)
 EXTRA = {"vils_lidar.cu": ["--fmad=false"], "vils_klt.cu": ["--fmad=false"], "vils_frontend.cu": ["--fmad=false"], "vils_assoc.cu": ["--fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

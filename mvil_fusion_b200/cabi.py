@@ -281,3 +281,16 @@ def jacobian_count(w):
     n = lambda k: 0 if w.get(k) is None else len(w[k])
     return (450 * n("imu") + 40 * n("kf_i") + 6 * n("plane_kf") + 18 * n("edge_kf") + 72 * len(w.get("icp") or [])
             + 36 * len(w.get("lps") or []))
+
+
+class VilsVgicpOpts(C.Structure):
+    """vils_vgicp_opts (include/vils_cabi.h)."""
+    _fields_ = [("resolution", C.c_double), ("rotation_epsilon", C.c_double), ("transformation_epsilon", C.c_double), ("lm_init_lambda_factor", C.c_double),
+                ("k_correspondences", C.c_int32), ("neighbor_search", C.c_int32), ("max_iterations", C.c_int32), ("lm_max_iterations", C.c_int32),
+                ("compute_fitness", C.c_int32), ("reserved", C.c_int32)]
+
+
+class VilsVgicpResult(C.Structure):
+    """vils_vgicp_result (include/vils_cabi.h)."""
+    _fields_ = [("T", C.c_double * 16), ("H", C.c_double * 36), ("error", C.c_double), ("fitness", C.c_double), ("iterations", C.c_int32), ("converged", C.c_int32),
+                ("n_corr", C.c_int32), ("n_voxels", C.c_int32), ("n_linearize", C.c_int32), ("elapsed_ms", C.c_float)]

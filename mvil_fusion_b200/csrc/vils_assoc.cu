@@ -14,6 +14,7 @@
 
 #include "../../include/vils_cabi.h"
 #include "common.h"
+#include "small_eig.cuh"
 
 namespace {
 
@@ -31,38 +32,6 @@ __device__ __forceinline__ void knn_insert(Knn& h, float d, int idx) {
     const bool sw = h.d[k] < h.d[k - 1] || (h.d[k] == h.d[k - 1] && h.i[k] < h.i[k - 1]);
     if (sw) { const float td = h.d[k]; h.d[k] = h.d[k - 1]; h.d[k - 1] = td; const int ti = h.i[k]; h.i[k] = h.i[k - 1]; h.i[k - 1] = ti; }
   }
-}
-
-// 3x3 symmetric eigen-decomposition (cyclic Jacobi, FP64): w ascending like Eigen::SelfAdjointEigenSolver, V columns = eigenvectors
-__device__ void eig3(double A[3][3], double w[3], double V[3][3]) {
-  #pragma unroll
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 30; sweep++) {
-    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-    if (off < 1e-300 || off <= 1e-17 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
-    #pragma unroll
-    for (int p = 0; p < 2; p++)
-      #pragma unroll
-      for (int q = p + 1; q < 3; q++) {
-        if (fabs(A[p][q]) < 1e-300) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        #pragma unroll
-        for (int k = 0; k < 3; k++) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-        #pragma unroll
-        for (int k = 0; k < 3; k++) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-        #pragma unroll
-        for (int k = 0; k < 3; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
-      }
-  }
-  #pragma unroll
-  for (int k = 0; k < 3; k++) w[k] = A[k][k];
-  #pragma unroll
-  for (int a = 0; a < 2; a++)
-    #pragma unroll
-    for (int b = 0; b < 2 - a; b++)
-      if (w[b] > w[b + 1]) { const double t = w[b]; w[b] = w[b + 1]; w[b + 1] = t; for (int k = 0; k < 3; k++) { const double v = V[k][b]; V[k][b] = V[k][b + 1]; V[k][b + 1] = v; } }
 }
 
 // least squares A n = b (5 x 3) by Householder QR, FP64
@@ -172,7 +141,7 @@ __global__ void __launch_bounds__(256) associate_kernel(const float4* __restrict
       c[0] /= 5.0; c[1] /= 5.0; c[2] /= 5.0;
       double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       for (int j = 0; j < 5; j++) { const double d0 = P5[j][0] - c[0], d1 = P5[j][1] - c[1], d2 = P5[j][2] - c[2]; const double d[3] = {d0, d1, d2}; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[a][b] += d[a] * d[b]; }
-      double w[3], V[3][3]; eig3(C, w, V);
+      double w[3], V[3][3]; vils_eig::eig3(C, w, V);
       if (w[2] > 3 * w[1]) {
         ok = 1;
         for (int a = 0; a < 3; a++) { o[3 + a] = 0.1 * V[a][2] + c[a]; o[6 + a] = -0.1 * V[a][2] + c[a]; }

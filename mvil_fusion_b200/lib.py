@@ -77,6 +77,11 @@ def load():
     L.vils_triangulate.argtypes = [C.c_int32, ip, ip, dp, C.c_int32, dp, dp, dp, dp, C.c_double, dp, C.c_int32]
     L.vils_lidar_associate.argtypes = [fp, C.c_int32, fp, C.c_int32, dp, dp, C.c_int32, dp, up, ip, C.POINTER(C.c_float), C.c_int32]
     L.vils_depth_register.argtypes = [fp, C.c_int32, fp, fp, C.c_int32, fp, C.c_int32, fp, C.POINTER(C.c_float), C.c_int32]
+    L.vils_vgicp_default_opts.argtypes = [C.POINTER(cabi.VilsVgicpOpts)]
+    L.vils_vgicp_default_opts.restype = None
+    L.vils_vgicp_covariances.argtypes = [fp, C.c_int32, dp, ip, C.c_int32]
+    L.vils_vgicp_linearize.argtypes = [fp, C.c_int32, fp, C.c_int32, dp, C.POINTER(cabi.VilsVgicpOpts), dp, dp, dp, ip, ip, dp, C.c_int32]
+    L.vils_vgicp_align.argtypes = [fp, C.c_int32, fp, C.c_int32, dp, C.POINTER(cabi.VilsVgicpOpts), C.POINTER(cabi.VilsVgicpResult), C.c_int32]
     L.vils_deskew.argtypes = [fp, C.c_int32, C.c_int32, fp, fp, C.c_float, C.c_float, C.c_float, C.c_int32]
     L.vils_stamp_rings.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, ip, C.c_int32]
     L.vils_point_to_ring.argtypes = [fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_float, fp, ip, C.c_int32]
@@ -351,6 +356,56 @@ def depth_register(cloud_xyzi, T1, T2, feat_xyz, num_bins=360, device=0):
     _check(load().vils_depth_register(c.ctypes.data_as(fp), len(c), T1.ctypes.data_as(fp), T2.ctypes.data_as(fp), num_bins, f.ctypes.data_as(fp), len(f),
                                       depth.ctypes.data_as(fp), C.byref(ms), device))
     return depth[:len(f)], ms.value
+
+
+def vgicp_opts(resolution=0.5, neighbor_search=1, **kw):
+    """vils_vgicp_default_opts + the estimator's resolution (estimator.cpp:270)."""
+    o = cabi.VilsVgicpOpts()
+    load().vils_vgicp_default_opts(C.byref(o))
+    o.resolution = resolution; o.neighbor_search = neighbor_search
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def vgicp_covariances(xyzi, device=0):
+    """vils_vgicp_covariances: returns (cov n x 3 x 3, nn n x 20)."""
+    p = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    c6 = np.zeros((max(len(p), 1), 6)); nn = np.zeros((max(len(p), 1), 20), np.int32)
+    _check(load().vils_vgicp_covariances(p.ctypes.data_as(cabi.c_float_p), len(p), _d(c6), nn.ctypes.data_as(cabi.c_int32_p), device))
+    return _sym6(c6[:len(p)]), nn[:len(p)]
+
+
+def _sym6(c6):
+    out = np.zeros((len(c6), 3, 3))
+    for e, (r, k) in enumerate(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))):
+        out[:, r, k] = c6[:, e]; out[:, k, r] = c6[:, e]
+    return out
+
+
+def vgicp_linearize(src_xyzi, tgt_xyzi, T, opts=None, device=0):
+    """vils_vgicp_linearize: returns dict(H 6x6, b 6, error, n_corr, n_voxels, voxels {first point index: (mean, cov 3x3, num)})."""
+    s = np.ascontiguousarray(src_xyzi, np.float32).reshape(-1, 4); t = np.ascontiguousarray(tgt_xyzi, np.float32).reshape(-1, 4)
+    T = np.ascontiguousarray(T, np.float64).reshape(16); opts = opts or vgicp_opts()
+    H = np.zeros((6, 6)); b = np.zeros(6); err = np.zeros(1); nc = np.zeros(1, np.int32); nv = np.zeros(1, np.int32); vox = np.zeros((max(len(t), 1), 10))
+    fp = cabi.c_float_p; ip = cabi.c_int32_p
+    _check(load().vils_vgicp_linearize(s.ctypes.data_as(fp), len(s), t.ctypes.data_as(fp), len(t), _d(T), C.byref(opts), _d(H), _d(b), _d(err), nc.ctypes.data_as(ip),
+                                       nv.ctypes.data_as(ip), _d(vox), device))
+    rows = np.nonzero(vox[:, 9] > 0)[0]
+    covs = _sym6(vox[rows, 3:9])
+    voxels = {int(r): (vox[r, :3].copy(), covs[k], int(vox[r, 9])) for k, r in enumerate(rows)}
+    return dict(H=H, b=b, error=float(err[0]), n_corr=int(nc[0]), n_voxels=int(nv[0]), voxels=voxels)
+
+
+def vgicp_align(src_xyzi, tgt_xyzi, guess=None, opts=None, device=0):
+    """vils_vgicp_align (FastVGICP::align + getFitnessScore): returns dict(T 4x4, H 6x6, error, fitness, iterations, converged, ...)."""
+    s = np.ascontiguousarray(src_xyzi, np.float32).reshape(-1, 4); t = np.ascontiguousarray(tgt_xyzi, np.float32).reshape(-1, 4)
+    opts = opts or vgicp_opts(); res = cabi.VilsVgicpResult()
+    g = None if guess is None else np.ascontiguousarray(guess, np.float64).reshape(16)
+    fp = cabi.c_float_p
+    _check(load().vils_vgicp_align(s.ctypes.data_as(fp), len(s), t.ctypes.data_as(fp), len(t), None if g is None else _d(g), C.byref(opts), C.byref(res), device))
+    return dict(T=np.array(res.T).reshape(4, 4), H=np.array(res.H).reshape(6, 6), error=res.error, fitness=res.fitness, iterations=res.iterations,
+                converged=bool(res.converged), n_corr=res.n_corr, n_voxels=res.n_voxels, n_linearize=res.n_linearize, elapsed_ms=res.elapsed_ms)
 
 
 class Frontend:
