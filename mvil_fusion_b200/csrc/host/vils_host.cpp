@@ -423,6 +423,35 @@ void FeatureTracker::undistortedPoints() {
   prev_un_pts_map_ = cur_map;
 }
 
+// ---- FastVGICP (estimator.cpp:269-297) --------------------------------------------------------------------------------------------
+FastVGICP::FastVGICP(int device) : device_(device) {
+  vils_vgicp_default_opts(&opts_);
+  std::memset(&res_, 0, sizeof(res_)); res_.fitness = -1.0;
+  for (int k = 0; k < 16; k++) final_[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+}
+static void pack_xyzi(std::vector<float>& dst, const float* xyzi, int n, int stride) {
+  dst.resize((size_t)4 * std::max(n, 0));
+  for (int i = 0; i < n; i++) { const float* p = xyzi + (size_t)stride * i; dst[4 * i] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = stride > 4 ? p[4] : (stride > 3 ? p[3] : 0.0f); }
+}
+void FastVGICP::setInputSource(const float* xyzi, int n, int stride) { pack_xyzi(src_, xyzi, n, stride); }
+void FastVGICP::setInputTarget(const float* xyzi, int n, int stride) { pack_xyzi(tgt_, xyzi, n, stride); }
+int FastVGICP::align(float* aligned, const float* guess) {
+  double g[16];
+  if (guess) for (int k = 0; k < 16; k++) g[k] = (double)guess[k];     // Eigen::Isometry3d(guess.cast<double>()), lsq_registration_impl.hpp:53
+  last_status = vils_vgicp_align(src_.data(), (int)(src_.size() / 4), tgt_.data(), (int)(tgt_.size() / 4), guess ? g : nullptr, &opts_, &res_, device_);
+  if (last_status != VILS_OK) return last_status;
+  for (int k = 0; k < 16; k++) final_[k] = (float)res_.T[k];            // final_transformation_ = x0.cast<float>().matrix()
+  if (aligned) {
+    const int n = (int)(src_.size() / 4);
+    for (int i = 0; i < n; i++) {
+      const float x = src_[4 * i], y = src_[4 * i + 1], z = src_[4 * i + 2];
+      for (int r = 0; r < 3; r++) aligned[4 * i + r] = ((final_[4 * r] * x + final_[4 * r + 1] * y) + final_[4 * r + 2] * z) + final_[4 * r + 3];
+      aligned[4 * i + 3] = src_[4 * i + 3];
+    }
+  }
+  return VILS_OK;
+}
+
 int TransformToEnd(float* xyzi, int n, const float q[4], const float t[3], float time_factor, double min_r, double max_r, int device) {
   return vils_deskew(xyzi, n, 8, q, t, time_factor, (float)min_r, (float)max_r, device);
 }
@@ -478,4 +507,14 @@ int vh_tracker_get_un(void* p, float* un_xy, float* vel, int cap) {
   return n;
 }
 int vh_transform_to_end(float* xyzi, int n, const float* q, const float* t, float tf, double mn, double mx) { return vils::TransformToEnd(xyzi, n, q, t, tf, mn, mx, 0); }
+// FastVGICP through a flat interface (tests): returns the status; out = T(16 floats) fitness converged iterations
+int vh_vgicp_align(const float* src, int n_src, const float* tgt, int n_tgt, int stride, double resolution, const float* guess, float* T16, double* info3) {
+  vils::FastVGICP g; g.setResolution(resolution); g.setNumThreads(4);
+  g.setInputSource(src, n_src, stride); g.setInputTarget(tgt, n_tgt, stride);
+  const int st = g.align(nullptr, guess);
+  if (st != VILS_OK) return st;
+  for (int k = 0; k < 16; k++) T16[k] = g.getFinalTransformation()[k];
+  info3[0] = g.getFitnessScore(); info3[1] = g.hasConverged() ? 1.0 : 0.0; info3[2] = g.last_result().iterations;
+  return VILS_OK;
+}
 }

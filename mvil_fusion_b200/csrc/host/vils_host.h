@@ -132,6 +132,37 @@ class FeatureTracker {
   bool has_img_ = false;
 };
 
+// fast_gicp::FastVGICP as estimator.cpp:269-297 drives it: setResolution / setNumThreads / setInputSource / setInputTarget /
+// align(guess) / getFitnessScore / getFinalTransformation / hasConverged.  Clouds are PCL PointXYZI buffers (stride floats per
+// point, 8 for PCL); the alignment runs on the device through vils_vgicp_align.  Matrices are row-major 4 x 4 floats (Eigen::Matrix4f
+// values; Eigen itself is column-major, the ROS-side adapter transposes).
+class FastVGICP {
+ public:
+  FastVGICP(int device = 0);
+  void setResolution(double r) { opts_.resolution = r; }
+  void setNumThreads(int) {}                                 // OpenMP knob of the CPU implementation; no meaning on the device
+  void setNeighborSearchMethod(int n_offsets) { opts_.neighbor_search = n_offsets; }   // 1 | 7 | 27 = DIRECT1 / 7 / 27
+  void setMaximumIterations(int n) { opts_.max_iterations = n; }
+  void setTransformationEpsilon(double e) { opts_.transformation_epsilon = e; }
+  void setRotationEpsilon(double e) { opts_.rotation_epsilon = e; }
+  void setInputSource(const float* xyzi, int n, int stride_floats = 8);
+  void setInputTarget(const float* xyzi, int n, int stride_floats = 8);
+  // aligned (may be null, capacity n_source x 4): the source moved by the float final transformation, like pcl::transformPointCloud
+  int align(float* aligned_xyzi = nullptr, const float* guess4x4 = nullptr);
+  double getFitnessScore() const { return res_.fitness; }
+  const float* getFinalTransformation() const { return final_; }
+  const double* getFinalHessian() const { return res_.H; }
+  bool hasConverged() const { return res_.converged != 0; }
+  vils_vgicp_result last_result() const { return res_; }
+  int last_status = VILS_OK;
+ private:
+  int device_;
+  vils_vgicp_opts opts_;
+  vils_vgicp_result res_;
+  std::vector<float> src_, tgt_;
+  float final_[16];
+};
+
 // lidar_frontend.h:287 — in place on a PCL PointXYZI buffer (8 floats per point)
 int TransformToEnd(float* xyzi, int n_points, const float q_xyzw[4], const float t[3], float time_factor, double min_r, double max_r, int device = 0);
 

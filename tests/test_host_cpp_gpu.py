@@ -42,6 +42,7 @@ def host():
     H.vh_tracker_update_ids.argtypes = [C.c_void_p]; H.vh_tracker_update_ids.restype = None
     H.vh_tracker_get_un.argtypes = [C.c_void_p, cabi.c_float_p, cabi.c_float_p, C.c_int]
     H.vh_transform_to_end.argtypes = [cabi.c_float_p, C.c_int, cabi.c_float_p, cabi.c_float_p, C.c_float, C.c_double, C.c_double]
+    H.vh_vgicp_align.argtypes = [cabi.c_float_p, C.c_int, cabi.c_float_p, C.c_int, C.c_int, C.c_double, cabi.c_float_p, cabi.c_float_p, cabi.c_double_p]
     return H
 
 
@@ -241,3 +242,25 @@ def test_feature_tracker_full_read_image_sequence(host):
     n = host.vh_tracker_get(ft, xy.ctypes.data_as(cabi.c_float_p), ids.ctypes.data_as(cabi.c_int32_p), cnt.ctypes.data_as(cabi.c_int32_p), 400)
     assert (cnt[:n] == 4).sum() >= 0.85 * (np.array(ref_out[-1][2]) == 4).sum()
     host.vh_tracker_destroy(ft)
+
+
+def test_fast_vgicp_host_class_matches_cabi(host):
+    """vils::FastVGICP driven like estimator.cpp:269-297 (PCL PointXYZI stride 8, float guess) gives the C-ABI result cast to float."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vgicp_oracle as vo
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(5)
+    tgt = vo.room_scan(rng, 3000)
+    T = np.eye(4); T[:3, :3] = vo.so3_exp(np.array([0.003, 0.002, -0.015])); T[:3, 3] = [-0.1, 0.06, 0.02]
+    src = vo.room_scan(rng, 3000, pose=T)
+    pcl = lambda c: np.ascontiguousarray(np.c_[c[:, :3], np.ones(len(c)), c[:, 3], np.zeros((len(c), 3))], np.float32)   # x y z pad intensity pad x 3
+    ps, pt = pcl(src), pcl(tgt)
+    guess = np.eye(4, dtype=np.float32); guess[:3, 3] = [-0.08, 0.05, 0.0]
+    Tf = np.zeros(16, np.float32); info = np.zeros(3)
+    fp = cabi.c_float_p
+    assert host.vh_vgicp_align(ps.ctypes.data_as(fp), len(ps), pt.ctypes.data_as(fp), len(pt), 8, 0.5, guess.ctypes.data_as(fp), Tf.ctypes.data_as(fp), d(info)) == 0
+    r = lib.vgicp_align(src, tgt, guess.astype(np.float64), lib.vgicp_opts(0.5))
+    assert (Tf.reshape(4, 4) == r["T"].astype(np.float32)).all()
+    assert info[0] == r["fitness"] and bool(info[1]) == r["converged"] and int(info[2]) == r["iterations"]
+    assert np.abs(Tf.reshape(4, 4)[:3, 3] - T[:3, 3]).max() < 0.03
