@@ -9,7 +9,7 @@
 //   impl/lsq_registration_impl.hpp:52-166  computeTransformation / is_converged / step_lm; so3/so3.hpp:56-76 so3_exp
 //   pcl::Registration::getFitnessScore: mean squared 1-NN distance of the transformed source in the target.
 // B200 layout: every cloud is binned into a dense grid whose cells ARE the reference's voxels (cell = floor(x / res - 0.5) - cmin):
-// integer histogram -> single-CTA scan -> scatter -> per-cell index sort, which leaves the points cell-major (z fastest) and in ascending
+// integer histogram -> single-CTA scan -> scatter -> rank inside the cell, which leaves the points cell-major (z fastest) and in ascending
 // original order inside a cell.  That one structure serves (i) the 20-NN search (one thread per query in cell order, so a warp walks the
 // same cells; shells of cells are visited until the 20th distance is inside the searched block; a column of cells along z is one
 // contiguous point range), (ii) the voxel map (one thread per cell sums its members in the reference's insertion order: bit-reproducible,
@@ -96,33 +96,40 @@ __global__ void vg_scatter_kernel(const int* __restrict__ cell_id, int n, int* _
   order[atomicAdd(cursor + cell_id[i], 1)] = i;
 }
 
-// one thread per cell: the cell's indices into ascending order (the scatter leaves them in arrival order), then the sorted point copies
-__global__ void vg_sort_cells_kernel(const int* __restrict__ start, int ncell, int* __restrict__ order, const float4* __restrict__ pts, float4* __restrict__ spts) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
-  const int b = start[c], e = start[c + 1];
-  for (int k = b + 1; k < e; k++) {
-    const int v = order[k];
-    int j = k - 1;
-    while (j >= b && order[j] > v) { order[j + 1] = order[j]; j--; }
-    order[j + 1] = v;
-  }
-  for (int k = b; k < e; k++) { float4 p = pts[order[k]]; p.w = __int_as_float(order[k]); spts[k] = p; }
+// The scatter leaves every cell's members in arrival order.  One thread per member: its rank among the members of its cell (a scan of
+// the cell's short list) is its final slot, which puts every cell into ascending original order without a sort; the sorted point copy
+// is written in the same pass.
+__global__ void vg_rank_kernel(const int* __restrict__ start, const int* __restrict__ cell_id, const int* __restrict__ arrival, int n, const float4* __restrict__ pts,
+                               int* __restrict__ order, float4* __restrict__ spts) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int v = arrival[k], c = cell_id[v], b = start[c], e = start[c + 1];
+  int rank = 0;
+  for (int j = b; j < e; j++) rank += arrival[j] < v;
+  float4 p = pts[v]; p.w = __int_as_float(v);
+  order[b + rank] = v; spts[b + rank] = p;
 }
 
 // ---- exact k-NN over the grid: shells of cells around the query's cell until the K-th best lies inside the searched block ---------------
 template <int K>
 __device__ __forceinline__ void knn_visit(const float4& q, const float4* __restrict__ spts, int b, int e, float (&d)[K], int (&id)[K]) {
-  for (int k = b; k < e; k++) {
-    const float4 p = spts[k];
-    const float dist = sqdist(q, p);
-    const int idx = __float_as_int(p.w);
-    if (dist < d[K - 1] || (dist == d[K - 1] && idx < id[K - 1])) {
-      d[K - 1] = dist; id[K - 1] = idx;
+  for (int k0 = b; k0 < e; k0 += 4) {
+    float4 pb[4];                                          // four loads in flight: at ~1.5 warps per scheduler nothing else hides the latency
 #pragma unroll
-      for (int s = K - 1; s > 0; s--) {
-        const bool sw = d[s] < d[s - 1] || (d[s] == d[s - 1] && id[s] < id[s - 1]);
-        if (sw) { const float td = d[s]; d[s] = d[s - 1]; d[s - 1] = td; const int ti = id[s]; id[s] = id[s - 1]; id[s - 1] = ti; }
+    for (int u = 0; u < 4; u++) pb[u] = spts[min(k0 + u, e - 1)];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k0 + u >= e) break;
+      const float4 p = pb[u];
+      const float dist = sqdist(q, p);
+      const int idx = __float_as_int(p.w);
+      if (dist < d[K - 1] || (dist == d[K - 1] && idx < id[K - 1])) {
+        d[K - 1] = dist; id[K - 1] = idx;
+#pragma unroll
+        for (int s = K - 1; s > 0; s--) {
+          const bool sw = d[s] < d[s - 1] || (d[s] == d[s - 1] && id[s] < id[s - 1]);
+          if (sw) { const float td = d[s]; d[s] = d[s - 1]; d[s - 1] = td; const int ti = id[s]; id[s] = id[s - 1]; id[s - 1] = ti; }
+        }
       }
     }
   }
@@ -387,7 +394,7 @@ thread_local Arena g_arena;
 // a cloud on the device with its voxel grid
 struct Cloud {
   int n = 0; Grid G{};
-  float4 *pts = nullptr, *spts = nullptr; int *cell_id = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr; double* cov = nullptr;
+  float4 *pts = nullptr, *spts = nullptr; int *cell_id = nullptr, *cnt = nullptr, *start = nullptr, *cursor = nullptr, *order = nullptr, *arrival = nullptr; double* cov = nullptr;
   // bounding box in voxel coordinates on the host (the same IEEE arithmetic as the kernels)
   int prepare(const float* xyzi, int n_, double res) {
     n = n_;
@@ -405,10 +412,10 @@ struct Cloud {
     return VILS_OK;
   }
   size_t bytes() const {
-    return 2 * Arena::need<float4>(n) + 2 * Arena::need<int>(n) + 2 * Arena::need<int>(G.ncell) + Arena::need<int>((size_t)G.ncell + 1) + Arena::need<double>(6 * (size_t)n);
+    return 2 * Arena::need<float4>(n) + 3 * Arena::need<int>(n) + 2 * Arena::need<int>(G.ncell) + Arena::need<int>((size_t)G.ncell + 1) + Arena::need<double>(6 * (size_t)n);
   }
   cudaError_t build(Arena& A, const float* xyzi) {
-    pts = A.take<float4>(n); spts = A.take<float4>(n); cell_id = A.take<int>(n); order = A.take<int>(n);
+    pts = A.take<float4>(n); spts = A.take<float4>(n); cell_id = A.take<int>(n); order = A.take<int>(n); arrival = A.take<int>(n);
     cnt = A.take<int>(G.ncell); start = A.take<int>((size_t)G.ncell + 1); cursor = A.take<int>(G.ncell); cov = A.take<double>(6 * (size_t)n);
     G.start = start; G.order = order; G.spts = spts;
     return cudaMemcpyAsync(pts, xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
@@ -417,8 +424,8 @@ struct Cloud {
     cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)G.ncell);
     vg_cell_kernel<<<(n + 255) / 256, 256>>>(pts, n, G, cell_id, cnt);
     vg_scan_kernel<<<1, VG_SCAN_T>>>(cnt, G.ncell, start, cursor);
-    vg_scatter_kernel<<<(n + 255) / 256, 256>>>(cell_id, n, cursor, order);
-    vg_sort_cells_kernel<<<(G.ncell + 127) / 128, 128>>>(start, G.ncell, order, pts, spts);
+    vg_scatter_kernel<<<(n + 255) / 256, 256>>>(cell_id, n, cursor, arrival);
+    vg_rank_kernel<<<(n + 255) / 256, 256>>>(start, cell_id, arrival, n, pts, order, spts);
     vg_cov_kernel<<<(n + VG_T - 1) / VG_T, VG_T>>>(G, pts, n, cov, nn_out);
   }
 };
