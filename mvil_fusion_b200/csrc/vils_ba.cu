@@ -539,9 +539,15 @@ __global__ void __launch_bounds__(EVP_T, MINB) eval_proj_kernel(EvalParams Q, in
 // pre-integration record, sqrt_info and the four state blocks in shared memory, lane 0 does the quaternion algebra, all
 // lanes assemble the 15 x 30 Jacobian through the table and whiten it; the rows then leave as coalesced stores.
 // Latency-bound and tiny (9 per window, 7 % of the bytes): launched ahead of the streaming kernels.
-constexpr int EVI_WARPS = 2;
+#ifndef EVI_WARPS_
+#define EVI_WARPS_ 2
+#endif
+#ifndef EVI_MINB
+#define EVI_MINB 8
+#endif
+constexpr int EVI_WARPS = EVI_WARPS_;
 __device__ void eval_prior_row(const EvalParams& Q, int slot, int row);
-__global__ void __launch_bounds__(32 * EVI_WARPS, 8) eval_imu_kernel(EvalParams Q, int nimu_max, int n, int imu_blocks, int prior_bpw) {
+__global__ void __launch_bounds__(32 * EVI_WARPS, EVI_MINB) eval_imu_kernel(EvalParams Q, int nimu_max, int n, int imu_blocks, int prior_bpw) {
   if ((int)blockIdx.x >= imu_blocks) {   // CTAs past the IMU factors: prior residual rows, prior_bpw CTAs per window
     const int b = blockIdx.x - imu_blocks;
     eval_prior_row(Q, Q.S.slot0 + b / prior_bpw, (b % prior_bpw) * 32 * EVI_WARPS + threadIdx.x);
@@ -1156,10 +1162,15 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   // Two streams: the latency-bound IMU warps and then the persistent projection kernel on one, the streaming LiDAR / prior /
   // constraint kernels on the other.
   cudaEventRecord(ba->ev_fork, ba->stream); cudaStreamWaitEvent(ba->stream2, ba->ev_fork, 0);
-  if (nimu || nprior) {
+  // VILS_EV_LAYOUT (experiments): 0 = IMU ahead of the projection kernel on stream 1 (default); 1 = IMU first on stream 2, next to the
+  // projection kernel; 2 = IMU last on stream 2
+  static const int layout = getenv("VILS_EV_LAYOUT") ? atoi(getenv("VILS_EV_LAYOUT")) : 0;
+  auto launch_imu = [&](cudaStream_t st) {
+    if (!(nimu || nprior)) return;
     const int ib = (nimu * n + EVI_WARPS - 1) / EVI_WARPS, pbw = (nprior + 32 * EVI_WARPS - 1) / (32 * EVI_WARPS);
-    eval_imu_kernel<<<ib + pbw * n, 32 * EVI_WARPS, 0, ba->stream>>>(Q, std::max(nimu, 1), n, ib, std::max(pbw, 1)); launches++;
-  }
+    eval_imu_kernel<<<ib + pbw * n, 32 * EVI_WARPS, 0, st>>>(Q, std::max(nimu, 1), n, ib, std::max(pbw, 1)); launches++;
+  };
+  if (layout == 0) launch_imu(ba->stream);
   const int pb = (np + EVP_T - 1) / EVP_T;
   if (pb) {
     const int items = pb * n, g = std::min(items, ba->n_sm * minb);
@@ -1168,10 +1179,12 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
     else eval_proj_kernel<3><<<g, EVP_T, proj_smem, ba->stream>>>(Q, items, pb, xs_doubles, feat_ints);
     launches++;
   }
+  if (layout == 1) launch_imu(ba->stream2);
   const int pc = (npl + EV_T - 1) / EV_T, ec = (ned + EV_T - 1) / EV_T;
   if (pc) { eval_lidar_kernel<false><<<dim3(pc, n), EV_T, EV_T * EV_LLD * 8, ba->stream2>>>(Q); launches++; }
   if (ec) { eval_lidar_kernel<true><<<dim3(ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q); launches++; }
   if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
+  if (layout == 2) launch_imu(ba->stream2);
   cudaEventRecord(ba->ev_join, ba->stream2);
   cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
   cudaEventRecord(ba->ev1, ba->stream);
