@@ -93,3 +93,41 @@ def test_bad_arguments():
         lib.vgicp_align(src, tgt, None, lib.vgicp_opts(0.5, 5))
     with pytest.raises(lib.VilsError):
         lib.vgicp_align(src, tgt, None, lib.vgicp_opts(0.5, 1, k_correspondences=10))
+
+
+def test_source_partly_outside_target_grid():
+    """A pose that pushes a good part of the source outside the target's bounding box: voxel lookups beyond the grid find nothing (as
+    the reference's hash map), DIRECT27 offsets reach back in, and the fitness 1-NN starts from the first shell that touches the grid."""
+    from mvil_fusion_b200 import lib
+    src, tgt, _ = pair(16, 3000)
+    T0 = np.eye(4); T0[:3, :3] = vo.so3_exp(np.array([0.0, 0.0, 0.2])); T0[:3, 3] = [3.3, -2.1, 0.7]
+    T0 = T0.astype(np.float32).astype(np.float64)
+    g = vo.FastVGICP(0.5, 27); g.set_input(src, tgt)
+    err, H, b = g.linearize(T0)
+    r = lib.vgicp_linearize(src, tgt, T0, lib.vgicp_opts(0.5, 27))
+    assert 0 < len(g.corr) and r["n_corr"] == len(g.corr)
+    assert abs(r["error"] - err) <= 1e-9 * abs(err)
+    assert np.abs(r["H"] - H).max() <= 1e-9 * np.abs(H).max() and np.abs(r["b"] - b).max() <= 1e-9 * np.abs(b).max()
+    g1 = vo.FastVGICP(0.5, 1); g1.src, g1.tgt, g1.src_cov, g1.vox = g.src, g.tgt, g.src_cov, g.vox
+    n1 = g1.update_correspondences(T0)
+    assert n1 < 0.9 * len(src)                                   # the pose really leaves points without a voxel
+    ra = lib.vgicp_align(src, tgt, T0, lib.vgicp_opts(0.5, 1, max_iterations=0))
+    assert (ra["T"] == T0).all() and ra["iterations"] == 0 and not ra["converged"] and (ra["H"] == np.eye(6)).all()
+    g.final = T0
+    f = g.fitness_score()
+    assert abs(ra["fitness"] - f) <= 1e-6 * f
+
+
+def test_capacity_and_non_finite_inputs():
+    from mvil_fusion_b200 import cabi, lib
+    src, tgt, _ = pair(17, 600)
+    far = tgt.copy(); far[5, :3] = [4.0e6, 0.0, 0.0]               # one stray return: the dense voxel grid would not fit
+    with pytest.raises(lib.VilsError) as e:
+        lib.vgicp_align(src, far, None, lib.vgicp_opts(0.5))
+    assert e.value.code == cabi.VILS_ERR_CAPACITY
+    nan = src.copy(); nan[7, 1] = np.nan
+    with pytest.raises(lib.VilsError) as e:
+        lib.vgicp_align(nan, tgt, None, lib.vgicp_opts(0.5))
+    assert e.value.code == cabi.VILS_ERR_NOT_FINITE
+    r = lib.vgicp_align(src, tgt, None, lib.vgicp_opts(0.5))      # the library is still usable afterwards
+    assert r["n_voxels"] > 0
