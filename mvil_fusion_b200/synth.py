@@ -395,3 +395,26 @@ def slide_old(w):
         t = w["truth"]
         out["truth"] = dict(pose=t["pose"][1:], speedbias=t["speedbias"][1:], inv_depth=t["inv_depth"][feats], td=t["td"], t_kf=t["t_kf"][1:])
     return out
+
+
+def room_scan(rng, n, pose=None, noise=0.01):
+    """A LiDAR-like scan of the 16 x 12 x 3 m room of SURVEY §8d seen from `pose` (4 x 4, sensor -> world): n x 4 float32 (x y z intensity)."""
+    per = n // 6
+    pts = []
+    for axis, val in ((0, -8.0), (0, 8.0), (1, -6.0), (1, 6.0), (2, 0.0), (2, 3.0)):
+        p = np.stack([rng.uniform(-8, 8, per), rng.uniform(-6, 6, per), rng.uniform(0, 3, per)], 1)
+        p[:, axis] = val
+        pts.append(p)
+    w = np.concatenate(pts) + rng.normal(0, noise, (per * 6, 3))
+    if pose is not None:
+        w = (w - pose[:3, 3]) @ pose[:3, :3]
+    return np.c_[w, rng.uniform(0, 100, len(w))].astype(np.float32)
+
+
+def rigid(rotvec, trans):
+    """4 x 4 rigid transform from a rotation vector (Rodrigues) and a translation."""
+    r = np.asarray(rotvec, float); th = np.linalg.norm(r)
+    K = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+    R = np.eye(3) if th < 1e-12 else np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = trans
+    return T

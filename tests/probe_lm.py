@@ -2,7 +2,7 @@
 windows — GPU batch vs the CPU restatement on all host threads."""
 import ctypes, os, sys, threading, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 from mvil_fusion_b200 import cabi, synth, lib
 import oracle_lib as ol

@@ -6,16 +6,15 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import vgicp_oracle as vo  # noqa: E402  (scan generator only)
-from mvil_fusion_b200 import lib  # noqa: E402
+sys.path.insert(0, ROOT)
+from mvil_fusion_b200 import lib, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 28800
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 rng = np.random.default_rng(14)
-tgt = vo.room_scan(rng, n)
-T = np.eye(4); T[:3, :3] = vo.so3_exp(np.array([0.01, -0.004, 0.03])); T[:3, 3] = [0.25, 0.1, -0.02]
-src = vo.room_scan(rng, n, pose=T)
+tgt = synth.room_scan(rng, n)
+T = synth.rigid([0.01, -0.004, 0.03], [0.25, 0.1, -0.02])
+src = synth.room_scan(rng, n, pose=T)
 opts = lib.vgicp_opts(0.5)
 r = lib.vgicp_align(src, tgt, None, opts)
 best_dev, best_wall = 1e9, 1e9
