@@ -111,25 +111,30 @@ __global__ void vg_rank_kernel(const int* __restrict__ start, const int* __restr
 }
 
 // ---- exact k-NN over the grid: shells of cells around the query's cell until the K-th best lies inside the searched block ---------------
-// Branch-free insertion into the ascending (distance, index) list: K independent comparisons, then every slot takes its predecessor,
-// the new entry or itself.  (A bubble of K - 1 dependent compare-and-swap steps, which the compiler turned into K - 1 branches, was 61 %
-// of the k-NN kernel's samples.)  Precondition: (v, vi) sorts before the last entry.
+// A list entry is one 64-bit key: the float bits of the (non-negative) squared distance above the point index, so that unsigned order
+// is (distance, index) order and a compare or a select is two instructions instead of four.
+typedef unsigned long long knn_key;
+constexpr knn_key KNN_SENTINEL = (0x7f7fffffull << 32) | 0x7fffffffull;      // (FLT_MAX, INT_MAX)
+__device__ __forceinline__ knn_key make_key(float dist, int idx) { return ((knn_key)__float_as_uint(dist) << 32) | (unsigned int)idx; }
+__device__ __forceinline__ float key_dist(knn_key k) { return __uint_as_float((unsigned int)(k >> 32)); }
+__device__ __forceinline__ int key_idx(knn_key k) { return (int)(unsigned int)(k & 0xffffffffull); }
+
+// Branch-free insertion into the ascending list: K independent comparisons, then every slot takes its predecessor, the new entry or
+// itself.  (A bubble of K - 1 dependent compare-and-swap steps, which the compiler turned into K - 1 branches, was 61 % of the k-NN
+// kernel's samples.)  Precondition: v sorts before the last entry.
 template <int K>
-__device__ __forceinline__ void sorted_insert(float (&d)[K], int (&id)[K], float v, int vi) {
+__device__ __forceinline__ void sorted_insert(knn_key (&key)[K], knn_key v) {
   bool g[K];
 #pragma unroll
-  for (int s = 0; s < K; s++) g[s] = d[s] > v || (d[s] == v && id[s] > vi);
+  for (int s = 0; s < K; s++) g[s] = key[s] > v;
 #pragma unroll
-  for (int s = K - 1; s > 0; s--) {
-    d[s] = g[s - 1] ? d[s - 1] : (g[s] ? v : d[s]);
-    id[s] = g[s - 1] ? id[s - 1] : (g[s] ? vi : id[s]);
-  }
-  d[0] = g[0] ? v : d[0]; id[0] = g[0] ? vi : id[0];
+  for (int s = K - 1; s > 0; s--) key[s] = g[s - 1] ? key[s - 1] : (g[s] ? v : key[s]);
+  key[0] = g[0] ? v : key[0];
 }
 // L lanes share one query (L = 4 for the 20-NN pass, 1 for the fitness 1-NN): lane `sub` takes every L-th point of a range and keeps
 // its own sorted K-list; the lists are merged at the end.
 template <int K, int L>
-__device__ __forceinline__ void knn_visit(const float4& q, const float4* __restrict__ spts, int b, int e, int sub, float (&d)[K], int (&id)[K]) {
+__device__ __forceinline__ void knn_visit(const float4& q, const float4* __restrict__ spts, int b, int e, int sub, knn_key (&key)[K]) {
   for (int k0 = b + sub; k0 < e; k0 += 4 * L) {
     float4 pb[4];                                          // four loads in flight per lane
 #pragma unroll
@@ -138,18 +143,17 @@ __device__ __forceinline__ void knn_visit(const float4& q, const float4* __restr
     for (int u = 0; u < 4; u++) {
       if (k0 + L * u >= e) break;
       const float4 p = pb[u];
-      const float dist = sqdist(q, p);
-      const int idx = __float_as_int(p.w);
-      if (dist < d[K - 1] || (dist == d[K - 1] && idx < id[K - 1])) sorted_insert<K>(d, id, dist, idx);
+      const knn_key v = make_key(sqdist(q, p), __float_as_int(p.w));
+      if (v < key[K - 1]) sorted_insert<K>(key, v);
     }
   }
 }
 // (cx, cy, cz): the query's cell relative to the grid origin; it may lie outside the grid (fitness queries).  gmask: the L lanes of the
 // group (their control flow is identical: the loops depend on the query only).
 template <int K, int L>
-__device__ void knn_grid(const Grid& G, const float4& q, long long cx, long long cy, long long cz, int sub, unsigned gmask, float (&d)[K], int (&id)[K]) {
+__device__ void knn_grid(const Grid& G, const float4& q, long long cx, long long cy, long long cz, int sub, unsigned gmask, knn_key (&key)[K]) {
 #pragma unroll
-  for (int k = 0; k < K; k++) { d[k] = FLT_MAX; id[k] = 0x7fffffff; }
+  for (int k = 0; k < K; k++) key[k] = KNN_SENTINEL;
   // first shell that can touch the grid
   long long r0 = 0;
   r0 = max(r0, max(-cx, cx - (G.dx - 1))); r0 = max(r0, max(-cy, cy - (G.dy - 1))); r0 = max(r0, max(-cz, cz - (G.dz - 1)));
@@ -169,16 +173,17 @@ __device__ void knn_grid(const Grid& G, const float4& q, long long cx, long long
           if (r > 0 && z2 >= 0 && z2 < G.dz) { b1 = G.start[col + z2]; e1 = G.start[col + z2 + 1]; }
         }
 #pragma unroll 1
-        for (int u = 0; u < 2; u++) knn_visit<K, L>(q, G.spts, u ? b1 : b0, u ? e1 : e0, sub, d, id);   // a single call site keeps the K-wide lists in registers
+        for (int u = 0; u < 2; u++) knn_visit<K, L>(q, G.spts, u ? b1 : b0, u ? e1 : e0, sub, key);   // a single call site keeps the K-wide lists in registers
       }
     // every point outside the block [c - r, c + r]^3 is at least r * res away from a query inside cell c: done once K candidates are closer
-    const float lim = (float)((double)r * G.res), lim2 = lim * lim * (1.0f - 1e-5f);
+    const float lim = (float)((double)r * G.res);
+    const knn_key limkey = make_key(lim * lim * (1.0f - 1e-5f), 0);          // key < limkey  <=>  distance < the limit
     bool stop;
-    if (L == 1) stop = d[K - 1] < lim2;
+    if (L == 1) stop = key[K - 1] < limkey;
     else {
       int cnt = 0;
 #pragma unroll
-      for (int k = 0; k < K; k++) cnt += d[k] < lim2;
+      for (int k = 0; k < K; k++) cnt += key[k] < limkey;
 #pragma unroll
       for (int s = 1; s < L; s <<= 1) cnt += __shfl_xor_sync(gmask, cnt, s);
       stop = cnt >= K;
@@ -199,24 +204,21 @@ __global__ void __launch_bounds__(VG_T) vg_cov_kernel(Grid G, const float4* __re
   const float4 q = G.spts[s];
   const int i = __float_as_int(q.w);
   long long c[3]; voxel_coord((double)q.x, (double)q.y, (double)q.z, G.res, c);
-  float d[VG_K]; int id[VG_K];
-  knn_grid<VG_K, VG_L>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, sub, gmask, d, id);
-  // merge: VG_K rounds, the group's smallest head (ties by index) wins and its lane pops; neighbour k lands in lane k % VG_L
+  knn_key key[VG_K];
+  knn_grid<VG_K, VG_L>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, sub, gmask, key);
+  // merge: VG_K rounds, the group's smallest head wins and its lane pops; neighbour k lands in lane k % VG_L
   int mine[VG_K / VG_L];
 #pragma unroll
   for (int k = 0; k < VG_K; k++) {
-    float bd = d[0]; int bi = id[0];
+    knn_key best = key[0];
 #pragma unroll
-    for (int x = 1; x < VG_L; x <<= 1) {
-      const float od = __shfl_xor_sync(gmask, bd, x); const int oi = __shfl_xor_sync(gmask, bi, x);
-      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-    }
-    if (d[0] == bd && id[0] == bi) {
+    for (int x = 1; x < VG_L; x <<= 1) { const knn_key o = __shfl_xor_sync(gmask, best, x); best = o < best ? o : best; }
+    if (key[0] == best) {
 #pragma unroll
-      for (int j = 0; j < VG_K - 1; j++) { d[j] = d[j + 1]; id[j] = id[j + 1]; }
-      d[VG_K - 1] = FLT_MAX; id[VG_K - 1] = 0x7fffffff;
+      for (int j = 0; j < VG_K - 1; j++) key[j] = key[j + 1];
+      key[VG_K - 1] = KNN_SENTINEL;
     }
-    if (k % VG_L == sub) mine[k / VG_L] = bi;
+    if (k % VG_L == sub) mine[k / VG_L] = key_idx(best);
   }
   double m[3] = {0, 0, 0};
 #pragma unroll
@@ -406,9 +408,9 @@ __global__ void __launch_bounds__(VG_T) vg_fitness_kernel(const float4* __restri
     q.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tf[8], p.x), __fmul_rn(Tf[9], p.y)), __fmul_rn(Tf[10], p.z)), Tf[11]);
     q.w = 0.0f;
     long long c[3]; voxel_coord((double)q.x, (double)q.y, (double)q.z, G.res, c);
-    float d[1]; int id[1];
-    knn_grid<1, 1>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, 0, 0u, d, id);
-    v = (double)d[0];
+    knn_key key[1];
+    knn_grid<1, 1>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, 0, 0u, key);
+    v = (double)key_dist(key[0]);
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) v += __shfl_down_sync(0xffffffffu, v, s);
