@@ -397,9 +397,10 @@ __global__ void vg_reduce_kernel(const double* __restrict__ part, int nblk, int 
 // pcl::Registration::getFitnessScore: the source moved by the FLOAT final transformation, squared 1-NN distance in the target
 __global__ void __launch_bounds__(VG_T) vg_fitness_kernel(const float4* __restrict__ src, int n, Grid G, const float* __restrict__ Tf /* 3x4 row-major */, double* __restrict__ part) {
   __shared__ double red[VG_T / 32];
-  const int i = blockIdx.x * VG_T + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = blockIdx.x * VG_T + threadIdx.x, i = t / VG_L, sub = t % VG_L, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // four lanes per query
   double v = 0.0;
   if (i < n) {
+    const unsigned gmask = ((1u << VG_L) - 1u) << (lane & ~(VG_L - 1));
     const float4 p = src[i];
     float4 q;
     // pcl::transformPointCloud: x * col0 + y * col1 + z * col2 + col3, left to right, float
@@ -409,8 +410,11 @@ __global__ void __launch_bounds__(VG_T) vg_fitness_kernel(const float4* __restri
     q.w = 0.0f;
     long long c[3]; voxel_coord((double)q.x, (double)q.y, (double)q.z, G.res, c);
     knn_key key[1];
-    knn_grid<1, 1>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, 0, 0u, key);
-    v = (double)key_dist(key[0]);
+    knn_grid<1, VG_L>(G, q, c[0] - G.cx0, c[1] - G.cy0, c[2] - G.cz0, sub, gmask, key);
+    knn_key best = key[0];
+#pragma unroll
+    for (int x = 1; x < VG_L; x <<= 1) { const knn_key o = __shfl_xor_sync(gmask, best, x); best = o < best ? o : best; }
+    v = sub == 0 ? (double)key_dist(best) : 0.0;
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) v += __shfl_down_sync(0xffffffffu, v, s);
@@ -497,7 +501,7 @@ struct Ctx {
 // uploads both clouds, builds their grids, computes the covariances and the target voxel map
 cudaError_t vg_setup(Ctx& c, const float* src, const float* tgt, int n_off, int device) {
   c.n_off = n_off; c.nblk = (c.S.n + VG_RT - 1) / VG_RT;
-  const int fblk = (c.S.n + VG_T - 1) / VG_T;
+  const int fblk = (int)(((size_t)c.S.n * VG_L + VG_T - 1) / VG_T);
   Arena& A = g_arena;
   VG_TRY(A.reserve(c.S.bytes() + c.T.bytes() + Arena::need<double>(10 * (size_t)c.T.n) + Arena::need<double>(VG_NS * (size_t)c.nblk) + Arena::need<double>(32) +
                    Arena::need<double>(fblk) + Arena::need<int32_t>(1) + Arena::need<float>(12), device));
@@ -693,10 +697,10 @@ int vils_vgicp_align(const float* src_xyzi, int32_t n_src, const float* tgt_xyzi
   if (e == cudaSuccess && opts->compute_fitness) {
     float Tf[12];
     for (int r = 0; r < 3; r++) for (int k = 0; k < 4; k++) Tf[4 * r + k] = (float)res->T[4 * r + k];
-    const int fblk = (n_src + VG_T - 1) / VG_T;
+    const int fblk = (int)(((size_t)n_src * VG_L + VG_T - 1) / VG_T);
     e = cudaMemcpy(c.Tf, Tf, sizeof(Tf), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-      vg_fitness_kernel<<<fblk, VG_T>>>(c.S.pts, n_src, c.T.G, c.Tf, c.fpart);
+      vg_fitness_kernel<<<fblk, VG_T>>>(c.S.spts, n_src, c.T.G, c.Tf, c.fpart);   // the source in its own cell order: a warp's queries walk the same target cells
       vg_reduce_kernel<<<1, dim3(32, 8)>>>(c.fpart, fblk, 1, c.out);
       double sum = 0.0;
       e = cudaMemcpy(&sum, c.out, sizeof(double), cudaMemcpyDeviceToHost);
