@@ -9,7 +9,9 @@ a 7-dim prior on [extrinsic, td]; 5 Gauss-Newton iterations per solve, FP64.  On
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the same metric
-through vils_ba_solve() with host buffers (pinned staging -> H2D -> solve -> D2H inside the timed region).
+through vils_ba_solve_windows() from the CALLER's vils_window arrays to solved states: host pack (all host threads) -> pinned
+staging -> H2D -> solve -> D2H, all inside the timed region.  `configs` carries the other single-GPU BASELINE configs
+(configs[2] KLT, configs[3] 20-KF window with the real marginalization prior) measured in the same run.
 """
 import argparse
 import ctypes
@@ -41,6 +43,15 @@ BYTES_PER_SOLVE = 5 * BYTES_PER_LINEARISATION + BYTES_PER_COST_EVAL
 SOLVE_DRAM_TRAFFIC_PER_WINDOW = 5265906   # (335.82 + 443.53) MB / 148 windows, ncu --set full capture of solve_kernel (profiles/r1_ncu_solve_s3.txt)
 # Materialised Evaluate() traffic per window (what the CPU reference moves per linearisation; §8d first table)
 BYTES_PER_EVAL_WINDOW = 906 * 460 + 9 * 6016 + 1500 * 116 + 500 * 244 + 2544
+# Algorithmic FP64 work per linearisation (Schur SYRK 2 D^2 M = 7.4 MFLOP, Cholesky D^3/3 = 1.3 MFLOP at D = 157, M = 150;
+# factor evaluation + J^T J: ~1500 flop per projection factor, ~200 per LiDAR factor, ~34 k per IMU factor), 5 linearisations per solve.
+FLOPS_PER_SOLVE = 5 * (2 * 157 * 157 * 150 + 157 ** 3 // 3 + 906 * 1500 + 2000 * 200 + 9 * 34000)
+FP64_PEAK_TFLOPS = 36.0      # measured DFMA peak of this part (profiles/r1_fp64_microbench.txt); B200 has no FP64 tensor-core path worth the name
+# configs[3] (N = 20, M = 300, 3333 projection + 3750 plane + 1250 edge factors, 3 ICP + 3 LPS, n = 136 prior), same accounting, D = 307
+CFG4_PRIOR_N = 136
+CFG4_READS = 3333 * 124 + 19 * 2296 + 3750 * 60 + 1250 * 76 + (CFG4_PRIOR_N * CFG4_PRIOR_N + 2 * CFG4_PRIOR_N) * 8 + 6 * 200 + (16 * 20 + 8 + 300) * 8
+CFG4_BYTES_PER_SOLVE = 5 * (CFG4_READS + (307 * 307 + 307) * 8) + CFG4_READS
+KLT_BYTES_PER_FRAME_PAIR = 816000   # both 4-level u8 pyramids read once
 
 
 def read_peaks():
@@ -146,6 +157,141 @@ def cpu_solves_per_sec(windows, cores, per_core, opts):
     return sum(done) / dt, dt
 
 
+def cpu_solves_generic(windows, cfg, opts, cores, total):
+    """`total` solves of arbitrary windows by the CPU restatement on `cores` threads -> solves/s."""
+    L = oracle_lib()
+    structs = [cabi.window_struct(w) for w in windows]
+    per = max(1, total // cores)
+
+    def work(t):
+        ws0, _ = structs[0]
+        N, M = ws0.n_kf, ws0.n_feat
+        pose = np.zeros((N, 7)); sb = np.zeros((N, 9)); ex = np.zeros(7); lam = np.zeros(max(M, 1)); td = ctypes.c_double(); s = cabi.VilsSummary()
+        dp = lambda a: a.ctypes.data_as(cabi.c_double_p)
+        for k in range(per):
+            ws, _ = structs[(t * per + k) % len(structs)]
+            L.vo_solve_window(ctypes.byref(cfg), ctypes.byref(ws), ctypes.byref(opts), dp(pose), dp(sb), dp(ex), dp(lam), ctypes.byref(td), ctypes.byref(s))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    return per * cores / (time.perf_counter() - t0)
+
+
+def build_config4_windows(lib, cfg4, n, opts):
+    """configs[3] windows with the REAL marginalization prior, produced by the product path only (no oracle): solve the 21-frame
+    window -> double2vector -> put_state -> vils_ba_marginalize(MARGIN_OLD) -> slide -> attach the prior."""
+    out = []
+    h = lib.BA(cfg4, 1)
+    for k in range(n):
+        big = synth.make_config4_big(k)
+        h.set_window(0, big); h.solve(1, opts)
+        s = h.get_state(0)
+        assert s["status"] == 0, s
+        pose, sb = lib.double2vector(big["pose"][0], s["pose"], s["speedbias"])
+        h.put_state(0, pose, sb, s["ex_pose"], s["inv_depth"], s["td"])
+        prior = h.marginalize(0, cabi.VILS_MARGIN_OLD)
+        solved = dict(big); solved.update(pose=pose, speedbias=sb, ex_pose=s["ex_pose"], inv_depth=s["inv_depth"], td=s["td"])
+        w = synth.attach_prior(synth.slide_old(solved), prior)
+        w.pop("truth", None); w.pop("raw", None)
+        out.append(w)
+    h.close()
+    return out
+
+
+def other_configs(lib, device, cores, opts):
+    """configs[2] (KLT) and configs[3] (20-KF window with the real prior) on this GPU: device ms, e2e ms, roofline fraction, CPU figure."""
+    peak, _ = read_peaks()
+    rec = {}
+    # ---- configs[3]
+    try:
+        cfg4 = cabi.default_config(max_kf=21, max_feat=320, max_proj=4000, max_lidar=5000, device=device)
+        ws4 = build_config4_windows(lib, cfg4, 4, opts)
+        B4 = 148
+        h = lib.BA(cfg4, B4)
+        batch = [ws4[k % len(ws4)] for k in range(B4)]
+        arr, keep = lib.BA.window_array(batch)
+        h.set_windows(0, batch, arr); h.upload(B4)
+        ms = []
+        for _ in range(6):
+            h.solve_device(B4, opts); ms.append(h.last_ms)
+        dev = float(np.mean(ms[2:]))
+        h.solve_device(1, opts); single = h.last_ms
+        for _ in range(2):
+            h.solve_windows(batch, opts, arr)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            h.solve_windows(batch, opts, arr)
+        e2e = 1e3 * (time.perf_counter() - t0) / 4
+        t0 = time.perf_counter(); h.solve_windows(batch[:1], opts, arr); e2e_single = 1e3 * (time.perf_counter() - t0)
+        st = h.get_state(0)
+        h.close()
+        cpu = cpu_solves_generic(ws4, cfg4, opts, cores, 2 * cores)
+        cpu1 = cpu_solves_generic(ws4, cfg4, opts, 1, 2)
+        ach = CFG4_BYTES_PER_SOLVE * B4 / (dev * 1e-3) / 1e9
+        rec["config4"] = {"workload": "configs[3]: 20-KF window, 300 feats (3333 proj factors), 5000 LiDAR factors, 3 ICP + 3 LPS, real marginalization prior n=%d, GN x5" % int(ws4[0]["prior_n"]),
+                          "windows": B4, "device_ms": dev, "solves_per_s_device": B4 / dev * 1e3, "single_window_device_ms": single,
+                          "e2e_ms_from_caller_arrays": e2e, "solves_per_s_e2e": B4 / e2e * 1e3, "single_window_e2e_ms": e2e_single,
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_solve": CFG4_BYTES_PER_SOLVE},
+                          "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port", "single_thread_value": cpu1},
+                          "status": int(st["status"]), "cost_initial": st["cost_initial"], "cost_final": st["cost_final"]}
+    except Exception as e:   # a sub-record must never take the headline line down
+        rec["config4"] = {"error": repr(e)}
+    # ---- configs[2]: pyramidal KLT 640x480, 150 corners, 3 pyramid levels above the base
+    try:
+        rng = np.random.default_rng(1)
+        try:
+            import cv2
+        except Exception:
+            cv2 = None
+        f = lib.Frontend(480, 640, 512, device=device)
+        if cv2 is not None:
+            img = cv2.GaussianBlur(rng.uniform(0, 255, (480, 640)).astype(np.float32), (0, 0), 2.0)
+            img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+        else:
+            base = rng.uniform(0, 255, (480 // 4, 640 // 4)); img = np.kron(base, np.ones((4, 4))).astype(np.uint8)
+        img = f.clahe(img)                                    # readImage applies CLAHE before LK (feature_tracker.cpp:87-93)
+        nxt = np.roll(np.roll(img, 3, axis=0), -4, axis=1)
+        if cv2 is not None:
+            M = np.float64([[1, 0, -4.3], [0, 1, 3.2]])
+            nxt = cv2.warpAffine(img, M, (640, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+        pts = f.good_features(img, 150, 0.01, 30.0)
+        k = lib.KLT(480, 640, 512, 21, 3, device=device)
+        k.upload(img, nxt, pts)
+        ms = []
+        for _ in range(30):
+            k.track_device(); ms.append(k.last_ms)
+        dev = float(np.mean(ms[5:]))
+        for _ in range(3):
+            k.track(img, nxt, pts)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            out, stt, err = k.track(img, nxt, pts)
+        e2e = 1e3 * (time.perf_counter() - t0) / 20
+        r = {"workload": "configs[2]: pyramidal LK 640x480 mono, %d corners, win 21, 3 pyramid levels above the base" % len(pts), "device_ms": dev,
+             "e2e_ms_host_buffers": e2e, "frame_pairs_per_s_device": 1e3 / dev, "frame_pairs_per_s_e2e": 1e3 / e2e, "tracked": int(stt.sum()),
+             "roofline": {"bound": "hbm", "achieved": KLT_BYTES_PER_FRAME_PAIR / dev / 1e6, "peak": peak, "unit": "GB/s", "frac": KLT_BYTES_PER_FRAME_PAIR / dev / 1e6 / peak,
+                          "algorithmic_bytes_per_frame_pair": KLT_BYTES_PER_FRAME_PAIR, "note": "one 0.8 MB frame pair cannot load HBM: launch/latency-bound"}}
+        if cv2 is not None:
+            def best(fn, n=10):
+                b = 1e9
+                for _ in range(n):
+                    t = time.perf_counter(); fn(); b = min(b, time.perf_counter() - t)
+                return b * 1e3
+            p3 = pts.reshape(-1, 1, 2)
+            cv2.setNumThreads(1); c1 = best(lambda: cv2.calcOpticalFlowPyrLK(img, nxt, p3, None, winSize=(21, 21), maxLevel=3))
+            cv2.setNumThreads(0); cn = best(lambda: cv2.calcOpticalFlowPyrLK(img, nxt, p3, None, winSize=(21, 21), maxLevel=3))
+            r["cpu_baseline"] = {"kind": "reference (cv2 %s, the library the reference calls)" % cv2.__version__, "ms_1_thread": c1, "ms_all_threads": cn, "cores": cores}
+        k.close(); f.close()
+        rec["klt"] = r
+    except Exception as e:
+        rec["klt"] = {"error": repr(e)}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +300,7 @@ def main():
     ap.add_argument("--windows", type=int, default=592, help="windows per GPU per step (4 x 148 SMs; 592 x 281 KB = 166 MB > 126 MB L2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] (KLT) and configs[3] (20-KF window) sub-records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     opts = cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, 1e-8)
@@ -192,10 +339,20 @@ def main():
     cfg = cabi.default_config(device=local)
     uniq = [synth.make_window(2, (rank * UNIQUE_WINDOWS + k)) for k in range(UNIQUE_WINDOWS)]
     ba = lib.BA(cfg, B)
+    batch = [uniq[k % UNIQUE_WINDOWS] for k in range(B)]
+    warr, wkeep = lib.BA.window_array(batch)          # the CALLER's arrays: B vils_window structs over host numpy buffers
+    # C-side pack alone (vils_ba_set_windows, no per-window ctypes): all host threads, and one thread on a second handle
+    ba.set_windows(0, batch, warr)
     t0 = time.perf_counter()
-    for k in range(B):
-        ba.set_window(k, uniq[k % UNIQUE_WINDOWS])
-    pack_ms = 1e3 * (time.perf_counter() - t0) / B
+    for _ in range(3):
+        ba.set_windows(0, batch, warr)
+    pack_ms = 1e3 * (time.perf_counter() - t0) / (3 * B)
+    os.environ["VILS_PACK_THREADS"] = "1"
+    ba1 = lib.BA(cfg, 64)
+    ba1.set_windows(0, batch[:64], warr)
+    t0 = time.perf_counter(); ba1.set_windows(0, batch[:64], warr); pack1_ms = 1e3 * (time.perf_counter() - t0) / 64
+    del os.environ["VILS_PACK_THREADS"]
+    ba1.close()
     ba.upload(B)
 
     def barrier():
@@ -215,16 +372,23 @@ def main():
         dev_ms += ba.last_ms
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - w0)
-    # ---- end to end through the C-ABI with host buffers
+    # ---- end to end through the C-ABI: caller arrays -> host pack -> H2D -> solve -> D2H -> states in host memory
     for _ in range(max(1, args.warmup // 2)):
-        ba.solve(B, opts)
+        ba.solve_windows(batch, opts, warr)
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        ba.solve(B, opts)                 # pinned staging -> chunked H2D | solve kernels | D2H of states + summaries, pipelined on 3 streams
+        ba.solve_windows(batch, opts, warr)   # pack (host threads) | chunked H2D | solve kernels | D2H, pipelined; one synchronisation
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e0)
     e2e_launches = ba.last_launches
+    # the same with the blobs already packed in pinned staging (round-1 definition, kept for comparison)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        ba.solve(B, opts)
+    barrier()
+    e2e_packed_ms = 1e3 * (time.perf_counter() - e0)
     # ---- Jacobian evaluation kernel (materialised Evaluate of every factor), the HBM-roofline kernel north_star names
     for _ in range(3):
         ba.evaluate_device(B, True)
@@ -234,8 +398,9 @@ def main():
     sampler.stop()
     st = ba.get_state(0)
     assert st["status"] == 0, st
+    extra = other_configs(lib, local, cores, opts) if (rank == 0 and not args.no_configs) else {}
     from mvil_fusion_b200.sharding import max_over_ranks
-    dev_ms, wall_ms, e2e_ms, ev_ms = max_over_ranks([dev_ms, wall_ms, e2e_ms, ev_ms], device="cuda")   # timing = max over ranks
+    dev_ms, wall_ms, e2e_ms, ev_ms, e2e_packed_ms = max_over_ranks([dev_ms, wall_ms, e2e_ms, ev_ms, e2e_packed_ms], device="cuda")   # timing = max over ranks
     if rank == 0:
         peak, peak_src = read_peaks()
         total = B * args.steps * world
@@ -258,20 +423,28 @@ def main():
             "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "windows_per_gpu_per_step": B, "unique_seeded_windows_per_gpu": UNIQUE_WINDOWS,
                        "l2_policy": "inputs larger than L2 (592 window blobs x 281 KB = 166 MB per GPU, each step re-reads all of them)",
-                       "solver": "GN x5, mu=1e-8 Jacobi damping, Cauchy(1) visual, Huber(0.1) LiDAR", "host_pack_ms_per_window": pack_ms,
-                       "wall_ms_per_step": wall_ms / args.steps},
+                       "solver": "GN x5, mu=1e-8 Jacobi damping, Cauchy(1) visual, Huber(0.1) LiDAR",
+                       "host_pack_ms_per_window_all_threads": pack_ms, "host_pack_ms_per_window_one_thread": pack1_ms, "host_threads": cores,
+                       "wall_ms_per_step": wall_ms / args.steps,
+                       "e2e_definition": "vils_ba_solve_windows: caller vils_window arrays -> pack on host threads -> pinned staging -> H2D -> solve -> D2H -> states"},
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "launches_per_step": e2e_launches, "pipeline": "chunks of n_sm/2 windows round-robin on 3 streams: H2D | solve_kernel (prep folded in) | D2H"},
+                    "launches_per_step": e2e_launches, "from": "caller arrays (host pack inside the timed region)",
+                    "prepacked_value": total / (e2e_packed_ms * 1e-3),
+                    "pipeline": "chunks of n_sm/2 windows: host pack (thread pool) | H2D | solve_kernel (prep folded in) | D2H on round-robin streams"},
             "gpu_launches": args.steps,
             "roofline": {"kernel": "solve_kernel (fused GN loop, one CTA per window)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": SOLVE_DRAM_TRAFFIC_PER_WINDOW * B if SOLVE_DRAM_TRAFFIC_PER_WINDOW else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_solve": BYTES_PER_SOLVE, "note": "latency-bound FP64 kernel; see DESIGN.md §4 and profiles/"},
+            "roofline_fp64": {"kernel": "solve_kernel", "bound": "fp64", "achieved": FLOPS_PER_SOLVE * B / (kern_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                              "frac": FLOPS_PER_SOLVE * B / (kern_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "flops_per_solve": FLOPS_PER_SOLVE,
+                              "peak_source": "measured DFMA peak, profiles/r1_fp64_microbench.txt"},
             "roofline_eval": {"kernel": "eval_imu + eval_proj + eval_lidar + eval_prior kernels (materialised residual+Jacobian of every factor)", "bound": "hbm", "achieved": ev_achieved, "peak": peak,
                               "unit": "GB/s", "frac": ev_achieved / peak, "ms_per_launch": ev_ms / args.steps, "algorithmic_bytes_per_window": BYTES_PER_EVAL_WINDOW},
             "cpu_baseline": {"value": tot / T, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{tot} GN-5 solves of the same config-2 windows by oracle/ (CPU restatement) on {cores} threads",
                              "single_thread_value": v_single},
             "clocks": sampler.summary(),
+            "configs": extra,
         }
         print(json.dumps(out))
     if world > 1:

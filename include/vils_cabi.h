@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VILS_ABI_VERSION 1
+#define VILS_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 #define VILS_OK 0
@@ -50,6 +50,10 @@ extern "C" {
 /* ---- solver modes -------------------------------------------------------------------------- */
 #define VILS_MODE_GN 0 /* exactly max_iters Gauss-Newton steps, Jacobi-diagonal regularised by mu   */
 #define VILS_MODE_LM 1 /* Levenberg-Marquardt trust region to convergence (<= max_iters)            */
+#define VILS_MODE_DOGLEG 2 /* ceres TRADITIONAL_DOGLEG trust region — what the reference configures
+                            * (options.trust_region_strategy_type = ceres::DOGLEG, estimator.cpp:1406):
+                            * Gauss-Newton step regularised by mu (min_mu 1e-8, x10 on failure), Cauchy point,
+                            * dogleg interpolation inside the elliptical region, Jacobi scaling fixed at x0       */
 
 #define VILS_MARGIN_OLD 0        /* estimator.h MarginalizationFlag MARGIN_OLD                      */
 #define VILS_MARGIN_SECOND_NEW 1 /* MARGIN_SECOND_NEW                                               */
@@ -159,13 +163,17 @@ typedef struct vils_solve_opts {
   double function_tolerance; /* LM: Ceres default 1e-6                                           */
   double parameter_tolerance;/* LM: Ceres default 1e-8                                           */
   double min_relative_decrease; /* LM: Ceres default 1e-3                                        */
+  double max_solver_time;    /* seconds, 0 = no cap: options.max_solver_time_in_seconds = SOLVER_TIME (estimator.cpp:1407-1411;
+                              * yaml max_solver_time 0.05, x4/5 when MARGIN_OLD).  Checked like ceres does, at the top of every
+                              * iteration, against the time THIS window's solve has been running on the device (%globaltimer);
+                              * a capped solve keeps its last accepted state and returns VILS_OK with summary.reserved = 1        */
 } vils_solve_opts;
 
 typedef struct vils_summary {
   int32_t status;            /* VILS_OK | VILS_ERR_NOT_FINITE | VILS_ERR_CHOLESKY                */
   int32_t iterations;        /* linearisations performed                                         */
   int32_t accepted;          /* steps accepted                                                   */
-  int32_t reserved;
+  int32_t reserved;          /* 1: stopped by max_solver_time                                     */
   double cost_initial;       /* 1/2 sum rho(|r|^2) before                                        */
   double cost_final;         /* ... after                                                        */
 } vils_summary;
@@ -199,6 +207,8 @@ void vils_ba_destroy(vils_ba* ba);
 /* Stage one window (host copy into pinned memory + index lists).  Replaces vector2double() +
  * problem.AddResidualBlock(...) (estimator.cpp:1169-1398). */
 int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w);
+/* The same for n windows into slots [slot0, slot0 + n), packed on all host threads (VILS_PACK_THREADS overrides the count). */
+int vils_ba_set_windows(vils_ba* ba, int32_t slot0, int32_t n, const vils_window* ws);
 /* Host->device copy of every staged window (async on the handle's stream, then synchronised). */
 int vils_ba_upload(vils_ba* ba, int32_t n_windows);
 /* Device-only solve of slots [0, n_windows): replaces ceres::Solve (estimator.cpp:1400-1414).
@@ -208,9 +218,18 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n_windows, const vils_solve_opts* 
 int vils_ba_download(vils_ba* ba, int32_t n_windows);
 /* upload + solve_device + download: the call a host makes per optimization(). */
 int vils_ba_solve(vils_ba* ba, int32_t n_windows, const vils_solve_opts* opts);
+/* vector2double() + AddResidualBlock(...) + ceres::Solve for n independent windows handed over as the caller's own arrays
+ * (estimator.cpp:1169-1414): window k is packed into slot k by the host thread pool WHILE earlier chunks are being copied and
+ * solved, so the call runs from vils_window arrays to solved states with one synchronisation. */
+int vils_ba_solve_windows(vils_ba* ba, int32_t n, const vils_window* ws, const vils_solve_opts* opts);
 /* Solved state of one slot (raw solver output, i.e. before double2vector()'s gauge re-anchoring). */
 int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* speedbias, double* ex_pose,
                       double* inv_depth, double* td, vils_summary* summary);
+/* Overwrite the solved state of one slot on the device.  The reference runs double2vector() (estimator.cpp:1419) and then
+ * vector2double() (:1487) BEFORE it builds MarginalizationInfo, so its prior is linearised — and its x0 snapshots are taken — at
+ * the yaw / position re-anchored state: solve -> vils_ba_get_state -> vils_double2vector -> vils_ba_put_state -> vils_ba_marginalize. */
+int vils_ba_put_state(vils_ba* ba, int32_t slot, const double* pose, const double* speedbias, const double* ex_pose,
+                      const double* inv_depth, double td);
 /* Estimator::double2vector() gauge re-anchoring (estimator.cpp:962-1011) applied on the host to a
  * solved state, given the pre-solve pose of frame 0. */
 int vils_double2vector(int32_t n_kf, const double* pose0_before, double* pose, double* speedbias);
@@ -228,7 +247,7 @@ int vils_ba_evaluate_device(vils_ba* ba, int32_t n_windows, int32_t apply_loss);
  * g_r (D) with landmarks eliminated, no damping. Also the cost. */
 int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* cost);
 /* Marginalization (estimator.cpp:1483-1684 + marginalization_factor.cpp:110-338) of one slot at its
- * SOLVED state. */
+ * SOLVED state (or the state written by vils_ba_put_state). */
 int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out* out);
 /* Timing of the last vils_ba_solve_device in ms (CUDA events on the handle's stream). */
 int vils_ba_last_device_ms(vils_ba* ba, float* ms);

@@ -17,7 +17,7 @@ VILS_ERR_CHOLESKY = 5
 VILS_ERR_CAPACITY = 6
 
 VILS_BLK_POSE, VILS_BLK_SPEEDBIAS, VILS_BLK_EXPOSE, VILS_BLK_TD = 0, 1, 2, 3
-VILS_MODE_GN, VILS_MODE_LM = 0, 1
+VILS_MODE_GN, VILS_MODE_LM, VILS_MODE_DOGLEG = 0, 1, 2
 VILS_MARGIN_OLD, VILS_MARGIN_SECOND_NEW = 0, 1
 
 
@@ -126,7 +126,7 @@ class VilsSolveOpts(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("max_iters", C.c_int32),
         ("mu", C.c_double), ("lm_initial_radius", C.c_double), ("function_tolerance", C.c_double),
-        ("parameter_tolerance", C.c_double), ("min_relative_decrease", C.c_double),
+        ("parameter_tolerance", C.c_double), ("min_relative_decrease", C.c_double), ("max_solver_time", C.c_double),
     ]
 
 
@@ -195,6 +195,7 @@ def default_solve_opts(mode=VILS_MODE_GN, max_iters=5, mu=1e-8):
     o.function_tolerance = 1e-6
     o.parameter_tolerance = 1e-8
     o.min_relative_decrease = 1e-3
+    o.max_solver_time = 0.0
     return o
 
 

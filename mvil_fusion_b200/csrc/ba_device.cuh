@@ -44,6 +44,7 @@ struct SolveParams {
   vf::BaCfg cfg;
   int32_t mode, max_iters;
   double mu, lm_radius, f_tol, p_tol, min_rel_dec;
+  long long time_cap_ns;          // 0 = none: stop iterating once this window's solve has run that long (max_solver_time_in_seconds)
   int32_t Ncap, Mcap;             // capacities the shared-memory carve-up is sized for
   int32_t h_in_smem, hv_in_smem;
   double* lin_out;                // != null: dump [S (D x D row-major) | g (D) | cost] of the first linearisation and stop
@@ -53,7 +54,7 @@ struct SolveParams {
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
-  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, rot, total;
+  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, rot, scc, ddc, gc, stp, craw, scl, total;
   int ntile_rows;
 };
 
@@ -67,6 +68,9 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   s.g = take(nb * TB); s.dx = take(nb * TB); s.hd = take(nb * TB); s.fx = take(nb * TB / 2 + 1); s.pid = take(Ncap * Ncap / 2 + 1);
   s.gv = take(Dvp); s.hdv = take(Dvp);
   s.cinv = take(Mcap); s.glam = take(Mcap);
+  // dogleg (VILS_MODE_DOGLEG): Jacobi scale and trust-region diagonal per camera dimension, unreduced camera gradient, combined step;
+  // raw landmark diagonal C and landmark Jacobi scale
+  s.scc = take(nb * TB); s.ddc = take(nb * TB); s.gc = take(nb * TB); s.stp = take(nb * TB); s.craw = take(Mcap); s.scl = take(Mcap);
   s.red = take(64 + SOLVE_WARPS * 2);
   s.tbl = take(114);                                         // IMU Jacobian assembly table (450 x uint16)
   s.rot = take((Ncap + 1) * 9);                              // rotation matrices of the keyframes + ric (pair pass)
@@ -438,7 +442,9 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
 }
 
 // L: per-landmark reduction of the factor partials (fixed order) -> cinv, glam, E rows (anchor / ex / td parts)
-__device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu) {
+// jac_mode (dogleg): 0 = plain clamp(C) damping; 1 = first linearisation: also fix the landmark Jacobi scale s = 1 / (1 + sqrt(C)); 2 = use the
+// stored scale.  With a scale the damping diagonal is clamp(C s^2, 1e-6, 1e32) / s^2 and the raw C is kept in craw.
+__device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu, int jac_mode = 0, double* craw = nullptr, double* scl = nullptr) {
   const int nlm = W.h->n_lm, np = W.h->n_proj;
   const int32_t* lm_start = W.i(OFF_LM_START); const int32_t* ix = W.i(OFF_PROJ_IDX);
   const double* part = scr + P.sl.part; double* E = scr + P.sl.E;
@@ -458,10 +464,17 @@ __device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv
     for (int k = 0; k < 6; k++) { e[6 * kfi + k] = s[2 + k]; e[6 * W.N + k] = s[8 + k]; }
     e[6 * W.N + 6] = s[14];
     const double C = s[0];
-    if (C > 0.0) {   // free landmark: (C + mu clamp(C))^-1   [ceres min/max_lm_diagonal 1e-6 / 1e32, squared]
-      cinv[rnk] = 1.0 / (C + mu * fmin(fmax(C, 1e-12), 1e64));
+    if (C > 0.0) {   // free landmark: (C + mu clamp(C))^-1   [ceres min/max_lm_diagonal 1e-6 / 1e32 on the squared column norm]
+      double dd = fmin(fmax(C, 1e-6), 1e32);
+      if (jac_mode) {
+        const double sj = jac_mode == 1 ? 1.0 / (1.0 + sqrt(C)) : scl[rnk];
+        if (jac_mode == 1) scl[rnk] = sj;
+        dd = fmin(fmax(C * sj * sj, 1e-6), 1e32) / (sj * sj);
+        craw[rnk] = C;
+      }
+      cinv[rnk] = 1.0 / (C + mu * dd);
       glam[rnk] = s[1];
-    } else { cinv[rnk] = 0.0; glam[rnk] = 0.0; }
+    } else { cinv[rnk] = 0.0; glam[rnk] = 0.0; if (jac_mode) craw[rnk] = 0.0; }
   }
 }
 

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) margin_kernel(SolveParams P,
   double* red = sm; double* stage = sm + 64;                       // stage: >= 466 doubles
   int* idx = reinterpret_cast<int*>(sm + 64 + 480);                // 64 ints
   int* touched = Q.iws + 8; int* drop = touched + Q.Tcap; int* order = drop + Q.Tcap; int* lmloc = order + Q.Tcap; int* blkout = lmloc + Q.Mcap;
-  int* top = blkout + 128; int* bot = top + Q.Tcap;
+  int* top = blkout + 2 * (2 * P.Ncap + 2); int* bot = top + Q.Tcap;
   double* H = Q.ws + Q.oH; double* g = Q.ws + Q.oG;
   // ---- dropped landmarks (MARGIN_OLD): those anchored at frame 0, local index D + k in feature order
   const int32_t* ix = W.i(OFF_PROJ_IDX); const int32_t* lm_start = W.i(OFF_LM_START); const int32_t* lm_feat = W.i(OFF_LM_FEAT);

@@ -7,8 +7,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ba_device.cuh"
@@ -138,7 +142,7 @@ __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
 
 // Full linearisation at state x: H (tiles, lower), g, hd and the cost (broadcast to all threads).
 __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x, double* H, double* Hv,
-                            double mu, bool need_cost = true) {
+                            double mu, bool need_cost = true, int jac_mode = 0) {
   double* g = sm + L.g; double* hd = sm + L.hd;
   PROF_T0();
   // IMU factors ride on the idle warps of the pair pass when their staging fits in the (still unused) Hv region
@@ -146,7 +150,7 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost, imu_inline ? sm + L.hv : nullptr, reinterpret_cast<const uint16_t*>(sm + L.tbl), sm + L.rot);
   __syncthreads();
   PROF(0);
-  landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu);
+  landmark_reduce(P, W, sm + L.cinv, sm + L.glam, scr, mu, jac_mode, sm + L.craw, sm + L.scl);
   for (int e = threadIdx.x; e < W.Dvp * W.Dv; e += blockDim.x) Hv[e] = 0.0;
   __syncthreads();
   PROF(1);
@@ -188,11 +192,18 @@ __device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, d
 // Constant blocks -> identity rows/cols (problem.SetParameterBlockConstant, estimator.cpp:1154-1166,1217-1221,1368-1370),
 // Levenberg/Jacobi damping d2 = mu clamp(diag), b = -g.  fx: per-dimension constant mask (tile padding included),
 // nfix: number of constant dimensions below D (0 in the common case -> no O(D^2) sweep).
-__device__ void damp_and_fix(const Win& W, double* H, double* g, const double* hd, const int* fx, int nfix, double mu) {
+// scc / ddc (dogleg): Jacobi scale per dimension (fixed at x0) and the resulting trust-region diagonal dd = clamp(hd s^2) / s^2, kept for the
+// dogleg algebra (0 for constant dimensions).
+__device__ void damp_and_fix(const Win& W, double* H, double* g, const double* hd, const int* fx, int nfix, double mu, const double* scc = nullptr, double* ddc = nullptr) {
   const int Dp = W.nb * TB;
   for (int i = threadIdx.x; i < Dp; i += blockDim.x) {
-    if (fx[i]) { H[tidx(i, i)] = 1.0 + mu; g[i] = 0.0; }
-    else { H[tidx(i, i)] += mu * fmin(fmax(hd[i], 1e-12), 1e64); g[i] = -g[i]; }
+    if (fx[i]) { H[tidx(i, i)] = 1.0 + mu; g[i] = 0.0; if (ddc) ddc[i] = 0.0; }
+    else {
+      double dd = fmin(fmax(hd[i], 1e-6), 1e32);
+      if (scc) { const double sj = scc[i]; dd = fmin(fmax(hd[i] * sj * sj, 1e-6), 1e32) / (sj * sj); }
+      if (ddc) ddc[i] = dd;
+      H[tidx(i, i)] += mu * dd; g[i] = -g[i];
+    }
   }
   if (nfix > 0)
     for (int e = threadIdx.x; e < W.D * W.D; e += blockDim.x) {
@@ -227,12 +238,50 @@ __device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, do
   __syncthreads();
 }
 
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// dogleg: x (+)= step with step_c = stp (already blended), step_l = -a glam / dd_l + b (-cinv (glam + E_f^T y_c)).  Returns this thread's
+// share of |step_l|^2 (tangent norm for the parameter-tolerance test).  xout != xin.
+__device__ double apply_step_dogleg(const SolveParams& P, const Win& W, const Smem& L, double* sm, const double* scr, const double* xin, double* xout, double a, double b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* y = sm + L.dx; const double* stp = sm + L.stp; const double* cinv = sm + L.cinv; const double* glam = sm + L.glam;
+  const double* craw = sm + L.craw; const double* scl = sm + L.scl;
+  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const int X = 16 * W.N + 8 + W.M;
+  double n2 = 0;
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
+  __syncthreads();
+  for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
+    double s = 0;
+    for (int q = lane; q < W.Dv; q += 32) s = fma(E[(size_t)rnk * W.Dvp + q], y[vis2cam(q, W.N)], s);
+    s = warp_sum(s);
+    if (lane == 0 && cinv[rnk] != 0.0) {
+      const double sj = scl[rnk], dd = fmin(fmax(craw[rnk] * sj * sj, 1e-6), 1e32) / (sj * sj);
+      const double st = -a * glam[rnk] / dd + b * (-cinv[rnk] * (glam[rnk] + s));
+      xout[XL(W.N) + lm_feat[rnk]] += st; n2 += st * st;
+    }
+  }
+  for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
+    if (k < W.N) {
+      vm::pose_plus(xout + XP(k), stp + 15 * k);
+      for (int i = 0; i < 9; i++) xout[XS(W.N, k) + i] += stp[15 * k + 6 + i];
+    } else {
+      vm::pose_plus(xout + XE(W.N), stp + 15 * W.N);
+      xout[XT(W.N)] += stp[15 * W.N + 6];
+    }
+  }
+  __syncthreads();
+  return n2;
+}
+
 // One CTA = one window for the whole solve.  SMEM_H: the tile-packed H and the visual sub-system Hv live in shared memory
-// (windows up to ~12 keyframes); otherwise they sit in the per-window scratch (L2).
-template <bool SMEM_H>
+// (windows up to ~12 keyframes); otherwise they sit in the per-window scratch (L2).  TR: the trust-region modes (Levenberg-Marquardt,
+// dogleg) are compiled into their own instantiation so that the fixed-count Gauss-Newton kernel keeps its register allocation.
+template <bool SMEM_H, bool TR>
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int chol_flag;
+  __shared__ int time_flag;
   const int slot = P.slot0 + blockIdx.x;
   const Win W = decode(P, slot);
   const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
@@ -243,53 +292,174 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   int* fx = reinterpret_cast<int*>(sm + L.fx);
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
+  const long long t_start = P.time_cap_ns > 0 ? global_ns() : 0;
   if (P.do_prep) prep_window(P, W, scr, sm + L.uni);     // vils_ba_solve: no separate prep launch in the upload -> solve chain
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
   { uint16_t* tb = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tb[k] = g_imu_tbl[k]; }
   double nf = 0;
   for (int d = threadIdx.x; d < W.nb * TB; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
-  if (threadIdx.x == 0) chol_flag = 0;
+  if (threadIdx.x == 0) { chol_flag = 0; time_flag = 0; }
   const int nfix = (int)block_sum(nf, sm + L.red);
   __syncthreads();
 
-  const bool lm = P.mode == VILS_MODE_LM;
-  int status = VILS_OK, iters = 0, accepted = 0, trials = 0;
+  const bool lm = TR && P.mode == VILS_MODE_LM;
+  const bool dl = TR && P.mode == VILS_MODE_DOGLEG;
+  int status = VILS_OK, iters = 0, accepted = 0, trials = 0, capped = 0;
   double cost0 = 0, cost = 0, radius = P.lm_radius, decrease = 2.0;
+  // dogleg state (ceres DoglegStrategy): mu of the regularised Gauss-Newton solve, reuse of the last GN point / gradient after a rejected step
+  double mu_dl = 1e-8, dl_gg = 0, dl_pHp = 0, dl_yy = 0, dl_gy = 0;
+  bool reuse = false, scale_set = false; int invalid = 0;
 
   for (int it = 0;; it++) {
-    // LM follows ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g ; GN uses P.mu.
-    const double mu = P.lin_out ? 0.0 : (lm ? 1.0 / radius : P.mu);
-    const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0);   // later costs come from cost_only()
-    if (it == 0) { cost0 = c_lin; cost = c_lin; if (lm) iters = 1; }
-    if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
-    if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
-      damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, 0.0);
+    if (P.time_cap_ns > 0 && it > 0) {   // Solver::Options::max_solver_time_in_seconds: checked after every iteration, like ceres
+      if (threadIdx.x == 0) time_flag = (global_ns() - t_start >= P.time_cap_ns) ? 1 : 0;
       __syncthreads();
-      const int D = W.D;
-      for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; P.lin_out[e] = H[tidx(max(i, j), min(i, j))]; }
-      for (int i = threadIdx.x; i < D; i += blockDim.x) P.lin_out[(size_t)D * D + i] = -sm[L.g + i];
-      if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = c_lin;
-      return;
+      if (time_flag) { capped = 1; break; }
     }
-    if (P.max_iters <= 0) break;
-    PROF_T0();
-    damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
+    // LM follows ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: (H + diag(clamp(H_ii))/radius) d = -g ; GN uses P.mu.
+    const double mu = P.lin_out ? 0.0 : (lm ? 1.0 / radius : (dl ? mu_dl : P.mu));
+    bool ok = true;
     double* bsave = sm + L.imu;   // LM: b = -g_r is overwritten by the fused forward solve; ((Ncap+1)/2)*466 doubles >= nb*16
-    __syncthreads();
-    if (lm) for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) bsave[i] = sm[L.g + i];
-    if (threadIdx.x == 0) chol_flag = 0;
-    __syncthreads();
-    PROF(7);
-    cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, P.prof);
-    const bool ok = chol_flag == 0;
-    PROF(8);
-    if (!ok && !lm) { status = VILS_ERR_CHOLESKY; break; }
-    const bool last = !lm && (iters + 1 >= P.max_iters);
+    const bool last = !TR && (iters + 1 >= P.max_iters);
+    if (!(dl && reuse)) {
+      const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0);   // later costs come from cost_only()
+      if (it == 0) { cost0 = c_lin; cost = c_lin; if (TR) iters = 1; }
+      if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
+      if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
+        damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, 0.0);
+        __syncthreads();
+        const int D = W.D;
+        for (int e = threadIdx.x; e < D * D; e += blockDim.x) { const int i = e / D, j = e % D; P.lin_out[e] = H[tidx(max(i, j), min(i, j))]; }
+        for (int i = threadIdx.x; i < D; i += blockDim.x) P.lin_out[(size_t)D * D + i] = -sm[L.g + i];
+        if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = c_lin;
+        return;
+      }
+      if (P.max_iters <= 0) break;
+      PROF_T0();
+      if (dl && !scale_set) {   // Jacobi scaling: s = 1 / (1 + |J column|), from the first linearisation only (ceres jacobi_scaling)
+        for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) sm[L.scc + i] = 1.0 / (1.0 + sqrt(fmax(sm[L.hd + i], 0.0)));
+        scale_set = true;
+        __syncthreads();
+      }
+      damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu, dl ? sm + L.scc : nullptr, dl ? sm + L.ddc : nullptr);
+      __syncthreads();
+      if (lm) for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) bsave[i] = sm[L.g + i];
+      if (dl) {   // unreduced camera gradient g_c = g_r + E Cd^-1 g_l = -(b) - gv on the visual dimensions
+        for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) {
+          double gci = 0.0;
+          if (i < W.D && !fx[i]) {
+            const int k = i / 15, o = i - 15 * k;
+            const int va = i < 15 * W.N ? (o < 6 ? 6 * k + o : -1) : 6 * W.N + (i - 15 * W.N);
+            gci = -sm[L.g + i] - (va >= 0 ? sm[L.gv + va] : 0.0);
+          }
+          sm[L.gc + i] = gci;
+        }
+      }
+      if (threadIdx.x == 0) chol_flag = 0;
+      __syncthreads();
+      PROF(7);
+      cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, P.prof);
+      ok = chol_flag == 0;
+      PROF(8);
+      if (!ok && !TR) { status = VILS_ERR_CHOLESKY; break; }
+      if (!ok && dl) {   // DoglegStrategy::ComputeGaussNewtonStep: raise mu and solve again (H was factored in place: re-linearise)
+        mu_dl *= 10.0;
+        if (mu_dl >= 1.0) { status = VILS_ERR_CHOLESKY; break; }
+        continue;
+      }
+      if (ok) { backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32); PROF(9); }
+    }
+    if (dl) {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const double* E = scr + P.sl.E;
+      if (!reuse) {
+        // scalars of the dogleg algebra over the FULL camera + landmark space (dogleg):
+        //   gg = |g / sqrt(dd)|^2, yy = |sqrt(dd) y|^2, gy = g.y, pHp = v^T H v with v = g / dd and
+        //   v^T H v = |L^T v_c|^2 - mu sum dd_c v_c^2 + sum_f [cinv_f t_f^2 + 2 t_f v_f + C_f v_f^2], t_f = E_f^T v_c
+        double gg = 0, yy = 0, gy = 0, q = 0;
+        for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) {
+          const double dd = sm[L.ddc + i], g_ = sm[L.gc + i], y_ = sm[L.dx + i];
+          const double v = dd > 0.0 ? g_ / dd : 0.0;
+          sm[L.stp + i] = v;
+          if (dd > 0.0) { gg += g_ * v; yy += dd * y_ * y_; gy += g_ * y_; q -= mu * dd * v * v; }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < W.D; j += blockDim.x) {   // (L^T v)_j
+          double wj = 0;
+          for (int i = j; i < W.D; i++) wj = fma(H[tidx(i, j)], sm[L.stp + i], wj);
+          q += wj * wj;
+        }
+        for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
+          double tv = 0, ty = 0;
+          for (int e = lane; e < W.Dv; e += 32) { const double ev = E[(size_t)rnk * W.Dvp + e]; const int ci = vis2cam(e, W.N); tv = fma(ev, sm[L.stp + ci], tv); ty = fma(ev, sm[L.dx + ci], ty); }
+          tv = warp_sum(tv); ty = warp_sum(ty);
+          const double ci = sm[L.cinv + rnk];
+          if (lane == 0 && ci != 0.0) {
+            const double gl = sm[L.glam + rnk], C = sm[L.craw + rnk], sj = sm[L.scl + rnk], dd = fmin(fmax(C * sj * sj, 1e-6), 1e32) / (sj * sj);
+            const double yl = -ci * (gl + ty), vl = gl / dd;
+            gg += gl * vl; yy += dd * yl * yl; gy += gl * yl;
+            q += ci * tv * tv + 2.0 * tv * vl + C * vl * vl;
+          }
+        }
+        dl_gg = block_sum(gg, sm + L.red); dl_yy = block_sum(yy, sm + L.red); dl_gy = block_sum(gy, sm + L.red); dl_pHp = block_sum(q, sm + L.red);
+      }
+      // dogleg_strategy.cc ComputeTraditionalDoglegStep (every thread, identical arithmetic)
+      const double alpha = dl_gg / dl_pHp, gn_norm = sqrt(dl_yy), g_norm = sqrt(dl_gg);
+      double a, b, step_norm;
+      if (gn_norm <= radius) { a = 0; b = 1; step_norm = gn_norm; }
+      else if (g_norm * alpha >= radius) { a = radius / g_norm; b = 0; step_norm = radius; }
+      else {
+        const double b_dot_a = -alpha * dl_gy, a_sq = (alpha * g_norm) * (alpha * g_norm), bma = a_sq - 2 * b_dot_a + dl_yy, c = b_dot_a - a_sq;
+        const double dsc = sqrt(c * c + bma * (radius * radius - a_sq));
+        const double beta = (c <= 0) ? (dsc - c) / bma : (radius * radius - a_sq) / (dsc + c);
+        a = alpha * (1.0 - beta); b = beta;
+        step_norm = sqrt(fmax(0.0, a * a * dl_gg - 2 * a * b * dl_gy + b * b * dl_yy));
+      }
+      const double g_step = -a * dl_gg + b * dl_gy;
+      const double sHs = a * a * dl_pHp + 2 * a * b * (dl_gg + mu * dl_gy) + b * b * (-dl_gy - mu * dl_yy);
+      const double model = -g_step - 0.5 * sHs;
+      trials++;
+      if (!(model > 0)) {   // StepIsInvalid
+        mu_dl *= 10.0; reuse = false;
+        if (++invalid >= 5 || mu_dl >= 1.0 || trials >= P.max_iters) break;
+        continue;
+      }
+      invalid = 0;
+      double dn = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) {
+        const double dd = sm[L.ddc + i];
+        const double st = dd > 0.0 ? -a * sm[L.gc + i] / dd + b * sm[L.dx + i] : 0.0;
+        sm[L.stp + i] = st; dn += st * st;
+      }
+      __syncthreads();
+      dn += apply_step_dogleg(P, W, L, sm, scr, xs, xc, a, b);
+      const double new_cost = cost_only(P, W, L, sm, scr, xc);
+      const double quality = isfinite(new_cost) ? (cost - new_cost) / model : -1;
+      if (quality > P.min_rel_dec) {
+        double xn = 0;
+        for (int k = threadIdx.x; k < X; k += blockDim.x) xn += xs[k] * xs[k];
+        xn = block_sum(xn, sm + L.red); dn = block_sum(dn, sm + L.red);
+        for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
+        __syncthreads();
+        accepted++;
+        if (quality < 0.25) radius *= 0.5;
+        if (quality > 0.75) radius = fmax(radius, 3.0 * step_norm);
+        mu_dl = fmax(1e-8, 2.0 * mu_dl / 10.0); reuse = false;
+        const double change = cost - new_cost; cost = new_cost;
+        if (fabs(change) / (cost + 1e-300) < P.f_tol) break;
+        if (sqrt(dn) <= P.p_tol * (sqrt(xn) + P.p_tol)) break;
+        if (trials >= P.max_iters) break;
+        iters++;
+      } else {
+        radius *= 0.5; reuse = true;
+        if (radius < 1e-32 || trials >= P.max_iters) break;
+      }
+      continue;
+    }
     double rho = -1, new_cost = 0;
     if (ok) {
-      backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
-      PROF(9);
       double model = 0;
       if (lm) {
         // With (H + D2) d = -g over the full camera + landmark system: cost - model(d) = -1/2 g^T d + 1/2 d^T D2 d, where
@@ -297,7 +467,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
         double p2 = 0;
         for (int i = threadIdx.x; i < W.D; i += blockDim.x) {
           const double d = sm[L.dx + i];
-          const double d2 = fx[i] ? mu : mu * fmin(fmax(sm[L.hd + i], 1e-12), 1e64);
+          const double d2 = fx[i] ? mu : mu * fmin(fmax(sm[L.hd + i], 1e-6), 1e32);
           p2 += 0.5 * bsave[i] * d + 0.5 * d2 * d * d;
         }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -308,19 +478,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
           sdot = warp_sum(sdot);
           if (lane == 0 && sm[L.cinv + rnk] != 0.0) {
             const double ci = sm[L.cinv + rnk], gl = sm[L.glam + rnk];
-            const double dl = -ci * (gl + sdot);
-            const double Cd = 1.0 / ci, C = Cd / (1.0 + mu);   // exact while C sits inside the clamp range [1e-12, 1e64]
-            p2 += -0.5 * ci * gl * sdot - 0.5 * gl * dl + 0.5 * (Cd - C) * dl * dl;
+            const double dl_ = -ci * (gl + sdot);
+            const double Cd = 1.0 / ci, C = Cd / (1.0 + mu);   // exact while C sits inside the clamp range [1e-6, 1e32]
+            p2 += -0.5 * ci * gl * sdot - 0.5 * gl * dl_ + 0.5 * (Cd - C) * dl_ * dl_;
           }
         }
         model = block_sum(p2, sm + L.red);
       }
+      PROF_T0();
       apply_step(P, W, L, sm, scr, xs, xc);
       PROF(10);
       if (lm || last) { new_cost = cost_only(P, W, L, sm, scr, xc); PROF(11); }
       if (lm) rho = (isfinite(new_cost) && model > 0) ? (cost - new_cost) / model : -1;
     }
-    if (!lm) {   // Gauss-Newton: every step is taken
+    if (!TR) {   // Gauss-Newton: every step is taken
       for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
       __syncthreads();
       iters++; accepted++;
@@ -347,10 +518,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
       if (radius < 1e-32 || trials >= P.max_iters) break;
     }
   }
+  if (!TR && capped) {   // a capped Gauss-Newton run reports the cost of the state it stopped at
+    cost = cost_only(P, W, L, sm, scr, xs);
+  }
   double* xo = P.xout + (size_t)slot * P.xout_stride;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xs[k];
   if (threadIdx.x == 0) {
-    vils_summary s; s.status = status; s.iterations = iters; s.accepted = accepted; s.reserved = 0; s.cost_initial = cost0; s.cost_final = cost;
+    vils_summary s; s.status = status; s.iterations = iters; s.accepted = accepted; s.reserved = capped; s.cost_initial = cost0; s.cost_final = cost;
     P.summary[slot] = s;
   }
 }
@@ -702,7 +876,8 @@ __global__ void eval_cons_kernel(EvalParams Q) {
 // =================================================================================================================
 // host
 // =================================================================================================================
-struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; int bytes = 0; };
+struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; bool on_device = false; int bytes = 0; };
+struct PackPool;
 
 struct vils_ba {
   vils_config cfg{};
@@ -724,9 +899,9 @@ struct vils_ba {
   std::vector<SlotMeta> meta;
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
   float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
-  bool prepped = false, eval_attr_set = false;
   double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
+  PackPool* pool = nullptr;                            // host packer threads (created on first use)
 };
 
 static inline size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -742,6 +917,7 @@ static size_t blob_capacity(const vils_config& c) {
   return (b + 255) & ~size_t(255);
 }
 
+static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s);
 static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   SolveParams P{};
   P.blobs = ba->d_blob; P.blob_stride = (int64_t)ba->blob_stride;
@@ -756,10 +932,17 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   if (o) {
     P.mode = o->mode; P.max_iters = o->max_iters; P.mu = o->mu; P.lm_radius = o->lm_initial_radius; P.f_tol = o->function_tolerance;
     P.p_tol = o->parameter_tolerance; P.min_rel_dec = o->min_relative_decrease;
+    P.time_cap_ns = (long long)(o->max_solver_time * 1e9);
   }
   P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
   P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr; P.do_prep = 0;
   return P;
+}
+
+static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s) {
+  const bool both = ba->h_in_smem && ba->hv_in_smem, tr = P.mode != VILS_MODE_GN;
+  if (both) { if (tr) solve_kernel<true, true><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); else solve_kernel<true, false><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); }
+  else { if (tr) solve_kernel<false, true><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); else solve_kernel<false, false><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); }
 }
 
 extern "C" {
@@ -784,7 +967,7 @@ void vils_default_config(vils_config* cfg) {
 void vils_default_solve_opts(vils_solve_opts* o) {
   if (!o) return;
   o->mode = VILS_MODE_GN; o->max_iters = 5; o->mu = 1e-8; o->lm_initial_radius = 1e4; o->function_tolerance = 1e-6;
-  o->parameter_tolerance = 1e-8; o->min_relative_decrease = 1e-3;
+  o->parameter_tolerance = 1e-8; o->min_relative_decrease = 1e-3; o->max_solver_time = 0.0;
 }
 
 int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
@@ -833,12 +1016,29 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaMalloc(&ba->d_sum, sizeof(vils_summary) * max_windows));
   CK(cudaMallocHost(&ba->h_sum, sizeof(vils_summary) * max_windows));
   CK(cudaMalloc(&ba->d_lin, n_lin * 8)); CK(cudaMallocHost(&ba->h_lin, n_lin * 8));
-  CK(cudaFuncSetAttribute(solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
-  CK(cudaFuncSetAttribute(solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
-  CK(cudaFuncSetAttribute(shard_lin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
-  CK(cudaFuncSetAttribute(shard_lin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
-  CK(cudaFuncSetAttribute(shard_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
-  CK(cudaFuncSetAttribute(shard_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba->smem_bytes));
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is per function AND per device, shared by every handle on that device: it is
+  // raised once to the device's opt-in limit (what a launch actually uses is its own smem_bytes), so handles of different
+  // capacities can live side by side.
+  {
+    static std::mutex attr_m; static bool attr_done[64] = {};
+    std::lock_guard<std::mutex> l(attr_m);
+    if (cfg->device >= 64 || !attr_done[cfg->device]) {
+      const int lim = (int)budget;
+      CK(cudaFuncSetAttribute(solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(solve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(solve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(shard_lin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(shard_lin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(shard_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(shard_upd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(eval_proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(eval_proj_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(eval_proj_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      CK(cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+      if (cfg->device < 64) attr_done[cfg->device] = true;
+    }
+  }
 #undef CK
   { uint16_t tbl[450]; vf::imu_build_table(tbl); cudaError_t e_ = cudaMemcpyToSymbol(g_imu_tbl, tbl, sizeof(tbl)); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, "imu table"); } }
   std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
@@ -860,71 +1060,94 @@ void vils_ba_destroy(vils_ba* ba) {
   if (ba->stream2) cudaStreamDestroy(ba->stream2);
   for (int k = 0; k < vils_ba::NPIPE; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
   if (ba->stream) cudaStreamDestroy(ba->stream);
+  delete ba->pool;
   delete ba;
 }
 
-int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
-  if (!ba || !w || slot < 0 || slot >= ba->max_windows) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_window: bad slot / null");
+// ---- host packer ------------------------------------------------------------------------------------------------------
+// One window -> one blob in pinned staging.  Thread-safe for distinct slots (touches only its slot's blob and SlotMeta and the
+// caller's PackScratch); never calls CUDA.  All orderings are stable counting sorts (landmark, keyframe pair, keyframe): no
+// allocation after the first use of a scratch.  Errors come back as (code, message) so that worker threads can hand them on.
+struct PackScratch {
+  std::vector<int> cnt, ord, rank_of, lm_start, lm_feat, pord, pairs, pair_id, plo, pls, edo, eds, pblk, pcol;
+};
+
+static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScratch& S, std::string& err) {
+#define PFAIL(code, msg) do { err = (msg); return (code); } while (0)
+  if (!ba || !w || slot < 0 || slot >= ba->max_windows) PFAIL(VILS_ERR_BAD_ARG, "vils_ba_set_window: bad slot / null");
   const vils_config& c = ba->cfg;
   const int N = w->n_kf, M = w->n_feat, np = w->n_proj, npl = w->n_plane, ned = w->n_edge;
   if (N < 2 || N > c.max_kf || M < 0 || M > c.max_feat || np < 0 || np > c.max_proj || npl < 0 || ned < 0 || npl + ned > c.max_lidar ||
       w->n_imu < 0 || w->n_imu > N - 1 + 0 || w->n_icp < 0 || w->n_icp > 16 || w->n_lps < 0 || w->n_lps > 16 || w->prior_n < 0 || w->prior_n > 15 * N + 7 ||
       w->prior_nblk < 0 || w->prior_nblk > 2 * N + 2)
-    return vils::fail(VILS_ERR_CAPACITY, "vils_ba_set_window: window exceeds the handle's capacity");
+    PFAIL(VILS_ERR_CAPACITY, "vils_ba_set_window: window exceeds the handle's capacity");
   if (!w->pose || !w->speedbias || !w->ex_pose || (M && !w->inv_depth) || (w->n_imu && (!w->imu || !w->imu_kf)) ||
       (np && (!w->pts_i || !w->pts_j || !w->vel_i || !w->vel_j || !w->td_i || !w->td_j || !w->row_i || !w->row_j || !w->kf_i || !w->kf_j || !w->feat)) ||
       (npl && (!w->plane_p || !w->plane_n || !w->plane_d || !w->plane_kf)) || (ned && (!w->edge_p || !w->edge_a || !w->edge_b || !w->edge_kf)) ||
       (w->n_icp && !w->icp) || (w->n_lps && !w->lps) || (w->prior_n && (!w->prior_J || !w->prior_r || !w->prior_blk || !w->prior_x0)))
-    return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_window: null array");
-  for (int k = 0; k < w->n_imu; k++) if (w->imu_kf[k] < 0 || w->imu_kf[k] + 1 >= N) return vils::fail(VILS_ERR_BAD_ARG, "imu_kf out of range");
+    PFAIL(VILS_ERR_BAD_ARG, "vils_ba_set_window: null array");
+  for (int k = 0; k < w->n_imu; k++) if (w->imu_kf[k] < 0 || w->imu_kf[k] + 1 >= N) PFAIL(VILS_ERR_BAD_ARG, "imu_kf out of range");
   for (int k = 0; k < np; k++)
     if (w->kf_i[k] < 0 || w->kf_i[k] >= N || w->kf_j[k] < 0 || w->kf_j[k] >= N || w->kf_i[k] == w->kf_j[k] || w->feat[k] < 0 || w->feat[k] >= M)
-      return vils::fail(VILS_ERR_BAD_ARG, "projection factor index out of range");
-  for (int k = 0; k < npl; k++) if (w->plane_kf[k] < 0 || w->plane_kf[k] >= N) return vils::fail(VILS_ERR_BAD_ARG, "plane_kf out of range");
-  for (int k = 0; k < ned; k++) if (w->edge_kf[k] < 0 || w->edge_kf[k] >= N) return vils::fail(VILS_ERR_BAD_ARG, "edge_kf out of range");
-  for (int k = 0; k < w->n_icp; k++) for (int b = 0; b < 4; b++) if (w->icp[k].kf[b] < 0 || w->icp[k].kf[b] >= N) return vils::fail(VILS_ERR_BAD_ARG, "icp kf out of range");
-  for (int k = 0; k < w->n_lps; k++) for (int b = 0; b < 2; b++) if (w->lps[k].kf[b] < 0 || w->lps[k].kf[b] >= N) return vils::fail(VILS_ERR_BAD_ARG, "lps kf out of range");
+      PFAIL(VILS_ERR_BAD_ARG, "projection factor index out of range");
+  for (int k = 0; k < npl; k++) if (w->plane_kf[k] < 0 || w->plane_kf[k] >= N) PFAIL(VILS_ERR_BAD_ARG, "plane_kf out of range");
+  for (int k = 0; k < ned; k++) if (w->edge_kf[k] < 0 || w->edge_kf[k] >= N) PFAIL(VILS_ERR_BAD_ARG, "edge_kf out of range");
+  for (int k = 0; k < w->n_icp; k++) for (int b = 0; b < 4; b++) if (w->icp[k].kf[b] < 0 || w->icp[k].kf[b] >= N) PFAIL(VILS_ERR_BAD_ARG, "icp kf out of range");
+  for (int k = 0; k < w->n_lps; k++) for (int b = 0; b < 2; b++) if (w->lps[k].kf[b] < 0 || w->lps[k].kf[b] >= N) PFAIL(VILS_ERR_BAD_ARG, "lps kf out of range");
+  // the prior's block table is validated BEFORE anything is written: a rejected window leaves the slot exactly as it was
+  const int n = w->prior_n;
+  int gs = 0, lsz = 0;
+  S.pblk.assign(4 * (size_t)w->prior_nblk, 0); S.pcol.clear();
+  for (int b = 0; b < w->prior_nblk; b++) {
+    const int id = w->prior_blk[b], type = VILS_BLK_TYPE(id), idx = VILS_BLK_INDEX(id);
+    if (type < 0 || type > 3 || ((type == VILS_BLK_POSE || type == VILS_BLK_SPEEDBIAS) && idx >= N)) PFAIL(VILS_ERR_BAD_ARG, "prior block id out of range");
+    const int g = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 7 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
+    const int l = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 6 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
+    const int off = type == VILS_BLK_POSE ? 15 * idx : type == VILS_BLK_SPEEDBIAS ? 15 * idx + 6 : type == VILS_BLK_EXPOSE ? 15 * N : 15 * N + 6;
+    S.pblk[4 * b] = type; S.pblk[4 * b + 1] = idx; S.pblk[4 * b + 2] = gs; S.pblk[4 * b + 3] = lsz;
+    for (int a = 0; a < l; a++) S.pcol.push_back(off + a);
+    gs += g; lsz += l;
+  }
+  if (lsz != n) PFAIL(VILS_ERR_BAD_ARG, "prior_n does not match the local sizes of prior_blk");
 
-  // ---- orderings
-  std::vector<int> ord(np); std::iota(ord.begin(), ord.end(), 0);
-  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return w->feat[a] < w->feat[b]; });
-  std::vector<int> lm_start, lm_feat, rank_of(np);
-  for (int s = 0; s < np; s++) {
-    const int f = w->feat[ord[s]];
-    if (lm_feat.empty() || lm_feat.back() != f) { lm_feat.push_back(f); lm_start.push_back(s); }
-    else if (w->kf_i[ord[s]] != w->kf_i[ord[lm_start.back()]]) return vils::fail(VILS_ERR_BAD_ARG, "factors of one feature must share the anchor keyframe");
-    rank_of[s] = (int)lm_feat.size() - 1;
-  }
-  lm_start.push_back(np);
-  const int nlm = (int)lm_feat.size();
-  // pairs: landmark-sorted positions grouped by (kf_i, kf_j). The anchor may be any frame, pairs are ordered (i, j).
-  std::vector<int> pord(np); std::iota(pord.begin(), pord.end(), 0);
-  auto key = [&](int s) { return w->kf_i[ord[s]] * N + w->kf_j[ord[s]]; };
-  std::stable_sort(pord.begin(), pord.end(), [&](int a, int b) { return key(a) < key(b); });
-  std::vector<int> pairs; std::vector<int> pair_id(N * N, -1);
-  for (int s = 0; s < np; s++) {
-    const int k = key(pord[s]);
-    if (pairs.empty() || pairs[pairs.size() - 2] * N + pairs.back() != k) {
-      pair_id[k] = (int)pairs.size() / 4;
-      pairs.push_back(s); pairs.push_back(0); pairs.push_back(k / N); pairs.push_back(k % N);
+  // ---- orderings (stable counting sorts)
+  // landmark order: factors by feature index, original order inside a feature
+  S.cnt.assign((size_t)M + 1, 0);
+  for (int k = 0; k < np; k++) S.cnt[w->feat[k] + 1]++;
+  S.lm_feat.clear(); S.lm_start.clear();
+  for (int f = 0; f < M; f++) { if (S.cnt[f + 1]) { S.lm_feat.push_back(f); S.lm_start.push_back(S.cnt[f]); } S.cnt[f + 1] += S.cnt[f]; }
+  S.lm_start.push_back(np);
+  const int nlm = (int)S.lm_feat.size();
+  S.ord.resize(np); S.rank_of.resize(np);
+  for (int k = 0; k < np; k++) S.ord[S.cnt[w->feat[k]]++] = k;
+  for (int r = 0; r < nlm; r++) {
+    const int s0 = S.lm_start[r], s1 = S.lm_start[r + 1], anchor = w->kf_i[S.ord[s0]];
+    for (int s = s0; s < s1; s++) {
+      if (w->kf_i[S.ord[s]] != anchor) PFAIL(VILS_ERR_BAD_ARG, "factors of one feature must share the anchor keyframe");
+      // the gather assumes anchor < observer (a feature's anchor is its first observation, estimator.cpp:1201-1206)
+      if (w->kf_i[S.ord[s]] >= w->kf_j[S.ord[s]]) PFAIL(VILS_ERR_BAD_ARG, "anchor keyframe must precede the observing keyframe");
+      S.rank_of[s] = r;
     }
-    pairs[pairs.size() - 3]++;
   }
-  const int npair = (int)pairs.size() / 4;
-  if (npair > N * (N - 1) / 2) {
-    // the gather assumes anchor < observer (a feature's anchor is its first observation, estimator.cpp:1201-1206)
-    return vils::fail(VILS_ERR_BAD_ARG, "more keyframe pairs than N(N-1)/2: anchor must precede the observing frame");
+  // pair order: landmark-sorted positions grouped by (kf_i, kf_j)
+  S.cnt.assign((size_t)N * N + 1, 0);
+  for (int s = 0; s < np; s++) S.cnt[w->kf_i[S.ord[s]] * N + w->kf_j[S.ord[s]] + 1]++;
+  S.pairs.clear(); S.pair_id.assign((size_t)N * N, -1);
+  for (int k = 0; k < N * N; k++) {
+    if (S.cnt[k + 1]) { S.pair_id[k] = (int)S.pairs.size() / 4; S.pairs.push_back(S.cnt[k]); S.pairs.push_back(S.cnt[k + 1]); S.pairs.push_back(k / N); S.pairs.push_back(k % N); }
+    S.cnt[k + 1] += S.cnt[k];
   }
-  for (int p = 0; p < npair; p++) if (pairs[4 * p + 2] >= pairs[4 * p + 3]) return vils::fail(VILS_ERR_BAD_ARG, "anchor keyframe must precede the observing keyframe");
-  auto sort_by_kf = [&](int n, const int32_t* kf, std::vector<int>& o, std::vector<int>& start) {
-    o.resize(n); std::iota(o.begin(), o.end(), 0);
-    std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return kf[a] < kf[b]; });
-    start.assign(N + 1, 0);
-    for (int k = 0; k < n; k++) start[kf[k] + 1]++;
+  const int npair = (int)S.pairs.size() / 4;
+  S.pord.resize(np);
+  for (int s = 0; s < np; s++) S.pord[S.cnt[w->kf_i[S.ord[s]] * N + w->kf_j[S.ord[s]]]++] = s;
+  auto sort_by_kf = [&](int cntf, const int32_t* kf, std::vector<int>& o, std::vector<int>& start) {
+    start.assign((size_t)N + 1, 0);
+    for (int k = 0; k < cntf; k++) start[kf[k] + 1]++;
     for (int k = 0; k < N; k++) start[k + 1] += start[k];
+    o.resize(cntf); S.cnt.assign(start.begin(), start.end());
+    for (int k = 0; k < cntf; k++) o[S.cnt[kf[k]]++] = k;
   };
-  std::vector<int> plo, pls, edo, eds;
-  sort_by_kf(npl, w->plane_kf, plo, pls); sort_by_kf(ned, w->edge_kf, edo, eds);
+  sort_by_kf(npl, w->plane_kf, S.plo, S.pls); sort_by_kf(ned, w->edge_kf, S.edo, S.eds);
 
   // ---- blob
   uint8_t* base = ba->h_blob + (size_t)slot * ba->blob_stride;
@@ -948,17 +1171,18 @@ int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
   double* pj = (double*)place(OFF_PROJ, (size_t)14 * np * 8);
   int32_t* pix = (int32_t*)place(OFF_PROJ_IDX, (size_t)4 * np * 4);
   for (int s = 0; s < np; s++) {
-    const int k = ord[s];
+    const int k = S.ord[s];
     const double v[14] = {w->pts_i[3 * k], w->pts_i[3 * k + 1], w->pts_i[3 * k + 2], w->pts_j[3 * k], w->pts_j[3 * k + 1], w->pts_j[3 * k + 2],
                           w->vel_i[2 * k], w->vel_i[2 * k + 1], w->vel_j[2 * k], w->vel_j[2 * k + 1], w->td_i[k], w->td_j[k], w->row_i[k], w->row_j[k]};
     for (int a = 0; a < 14; a++) pj[(size_t)a * np + s] = v[a];
-    pix[s] = w->kf_i[k]; pix[np + s] = w->kf_j[k]; pix[2 * np + s] = rank_of[s]; pix[3 * np + s] = k;
+    pix[s] = w->kf_i[k]; pix[np + s] = w->kf_j[k]; pix[2 * np + s] = S.rank_of[s]; pix[3 * np + s] = k;
   }
-  int32_t* ls = (int32_t*)place(OFF_LM_START, (size_t)(nlm + 1) * 4); for (int k = 0; k <= nlm; k++) ls[k] = lm_start[k];
-  int32_t* lf = (int32_t*)place(OFF_LM_FEAT, (size_t)nlm * 4); for (int k = 0; k < nlm; k++) lf[k] = lm_feat[k];
-  int32_t* pr = (int32_t*)place(OFF_PAIR, (size_t)npair * 16); for (int k = 0; k < 4 * npair; k++) pr[k] = pairs[k];
-  int32_t* pp = (int32_t*)place(OFF_PAIR_PERM, (size_t)np * 4); for (int k = 0; k < np; k++) pp[k] = pord[k];
-  int32_t* pi = (int32_t*)place(OFF_PAIR_ID, (size_t)N * N * 4); for (int k = 0; k < N * N; k++) pi[k] = pair_id[k];
+  int32_t* ls = (int32_t*)place(OFF_LM_START, (size_t)(nlm + 1) * 4); for (int k = 0; k <= nlm; k++) ls[k] = S.lm_start[k];
+  int32_t* lf = (int32_t*)place(OFF_LM_FEAT, (size_t)nlm * 4); for (int k = 0; k < nlm; k++) lf[k] = S.lm_feat[k];
+  int32_t* pr = (int32_t*)place(OFF_PAIR, (size_t)npair * 16);
+  for (int k = 0; k < npair; k++) { pr[4 * k] = S.pairs[4 * k]; pr[4 * k + 1] = S.pairs[4 * k + 1]; pr[4 * k + 2] = S.pairs[4 * k + 2]; pr[4 * k + 3] = S.pairs[4 * k + 3]; }
+  int32_t* pp = (int32_t*)place(OFF_PAIR_PERM, (size_t)np * 4); for (int k = 0; k < np; k++) pp[k] = S.pord[k];
+  int32_t* pi = (int32_t*)place(OFF_PAIR_ID, (size_t)N * N * 4); for (int k = 0; k < N * N; k++) pi[k] = S.pair_id[k];
   // LiDAR points go to the body frame once, here: p_b = RLB^T (p_l - TLB)   (estimator.cpp:449-451)
   auto to_body = [&](const double* p, double* out) {
     const double d[3] = {p[0] - c.tlb[0], p[1] - c.tlb[1], p[2] - c.tlb[2]};
@@ -967,19 +1191,19 @@ int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
   double* pl = (double*)place(OFF_PLANE, (size_t)7 * npl * 8);
   int32_t* plx = (int32_t*)place(OFF_PLANE_IDX, (size_t)2 * npl * 4);
   for (int s = 0; s < npl; s++) {
-    const int k = plo[s]; double pb[3]; to_body(w->plane_p + 3 * k, pb);
+    const int k = S.plo[s]; double pb[3]; to_body(w->plane_p + 3 * k, pb);
     for (int a = 0; a < 3; a++) { pl[(size_t)a * npl + s] = pb[a]; pl[(size_t)(3 + a) * npl + s] = w->plane_n[3 * k + a]; }
     pl[(size_t)6 * npl + s] = w->plane_d[k]; plx[s] = w->plane_kf[k]; plx[npl + s] = k;
   }
-  int32_t* plst = (int32_t*)place(OFF_PLANE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) plst[k] = pls[k];
+  int32_t* plst = (int32_t*)place(OFF_PLANE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) plst[k] = S.pls[k];
   double* ed = (double*)place(OFF_EDGE, (size_t)9 * ned * 8);
   int32_t* edx = (int32_t*)place(OFF_EDGE_IDX, (size_t)2 * ned * 4);
   for (int s = 0; s < ned; s++) {
-    const int k = edo[s]; double pb[3]; to_body(w->edge_p + 3 * k, pb);
+    const int k = S.edo[s]; double pb[3]; to_body(w->edge_p + 3 * k, pb);
     for (int a = 0; a < 3; a++) { ed[(size_t)a * ned + s] = pb[a]; ed[(size_t)(3 + a) * ned + s] = w->edge_a[3 * k + a]; ed[(size_t)(6 + a) * ned + s] = w->edge_b[3 * k + a]; }
     edx[s] = w->edge_kf[k]; edx[ned + s] = k;
   }
-  int32_t* edst = (int32_t*)place(OFF_EDGE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) edst[k] = eds[k];
+  int32_t* edst = (int32_t*)place(OFF_EDGE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) edst[k] = S.eds[k];
   double* ic = (double*)place(OFF_ICP, (size_t)w->n_icp * 14 * 8);
   for (int k = 0; k < w->n_icp; k++) {
     const vils_icp& q = w->icp[k]; double* d = ic + 14 * k;
@@ -991,32 +1215,107 @@ int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
     const vils_lps& q = w->lps[k]; double* d = lp + 9 * k;
     d[0] = q.tl; d[1] = q.tr; d[2] = q.tk; for (int a = 0; a < 4; a++) d[3 + a] = q.q[a]; d[7] = q.kf[0]; d[8] = q.kf[1];
   }
-  const int n = w->prior_n;
   double* PJ = (double*)place(OFF_PRIOR_J, (size_t)n * n * 8); if (n) std::memcpy(PJ, w->prior_J, sizeof(double) * n * n);
   double* PR = (double*)place(OFF_PRIOR_R, (size_t)n * 8); if (n) std::memcpy(PR, w->prior_r, sizeof(double) * n);
-  int gs = 0, lsz = 0;
-  std::vector<int> pblk(4 * w->prior_nblk), pcol;
-  for (int b = 0; b < w->prior_nblk; b++) {
-    const int id = w->prior_blk[b], type = VILS_BLK_TYPE(id), idx = VILS_BLK_INDEX(id);
-    if (type < 0 || type > 3 || ((type == VILS_BLK_POSE || type == VILS_BLK_SPEEDBIAS) && idx >= N)) return vils::fail(VILS_ERR_BAD_ARG, "prior block id out of range");
-    const int g = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 7 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
-    const int l = (type == VILS_BLK_POSE || type == VILS_BLK_EXPOSE) ? 6 : type == VILS_BLK_SPEEDBIAS ? 9 : 1;
-    const int off = type == VILS_BLK_POSE ? 15 * idx : type == VILS_BLK_SPEEDBIAS ? 15 * idx + 6 : type == VILS_BLK_EXPOSE ? 15 * N : 15 * N + 6;
-    pblk[4 * b] = type; pblk[4 * b + 1] = idx; pblk[4 * b + 2] = gs; pblk[4 * b + 3] = lsz;
-    for (int a = 0; a < l; a++) pcol.push_back(off + a);
-    gs += g; lsz += l;
-  }
-  if (lsz != n) return vils::fail(VILS_ERR_BAD_ARG, "prior_n does not match the local sizes of prior_blk");
   double* PX = (double*)place(OFF_PRIOR_X0, (size_t)gs * 8); if (gs) std::memcpy(PX, w->prior_x0, sizeof(double) * gs);
-  int32_t* PB = (int32_t*)place(OFF_PRIOR_BLK, (size_t)4 * w->prior_nblk * 4); for (size_t k = 0; k < pblk.size(); k++) PB[k] = pblk[k];
-  int32_t* PC = (int32_t*)place(OFF_PRIOR_COL, (size_t)n * 4); for (int k = 0; k < n; k++) PC[k] = pcol[k];
-  if (o > ba->blob_stride) return vils::fail(VILS_ERR_CAPACITY, "vils_ba_set_window: blob overflow");
-  h->bytes = (int32_t)o;
+  int32_t* PB = (int32_t*)place(OFF_PRIOR_BLK, (size_t)4 * w->prior_nblk * 4); for (size_t k = 0; k < S.pblk.size(); k++) PB[k] = S.pblk[k];
+  int32_t* PC = (int32_t*)place(OFF_PRIOR_COL, (size_t)n * 4); for (int k = 0; k < n; k++) PC[k] = S.pcol[k];
   SlotMeta& m = ba->meta[slot];
-  m.set = true; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
+  if (o > ba->blob_stride) { m.set = false; PFAIL(VILS_ERR_CAPACITY, "vils_ba_set_window: blob overflow"); }   // cannot happen for windows inside the capacities checked above
+  h->bytes = (int32_t)o;
+  m.set = true; m.on_device = false; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
   m.n_res = 15 * w->n_imu + 2 * np + npl + 3 * ned + 3 * w->n_icp + 3 * w->n_lps + n;
   m.n_jac = (int64_t)450 * w->n_imu + (int64_t)40 * np + 6 * npl + 18 * ned + 72 * w->n_icp + 36 * w->n_lps;
   m.items = w->n_imu + np + npl + ned + w->n_icp + w->n_lps + n;
+  return VILS_OK;
+#undef PFAIL
+}
+
+int vils_ba_set_window(vils_ba* ba, int32_t slot, const vils_window* w) {
+  static thread_local PackScratch S;
+  std::string err;
+  const int st = pack_window(ba, slot, w, S, err);
+  return st == VILS_OK ? VILS_OK : vils::fail(st, err);
+}
+
+// Persistent host threads that pack windows (vils_ba_set_windows / vils_ba_solve_windows).  Work items are window indices
+// handed out in ascending order by an atomic counter; the calling thread packs too, so a pool of T threads gives T + 1 packers.
+struct PackPool {
+  std::vector<std::thread> th;
+  std::mutex m; std::condition_variable cv;
+  uint64_t generation = 0; bool stop = false;
+  // current job
+  vils_ba* ba = nullptr; const vils_window* ws = nullptr; int slot0 = 0, n = 0, chunk = 1;
+  std::atomic<int> next{0}, active{0};
+  std::vector<std::atomic<int>> chunk_done;
+  std::atomic<int> err_code{0}; std::string err_msg;
+  explicit PackPool(int T) : chunk_done(0) { for (int t = 0; t < T; t++) th.emplace_back([this] { run(); }); }
+  ~PackPool() { { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+  void work(PackScratch& S) {
+    for (;;) {
+      const int k = next.fetch_add(1, std::memory_order_relaxed);
+      if (k >= n) break;
+      if (err_code.load(std::memory_order_relaxed) == 0) {
+        std::string e;
+        const int st = pack_window(ba, slot0 + k, ws + k, S, e);
+        if (st != VILS_OK) { std::lock_guard<std::mutex> l(m); if (err_code.load() == 0) { err_msg = e; err_code.store(st); } }
+      }
+      chunk_done[k / chunk].fetch_add(1, std::memory_order_release);
+    }
+  }
+  void run() {
+    PackScratch S; uint64_t seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || generation != seen; }); if (stop) return; seen = generation; active.fetch_add(1); }
+      work(S);
+      active.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  void begin(vils_ba* b, const vils_window* w, int s0, int cnt, int ch) {
+    while (active.load(std::memory_order_acquire) != 0) std::this_thread::yield();      // stragglers of the previous job
+    { std::lock_guard<std::mutex> l(m);
+      ba = b; ws = w; slot0 = s0; n = cnt; chunk = ch; err_code.store(0); err_msg.clear();
+      const int nc = (cnt + ch - 1) / ch;
+      if ((int)chunk_done.size() < nc) { std::vector<std::atomic<int>> v(nc); chunk_done.swap(v); }
+      for (auto& c : chunk_done) c.store(0, std::memory_order_relaxed);
+      next.store(0); generation++; }
+    cv.notify_all();
+  }
+  // the caller packs until chunk c is complete (or nothing is left to hand out, then it yields)
+  void wait_chunk(int c, int cn, PackScratch& S) {
+    while (chunk_done[c].load(std::memory_order_acquire) < cn) {
+      const int k = next.fetch_add(1, std::memory_order_relaxed);
+      if (k < n) {
+        if (err_code.load(std::memory_order_relaxed) == 0) {
+          std::string e;
+          const int st = pack_window(ba, slot0 + k, ws + k, S, e);
+          if (st != VILS_OK) { std::lock_guard<std::mutex> l(m); if (err_code.load() == 0) { err_msg = e; err_code.store(st); } }
+        }
+        chunk_done[k / chunk].fetch_add(1, std::memory_order_release);
+      } else std::this_thread::yield();
+    }
+  }
+};
+
+static PackPool* pack_pool(vils_ba* ba) {
+  if (!ba->pool) {
+    int T = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("VILS_PACK_THREADS")) T = atoi(e);
+    T = std::max(1, std::min(T, 64)) - 1;                         // the calling thread is one of the packers
+    ba->pool = new PackPool(T);
+  }
+  return ba->pool;
+}
+
+// Stage n windows into slots [slot0, slot0 + n) on all host threads.
+int vils_ba_set_windows(vils_ba* ba, int32_t slot0, int32_t n, const vils_window* ws) {
+  if (!ba || !ws || n <= 0 || slot0 < 0 || slot0 + n > ba->max_windows) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_windows: bad argument");
+  static thread_local PackScratch S;
+  if (n == 1) return vils_ba_set_window(ba, slot0, ws);
+  PackPool* pool = pack_pool(ba);
+  pool->begin(ba, ws, slot0, n, n);
+  pool->wait_chunk(0, n, S);
+  if (pool->err_code.load()) return vils::fail(pool->err_code.load(), pool->err_msg);
   return VILS_OK;
 }
 
@@ -1025,6 +1324,14 @@ static int check_n(vils_ba* ba, int n, const char* who) {
   for (int k = 0; k < n; k++) if (!ba->meta[k].set) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": slot not set");
   return cudaSetDevice(ba->cfg.device) == cudaSuccess ? VILS_OK : vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
 }
+// Device-side entry points work on the UPLOADED blob: a slot re-staged by vils_ba_set_window since its last upload is stale.
+static int check_on_device(vils_ba* ba, int slot0, int n, const char* who) {
+  for (int k = slot0; k < slot0 + n; k++)
+    if (!ba->meta[k].on_device) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": slot staged but not uploaded (call vils_ba_upload / vils_ba_solve first)");
+  return VILS_OK;
+}
+// A launch-configuration error is reported by cudaGetLastError() right after the launch, never by the stream synchronisation.
+#define VILS_LAUNCH_CHECK(what) do { const cudaError_t le_ = cudaGetLastError(); if (le_ != cudaSuccess) return vils::fail_cuda(le_, what); } while (0)
 
 int vils_ba_upload(vils_ba* ba, int32_t n) {
   int st = check_n(ba, n, "vils_ba_upload"); if (st) return st;
@@ -1034,23 +1341,25 @@ int vils_ba_upload(vils_ba* ba, int32_t n) {
   if (e != cudaSuccess) return vils::fail_cuda(e, "upload");
   SolveParams P = make_params(ba, nullptr);
   prep_kernel<<<n, 256, 0, ba->stream>>>(P);
+  VILS_LAUNCH_CHECK("prep_kernel launch");
   e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "upload sync");
-  ba->prepped = true;
+  for (int k = 0; k < n; k++) ba->meta[k].on_device = true;
   return VILS_OK;
 }
 
 int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   int st = check_n(ba, n, "vils_ba_solve_device"); if (st) return st;
-  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "solve: call vils_ba_upload first");
+  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM && opts->mode != VILS_MODE_DOGLEG) || opts->max_solver_time < 0)
+    return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
+  st = check_on_device(ba, 0, n, "vils_ba_solve_device"); if (st) return st;
   SolveParams P = make_params(ba, opts);
   static const bool prof = getenv("VILS_PROF") != nullptr;
   long long* d_prof = nullptr;
   if (prof) { cudaMalloc(&d_prof, 24 * sizeof(long long)); cudaMemset(d_prof, 0, 24 * sizeof(long long)); P.prof = d_prof; }
   cudaEventRecord(ba->ev0, ba->stream);
-  if (ba->h_in_smem && ba->hv_in_smem) solve_kernel<true><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
-  else solve_kernel<false><<<n, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  launch_solve(ba, P, n, ba->stream);
+  VILS_LAUNCH_CHECK("solve_kernel launch");
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "solve_kernel");
@@ -1079,9 +1388,14 @@ int vils_ba_download(vils_ba* ba, int32_t n) {
 // the SM count (one CTA per window, one CTA per SM), each chunk on one of three streams: the host->device copy of chunk
 // c+1 runs on the copy engine while chunk c is being solved, the small device->host copies ride behind each solve, and a
 // single synchronisation closes the call (a one-window call therefore pays one sync instead of three).
-int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
-  int st = check_n(ba, n, "vils_ba_solve"); if (st) return st;
-  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM)) return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
+// ws != nullptr (vils_ba_solve_windows): the windows are packed from the caller's arrays INSIDE the pipeline — the host threads
+// of the pack pool stage chunk c+1 while chunk c is being copied and solved — so the call runs from vils_window arrays to states.
+static int solve_pipeline(vils_ba* ba, int32_t n, const vils_window* ws, const vils_solve_opts* opts, const char* who) {
+  if (!ba || n <= 0 || n > ba->max_windows) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": bad window count");
+  if (!opts || opts->max_iters < 0 || (opts->mode != VILS_MODE_GN && opts->mode != VILS_MODE_LM && opts->mode != VILS_MODE_DOGLEG) || opts->max_solver_time < 0)
+    return vils::fail(VILS_ERR_BAD_ARG, "solve: bad options");
+  if (!ws) for (int k = 0; k < n; k++) if (!ba->meta[k].set) return vils::fail(VILS_ERR_BAD_ARG, std::string(who) + ": slot not set");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   static const int chunk_env = getenv("VILS_CHUNK") ? atoi(getenv("VILS_CHUNK")) : 0;
   static const int ns_env = getenv("VILS_STREAMS") ? atoi(getenv("VILS_STREAMS")) : 0;
   const int chunk = chunk_env > 0 ? chunk_env : std::max(1, ba->n_sm / 2);
@@ -1090,29 +1404,56 @@ int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   SolveParams P = make_params(ba, opts);
   const bool both = ba->h_in_smem && ba->hv_in_smem;
   size_t h2d = 0; int launches = 0;
+  static thread_local PackScratch S;
+  PackPool* pool = nullptr;
+  if (ws && n > 1) { pool = pack_pool(ba); pool->begin(ba, ws, 0, n, chunk); }
   cudaEventRecord(ba->ev_fork, ba->stream);                 // order after anything still queued on the handle's main stream
   for (int k = 0; k < NS; k++) cudaStreamWaitEvent(ba->pipe[k], ba->ev_fork, 0);
+  int err = VILS_OK; std::string err_msg; cudaError_t le = cudaSuccess;
   for (int c0 = 0, c = 0; c0 < n; c0 += chunk, c++) {
     const int cn = std::min(chunk, n - c0);
+    if (pool) {
+      pool->wait_chunk(c, cn, S);
+      if (pool->err_code.load()) { err = pool->err_code.load(); break; }
+    } else if (ws) {
+      err = pack_window(ba, 0, ws, S, err_msg);
+      if (err) break;
+    }
     cudaStream_t s = ba->pipe[c % NS];
     size_t width = 0; for (int k = c0; k < c0 + cn; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
     h2d += width * cn;
     cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
                       cudaMemcpyHostToDevice, s);
     P.slot0 = c0; P.do_prep = 1;
-    if (both) solve_kernel<true><<<cn, SOLVE_THREADS, ba->smem_bytes, s>>>(P);
-    else solve_kernel<false><<<cn, SOLVE_THREADS, ba->smem_bytes, s>>>(P);
+    launch_solve(ba, P, cn, s);
+    if (le == cudaSuccess) le = cudaGetLastError();
     launches += 1;
     cudaMemcpyAsync(ba->h_xout + (size_t)c0 * ba->xstride, ba->d_xout + (size_t)c0 * ba->xstride, (size_t)ba->xstride * 8 * cn, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(ba->h_sum + c0, ba->d_sum + c0, sizeof(vils_summary) * cn, cudaMemcpyDeviceToHost, s);
   }
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < NS; k++) { const cudaError_t ek = cudaStreamSynchronize(ba->pipe[k]); if (e == cudaSuccess) e = ek; }
-  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_ba_solve");
-  ba->prepped = true;
+  if (pool) {   // drain the job so that the pool is idle again (after an error the remaining windows are skipped, not packed)
+    const int nc = (n + chunk - 1) / chunk;
+    for (int c = 0; c < nc; c++) pool->wait_chunk(c, std::min(chunk, n - c * chunk), S);
+    if (pool->err_code.load()) { err = pool->err_code.load(); err_msg = pool->err_msg; }
+  }
+  if (err) return vils::fail(err, err_msg);
+  if (le != cudaSuccess) return vils::fail_cuda(le, "solve_kernel launch");
+  if (e != cudaSuccess) return vils::fail_cuda(e, who);
+  for (int k = 0; k < n; k++) ba->meta[k].on_device = true;
   ba->last_h2d = h2d; ba->last_d2h = (size_t)ba->xstride * 8 * n + sizeof(vils_summary) * n;
   ba->last_launches = launches;
   return VILS_OK;
+}
+
+int vils_ba_solve(vils_ba* ba, int32_t n, const vils_solve_opts* opts) { return solve_pipeline(ba, n, nullptr, opts, "vils_ba_solve"); }
+
+// vector2double() + AddResidualBlock(...) + ceres::Solve in one call (estimator.cpp:1169-1414) for n independent windows given as
+// the caller's own arrays: pack (all host threads) | H2D | solve | D2H, pipelined chunk by chunk.  Window k lands in slot k.
+int vils_ba_solve_windows(vils_ba* ba, int32_t n, const vils_window* ws, const vils_solve_opts* opts) {
+  if (!ws) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_solve_windows: null windows");
+  return solve_pipeline(ba, n, ws, opts, "vils_ba_solve_windows");
 }
 
 int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* sb, double* ex, double* lam, double* td, vils_summary* sum) {
@@ -1126,6 +1467,21 @@ int vils_ba_get_state(vils_ba* ba, int32_t slot, double* pose, double* sb, doubl
   if (lam && M) std::memcpy(lam, x + 16 * N + 8, sizeof(double) * M);
   if (sum) *sum = ba->h_sum[slot];
   return ba->h_sum[slot].status;
+}
+
+int vils_ba_put_state(vils_ba* ba, int32_t slot, const double* pose, const double* sb, const double* ex, const double* lam, double td) {
+  if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set || !pose || !sb || !ex) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_put_state: bad argument");
+  { const int sd = check_on_device(ba, slot, 1, "vils_ba_put_state"); if (sd) return sd; }
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  const int N = ba->meta[slot].n_kf, M = ba->meta[slot].n_feat;
+  if (M && !lam) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_put_state: null inv_depth");
+  double* x = ba->h_xout + (size_t)slot * ba->xstride;
+  std::memcpy(x, pose, sizeof(double) * 7 * N); std::memcpy(x + 7 * N, sb, sizeof(double) * 9 * N);
+  std::memcpy(x + 16 * N, ex, sizeof(double) * 7); x[16 * N + 7] = td;
+  if (M) std::memcpy(x + 16 * N + 8, lam, sizeof(double) * M);
+  cudaError_t e = cudaMemcpyAsync(ba->d_xout + (size_t)slot * ba->xstride, x, sizeof(double) * (16 * N + 8 + M), cudaMemcpyHostToDevice, ba->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ba->stream);
+  return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "vils_ba_put_state");
 }
 
 static int ensure_eval_buffers(vils_ba* ba) {
@@ -1151,12 +1507,6 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   const int xs_doubles = (16 * ba->cfg.max_kf + 8 + ba->cfg.max_feat + 1) & ~1, feat_ints = (ba->cfg.max_feat + 3) & ~3;
   const size_t proj_smem = (size_t)(EVP_T * EV_PLD + 14 * EVP_T + 2 * xs_doubles) * 8 + (size_t)(3 * EVP_T + 2 * feat_ints) * 4;
   static const int minb = getenv("VILS_EV_MINB") ? atoi(getenv("VILS_EV_MINB")) : 3;
-  if (!ba->eval_attr_set) {   // per handle, i.e. per device: function attributes belong to the device the handle lives on
-    cudaFuncSetAttribute(eval_proj_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
-    cudaFuncSetAttribute(eval_proj_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
-    cudaFuncSetAttribute(eval_proj_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem);
-    ba->eval_attr_set = true;
-  }
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
   // Two streams: the latency-bound IMU warps and then the persistent projection kernel on one, the streaming LiDAR / prior /
@@ -1185,10 +1535,12 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   if (ec) { eval_lidar_kernel<true><<<dim3(ec, n), EV_T, EV_T * EV_ELD * 8, ba->stream2>>>(Q); launches++; }
   if (cons) { eval_cons_kernel<<<dim3(1, n), 32, 0, ba->stream2>>>(Q); launches++; }
   if (layout == 2) launch_imu(ba->stream2);
+  const cudaError_t le = cudaGetLastError();
   cudaEventRecord(ba->ev_join, ba->stream2);
   cudaStreamWaitEvent(ba->stream, ba->ev_join, 0);
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
+  if (le != cudaSuccess) return vils::fail_cuda(le, "eval kernel launch");
   if (e != cudaSuccess) return vils::fail_cuda(e, "eval kernels");
   cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
   ba->last_launches = launches;
@@ -1197,13 +1549,13 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
 
 int vils_ba_evaluate_device(vils_ba* ba, int32_t n, int32_t apply_loss) {
   int st = check_n(ba, n, "vils_ba_evaluate_device"); if (st) return st;
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "evaluate: call vils_ba_upload first");
+  st = check_on_device(ba, 0, n, "vils_ba_evaluate_device"); if (st) return st;
   return launch_eval(ba, 0, n, apply_loss);
 }
 
 int vils_ba_evaluate(vils_ba* ba, int32_t slot, int32_t apply_loss, double* residuals, double* jacobians) {
   if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_evaluate: bad slot");
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "evaluate: call vils_ba_upload first");
+  { const int sd = check_on_device(ba, slot, 1, "vils_ba_evaluate"); if (sd) return sd; }
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   int st = launch_eval(ba, slot, 1, apply_loss); if (st) return st;
   const SlotMeta& m = ba->meta[slot];
@@ -1235,12 +1587,12 @@ int vils_ba_evaluate(vils_ba* ba, int32_t slot, int32_t apply_loss, double* resi
 
 int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* cost) {
   if (!ba || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_linearize: bad slot");
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "linearize: call vils_ba_upload first");
+  { const int sd = check_on_device(ba, slot, 1, "vils_ba_linearize"); if (sd) return sd; }
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   vils_solve_opts o; vils_default_solve_opts(&o); o.mu = 0;
   SolveParams P = make_params(ba, &o); P.slot0 = slot; P.lin_out = ba->d_lin;
-  if (ba->h_in_smem && ba->hv_in_smem) solve_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
-  else solve_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P);
+  launch_solve(ba, P, 1, ba->stream);
+  VILS_LAUNCH_CHECK("solve_kernel (linearize) launch");
   const int D = 15 * ba->meta[slot].n_kf + 7;
   cudaMemcpyAsync(ba->h_lin, ba->d_lin, ((size_t)D * D + D + 1) * 8, cudaMemcpyDeviceToHost, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
@@ -1256,7 +1608,7 @@ int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* c
 int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out* out) {
   if (!ba || !out || slot < 0 || slot >= ba->max_windows || !ba->meta[slot].set || (flag != VILS_MARGIN_OLD && flag != VILS_MARGIN_SECOND_NEW))
     return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_marginalize: bad argument");
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "marginalize: solve the window first");
+  { const int sd = check_on_device(ba, slot, 1, "vils_ba_marginalize"); if (sd) return sd; }
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   const vils_config& c = ba->cfg;
   const int D = 15 * c.max_kf + 7, Tcap = D + c.max_feat;
@@ -1267,18 +1619,18 @@ int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out*
     q.oH = take(T2); q.oG = take(Tcap); q.oA = take(T2); q.oB = take(Tcap); q.oV = take(T2); q.oW = take(Tcap); q.oAinv = take(T2); q.oArm = take(T2);
     q.oAr = take((int64_t)D * D); q.oBr = take(Tcap); q.oV2 = take(T2); q.oS = take(Tcap);
     q.oStage = take(std::max<int64_t>((int64_t)c.max_proj * 44, 512)); q.oJout = take((int64_t)D * D); q.oRout = take(D); q.oX0 = take((2 * c.max_kf + 2) * 9);
-    ba->mws_doubles = o; ba->mi_ints = 8 + 5 * Tcap + c.max_feat + 128;
+    ba->mws_doubles = o; ba->mi_ints = 8 + 5 * Tcap + c.max_feat + 2 * (2 * c.max_kf + 2);
     q.Tcap = Tcap; q.Mcap = c.max_feat;
     cudaError_t e = cudaMalloc(&ba->d_mws, (size_t)o * 8);
     if (e == cudaSuccess) e = cudaMalloc(&ba->d_miws, sizeof(int32_t) * ba->mi_ints);
     if (e != cudaSuccess) return vils::fail_cuda(e, "marginalize workspace");
     q.ws = ba->d_mws; q.iws = ba->d_miws;
-    cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
   }
   MargParams q = ba->mq; q.slot = slot; q.flag = flag;
   SolveParams P = make_params(ba, nullptr);
   cudaMemsetAsync(ba->d_miws, 0, sizeof(int32_t) * 8, ba->stream);
   margin_kernel<<<1, SOLVE_THREADS, 16384, ba->stream>>>(P, q);
+  VILS_LAUNCH_CHECK("margin_kernel launch");
   int32_t hdr[8];
   cudaMemcpyAsync(hdr, ba->d_miws, sizeof(hdr), cudaMemcpyDeviceToHost, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
@@ -1317,7 +1669,7 @@ int vils_ba_sharded_buffer(vils_ba* ba, void** dev_ptr, size_t* n_doubles) {
 }
 int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_opts* opts) {
   if (!ba || !opts || iteration < 0 || !ba->meta[0].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_linearize: bad argument");
-  if (!ba->prepped) return vils::fail(VILS_ERR_BAD_ARG, "sharded: call vils_ba_upload first");
+  { const int sd = check_on_device(ba, 0, 1, "vils_ba_sharded_linearize"); if (sd) return sd; }
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   int st = ensure_shard_buffer(ba); if (st) return st;
   SolveParams P = make_params(ba, opts);
@@ -1325,6 +1677,7 @@ int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_o
   cudaEventRecord(ba->ev0, ba->stream);
   if (ba->h_in_smem && ba->hv_in_smem) shard_lin_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, iteration == 0, opts->mu);
   else shard_lin_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, iteration == 0, opts->mu);
+  VILS_LAUNCH_CHECK("shard_lin_kernel launch");
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);      // the caller's all-reduce runs on its own stream: hand over a finished buffer
   if (e != cudaSuccess) return vils::fail_cuda(e, "shard_lin_kernel");
@@ -1338,6 +1691,7 @@ int vils_ba_sharded_update(vils_ba* ba, const vils_solve_opts* opts) {
   cudaEventRecord(ba->ev0, ba->stream);
   if (ba->h_in_smem && ba->hv_in_smem) shard_upd_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, opts->mu);
   else shard_upd_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, opts->mu);
+  VILS_LAUNCH_CHECK("shard_upd_kernel launch");
   cudaEventRecord(ba->ev1, ba->stream);
   cudaError_t e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "shard_upd_kernel");

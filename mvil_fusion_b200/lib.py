@@ -36,6 +36,9 @@ def load():
     L.vils_ba_destroy.argtypes = [vp]
     L.vils_ba_destroy.restype = None
     L.vils_ba_set_window.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsWindow)]
+    L.vils_ba_set_windows.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(cabi.VilsWindow)]
+    L.vils_ba_solve_windows.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsWindow), C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_ba_put_state.argtypes = [vp, C.c_int32, dp, dp, dp, dp, C.c_double]
     L.vils_ba_upload.argtypes = [vp, C.c_int32]
     L.vils_ba_solve_device.argtypes = [vp, C.c_int32, C.POINTER(cabi.VilsSolveOpts)]
     L.vils_ba_download.argtypes = [vp, C.c_int32]
@@ -130,6 +133,39 @@ class BA:
         ws, keep = cabi.window_struct(w)
         _check(self.L.vils_ba_set_window(self.h, slot, C.byref(ws)))
         self._dims[slot] = (ws.n_kf, ws.n_feat, cabi.residual_count(w), cabi.jacobian_count(w))
+
+    @staticmethod
+    def window_array(ws):
+        """list of window dicts -> (contiguous VilsWindow array, keepalive): the caller-side arrays handed to the batched calls."""
+        arr = (cabi.VilsWindow * len(ws))()
+        keep = []
+        for k, w in enumerate(ws):
+            s, kp = cabi.window_struct(w)
+            arr[k] = s
+            keep.append((s, kp))
+        return arr, keep
+
+    def _note_dims(self, slot0, ws):
+        for k, w in enumerate(ws):
+            self._dims[slot0 + k] = (int(w["pose"].shape[0]), int(w["inv_depth"].shape[0]), cabi.residual_count(w), cabi.jacobian_count(w))
+
+    def set_windows(self, slot0, ws, arr=None):
+        """vils_ba_set_windows: pack len(ws) windows on all host threads."""
+        if arr is None:
+            arr, keep = self.window_array(ws)
+        _check(self.L.vils_ba_set_windows(self.h, slot0, len(ws), arr))
+        self._note_dims(slot0, ws)
+
+    def solve_windows(self, ws, opts, arr=None):
+        """vils_ba_solve_windows: caller arrays -> solved states (pack | H2D | solve | D2H pipelined)."""
+        if arr is None:
+            arr, keep = self.window_array(ws)
+        _check(self.L.vils_ba_solve_windows(self.h, len(ws), arr, C.byref(opts)))
+        self._note_dims(0, ws)
+
+    def put_state(self, slot, pose, sb, ex, lam, td):
+        a = [np.ascontiguousarray(v, np.float64) for v in (pose, sb, ex, lam)]
+        _check(self.L.vils_ba_put_state(self.h, slot, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]) if a[3].size else None, float(td)))
 
     def upload(self, n):
         _check(self.L.vils_ba_upload(self.h, n))

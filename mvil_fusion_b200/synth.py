@@ -188,7 +188,7 @@ def preintegrate(dt, acc, gyr, acc0, gyr0, ba, bg, noise=(cabi.ACC_N, cabi.GYR_N
 ROOM = dict(x=(-8.0, 8.0), y=(-6.0, 6.0), z=(-1.5, 3.0))
 
 
-def _lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz=1.0):
+def _lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz=1.0, kf0=0):
     n_edge = n_lidar // 4
     n_plane = n_lidar - n_edge
     axes = "xyz"
@@ -205,7 +205,7 @@ def _lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz=1.0):
     pw[np.arange(n_plane), pax] = pval
     pn = np.zeros((n_plane, 3)); pn[np.arange(n_plane), pax] = 1.0
     pd = -pval
-    pkf = (np.arange(n_plane) % N).astype(np.int32)
+    pkf = (kf0 + np.arange(n_plane) % (N - kf0)).astype(np.int32)
     plane_p = to_lidar(pw, pkf)
     # edges: intersection of two walls/floor/ceiling -> line along the third axis
     eax = rng.integers(0, 3, n_edge)                 # direction axis
@@ -217,13 +217,13 @@ def _lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz=1.0):
     d = np.zeros((n_edge, 3)); d[np.arange(n_edge), eax] = 1.0
     ea, eb = c + 0.1 * d, c - 0.1 * d                 # localMapping.cpp:661-662
     pw_e = c + d * rng.uniform(-1.0, 1.0, (n_edge, 1))
-    ekf = ((np.arange(n_edge) + n_plane) % N).astype(np.int32)
+    ekf = (kf0 + (np.arange(n_edge) + n_plane) % (N - kf0)).astype(np.int32)
     edge_p = to_lidar(pw_e, ekf)
     return dict(plane_p=plane_p, plane_n=pn, plane_d=pd, plane_kf=pkf, edge_p=edge_p, edge_a=ea, edge_b=eb, edge_kf=ekf)
 
 
 def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n_lps=0, noise_free=False,
-                perturb=True, seed=None, ex_prior=True):
+                perturb=True, seed=None, ex_prior=True, start=None, lidar_kf0=0, icp_anchors=None, lps_anchors=None):
     """One synthetic window as a dict of numpy arrays keyed like vils_window (include/vils_cabi.h).
 
     Extra keys: 'truth' (dict of true state) and 'cfg' constants are NOT part of the C struct."""
@@ -263,7 +263,9 @@ def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n
     # --- landmarks
     Rc = Rk @ ric                      # camera->world rotation per KF
     Pc = Pk + Rk @ tic
-    start = (np.arange(M) % max(N - 3, 1)).astype(np.int32)   # start_frame < WINDOW_SIZE - 2 (estimator.cpp:1192)
+    if start is None:
+        start = (np.arange(M) % max(N - 3, 1)).astype(np.int32)   # start_frame < WINDOW_SIZE - 2 (estimator.cpp:1192)
+    start = np.asarray(start, np.int32)
     lm_w = np.zeros((M, 3)); depth = np.zeros(M); bear = np.zeros((M, 3))
     for f in range(M):
         for _ in range(100):
@@ -312,11 +314,14 @@ def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n
         prior_n=0,
     )
     if n_lidar > 0:
-        w_.update(_lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz))
+        w_.update(_lidar_factors(rng, n_lidar, N, Rk, Pk, RLB, TLB, nz, lidar_kf0))
     tk = t0 + KF_DT * np.arange(N)
     icp, lps = [], []
-    for k in range(n_icp):   # constraint_mode 3 (estimator.cpp:1376-1395): sqrt_info = 100 / fitness, fitness 0.2
-        a_ = int(rng.integers(0, N - 3)); c_ = a_ + 2
+    # anchors (first keyframe of each constraint): random unless the caller fixes them (config 4 keeps 3 + 3 clear of frame 0)
+    icp_a = list(icp_anchors) if icp_anchors is not None else [int(rng.integers(0, N - 3)) for _ in range(n_icp)]
+    lps_a = list(lps_anchors) if lps_anchors is not None else [int(rng.integers(0, N - 1)) for _ in range(n_lps)]
+    for a_ in icp_a:   # constraint_mode 3 (estimator.cpp:1376-1395): sqrt_info = 100 / fitness, fitness 0.2
+        c_ = a_ + 2
         ti, tj = tk[a_] + rng.uniform(0.01, 0.09), tk[c_] + rng.uniform(0.01, 0.09)
         si, sj = (ti - tk[a_]) / KF_DT, (tj - tk[c_]) / KF_DT
         Qi = quat_slerp(Qk[a_], Qk[a_ + 1], si); Qj = quat_slerp(Qk[c_], Qk[c_ + 1], sj)
@@ -324,8 +329,7 @@ def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n
         tm = quat_rot(quat_conj(Qi / np.linalg.norm(Qi)), Pj - Pi) + nz * rng.normal(0, 0.01, 3)
         icp.append(dict(t=(tk[a_], tk[a_ + 1], tk[c_], tk[c_ + 1], ti, tj), trans_t=tm, sqrt_info=100.0 / 0.2,
                         kf=(a_, a_ + 1, c_, c_ + 1)))
-    for k in range(n_lps):
-        a_ = int(rng.integers(0, N - 1))
+    for a_ in lps_a:
         tm_ = tk[a_] + rng.uniform(0.01, 0.09)
         Qi = quat_slerp(Qk[a_], Qk[a_ + 1], (tm_ - tk[a_]) / KF_DT)
         Qm = quat_mul(Qi / np.linalg.norm(Qi), small_quat(nz * rng.normal(0, 0.002, 3)))
@@ -347,6 +351,16 @@ def make_window(config_id=2, window_idx=0, N=10, M=150, n_lidar=2000, n_icp=0, n
     w_["truth"] = dict(pose=np.concatenate([Pk, Qk], 1), speedbias=np.concatenate([Vk, np.tile(ba_true, (N, 1)), np.tile(bg_true, (N, 1))], 1),
                        inv_depth=lam_true, td=cabi.TD0, t_kf=tk)
     return w_
+
+
+def make_config4_big(window_idx=0, N=20, M=300, n_lidar=5000, M0=18):
+    """BASELINE configs[3] as SURVEY.md 8d states it: the (N+1)-frame window whose solve -> MARGIN_OLD marginalization -> slide leaves an
+    N-frame window with exactly M landmarks (3333 projection factors at N=20, M=300), n_lidar LiDAR factors (3:1 plane:edge), 3 ICP + 3 LPS
+    constraints and the REAL n = 6(N-1)+16 = 130-dim prior.  Frame 0 additionally carries M0 landmarks anchored there, one ICP and one LPS
+    constraint (all marginalised, estimator.cpp:1489-1589); LiDAR point factors sit on frames 1..N only."""
+    start = np.concatenate([np.zeros(M0, np.int32), 1 + (np.arange(M) % (N - 3))]).astype(np.int32)
+    return make_window(4, window_idx, N=N + 1, M=M + M0, n_lidar=n_lidar, start=start, lidar_kf0=1,
+                       icp_anchors=[0, 2, 7, 13], lps_anchors=[0, 3, 9, 16])
 
 
 def attach_prior(w, prior):

@@ -654,8 +654,10 @@ bool schur_solve(const Normal& ne, const dvec& d2, dvec& dc, dvec& dl, dvec* S_o
   return true;
 }
 
-const double kMinDiag = 1e-12;  // Ceres min_lm_diagonal = 1e-6 on sqrt(diag(J^T J))  => squared
-const double kMaxDiag = 1e64;   // Ceres max_lm_diagonal = 1e32, squared
+// Ceres clamps the SQUARED column norms diag(J^T J) to [min_lm_diagonal, max_lm_diagonal] = [1e-6, 1e32] before taking the
+// square root (levenberg_marquardt_strategy.cc / dogleg_strategy.cc [upstream]).
+const double kMinDiag = 1e-6;
+const double kMaxDiag = 1e32;
 
 int solve_window(const vils_config* cfg, const vils_window* w, const vils_solve_opts* o, State& s, vils_summary* sum) {
   s.from(w);
@@ -675,6 +677,93 @@ int solve_window(const vils_config* cfg, const vils_window* w, const vils_solve_
     }
     sum->cost_final = total_cost(cfg, w, s);
     if (!std::isfinite(sum->cost_final)) sum->status = VILS_ERR_NOT_FINITE;
+    return sum->status;
+  }
+  if (o->mode == VILS_MODE_DOGLEG) {
+    // ceres TrustRegionMinimizer + DoglegStrategy (TRADITIONAL_DOGLEG) [upstream; what estimator.cpp:1402-1411 configures], written in
+    // the unscaled parameter space.  Jacobi scaling (Solver::Options::jacobi_scaling = true): column i of J is multiplied by
+    // s_i = 1 / (1 + |J_i|) with the norms taken ONCE at x0; the strategy's diagonal is clamp(|J_i s_i|^2, 1e-6, 1e32), i.e. in
+    // unscaled space the elliptical trust region is |diag(sqrt(dd)) step| <= radius with dd_i = clamp(H_ii s_i^2) / s_i^2.
+    //   Gauss-Newton point : (H + mu diag(dd)) y = -g, mu from min_mu = 1e-8, x10 on a failed factorisation (max_mu = 1)
+    //   Cauchy point       : -alpha g / dd, alpha = |g / sqrt(dd)|^2 / (v^T H v), v = g / dd
+    //   step = a p + b y (p = -g / dd): the three dogleg cases;  accepted: radius = max(radius, 3 |step|) if quality > 0.75, halved if
+    //   < 0.25, mu = max(1e-8, 2 mu / 10);  rejected: radius halved and the SAME y, g reused;  invalid (no descent): mu x10.
+    const int T = D + M;
+    double radius = o->lm_initial_radius, mu = 1e-8;
+    const double min_mu = 1e-8, max_mu = 1.0, mu_inc = 10.0;
+    assemble(cfg, w, s, ne); sum->iterations = 1;
+    double x_cost = ne.cost; sum->cost_initial = x_cost; sum->cost_final = x_cost;
+    if (!std::isfinite(x_cost)) { sum->status = VILS_ERR_NOT_FINITE; return sum->status; }
+    dvec sc(T);
+    for (int i = 0; i < T; i++) sc[i] = 1.0 / (1.0 + std::sqrt(ne.H[(size_t)i * T + i]));
+    dvec dd(T), y(T);
+    double gg = 0, pHp = 0, yy = 0, gy = 0, alpha = 0;
+    bool reuse = false;
+    int invalid = 0;
+    for (int it = 0; it < o->max_iters; it++) {
+      if (!reuse) {
+        for (int i = 0; i < T; i++) dd[i] = std::min(std::max(ne.H[(size_t)i * T + i] * sc[i] * sc[i], kMinDiag), kMaxDiag) / (sc[i] * sc[i]);
+        bool ok = false;
+        while (mu < max_mu) {
+          d2.assign(T, 0.0);
+          for (int i = 0; i < T; i++) d2[i] = mu * dd[i];
+          if (schur_solve(ne, d2, dc, dl)) { ok = true; break; }
+          mu *= mu_inc;
+        }
+        if (!ok) { sum->status = VILS_ERR_CHOLESKY; return sum->status; }
+        for (int i = 0; i < D; i++) y[i] = dc[i];
+        for (int f = 0; f < M; f++) y[D + f] = dl[f];
+        gg = 0; yy = 0; gy = 0; pHp = 0;
+        dvec v(T);
+        for (int i = 0; i < T; i++) { v[i] = ne.g[i] / dd[i]; gg += ne.g[i] * ne.g[i] / dd[i]; yy += dd[i] * y[i] * y[i]; gy += ne.g[i] * y[i]; }
+        for (int i = 0; i < T; i++) { if (v[i] == 0.0) continue; double a = 0; for (int j = 0; j < T; j++) a += ne.H[(size_t)i * T + j] * v[j]; pHp += v[i] * a; }
+        alpha = gg / pHp;
+      }
+      // dogleg_strategy.cc ComputeTraditionalDoglegStep
+      double a, b, step_norm;
+      const double gn_norm = std::sqrt(yy), g_norm = std::sqrt(gg);
+      if (gn_norm <= radius) { a = 0; b = 1; step_norm = gn_norm; }
+      else if (g_norm * alpha >= radius) { a = radius / g_norm; b = 0; step_norm = radius; }
+      else {
+        const double b_dot_a = -alpha * gy, a_sq = (alpha * g_norm) * (alpha * g_norm), bma = a_sq - 2 * b_dot_a + yy, c = b_dot_a - a_sq;
+        const double dsc = std::sqrt(c * c + bma * (radius * radius - a_sq));
+        const double beta = (c <= 0) ? (dsc - c) / bma : (radius * radius - a_sq) / (dsc + c);
+        a = alpha * (1.0 - beta); b = beta;
+        step_norm = std::sqrt(std::max(0.0, a * a * gg - 2 * a * b * gy + b * b * yy));
+      }
+      // model_cost_change = -g^T step - 1/2 step^T H step, with H y = -g - mu dd y
+      const double g_step = -a * gg + b * gy;
+      const double sHs = a * a * pHp + 2 * a * b * (gg + mu * gy) + b * b * (-gy - mu * yy);
+      const double model_change = -g_step - 0.5 * sHs;
+      dvec stc(D), stl(M);
+      for (int i = 0; i < D; i++) stc[i] = -a * ne.g[i] / dd[i] + b * y[i];
+      for (int f = 0; f < M; f++) stl[f] = -a * ne.g[D + f] / dd[D + f] + b * y[D + f];
+      if (!(model_change > 0)) {   // StepIsInvalid
+        mu *= mu_inc; reuse = false;
+        if (++invalid >= 5 || mu >= max_mu) break;    // max_num_consecutive_invalid_steps
+        continue;
+      }
+      invalid = 0;
+      State cand = s; state_plus(cand, stc.data(), stl.data());
+      const double new_cost = total_cost(cfg, w, cand);
+      const double quality = std::isfinite(new_cost) ? (x_cost - new_cost) / model_change : -1;
+      if (quality > o->min_relative_decrease) {
+        double xn = 0, dn = 0;
+        for (double v : s.pose) xn += v * v; for (double v : s.sb) xn += v * v; for (double v : s.ex) xn += v * v; for (double v : s.lam) xn += v * v; xn += s.td * s.td;
+        for (double v : stc) dn += v * v; for (double v : stl) dn += v * v;
+        s = cand; sum->accepted++;
+        if (quality < 0.25) radius *= 0.5;
+        if (quality > 0.75) radius = std::max(radius, 3.0 * step_norm);
+        mu = std::max(min_mu, 2.0 * mu / mu_inc); reuse = false;
+        const double change = x_cost - new_cost; x_cost = new_cost; sum->cost_final = x_cost;
+        if (std::fabs(change) / (x_cost + 1e-300) < o->function_tolerance) break;
+        if (std::sqrt(dn) <= o->parameter_tolerance * (std::sqrt(xn) + o->parameter_tolerance)) break;
+        if (it + 1 < o->max_iters) { assemble(cfg, w, s, ne); sum->iterations++; }
+      } else {
+        radius *= 0.5; reuse = true;
+        if (radius < 1e-32) break;
+      }
+    }
     return sum->status;
   }
   // Levenberg-Marquardt, following ceres TrustRegionMinimizer + LevenbergMarquardtStrategy [upstream]:

@@ -216,3 +216,103 @@ def test_config4_large_window_global_memory_path(lib):
     assert gs["status"] == 0 and o["status"] == 0
     assert abs(gs["cost_final"] - o["cost_final"]) <= 1e-7 * o["cost_final"]
     assert helpers.rel_state_delta(gs, o) <= 1e-5
+
+
+def test_dogleg_matches_oracle_dogleg(lib):
+    """VILS_MODE_DOGLEG = what the reference configures (estimator.cpp:1402-1411: DENSE_SCHUR + DOGLEG): same trial / acceptance sequence
+    as the CPU restatement of ceres' TRADITIONAL_DOGLEG (Jacobi scaling, mu schedule, radius update), state <= 1e-5."""
+    cfg = cabi.default_config()
+    for idx, iters in ((5, 30), (6, 8)):     # 8 = NUM_ITERATIONS of config/*.yaml (max_num_iterations)
+        w = synth.make_window(2, idx)
+        opts = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, iters, 0.0)
+        (g, o), = solve_both(lib, cfg, [w], opts)
+        assert g["status"] == 0 and o["status"] == 0
+        assert g["iterations"] == o["iterations"] and g["accepted"] == o["accepted"]
+        assert abs(g["cost_final"] - o["cost_final"]) <= 1e-8 * o["cost_final"]
+        assert helpers.rel_state_delta(g, o) <= 1e-5
+    # a small trust region forces the Cauchy / interpolation branches and rejected steps (radius halving with the GN point reused)
+    w = synth.make_window(config_id=9, window_idx=31, N=6, M=30, n_lidar=200, n_icp=1, n_lps=1)
+    opts = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 25, 0.0); opts.lm_initial_radius = 3.0
+    (g, o), = solve_both(lib, cfg, [w], opts)
+    assert g["status"] == 0 and o["status"] == 0
+    assert g["iterations"] == o["iterations"] and g["accepted"] == o["accepted"]
+    assert helpers.rel_state_delta(g, o) <= 1e-5
+
+
+def test_max_solver_time_caps_the_iteration_loop(lib):
+    """options.max_solver_time_in_seconds (estimator.cpp:1407-1411): a 1 us cap stops after the first iteration and keeps its state."""
+    cfg = cabi.default_config()
+    w = synth.make_window(2, 7)
+    ba = lib.BA(cfg, 1)
+    ba.set_window(0, w)
+    for mode in (cabi.VILS_MODE_GN, cabi.VILS_MODE_DOGLEG):
+        opts = cabi.default_solve_opts(mode, 30, 1e-8); opts.max_solver_time = 1e-6
+        ba.solve(1, opts)
+        s = ba.get_state(0)
+        assert s["status"] == 0 and s["accepted"] == 1 and s["iterations"] <= 2
+        assert s["cost_final"] < s["cost_initial"]
+        one = cabi.default_solve_opts(mode, 1, 1e-8)
+        ba.solve(1, one)
+        s1 = ba.get_state(0)
+        assert np.array_equal(s["pose"], s1["pose"])          # exactly the state after one accepted step
+        opts.max_solver_time = 10.0                           # a generous cap changes nothing
+        ba.solve(1, opts); a = ba.get_state(0)
+        opts.max_solver_time = 0.0
+        ba.solve(1, opts); b = ba.get_state(0)
+        assert np.array_equal(a["pose"], b["pose"]) and a["iterations"] == b["iterations"]
+    ba.close()
+
+
+def test_solve_windows_from_caller_arrays(lib):
+    """vils_ba_solve_windows (pack on the host thread pool inside the H2D | solve | D2H pipeline) == set_window + solve, bit for bit,
+    for a batch spanning several pipeline chunks with ragged windows; a bad window fails the call and leaves the handle usable."""
+    cfg = cabi.default_config()
+    ws = [synth.make_window(2, 200 + k) for k in range(5)] + [synth.make_window(config_id=9, window_idx=40 + k, N=4 + k, M=12 + 5 * k, n_lidar=50 * k) for k in range(4)]
+    ws = (ws * 20)[:170]                                    # 3 chunks of 74 on a 148-SM part
+    opts = cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, 1e-8)
+    a = lib.BA(cfg, len(ws)); b = lib.BA(cfg, len(ws))
+    for k, w in enumerate(ws):
+        a.set_window(k, w)
+    a.solve(len(ws), opts)
+    b.solve_windows(ws, opts)
+    for k in (0, 3, 7, 8, 75, 149, 169):
+        sa, sb = a.get_state(k), b.get_state(k)
+        assert sa["status"] == sb["status"] == 0
+        for key in ("pose", "speedbias", "ex_pose", "inv_depth"):
+            assert np.array_equal(sa[key], sb[key])
+    c = lib.BA(cfg, len(ws))
+    c.set_windows(0, ws); c.solve(len(ws), opts)
+    assert np.array_equal(c.get_state(100)["pose"], a.get_state(100)["pose"])
+    bad = list(ws); bw = dict(ws[90]); bw["feat"] = ws[90]["feat"].copy(); bw["feat"][3] = 10 ** 6; bad[90] = bw
+    with pytest.raises(lib.VilsError) as e:
+        b.solve_windows(bad, opts)
+    assert e.value.code == cabi.VILS_ERR_BAD_ARG
+    b.solve_windows(ws[:10], opts)
+    assert np.array_equal(b.get_state(9)["pose"], a.get_state(9)["pose"])
+    for h in (a, b, c):
+        h.close()
+
+
+def test_restaged_slot_is_not_used_stale_and_two_handles_coexist(lib):
+    """A slot re-staged after its upload must be uploaded again before device-side calls; handles of different capacities share the
+    kernels' shared-memory attribute."""
+    small = cabi.default_config(max_kf=6, max_feat=30, max_proj=200, max_lidar=200)
+    big = cabi.default_config()
+    opts = cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, 1e-8)
+    wb = synth.make_window(2, 3); wsm = synth.make_window(config_id=9, window_idx=99, N=6, M=30, n_lidar=200)
+    hb = lib.BA(big, 1); hb.set_window(0, wb); hb.solve(1, opts); ref = hb.get_state(0)
+    hs = lib.BA(small, 1); hs.set_window(0, wsm); hs.solve(1, opts)          # created while the larger handle is alive
+    assert hs.get_state(0)["status"] == 0
+    hb.solve(1, opts)                                                        # the larger handle still launches with its own shared-memory size
+    again = hb.get_state(0)
+    assert again["status"] == 0 and np.array_equal(again["pose"], ref["pose"])
+    r, J = hb.evaluate(0, True)
+    hb.set_window(0, synth.make_window(2, 4))
+    with pytest.raises(lib.VilsError) as e:
+        hb.evaluate(0, True)
+    assert e.value.code == cabi.VILS_ERR_BAD_ARG
+    with pytest.raises(lib.VilsError):
+        hb.solve_device(1, opts)
+    hb.upload(1); hb.solve_device(1, opts); hb.download(1)
+    assert hb.get_state(0)["status"] == 0
+    hb.close(); hs.close()

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 30
     missing = [s for s in syms if not hasattr(L, s)]
     assert not missing, missing
-    assert L.vils_abi_version() == 1
+    assert L.vils_abi_version() == 2
 
 
 def test_host_mirror_library_builds_and_exports_the_reference_api():
@@ -42,7 +42,7 @@ def test_host_mirror_library_builds_and_exports_the_reference_api():
 def test_struct_layouts_match_header_sizes():
     assert C.sizeof(cabi.VilsPreint) == 467 * 8
     assert C.sizeof(cabi.VilsSummary) == 32
-    assert C.sizeof(cabi.VilsSolveOpts) == 48
+    assert C.sizeof(cabi.VilsSolveOpts) == 56
     assert C.sizeof(cabi.VilsIcp) == 10 * 8 + 16
     assert C.sizeof(cabi.VilsLps) == 7 * 8 + 8
 
