@@ -269,6 +269,14 @@ int vils_ba_last_transfer_bytes(vils_ba* ba, size_t* h2d, size_t* d2h);
 int vils_ba_sharded_buffer(vils_ba* ba, void** dev_ptr, size_t* n_doubles);
 int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_opts* opts);
 int vils_ba_sharded_update(vils_ba* ba, const vils_solve_opts* opts);
+/* Native form ("one ncclAllReduce per GN iteration ... fused directly behind the assembly kernel, same stream, no host
+ * sync"): the library owns an NCCL communicator with one rank per GPU.  vils_nccl_unique_id on rank 0, distribute the 128 bytes by any
+ * means, vils_ba_sharded_init on every rank; vils_ba_sharded_solve then enqueues, for every Gauss-Newton iteration, linearise ->
+ * ncclAllReduce(sum, double, D^2 + 2D + 1) -> update on the handle's stream, exchanges the inverse depths with one last all-reduce (every
+ * rank ends with the FULL solved state, readable with vils_ba_get_state) and synchronises once.  libnccl.so.2 is bound at first use. */
+int vils_nccl_unique_id(uint8_t id[128]);
+int vils_ba_sharded_init(vils_ba* ba, int32_t rank, int32_t nranks, const uint8_t id[128]);
+int vils_ba_sharded_solve(vils_ba* ba, const vils_solve_opts* opts, vils_summary* summary);
 /* Host-mediated access to the same buffer (tests; transports other than NCCL). */
 int vils_ba_sharded_read(vils_ba* ba, double* host);
 int vils_ba_sharded_write(vils_ba* ba, const double* host);

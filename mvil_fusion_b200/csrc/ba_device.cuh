@@ -74,7 +74,7 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   s.red = take(64 + SOLVE_WARPS * 2);
   s.tbl = take(114);                                         // IMU Jacobian assembly table (450 x uint16)
   s.rot = take((Ncap + 1) * 9);                              // rotation matrices of the keyframes + ric (pair pass)
-  s.linv = take(nb * TB * TB);
+  s.linv = h_in_smem ? take(nb * TB * TB) : -1;             // large windows keep the tile inverses in the L2 scratch
   int uni = PAIR_CHUNK * 2 * STAGE_LD;                       // pair-pass staging
   if (ECHUNK * Dvp > uni) uni = ECHUNK * Dvp;                // Schur chunk
   if (h_in_smem && tri(nb) * TSZ > uni) uni = tri(nb) * TSZ;

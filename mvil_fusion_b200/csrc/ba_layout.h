@@ -52,7 +52,7 @@ __host__ __device__ inline int XL(int N) { return 16 * N + 8; }
 
 // per-slot device scratch (doubles)
 struct ScratchLayout {
-  int64_t w_imu, E, part, pairpart, pairctx, priorA, priorb0, lmsave, imuprod, Hg, Hvg, total;
+  int64_t w_imu, E, part, pairpart, pairctx, priorA, priorb0, lmsave, imuprod, Hg, Hvg, linvg, total;
   int32_t Dv_pad;
 };
 

@@ -15,6 +15,10 @@
 #include <thread>
 #include <vector>
 
+#include <dlfcn.h>
+#include <immintrin.h>
+#include <nccl.h>
+
 #include "ba_device.cuh"
 #include "common.h"
 #include "margin_device.cuh"
@@ -184,7 +188,7 @@ __device__ double cost_only(const SolveParams& P, const Win& W, const Smem& L, d
   c += lidar_pass(P, W, x, nullptr, nullptr, nullptr, false);
   __syncthreads();
   c += icp_lps_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.imu, false);
-  c += prior_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.dx, scr, false);
+  c += prior_pass(P, W, x, nullptr, nullptr, nullptr, sm + L.g, scr, false);   // L.g is dead after the back-substitution; L.dx still holds the GN point (dogleg reuse)
   __syncthreads();
   return block_sum(c, sm + L.red);
 }
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
   double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
   double* Hv = SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg);
   double* xs = sm + L.xs; double* xc = sm + L.xc;
+  double* linv = L.linv >= 0 ? sm + L.linv : scr + P.sl.linvg;   // diagonal-tile inverses: shared memory, or L2 scratch for large windows
   int* fx = reinterpret_cast<int*>(sm + L.fx);
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       PROF(7);
-      cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, P.prof);
+      cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof);
       ok = chol_flag == 0;
       PROF(8);
       if (!ok && !TR) { status = VILS_ERR_CHOLESKY; break; }
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) 
         if (mu_dl >= 1.0) { status = VILS_ERR_CHOLESKY; break; }
         continue;
       }
-      if (ok) { backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32); PROF(9); }
+      if (ok) { backsub_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, sm + L.red + 32); PROF(9); }
     }
     if (dl) {
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -584,11 +589,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_upd_kernel(SolveParams
   __syncthreads();
   damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
   __syncthreads();
-  cholesky_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+  double* linv = L.linv >= 0 ? sm + L.linv : scr + P.sl.linvg;
+  cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
   int status = VILS_OK;
   if (chol_flag) status = VILS_ERR_CHOLESKY;
   else {
-    backsub_tiles(H, sm + L.g, sm + L.linv, sm + L.dx, W.nb, sm + L.red + 32);
+    backsub_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, sm + L.red + 32);
     apply_step(P, W, L, sm, scr, xs, xc);
     for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xc[k];
   }
@@ -902,6 +908,8 @@ struct vils_ba {
   double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
   PackPool* pool = nullptr;                            // host packer threads (created on first use)
+  ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 0;   // factor-sharded mode: one rank per GPU (vils_ba_sharded_init)
+  double* d_lamred = nullptr;                          // [lam * own | own] for the final inverse-depth exchange
 };
 
 static inline size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -918,6 +926,7 @@ static size_t blob_capacity(const vils_config& c) {
 }
 
 static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s);
+extern "C" { static void nccl_comm_destroy(ncclComm_t c); }
 static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   SolveParams P{};
   P.blobs = ba->d_blob; P.blob_stride = (int64_t)ba->blob_stride;
@@ -998,6 +1007,7 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   if (ba->smem_bytes > budget) { delete ba; return vils::fail(VILS_ERR_CAPACITY, "vils_ba_create: window too large for shared memory plan"); }
   s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TSZ);
   s.Hvg = ba->hv_in_smem ? 0 : take((int64_t)Dvp * Dvp);
+  s.linvg = ba->h_in_smem ? 0 : take((int64_t)nb * TB * TB);
   s.total = o;
   ba->xstride = 16 * N + 8 + M;
   const int64_t n_lin = (int64_t)D * D + D + 1;
@@ -1061,6 +1071,8 @@ void vils_ba_destroy(vils_ba* ba) {
   for (int k = 0; k < vils_ba::NPIPE; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
   if (ba->stream) cudaStreamDestroy(ba->stream);
   delete ba->pool;
+  if (ba->comm) nccl_comm_destroy(ba->comm);
+  cudaFree(ba->d_lamred);
   delete ba;
 }
 
@@ -1068,6 +1080,13 @@ void vils_ba_destroy(vils_ba* ba) {
 // One window -> one blob in pinned staging.  Thread-safe for distinct slots (touches only its slot's blob and SlotMeta and the
 // caller's PackScratch); never calls CUDA.  All orderings are stable counting sorts (landmark, keyframe pair, keyframe): no
 // allocation after the first use of a scratch.  Errors come back as (code, message) so that worker threads can hand them on.
+// 8-byte streaming store (movnti): the staging blob is written once and read only by the DMA engine, so it should not cost a
+// read-for-ownership nor evict the caller's arrays from the cache.  VILS_PACK_NT=0 falls back to plain stores.
+static const bool g_pack_nt = !(getenv("VILS_PACK_NT") && atoi(getenv("VILS_PACK_NT")) == 0);
+static inline void nt_store(double* p, double v) {
+  if (g_pack_nt) { long long b; std::memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long*>(p), b); }
+  else *p = v;
+}
 struct PackScratch {
   std::vector<int> cnt, ord, rank_of, lm_start, lm_feat, pord, pairs, pair_id, plo, pls, edo, eds, pblk, pcol;
 };
@@ -1168,14 +1187,20 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
   if (w->n_imu) std::memcpy(imu, w->imu, sizeof(vils_preint) * w->n_imu);
   int32_t* ikf = (int32_t*)place(OFF_IMU_KF, (size_t)w->n_imu * 4);
   for (int k = 0; k < w->n_imu; k++) ikf[k] = w->imu_kf[k];
+  // SoA arrays are written one field at a time: each destination is ONE sequential stream (streaming stores, the blob is only ever read
+  // by the copy engine), the sources are read nearly in order (callers hand factors over grouped by feature)
   double* pj = (double*)place(OFF_PROJ, (size_t)14 * np * 8);
   int32_t* pix = (int32_t*)place(OFF_PROJ_IDX, (size_t)4 * np * 4);
-  for (int s = 0; s < np; s++) {
-    const int k = S.ord[s];
-    const double v[14] = {w->pts_i[3 * k], w->pts_i[3 * k + 1], w->pts_i[3 * k + 2], w->pts_j[3 * k], w->pts_j[3 * k + 1], w->pts_j[3 * k + 2],
-                          w->vel_i[2 * k], w->vel_i[2 * k + 1], w->vel_j[2 * k], w->vel_j[2 * k + 1], w->td_i[k], w->td_j[k], w->row_i[k], w->row_j[k]};
-    for (int a = 0; a < 14; a++) pj[(size_t)a * np + s] = v[a];
-    pix[s] = w->kf_i[k]; pix[np + s] = w->kf_j[k]; pix[2 * np + s] = S.rank_of[s]; pix[3 * np + s] = k;
+  {
+    const int* od = S.ord.data();
+    auto field = [&](int a, const double* src, int stride, int c) { double* d = pj + (size_t)a * np; for (int s = 0; s < np; s++) nt_store(d + s, src[(size_t)stride * od[s] + c]); };
+    for (int c2 = 0; c2 < 3; c2++) { field(c2, w->pts_i, 3, c2); field(3 + c2, w->pts_j, 3, c2); }
+    for (int c2 = 0; c2 < 2; c2++) { field(6 + c2, w->vel_i, 2, c2); field(8 + c2, w->vel_j, 2, c2); }
+    field(10, w->td_i, 1, 0); field(11, w->td_j, 1, 0); field(12, w->row_i, 1, 0); field(13, w->row_j, 1, 0);
+    for (int s = 0; s < np; s++) pix[s] = w->kf_i[od[s]];
+    for (int s = 0; s < np; s++) pix[np + s] = w->kf_j[od[s]];
+    for (int s = 0; s < np; s++) pix[2 * np + s] = S.rank_of[s];
+    for (int s = 0; s < np; s++) pix[3 * np + s] = od[s];
   }
   int32_t* ls = (int32_t*)place(OFF_LM_START, (size_t)(nlm + 1) * 4); for (int k = 0; k <= nlm; k++) ls[k] = S.lm_start[k];
   int32_t* lf = (int32_t*)place(OFF_LM_FEAT, (size_t)nlm * 4); for (int k = 0; k < nlm; k++) lf[k] = S.lm_feat[k];
@@ -1192,16 +1217,23 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
   int32_t* plx = (int32_t*)place(OFF_PLANE_IDX, (size_t)2 * npl * 4);
   for (int s = 0; s < npl; s++) {
     const int k = S.plo[s]; double pb[3]; to_body(w->plane_p + 3 * k, pb);
-    for (int a = 0; a < 3; a++) { pl[(size_t)a * npl + s] = pb[a]; pl[(size_t)(3 + a) * npl + s] = w->plane_n[3 * k + a]; }
-    pl[(size_t)6 * npl + s] = w->plane_d[k]; plx[s] = w->plane_kf[k]; plx[npl + s] = k;
+    for (int a = 0; a < 3; a++) nt_store(pl + (size_t)a * npl + s, pb[a]);
+    plx[s] = w->plane_kf[k]; plx[npl + s] = k;
   }
+  for (int a = 0; a < 3; a++) { double* d = pl + (size_t)(3 + a) * npl; for (int s = 0; s < npl; s++) nt_store(d + s, w->plane_n[3 * (size_t)S.plo[s] + a]); }
+  { double* d = pl + (size_t)6 * npl; for (int s = 0; s < npl; s++) nt_store(d + s, w->plane_d[S.plo[s]]); }
   int32_t* plst = (int32_t*)place(OFF_PLANE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) plst[k] = S.pls[k];
   double* ed = (double*)place(OFF_EDGE, (size_t)9 * ned * 8);
   int32_t* edx = (int32_t*)place(OFF_EDGE_IDX, (size_t)2 * ned * 4);
   for (int s = 0; s < ned; s++) {
     const int k = S.edo[s]; double pb[3]; to_body(w->edge_p + 3 * k, pb);
-    for (int a = 0; a < 3; a++) { ed[(size_t)a * ned + s] = pb[a]; ed[(size_t)(3 + a) * ned + s] = w->edge_a[3 * k + a]; ed[(size_t)(6 + a) * ned + s] = w->edge_b[3 * k + a]; }
+    for (int a = 0; a < 3; a++) nt_store(ed + (size_t)a * ned + s, pb[a]);
     edx[s] = w->edge_kf[k]; edx[ned + s] = k;
+  }
+  for (int a = 0; a < 3; a++) {
+    double* da = ed + (size_t)(3 + a) * ned; double* db = ed + (size_t)(6 + a) * ned;
+    for (int s = 0; s < ned; s++) nt_store(da + s, w->edge_a[3 * (size_t)S.edo[s] + a]);
+    for (int s = 0; s < ned; s++) nt_store(db + s, w->edge_b[3 * (size_t)S.edo[s] + a]);
   }
   int32_t* edst = (int32_t*)place(OFF_EDGE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) edst[k] = S.eds[k];
   double* ic = (double*)place(OFF_ICP, (size_t)w->n_icp * 14 * 8);
@@ -1223,6 +1255,7 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
   SlotMeta& m = ba->meta[slot];
   if (o > ba->blob_stride) { m.set = false; PFAIL(VILS_ERR_CAPACITY, "vils_ba_set_window: blob overflow"); }   // cannot happen for windows inside the capacities checked above
   h->bytes = (int32_t)o;
+  _mm_sfence();                                             // streaming stores visible before the copy engine is pointed at the blob
   m.set = true; m.on_device = false; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
   m.n_res = 15 * w->n_imu + 2 * np + npl + 3 * ned + 3 * w->n_icp + 3 * w->n_lps + n;
   m.n_jac = (int64_t)450 * w->n_imu + (int64_t)40 * np + 6 * npl + 18 * ned + 72 * w->n_icp + 36 * w->n_lps;
@@ -1710,6 +1743,124 @@ int vils_ba_sharded_write(vils_ba* ba, const double* host) {
   const int D = 15 * ba->meta[0].n_kf + 7;
   cudaError_t e = cudaMemcpy(ba->d_shard, host, ((size_t)D * D + 2 * D + 1) * 8, cudaMemcpyHostToDevice);
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "sharded write");
+}
+
+// ---- native factor-sharded solve over NCCL ----------------------------------------------------------------------------------
+// libnccl is bound lazily (dlopen) the first time the sharded API is used: a process that already carries an NCCL (torch's bundled copy)
+// shares it, everything else in the library works on a box without NCCL.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api; static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  });
+  return api.ok ? &api : nullptr;
+}
+static void nccl_comm_destroy(ncclComm_t c) { if (NcclApi* a = nccl_api()) a->CommDestroy(c); }
+static int fail_nccl(ncclResult_t r, const char* what) { NcclApi* a = nccl_api(); return vils::fail(VILS_ERR_CUDA, std::string(what) + ": " + (a ? a->GetErrorString(r) : "NCCL unavailable")); }
+
+int vils_nccl_unique_id(uint8_t id[128]) {
+  NcclApi* a = nccl_api();
+  if (!a) return vils::fail(VILS_ERR_NO_DEVICE, "vils_nccl_unique_id: libnccl.so.2 not found");
+  if (!id) return vils::fail(VILS_ERR_BAD_ARG, "vils_nccl_unique_id: null");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u; const ncclResult_t r = a->GetUniqueId(&u);
+  if (r != ncclSuccess) return fail_nccl(r, "ncclGetUniqueId");
+  std::memcpy(id, &u, 128);
+  return VILS_OK;
+}
+
+int vils_ba_sharded_init(vils_ba* ba, int32_t rank, int32_t nranks, const uint8_t id[128]) {
+  NcclApi* a = nccl_api();
+  if (!a) return vils::fail(VILS_ERR_NO_DEVICE, "vils_ba_sharded_init: libnccl.so.2 not found");
+  if (!ba || !id || nranks < 1 || rank < 0 || rank >= nranks) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_init: bad argument");
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  if (ba->comm) { a->CommDestroy(ba->comm); ba->comm = nullptr; }
+  ncclUniqueId u; std::memcpy(&u, id, 128);
+  const ncclResult_t r = a->CommInitRank(&ba->comm, nranks, u, rank);
+  if (r != ncclSuccess) { ba->comm = nullptr; return fail_nccl(r, "ncclCommInitRank"); }
+  ba->comm_rank = rank; ba->comm_size = nranks;
+  return VILS_OK;
+}
+
+// out[0..M) = inverse depth of the landmarks THIS rank holds projection factors for (0 elsewhere), out[M..2M) = 1 / 0 ownership.
+__global__ void lam_pack_kernel(SolveParams P, double* out) {
+  const Win W = decode(P, P.slot0);
+  const double* x = P.xout + (size_t)P.slot0 * P.xout_stride;
+  const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < 2 * W.M; f += gridDim.x * blockDim.x) out[f] = 0.0;
+  __syncthreads();     // one block
+  for (int r = threadIdx.x; r < W.h->n_lm; r += blockDim.x) { const int f = lm_feat[r]; out[f] = x[XL(W.N) + f]; out[W.M + f] = 1.0; }
+}
+// after the sum over ranks: landmarks somebody owns take the owner's value, the others keep the local (= initial) one
+__global__ void lam_unpack_kernel(SolveParams P, const double* in) {
+  const Win W = decode(P, P.slot0);
+  double* x = P.xout + (size_t)P.slot0 * P.xout_stride;
+  for (int f = threadIdx.x; f < W.M; f += blockDim.x) if (in[W.M + f] > 0.0) x[XL(W.N) + f] = in[f] / in[W.M + f];
+}
+
+// All Gauss-Newton iterations of the factor-sharded solve of slot 0, enqueued on the handle's stream without a host synchronisation in
+// between: shard_lin_kernel -> ncclAllReduce (in place, D^2 + 2D + 1 doubles, NVLink / NVSwitch) -> shard_upd_kernel, max_iters times; then
+// the inverse depths (each landmark lives on exactly one rank) are exchanged with one more all-reduce, so every rank ends with the full state.
+int vils_ba_sharded_solve(vils_ba* ba, const vils_solve_opts* opts, vils_summary* summary) {
+  NcclApi* a = nccl_api();
+  if (!ba || !opts || !ba->meta[0].set) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_solve: stage the window in slot 0 first");
+  if (!a || !ba->comm) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_solve: call vils_ba_sharded_init first");
+  if (opts->mode != VILS_MODE_GN || opts->max_iters <= 0) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_sharded_solve: Gauss-Newton mode only");
+  { const int sd = check_on_device(ba, 0, 1, "vils_ba_sharded_solve"); if (sd) return sd; }
+  if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
+  int st = ensure_shard_buffer(ba); if (st) return st;
+  if (!ba->d_lamred) { const cudaError_t e = cudaMalloc(&ba->d_lamred, sizeof(double) * 2 * std::max(1, ba->cfg.max_feat)); if (e != cudaSuccess) return vils::fail_cuda(e, "sharded depth buffer"); }
+  SolveParams P = make_params(ba, opts);
+  const bool both = ba->h_in_smem && ba->hv_in_smem;
+  const int D = 15 * ba->meta[0].n_kf + 7, M = ba->meta[0].n_feat;
+  const size_t cnt = (size_t)D * D + 2 * (size_t)D + 1;
+  cudaStream_t s = ba->stream;
+  cudaMemsetAsync(ba->d_sum, 0, sizeof(vils_summary), s);
+  cudaEventRecord(ba->ev0, s);
+  cudaError_t le = cudaSuccess; ncclResult_t nr = ncclSuccess;
+  for (int it = 0; it < opts->max_iters && nr == ncclSuccess; it++) {
+    if (both) shard_lin_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, s>>>(P, ba->d_shard, it == 0, opts->mu);
+    else shard_lin_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, s>>>(P, ba->d_shard, it == 0, opts->mu);
+    if (le == cudaSuccess) le = cudaGetLastError();
+    nr = a->AllReduce(ba->d_shard, ba->d_shard, cnt, ncclDouble, ncclSum, ba->comm, s);
+    if (both) shard_upd_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, s>>>(P, ba->d_shard, opts->mu);
+    else shard_upd_kernel<false><<<1, SOLVE_THREADS, ba->smem_bytes, s>>>(P, ba->d_shard, opts->mu);
+    if (le == cudaSuccess) le = cudaGetLastError();
+  }
+  if (nr == ncclSuccess && M > 0) {
+    lam_pack_kernel<<<1, 256, 0, s>>>(P, ba->d_lamred);
+    nr = a->AllReduce(ba->d_lamred, ba->d_lamred, 2 * (size_t)M, ncclDouble, ncclSum, ba->comm, s);
+    lam_unpack_kernel<<<1, 256, 0, s>>>(P, ba->d_lamred);
+    if (le == cudaSuccess) le = cudaGetLastError();
+  }
+  cudaEventRecord(ba->ev1, s);
+  cudaMemcpyAsync(ba->h_xout, ba->d_xout, (size_t)ba->xstride * 8, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(ba->h_sum, ba->d_sum, sizeof(vils_summary), cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);               // the only host synchronisation of the call
+  if (nr != ncclSuccess) return fail_nccl(nr, "ncclAllReduce");
+  if (le != cudaSuccess) return vils::fail_cuda(le, "sharded kernel launch");
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_ba_sharded_solve");
+  cudaEventElapsedTime(&ba->last_ms, ba->ev0, ba->ev1);
+  ba->last_launches = 2 * opts->max_iters + 2;
+  if (summary) *summary = ba->h_sum[0];
+  return ba->h_sum[0].status;
 }
 
 int vils_ba_last_device_ms(vils_ba* ba, float* ms) { if (!ba || !ms) return VILS_ERR_BAD_ARG; *ms = ba->last_ms; return VILS_OK; }

@@ -57,6 +57,9 @@ def load():
     L.vils_ba_sharded_read.argtypes = [vp, dp]
     L.vils_ba_sharded_write.argtypes = [vp, dp]
     L.vils_ba_sharded_update.argtypes = [vp, C.POINTER(cabi.VilsSolveOpts)]
+    L.vils_nccl_unique_id.argtypes = [up]
+    L.vils_ba_sharded_init.argtypes = [vp, C.c_int32, C.c_int32, up]
+    L.vils_ba_sharded_solve.argtypes = [vp, C.POINTER(cabi.VilsSolveOpts), C.POINTER(cabi.VilsSummary)]
     L.vils_preintegrate.argtypes = [C.c_int32, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(cabi.VilsPreint), C.c_int32]
     L.vils_klt_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.vils_klt_destroy.argtypes = [vp]
@@ -230,6 +233,19 @@ class BA:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Arr(), device=f"cuda:{self.cfg.device}")
 
+    def sharded_init(self, rank, nranks, uid):
+        """uid: the 128 bytes of nccl_unique_id() from rank 0."""
+        a = np.frombuffer(bytes(uid), np.uint8).copy()
+        _check(self.L.vils_ba_sharded_init(self.h, rank, nranks, a.ctypes.data_as(cabi.c_uint8_p)))
+
+    def sharded_solve(self, opts):
+        """All GN iterations natively: linearise -> ncclAllReduce -> update on the library stream, one host sync."""
+        s = cabi.VilsSummary()
+        st = self.L.vils_ba_sharded_solve(self.h, C.byref(opts), C.byref(s))
+        if st not in (0, cabi.VILS_ERR_CHOLESKY, cabi.VILS_ERR_NOT_FINITE):
+            _check(st)
+        return s
+
     def sharded_linearize(self, iteration, opts):
         _check(self.L.vils_ba_sharded_linearize(self.h, iteration, C.byref(opts)))
 
@@ -263,6 +279,12 @@ class BA:
         n = C.c_int32()
         self.L.vils_ba_last_launches(self.h, C.byref(n))
         return n.value
+
+
+def nccl_unique_id():
+    a = np.zeros(128, np.uint8)
+    _check(load().vils_nccl_unique_id(a.ctypes.data_as(cabi.c_uint8_p)))
+    return a.tobytes()
 
 
 def double2vector(pose0_before, pose, sb):
