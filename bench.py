@@ -399,6 +399,22 @@ def main():
     st = ba.get_state(0)
     assert st["status"] == 0, st
     extra = other_configs(lib, local, cores, opts) if (rank == 0 and not args.no_configs) else {}
+    sharded = None
+    if world > 1 and not args.no_configs:
+        # configs[4] names "NCCL Hessian allreduce": ONE config-4 window factor-sharded over all ranks by vils_ba_sharded_solve
+        # (library-owned communicator, linearise -> ncclAllReduce -> update on the library stream), next to the single-GPU solve of it
+        try:
+            from mvil_fusion_b200.sharding import native_sharded_solve_benchmark
+            cfg4 = cabi.default_config(max_kf=21, max_feat=320, max_proj=4000, max_lidar=5000, device=local)
+            w4 = build_config4_windows(lib, cfg4, 1, opts)[0]
+            sharded, _ = native_sharded_solve_benchmark(lib, cfg4, w4, opts, rank, world)
+            f4 = lib.BA(cfg4, 1); f4.set_window(0, w4); f4.upload(1)
+            for _ in range(3):
+                f4.solve_device(1, opts)
+            sharded["single_gpu_device_ms"] = f4.last_ms; f4.close()
+            sharded["workload"] = "one configs[3] window (D = 307) factor-sharded over %d GPUs, one ncclAllReduce of the partial reduced system per GN iteration" % world
+        except Exception as e:
+            sharded = {"error": repr(e)}
     from mvil_fusion_b200.sharding import max_over_ranks
     dev_ms, wall_ms, e2e_ms, ev_ms, e2e_packed_ms = max_over_ranks([dev_ms, wall_ms, e2e_ms, ev_ms, e2e_packed_ms], device="cuda")   # timing = max over ranks
     if rank == 0:
@@ -446,6 +462,8 @@ def main():
             "clocks": sampler.summary(),
             "configs": extra,
         }
+        if sharded is not None:
+            out["sharded"] = sharded
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -31,7 +31,14 @@ constexpr int TSZ = TB * TLD + 2; // padded tile stride: neighbouring tiles star
 constexpr int SOLVE_THREADS = VILS_SOLVE_THREADS;
 constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
 constexpr int STAGE_LD = 25;      // pair-pass staging row: 19 Jacobian cols + residual + pad (odd stride: fewer bank conflicts)
-constexpr int PAIR_CHUNK = 304;   // keep PAIR_WARPS below in sync   // projection factors evaluated per round (one per thread), staged in shared memory
+#ifndef VILS_PAIR_CHUNK
+#define VILS_PAIR_CHUNK 304
+#endif
+#ifndef VILS_SOLVE_MINB
+#define VILS_SOLVE_MINB 1
+#endif
+constexpr int PAIR_CHUNK = VILS_PAIR_CHUNK;   // projection factors evaluated per round (one per thread), staged in shared memory
+constexpr int SOLVE_MINB = VILS_SOLVE_MINB;   // resident CTAs (windows) per SM the solve kernels are compiled for
 constexpr int PAIR_LD = 20;       // pair-local block: [pose_i 6 | pose_j 6 | ex 6 | td | r]
 constexpr int ECHUNK = 32;        // landmarks per Schur chunk
 constexpr int PART_LD = 16;       // per-factor landmark partial: C, g_l, e_i(6), e_ex(6), e_td, pad
@@ -152,7 +159,7 @@ __device__ uint16_t g_imu_tbl[450];
 // stage (shared memory, private to the warp): J 450 | r 15 | pad | core IMU_CORE_LD | W 226.   On exit J = W J_raw, r = W r_raw.
 constexpr int IMU_SLOT = 466 + vf::IMU_CORE_LD + 226;
 constexpr int IMU_PROD_LD = 512;                  // per-factor products in the scratch: lower J^T J (465) | J^T r (30)
-constexpr int PAIR_WARPS = (304 + 31) / 32;       // warps that evaluate projection factors in a pair-pass round (PAIR_CHUNK = 304)
+constexpr int PAIR_WARPS = (PAIR_CHUNK + 31) / 32;       // warps that evaluate projection factors in a pair-pass round
 constexpr int IMU_IDLE = SOLVE_WARPS - PAIR_WARPS;   // warps free for IMU stages in every round
 __device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared memory copy of g_imu_tbl */, const double* pre, const double* Wk, const double* G,
                                                   const double* pi, const double* sbi, const double* pj, const double* sbj, double* stage, bool want_J,

@@ -282,7 +282,7 @@ __device__ double apply_step_dogleg(const SolveParams& P, const Win& W, const Sm
 // (windows up to ~12 keyframes); otherwise they sit in the per-window scratch (L2).  TR: the trust-region modes (Levenberg-Marquardt,
 // dogleg) are compiled into their own instantiation so that the fixed-count Gauss-Newton kernel keeps its register allocation.
 template <bool SMEM_H, bool TR>
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_kernel(SolveParams P) {
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveParams P) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int chol_flag;
   __shared__ int time_flag;
@@ -1000,9 +1000,11 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   // shared-memory plan: prefer H and Hv both in shared memory, then Hv only, then neither
   int dev_smem = 0; cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
   const size_t budget = (size_t)dev_smem - 1024;
+  // VILS_SMEM_BUDGET (experiments): cap the per-CTA shared-memory plan, e.g. to make two windows resident per SM
+  const size_t plan_budget = getenv("VILS_SMEM_BUDGET") ? std::min(budget, (size_t)atol(getenv("VILS_SMEM_BUDGET"))) : budget;
   ba->h_in_smem = 1; ba->hv_in_smem = 1;
-  if ((size_t)smem_layout(N, M, 1, 1).total * 8 > budget) { ba->h_in_smem = 0; }
-  if ((size_t)smem_layout(N, M, ba->h_in_smem, 1).total * 8 > budget) { ba->hv_in_smem = 0; }
+  if ((size_t)smem_layout(N, M, 1, 1).total * 8 > plan_budget) { ba->h_in_smem = 0; }
+  if ((size_t)smem_layout(N, M, ba->h_in_smem, 1).total * 8 > plan_budget) { ba->hv_in_smem = 0; }
   ba->smem_bytes = (size_t)smem_layout(N, M, ba->h_in_smem, ba->hv_in_smem).total * 8;
   if (ba->smem_bytes > budget) { delete ba; return vils::fail(VILS_ERR_CAPACITY, "vils_ba_create: window too large for shared memory plan"); }
   s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TSZ);

@@ -58,3 +58,33 @@ def split_window(w, world, rank):
         for k in ["prior_J", "prior_r", "prior_blk", "prior_x0"]:
             out.pop(k, None)
     return out
+
+
+def native_sharded_solve_benchmark(lib, cfg, w, opts, rank, world, reps=5):
+    """Factor-sharded solve of ONE window over `world` GPUs through vils_ba_sharded_solve (library-owned NCCL communicator, all
+    Gauss-Newton iterations enqueued on the library stream with the all-reduce between the linearise and update kernels, one host
+    synchronisation).  torch.distributed must be initialised (only used to hand the NCCL unique id around and for the max over ranks).
+    Returns (record dict on every rank, solved state of this rank)."""
+    import time
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    uid = [lib.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    h = lib.BA(cfg, 1)
+    h.sharded_init(rank, world, uid[0])
+    h.set_window(0, split_window(w, world, rank)); h.upload(1)
+    dev_ms, wall_ms = [], []
+    for _ in range(reps + 2):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        s = h.sharded_solve(opts)
+        wall_ms.append(1e3 * (time.perf_counter() - t0)); dev_ms.append(h.last_ms)
+    dev = max_over_ranks([float(np.mean(dev_ms[2:]))], device="cuda")[0]
+    wall = max_over_ranks([float(np.mean(wall_ms[2:]))], device="cuda")[0]
+    st = h.get_state(0)
+    D = 15 * w["pose"].shape[0] + 7
+    rec = {"n_gpus": world, "D": D, "allreduce_bytes_per_iteration": (D * D + 2 * D + 1) * 8, "iterations": int(opts.max_iters),
+           "device_ms_per_solve": dev, "wall_ms_per_solve": wall, "status": int(s.status), "launches_per_solve": h.last_launches}
+    h.close()
+    return rec, st
