@@ -76,6 +76,8 @@ typedef struct vils_config {
   int32_t max_lidar;         /* capacity: plane + edge factors per window                                 */
   int32_t device;            /* CUDA device ordinal                                                       */
   int32_t reserved;
+  double imu_noise[4];       /* ACC_N GYR_N ACC_W GYR_W (parameters.cpp:96-99; yaml acc_n gyr_n acc_w gyr_w): the noise of
+                              * IntegrationBase (integration_base.h:21-27), used by the host mirror's re-propagation  */
 } vils_config;
 
 /* Result of IntegrationBase (vils_estimator/src/factor/integration_base.h:203-220). 467 doubles. */

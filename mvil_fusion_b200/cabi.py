@@ -65,6 +65,7 @@ class VilsConfig(C.Structure):
         ("max_lidar", C.c_int32),
         ("device", C.c_int32),
         ("reserved", C.c_int32),
+        ("imu_noise", C.c_double * 4),
     ]
 
 
@@ -184,6 +185,7 @@ def default_config(max_kf=10, max_feat=150, max_proj=1400, max_lidar=2000, devic
     cfg.estimate_extrinsic = 1
     cfg.estimate_td = 1
     cfg.max_kf, cfg.max_feat, cfg.max_proj, cfg.max_lidar = max_kf, max_feat, max_proj, max_lidar
+    cfg.imu_noise[:] = [ACC_N, GYR_N, ACC_W, GYR_W]
     cfg.device = device
     return cfg
 

@@ -28,6 +28,55 @@ inline void R2q(const double m[9], double q[4]) {   // Eigen Quaternion(Matrix3)
     t = std::sqrt(m[i * 4] - m[j * 4] - m[k * 4] + 1.0); q[i] = 0.5 * t; t = 0.5 / t; q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t; q[j] = (m[j * 3 + i] + m[i * 3 + j]) * t; q[k] = (m[k * 3 + i] + m[i * 3 + k]) * t; }
 }
 
+inline void q2R(const double* q, double* R) {   // Eigen toRotationMatrix, row-major
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+inline void mat3_mul(const double* A, const double* B, double* C) { double t[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j]; std::memcpy(C, t, sizeof(t)); }
+inline void mat3_T(const double* A, double* B) { double t[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * j + i]; std::memcpy(B, t, sizeof(t)); }
+inline void mat3_vec(const double* A, const double* v, double* o) { double t[3]; for (int i = 0; i < 3; i++) t[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2]; std::memcpy(o, t, sizeof(t)); }
+inline void mat4_mul(const double* A, const double* B, double* C) { double t[16]; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { double a = 0; for (int k = 0; k < 4; k++) a += A[4 * i + k] * B[4 * k + j]; t[4 * i + j] = a; } std::memcpy(C, t, sizeof(t)); }
+inline void rigid4(const double* R, const double* t, double* T) { for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T[4 * i + j] = R[3 * i + j]; T[4 * i + 3] = t[i]; } T[12] = T[13] = T[14] = 0; T[15] = 1; }
+inline void rigid4_inv(const double* T, double* Ti) {   // [R t]^-1 = [R^T  -R^T t]
+  double R[9], t[3] = {T[3], T[7], T[11]}, Rt[9], o[3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R[3 * i + j] = T[4 * i + j];
+  mat3_T(R, Rt); mat3_vec(Rt, t, o); for (int i = 0; i < 3; i++) o[i] = -o[i];
+  rigid4(Rt, o, Ti);
+}
+// Eigen QuaternionBase::slerp (shortest arc; linear blend when the quaternions are closer than epsilon)
+inline void qslerp(const double a[4], const double b[4], double t, double o[4]) {
+  const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3], ad = std::fabs(d);
+  double s0, s1;
+  if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - t; s1 = t; }
+  else { const double th = std::acos(ad), st = std::sin(th); s0 = std::sin((1.0 - t) * th) / st; s1 = std::sin(t * th) / st; }
+  if (d < 0) s1 = -s1;
+  for (int i = 0; i < 4; i++) o[i] = s0 * a[i] + s1 * b[i];
+}
+inline void qinv(const double q[4], double o[4]) { const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]; o[0] = -q[0] / n2; o[1] = -q[1] / n2; o[2] = -q[2] / n2; o[3] = q[3] / n2; }
+inline double yaw_deg(const double* R) { return std::atan2(R[3], R[0]) / M_PI * 180.0; }   // Utility::R2ypr(R).x()
+
+// pcl::ApproximateVoxelGrid<PointXYZI> [upstream PCL 1.8 filters/impl/approximate_voxel_grid.hpp, restated from memory; PCL is not in the
+// reference tree]: a 512-entry hash history keyed by (ix * 7171 + iy * 3079 + iz * 4231) & 511 over floor(p / leaf); a colliding voxel flushes the
+// resident centroid (x, y, z, intensity averaged in float, downsample_all_data = true) to the output; everything left is flushed at the end.
+void approximate_voxel_grid(const float* xyzi, int n, int stride, float leaf, std::vector<float>& out) {
+  struct He { int ix = 0, iy = 0, iz = 0, count = 0; float c[4] = {0, 0, 0, 0}; };
+  const int hist = 512; std::vector<He> h(hist);
+  out.clear(); out.reserve((size_t)4 * n);
+  const float inv = 1.0f / leaf;
+  auto flush = [&](He& e) { const float k = (float)e.count; for (int a = 0; a < 4; a++) out.push_back(e.c[a] / k); };
+  for (int i = 0; i < n; i++) {
+    const float* p = xyzi + (size_t)stride * i; const float inten = stride > 4 ? p[4] : p[3];
+    const int ix = (int)std::floor(p[0] * inv), iy = (int)std::floor(p[1] * inv), iz = (int)std::floor(p[2] * inv);
+    He& e = h[(unsigned int)(ix * 7171 + iy * 3079 + iz * 4231) & (hist - 1)];
+    if (e.count && (ix != e.ix || iy != e.iy || iz != e.iz)) { flush(e); e.count = 0; e.c[0] = e.c[1] = e.c[2] = e.c[3] = 0; }
+    e.ix = ix; e.iy = iy; e.iz = iz; e.count++;
+    e.c[0] += p[0]; e.c[1] += p[1]; e.c[2] += p[2]; e.c[3] += inten;
+  }
+  for (auto& e : h) if (e.count) flush(e);
+}
+
 }  // namespace
 
 Estimator::Estimator(const vils_config& cfg, int window_size, int num_iterations) : WINDOW_SIZE(window_size), cfg_(cfg) {
@@ -37,13 +86,18 @@ Estimator::Estimator(const vils_config& cfg, int window_size, int num_iterations
   Headers.assign(F, Header()); imu_.assign(F, ImuBuf());
   for (int i = 0; i < 3; i++) g[i] = cfg.gravity[i];
   vils_default_solve_opts(&solve_opts);
-  solve_opts.mode = VILS_MODE_LM; solve_opts.max_iters = num_iterations;   // ceres DOGLEG, max_num_iterations (estimator.cpp:1402-1404)
+  // ceres DENSE_SCHUR + DOGLEG, max_num_iterations = NUM_ITERATIONS, max_solver_time_in_seconds = SOLVER_TIME (estimator.cpp:1402-1411)
+  solve_opts.mode = VILS_MODE_DOGLEG; solve_opts.max_iters = num_iterations; solve_opts.max_solver_time = SOLVER_TIME;
+  for (int i = 0; i < 9; i++) RLB[i] = cfg.rlb[i];
+  for (int i = 0; i < 3; i++) TLB[i] = cfg.tlb[i];
+  { double Rt[9]; mat3_T(RLB, Rt); mat3_vec(Rt, TLB, TBL); for (int i = 0; i < 3; i++) TBL[i] = -TBL[i]; }   // TBL = -RLB^T TLB (estimator.cpp:451)
   last_status = vils_ba_create(&cfg_, 1, &ba_);
 }
 Estimator::~Estimator() { vils_ba_destroy(ba_); }
 
 void Estimator::setParameter(const double r[9], const double t[3], double td_) {
   R2q(r, ric); qnorm(ric); for (int i = 0; i < 3; i++) tic[i] = t[i]; td = td_;
+  if (r != ric_cfg_) { std::memcpy(ric_cfg_, r, sizeof(ric_cfg_)); std::memcpy(tic_cfg_, t, sizeof(tic_cfg_)); td_cfg_ = td_; }
 }
 
 void Estimator::clearState() {
@@ -51,6 +105,209 @@ void Estimator::clearState() {
   Ps.assign(F, {0, 0, 0}); Vs.assign(F, {0, 0, 0}); Bas.assign(F, {0, 0, 0}); Bgs.assign(F, {0, 0, 0}); Qs.assign(F, {0, 0, 0, 1});
   imu_.assign(F, ImuBuf()); feature.clear(); frame_count = 0; first_imu_ = false; solver_flag = INITIAL; prior_n_ = 0;
   prior_J_.clear(); prior_r_.clear(); prior_x0_.clear(); prior_blk_.clear();
+  all_image_frame.clear(); tmp_pre_ = ImuBuf(); initial_timestamp = 0; td = 0;
+  // the LiDAR side of clearState (estimator.cpp:66-83): queues, frames, counters
+  LidarICPConstraints.clear(); LidarLPSConstraints.clear(); all_lidar_frame.clear(); lidar_count = 0; lidar_count_ = 0; first_zv_ = true; LPS_call_ = false;
+  lp_plane_.clear(); lp_edge_.clear(); lp_plane_kf_.clear(); lp_edge_kf_.clear();
+}
+
+void Estimator::setLPS(const double q[4], const double t[3], double time) {
+  if (!ADD_LPS) return;                                     // estimator_node.cpp:560
+  for (int i = 0; i < 4; i++) LPS_q_[i] = q[i];
+  for (int i = 0; i < 3; i++) LPS_t_[i] = t[i];
+  LPS_time_ = time; LPS_call_ = true;
+}
+
+void Estimator::setLidarPointFactors(int n_plane, const double* pl, const int32_t* pkf, int n_edge, const double* ed, const int32_t* ekf) {
+  lp_plane_.assign(pl, pl + (size_t)7 * std::max(n_plane, 0)); lp_plane_kf_.assign(pkf, pkf + std::max(n_plane, 0));
+  lp_edge_.assign(ed, ed + (size_t)9 * std::max(n_edge, 0)); lp_edge_kf_.assign(ekf, ekf + std::max(n_edge, 0));
+}
+
+// lidar_backend.cpp:3-36: the two window frames that bracket time tl
+bool Estimator::FindNearest2ID(double tl, int& id_a, int& id_b) const {
+  std::vector<double> header;
+  for (int i = 0; i < WINDOW_SIZE + 1; i++) header.push_back(Headers[i].stamp);
+  header.push_back(tl);
+  std::sort(header.begin(), header.end());
+  auto it = std::find(header.begin(), header.end(), tl);
+  if (it == header.end()) return false;
+  const int index = (int)(it - header.begin());
+  id_a = index - 1; id_b = index;
+  return !(id_b > WINDOW_SIZE || id_a < 0);
+}
+
+// lidar_backend.cpp:38-97, including its fall-throughs (ids that are not found keep their initial 0, b == c shifts the first pair back)
+bool Estimator::FindWindowsID(double ta, double tb, double tc, double td_, int& id_a, int& id_b, int& id_c, int& id_d) const {
+  if (Headers[0].stamp > ta || Headers[WINDOW_SIZE].stamp < td_ || (tb - ta) > 0.5) return false;
+  auto find = [&](double t, int& id) { for (int i = 0; i < WINDOW_SIZE + 1; i++) if (Headers[i].stamp == t) { id = i; return; } };
+  find(ta, id_a); find(tb, id_b); find(tc, id_c); find(td_, id_d);
+  if (id_b == id_c) { id_a--; id_b--; }
+  return id_b > id_a && id_d > id_c && id_a >= 0 && id_a != id_c;
+}
+
+namespace {
+// lidar_frontend.cpp:941-987
+void Predict_r(const LidarFrame& f, double R[9]) {
+  const double t = (f.time - f.vioData.ti) / (f.vioData.tj - f.vioData.ti);
+  double q[4];
+  if (t > 0) qslerp(f.vioData.Qwbi, f.vioData.Qwbj, t, q); else std::memcpy(q, f.vioData.Qwbi, sizeof(q));
+  q2R(q, R);
+}
+void Predict_t(const LidarFrame& f, double P[3]) {
+  const double dt = f.time - f.vioData.ti;
+  for (int i = 0; i < 3; i++) {
+    if (dt >= 0) { const double a = (f.vioData.Vbj[i] - f.vioData.Vbi[i]) / (f.vioData.tj - f.vioData.ti); P[i] = f.vioData.Pwbi[i] + f.vioData.Vbi[i] * dt + 0.5 * a * dt * dt; }
+    else P[i] = f.vioData.Pwbi[i];
+  }
+}
+// lidar_frontend.cpp:921-939: relative body motion between two LiDAR stamps predicted from the VIO states; also leaves the predicted LiDAR poses in the frames
+void PredictRelative_rt(LidarFrame& fi, LidarFrame& fj, const double RBL[9], const double TBL[3], double Lij[16]) {
+  double Rbi[9], Rbj[9], Tbi[3], Tbj[3], RbiT[9], Rij[9], d[3], Tij[3];
+  Predict_r(fj, Rbj); Predict_r(fi, Rbi); Predict_t(fj, Tbj); Predict_t(fi, Tbi);
+  mat3_T(Rbi, RbiT); mat3_mul(RbiT, Rbj, Rij);
+  for (int i = 0; i < 3; i++) d[i] = Tbj[i] - Tbi[i];
+  mat3_vec(RbiT, d, Tij);
+  rigid4(Rij, Tij, Lij);
+  double o[3];
+  mat3_mul(Rbi, RBL, fi.lidar_R); mat3_mul(Rbj, RBL, fj.lidar_R);
+  mat3_vec(Rbi, TBL, o); for (int i = 0; i < 3; i++) fi.lidar_T[i] = Tbi[i] + o[i];
+  mat3_vec(Rbj, TBL, o); for (int i = 0; i < 3; i++) fj.lidar_T[i] = Tbj[i] + o[i];
+}
+}  // namespace
+
+// estimator.cpp:122-504
+void Estimator::processLidar(float* xyzi, int n, int stride, double cloud_time, double time_) {
+  current_lidar = LidarFrame(); current_lidar.frameID = lidar_count_; current_lidar.time = cloud_time; current_lidar_points = n;
+  last_status = VILS_OK;
+  const double tm = cloud_time;
+  int idl = 0, idr = 0;
+  if (solver_flag != INITIAL && n > 0 && FindNearest2ID(tm, idl, idr)) {
+    auto iterj = all_image_frame.find(Headers[idr].stamp), iteri = all_image_frame.find(Headers[idl].stamp);
+    current_lidar.keylidar = iterj != all_image_frame.end() && iteri != all_image_frame.end();
+    if (current_lidar.keylidar) {
+      VIOData& v = current_lidar.vioData;
+      current_lidar.next_image_t = iterj->second.t; v.tj = iterj->first + time_;
+      current_lidar.last_image_t = iteri->second.t; v.ti = iteri->first + time_; v.dt = time_;
+      for (int i = 0; i < 4; i++) { v.Qwbi[i] = Qs[idl][i]; v.Qwbj[i] = Qs[idr][i]; }
+      for (int i = 0; i < 3; i++) { v.Pwbi[i] = Ps[idl][i]; v.Vbi[i] = Vs[idl][i]; v.Pwbj[i] = Ps[idr][i]; v.Vbj[i] = Vs[idr][i]; }
+      double trans_lb[16], trans_lb_inv[16];
+      rigid4(RLB, TLB, trans_lb); rigid4_inv(trans_lb, trans_lb_inv);
+      // step 1: distortion adjust (only once the LiDAR extrinsic is in place), VERS2 of :190-237
+      if (!lidar_init_flag) {
+        const float time_factor = (float)(1.0 / LidarTimeStep);
+        const double ta = v.ti, tb = v.tj, tls = tm - 0.5 * LidarTimeStep, tle = tm + 0.5 * LidarTimeStep;   // LiDAR stamp sits in the middle of the sweep
+        const double ss = (tls - ta) / (tb - ta), se = (tle - ta) / (tb - ta);
+        double qls[4], qle[4], qlei[4], qr[4], Rb[9], Rwbj[9], RwbjT[9], dP[3], tb3[3];
+        qslerp(v.Qwbi, v.Qwbj, ss, qls); qslerp(v.Qwbi, v.Qwbj, se, qle);
+        qinv(qle, qlei); qmul(qlei, qls, qr); q2R(qr, Rb);
+        q2R(v.Qwbj, Rwbj); mat3_T(Rwbj, RwbjT);
+        for (int i = 0; i < 3; i++) dP[i] = v.Pwbi[i] - v.Pwbj[i];
+        mat3_vec(RwbjT, dP, tb3); for (int i = 0; i < 3; i++) tb3[i] *= LidarTimeStep / (tb - ta);
+        double trans_b[16], tmp[16], trans_l[16];
+        rigid4(Rb, tb3, trans_b); mat4_mul(trans_lb, trans_b, tmp); mat4_mul(tmp, trans_lb_inv, trans_l);
+        float Rf[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rf[3 * i + j] = (float)trans_l[4 * i + j];
+        double Rd[9], qd[4]; for (int i = 0; i < 9; i++) Rd[i] = Rf[i];
+        R2q(Rd, qd);                                            // Eigen::Quaternionf(Matrix3f): same branch structure, evaluated here in double on the float entries
+        const float qf[4] = {(float)qd[0], (float)qd[1], (float)qd[2], (float)qd[3]};
+        const float tf[3] = {(float)trans_l[3], (float)trans_l[7], (float)trans_l[11]};
+        last_status = vils_deskew(xyzi, n, stride, qf, tf, time_factor, (float)MinDistance, (float)MaxDistance, cfg_.device);   // TransformToEnd (:233)
+        if (last_status != VILS_OK) return;
+        int kept = 0;                                           // pcl::removeNaNFromPointCloud (:236)
+        for (int i = 0; i < n; i++) {
+          const float* p = xyzi + (size_t)stride * i;
+          if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) { if (kept != i) std::memmove(xyzi + (size_t)stride * kept, p, sizeof(float) * stride); kept++; }
+        }
+        n = kept; current_lidar_points = n;
+      }
+      // step 2: downsampling (:241-247)
+      approximate_voxel_grid(xyzi, n, stride, (float)LeafSize, current_lidar.cloud);
+      // step 3: fast-gicp against the previous key LiDAR frame
+      all_lidar_frame[tm] = current_lidar;
+      if (all_lidar_frame.size() > 1) {
+        if (all_lidar_frame.size() > 2) all_lidar_frame.erase(all_lidar_frame.begin());
+        auto lframej = std::prev(all_lidar_frame.end()); auto lframei = std::prev(lframej);
+        FastVGICP gicp(cfg_.device);
+        gicp.setResolution(0.5);
+        gicp.setInputSource(lframej->second.cloud.data(), (int)(lframej->second.cloud.size() / 4), 4);
+        gicp.setInputTarget(lframei->second.cloud.data(), (int)(lframei->second.cloud.size() / 4), 4);
+        double init_guss[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        if (!lidar_init_flag) {
+          double RBL[9], Lij[16], tem_r[9], tem_t[3], A[9], o1[3], o2[3];
+          mat3_T(RLB, RBL);
+          PredictRelative_rt(lframei->second, lframej->second, RBL, TBL, Lij);
+          for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) tem_r[3 * i + j] = Lij[4 * i + j]; tem_t[i] = Lij[4 * i + 3]; }
+          mat3_mul(RLB, tem_r, A);                               // init_guss = [RLB tem_r RLB^T | RLB tem_r TBL + TLB + RLB tem_t] (:283-285)
+          double Rg[9]; mat3_mul(A, RBL, Rg);
+          mat3_vec(A, TBL, o1); mat3_vec(RLB, tem_t, o2);
+          double tg[3]; for (int i = 0; i < 3; i++) tg[i] = o1[i] + TLB[i] + o2[i];
+          rigid4(Rg, tg, init_guss);
+          float guss[16]; for (int i = 0; i < 16; i++) guss[i] = (float)init_guss[i];
+          last_status = gicp.align(nullptr, guss);
+          std::memcpy(current_lidar.lidar_R, lframej->second.lidar_R, sizeof(current_lidar.lidar_R));
+          std::memcpy(current_lidar.lidar_T, lframej->second.lidar_T, sizeof(current_lidar.lidar_T));
+        } else last_status = gicp.align(nullptr, nullptr);
+        if (last_status != VILS_OK) return;
+        const double fitness_core = gicp.getFitnessScore();     // step 4
+        double T[16]; for (int i = 0; i < 16; i++) T[i] = (double)gicp.getFinalTransformation()[i];
+        const double Tij[3] = {T[3], T[7], T[11]};
+        // step 7: classify and queue the LiDAR constraint (:322-436)
+        if (!lidar_init_flag) {
+          const double tem_T = std::fabs(init_guss[3] - Tij[0]) + std::fabs(init_guss[7] - Tij[1]) + std::fabs(init_guss[11] - Tij[2]);
+          LidarICPConstraint c; c.constraint_mode = 0;
+          double Rg[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rg[3 * i + j] = init_guss[4 * i + j];
+          const double temYaw = yaw_deg(Rg);
+          if (fitness_core < 1.0 && tem_T > 0.1) c.constraint_mode = 3;
+          else if (fitness_core < 1.0 && tem_T <= 0.1) c.constraint_mode = 2;
+          else if (fitness_core > 1.0) c.constraint_mode = 1;
+          if (std::fabs(Tij[0]) + std::fabs(Tij[1]) + std::fabs(Tij[2]) < 0.01) c.constraint_mode = std::fabs(temYaw) < 0.5 ? 4 : 5;   // zero velocity / pure rotation
+          current_lidar.mode = c.constraint_mode;
+          if (!ADD_LIDAR_ICP) c.constraint_mode = 0;
+          c.lidar_ta = lframei->second.last_image_t; c.lidar_tb = lframei->second.next_image_t;
+          c.lidar_tc = lframej->second.last_image_t; c.lidar_td = lframej->second.next_image_t;
+          c.lidar_ti = lframei->first; c.lidar_tj = lframej->first;
+          if (c.constraint_mode == 4) {
+            c.lidar_sqrt_info00 = 1e12;                         // lidar_trans stays the identity
+            if (first_zv_) {
+              std::memcpy(tem_zv_r_, lframei->second.lidar_R, sizeof(tem_zv_r_)); std::memcpy(tem_zv_t_, lframei->second.lidar_T, sizeof(tem_zv_t_));
+              first_zv_ = false;
+              while (LidarICPConstraints.size() > 1) LidarICPConstraints.pop_front();
+            }
+            std::memcpy(current_lidar.lidar_R, tem_zv_r_, sizeof(tem_zv_r_)); std::memcpy(current_lidar.lidar_T, tem_zv_t_, sizeof(tem_zv_t_));
+          } else if (c.constraint_mode == 3) {
+            double tmp[16]; mat4_mul(trans_lb_inv, T, tmp); mat4_mul(tmp, trans_lb, c.lidar_trans);   // EX_LB^-1 T EX_LB (:415)
+            c.lidar_sqrt_info00 = 1.0 / fitness_core * 100.0;   // :417
+            if (!first_zv_ && LidarICPConstraints.size() == 1) { LidarICPConstraints.pop_front(); first_zv_ = true; }   // start moving again
+          }
+          LidarICPConstraints.push_back(c);
+        }
+        // step 8: LiDAR-IMU initialisation: the reference adopts the configured ("gt") extrinsic after 15 key LiDAR frames (:439-497, USE_ES off)
+        if (solver_flag != INITIAL && lidar_init_flag && current_lidar.frameID > 15) {
+          for (int i = 0; i < 9; i++) RLB[i] = cfg_.rlb[i];
+          for (int i = 0; i < 3; i++) TLB[i] = cfg_.tlb[i];
+          { double Rt[9]; mat3_T(RLB, Rt); mat3_vec(Rt, TLB, TBL); for (int i = 0; i < 3; i++) TBL[i] = -TBL[i]; }
+          lidar_init_flag = false;
+          double Ri[9], ti[3], RBL[9], o[3];
+          Predict_r(current_lidar, Ri); Predict_t(current_lidar, ti); mat3_T(RLB, RBL);
+          mat3_vec(Ri, TBL, o); for (int i = 0; i < 3; i++) current_lidar.lidar_T[i] = ti[i] + o[i];
+          mat3_mul(Ri, RBL, current_lidar.lidar_R);
+        }
+      }
+      lidar_count_++;
+    }
+  }
+  lidar_count++;
+}
+
+// estimator.cpp:1076-1122 (the commented-out early returns stay out)
+bool Estimator::failureDetection() {
+  const int Wn = WINDOW_SIZE;
+  auto norm3 = [](const std::array<double, 3>& v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+  if (norm3(Bas[Wn]) > 2.5) return true;
+  if (norm3(Bgs[Wn]) > 1.0) return true;
+  const double d[3] = {Ps[Wn][0] - last_P[0], Ps[Wn][1] - last_P[1], Ps[Wn][2] - last_P[2]};
+  if (std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 10) return true;
+  if (std::fabs(d[2]) > 1) return true;
+  return false;
 }
 
 void Estimator::setFrameState(int k, const double P[3], const double Q[4], const double V[3], const double Ba[3], const double Bg[3]) {
@@ -119,15 +376,35 @@ bool Estimator::addFeatureCheckParallax(int fc, const ImageFeatures& image, doub
 void Estimator::processImage(const ImageFeatures& image, const Header& header) {
   marginalization_flag = addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;   // :512-515
   Headers[frame_count] = header;
-  if (solver_flag == INITIAL) {   // the visual-inertial bootstrap is out of scope: keep filling the window
-    if (frame_count < WINDOW_SIZE) frame_count++;
+  { ImageFrame fr; fr.t = header.stamp; fr.points = image; fr.pre = tmp_pre_; all_image_frame[header.stamp] = fr; }   // :523-525
+  tmp_pre_ = ImuBuf();                                        // tmp_pre_integration = new IntegrationBase{acc_0, gyr_0, Bas[frame_count], Bgs[frame_count]}
+  tmp_pre_.started = true; std::memcpy(tmp_pre_.acc0, acc_0_, 24); std::memcpy(tmp_pre_.gyr0, gyr_0_, 24);
+  for (int i = 0; i < 3; i++) { tmp_pre_.ba[i] = Bas[frame_count][i]; tmp_pre_.bg[i] = Bgs[frame_count][i]; }
+  auto remember = [&] { for (int i = 0; i < 3; i++) { last_P[i] = Ps[WINDOW_SIZE][i]; last_P0[i] = Ps[0][i]; } for (int i = 0; i < 4; i++) { last_Q[i] = Qs[WINDOW_SIZE][i]; last_Q0[i] = Qs[0][i]; } };
+  if (frame_count < WINDOW_SIZE) { frame_count++; return; }  // the window is still filling (:578-579; also the setFrameState bootstrap)
+  if (solver_flag == INITIAL) {                               // :553-580
+    bool result = false;
+    if (header.stamp - initial_timestamp > 0.1) { result = initialStructure(); initial_timestamp = header.stamp; }
+    if (result) {
+      solver_flag = NON_LINEAR;
+      if (TRIANGULATE) triangulate();
+      if (last_status == VILS_OK) optimization();             // solveOdometry
+      slideWindow();
+      removeFailures();
+      remember();
+    } else slideWindow();
     return;
   }
-  if (frame_count < WINDOW_SIZE) { frame_count++; return; }
   if (TRIANGULATE) { triangulate(); if (last_status != VILS_OK) return; }   // solveOdometry (:903-914)
   optimization();
-  if (last_status == VILS_OK) removeFailures();
+  if (last_status == VILS_OK && failureDetection()) {         // :588-597: reboot
+    failure_occur = 1;
+    clearState(); setParameter(ric_cfg_, tic_cfg_, td_cfg_);   // back to the configured RIC / TIC / TD (estimator.cpp:21-33)
+    return;
+  }
   slideWindow();
+  if (last_status == VILS_OK) removeFailures();
+  remember();
 }
 
 // FeatureManager::triangulate (feature_manager.cpp:214-268): every feature that enters the solve and has no depth yet gets the DLT / SVD
@@ -185,7 +462,7 @@ void Estimator::optimization() {
     off.push_back((int32_t)dt.size()); imu_kf.push_back(j - 1);
   }
   std::vector<vils_preint> pre(imu_kf.size());
-  const double noise[4] = {0.02065, 0.00519, 0.00667, 0.00088056};   // ACC_N GYR_N ACC_W GYR_W (config/mynteye_leishen_indoor.yaml:81-86)
+  const double* noise = cfg_.imu_noise;                              // ACC_N GYR_N ACC_W GYR_W (parameters.cpp:96-99)
   if (!imu_kf.empty()) {
     last_status = vils_preintegrate((int)imu_kf.size(), off.data(), dt.data(), acc.data(), gyr.data(), acc0.data(), gyr0.data(), ba.data(), bg.data(), noise, pre.data(), cfg_.device);
     if (last_status != VILS_OK) return;
@@ -210,13 +487,63 @@ void Estimator::optimization() {
       td_i.push_back(f0.cur_td); td_j.push_back(fj.cur_td); row_i.push_back(f0.uv[1]); row_j.push_back(fj.uv[1]);
     }
   }
+  // LPS absolute-rotation constraints (:1283-1326): a new mapper pose arrived -> queue it (moved to the body frame) and add every queued
+  // constraint whose bracketing frames are < 0.2 s apart
+  std::vector<vils_lps> lps;
+  while (LidarLPSConstraints.size() > 7) LidarLPSConstraints.pop_front();
+  if (LPS_call_) {
+    LidarLPSConstraint cur; double Rq[9], o[3], qrlb[4];
+    q2R(LPS_q_, Rq); mat3_vec(Rq, TLB, o);
+    for (int i = 0; i < 3; i++) cur.LPSt[i] = o[i] + LPS_t_[i];                       // LPS_t = LPS_q TLB + LPS_t
+    R2q(RLB, qrlb); qmul(LPS_q_, qrlb, cur.LPSq);                                       // LPS_q = LPS_q * Quaterniond(RLB)
+    cur.lidar_t = LPS_time_;
+    LidarLPSConstraints.push_back(cur);
+    LPS_call_ = false;
+    for (const auto& c : LidarLPSConstraints) {
+      int id_l = 0, id_r = 0;
+      if (!FindNearest2ID(c.lidar_t, id_l, id_r)) continue;
+      if (Headers[id_r].stamp - Headers[id_l].stamp >= 0.2) continue;
+      vils_lps q{}; q.tl = Headers[id_l].stamp; q.tr = Headers[id_r].stamp; q.tk = c.lidar_t;
+      for (int i = 0; i < 4; i++) q.q[i] = c.LPSq[i];
+      q.kf[0] = id_l; q.kf[1] = id_r;
+      lps.push_back(q);
+    }
+  }
+  // LiDAR ICP relative constraints (:1345-1398): mode 3 inside the window -> LidarICPConstraint_b; mode 4 (zero velocity) -> frame WINDOW_SIZE-1
+  // gets V = 0 and its pose / speed-bias blocks are held constant
+  std::vector<vils_icp> icp; std::vector<uint8_t> kffix(F, 0); int nfixed = 0;
+  while (LidarICPConstraints.size() > 5) LidarICPConstraints.pop_front();
+  for (const auto& c : LidarICPConstraints) {
+    int a = 0, b = 0, cc = 0, d = 0;
+    if (c.constraint_mode == 4) {
+      for (int i = 0; i < 3; i++) sb[9 * (WINDOW_SIZE - 1) + i] = 0.0;
+      if (!kffix[WINDOW_SIZE - 1]) nfixed++;
+      kffix[WINDOW_SIZE - 1] = 1;
+    } else if (c.constraint_mode == 3 && FindWindowsID(c.lidar_ta, c.lidar_tb, c.lidar_tc, c.lidar_td, a, b, cc, d)) {
+      if (a == b || a == cc || a == d || b == cc || b == d || cc == d || b > WINDOW_SIZE || d > WINDOW_SIZE) continue;   // ceres rejects duplicate blocks
+      vils_icp q{}; q.ta = c.lidar_ta; q.tb = c.lidar_tb; q.tc = c.lidar_tc; q.td = c.lidar_td; q.ti = c.lidar_ti; q.tj = c.lidar_tj;
+      q.trans_t[0] = c.lidar_trans[3]; q.trans_t[1] = c.lidar_trans[7]; q.trans_t[2] = c.lidar_trans[11]; q.sqrt_info = c.lidar_sqrt_info00;
+      q.kf[0] = a; q.kf[1] = b; q.kf[2] = cc; q.kf[3] = d;
+      icp.push_back(q);
+    }
+  }
+  // scan-to-map point factors handed over through setLidarPointFactors (SoA split of the 7 / 9 doubles per row)
+  const int npl = (int)lp_plane_kf_.size(), ned = (int)lp_edge_kf_.size();
+  std::vector<double> pl_p(3 * (size_t)npl), pl_n(3 * (size_t)npl), pl_d(npl), ed_p(3 * (size_t)ned), ed_a(3 * (size_t)ned), ed_b(3 * (size_t)ned);
+  for (int k = 0; k < npl; k++) { for (int a = 0; a < 3; a++) { pl_p[3 * k + a] = lp_plane_[7 * (size_t)k + a]; pl_n[3 * k + a] = lp_plane_[7 * (size_t)k + 3 + a]; } pl_d[k] = lp_plane_[7 * (size_t)k + 6]; }
+  for (int k = 0; k < ned; k++) for (int a = 0; a < 3; a++) { ed_p[3 * k + a] = lp_edge_[9 * (size_t)k + a]; ed_a[3 * k + a] = lp_edge_[9 * (size_t)k + 3 + a]; ed_b[3 * k + a] = lp_edge_[9 * (size_t)k + 6 + a]; }
   vils_window w{};
   w.n_kf = F; w.n_feat = (int)lam.size(); w.n_imu = (int)imu_kf.size(); w.n_proj = (int)kf_i.size();
-  w.pose = pose.data(); w.speedbias = sb.data(); w.ex_pose = ex.data(); w.inv_depth = lam.data(); w.depth_fixed = dfix.data(); w.td = td;
+  w.pose = pose.data(); w.speedbias = sb.data(); w.ex_pose = ex.data(); w.inv_depth = lam.data(); w.depth_fixed = dfix.data(); w.kf_fixed = kffix.data(); w.td = td;
   w.imu = pre.data(); w.imu_kf = imu_kf.data();
   w.pts_i = pts_i.data(); w.pts_j = pts_j.data(); w.vel_i = vel_i.data(); w.vel_j = vel_j.data(); w.td_i = td_i.data(); w.td_j = td_j.data();
   w.row_i = row_i.data(); w.row_j = row_j.data(); w.kf_i = kf_i.data(); w.kf_j = kf_j.data(); w.feat = feat.data();
+  w.n_plane = npl; w.plane_p = pl_p.data(); w.plane_n = pl_n.data(); w.plane_d = pl_d.data(); w.plane_kf = lp_plane_kf_.data();
+  w.n_edge = ned; w.edge_p = ed_p.data(); w.edge_a = ed_a.data(); w.edge_b = ed_b.data(); w.edge_kf = lp_edge_kf_.data();
+  w.n_icp = (int)icp.size(); w.icp = icp.data(); w.n_lps = (int)lps.size(); w.lps = lps.data();
   w.prior_n = prior_n_; w.prior_nblk = (int)prior_blk_.size(); w.prior_J = prior_J_.data(); w.prior_r = prior_r_.data(); w.prior_blk = prior_blk_.data(); w.prior_x0 = prior_x0_.data();
+  last_n_icp = w.n_icp; last_n_lps = w.n_lps; last_n_fixed = nfixed; last_n_plane = npl; last_n_edge = ned;
+  lp_plane_.clear(); lp_plane_kf_.clear(); lp_edge_.clear(); lp_edge_kf_.clear();
   last_n_proj = w.n_proj; last_n_feat = w.n_feat; last_prior_n = prior_n_;
   last_status = vils_ba_set_window(ba_, 0, &w);
   if (last_status != VILS_OK) return;
@@ -239,7 +566,10 @@ void Estimator::optimization() {
     used[f]->estimated_depth = 1.0 / lam[f];
     used[f]->solve_flag = used[f]->estimated_depth < 0 ? 2 : 1;
   }
-  // marginalization (:1483-1684): the new prior, block ids already re-addressed to the slid window
+  // marginalization (:1483-1684): the new prior, block ids already re-addressed to the slid window.  The reference re-packs the RE-ANCHORED
+  // state (vector2double, :1487) before it builds MarginalizationInfo, so the prior is linearised — and its x0 snapshots are taken — there.
+  last_status = vils_ba_put_state(ba_, 0, pose.data(), sb.data(), ex.data(), lam.data(), tdo);
+  if (last_status != VILS_OK) return;
   const int cap = 15 * F + 7;
   std::vector<double> J((size_t)cap * cap), r(cap), x0((size_t)(2 * F + 2) * 9); std::vector<int32_t> blk(2 * F + 2);
   vils_prior_out po{}; po.capacity_n = cap; po.J = J.data(); po.r = r.data(); po.blk = blk.data(); po.x0 = x0.data();
@@ -258,6 +588,19 @@ void Estimator::removeBackShiftDepth() {
   // handled inside slideWindow (needs the marginalised and the new first camera pose)
 }
 
+// feature_manager.cpp:346-362
+void Estimator::removeBack() {
+  for (auto it = feature.begin(); it != feature.end();) {
+    if (it->start_frame != 0) { it->start_frame--; ++it; continue; }
+    it->feature_per_frame.erase(it->feature_per_frame.begin());
+    it = it->feature_per_frame.empty() ? feature.erase(it) : std::next(it);
+  }
+}
+
+#ifndef VILS_HOST_HAS_INITIAL
+bool Estimator::initialStructure() { return false; }
+#endif
+
 void Estimator::removeFront(int fc) {
   for (auto it = feature.begin(); it != feature.end();) {
     if (it->start_frame == fc) { it->start_frame--; ++it; continue; }
@@ -273,6 +616,7 @@ void Estimator::slideWindow() {
   if (frame_count != WINDOW_SIZE) return;
   const int Wn = WINDOW_SIZE;
   if (marginalization_flag == MARGIN_OLD) {
+    const double t_0 = Headers[0].stamp;
     double back_Q0[4], back_P0[3];
     for (int i = 0; i < 4; i++) back_Q0[i] = Qs[0][i];
     for (int i = 0; i < 3; i++) back_P0[i] = Ps[0][i];
@@ -282,6 +626,8 @@ void Estimator::slideWindow() {
     }
     Headers[Wn] = Headers[Wn - 1]; Ps[Wn] = Ps[Wn - 1]; Vs[Wn] = Vs[Wn - 1]; Qs[Wn] = Qs[Wn - 1]; Bas[Wn] = Bas[Wn - 1]; Bgs[Wn] = Bgs[Wn - 1];
     imu_[Wn] = ImuBuf();
+    { auto it0 = all_image_frame.find(t_0); if (it0 != all_image_frame.end()) all_image_frame.erase(all_image_frame.begin(), std::next(it0)); }   // :1731-1747
+    if (solver_flag != NON_LINEAR) { removeBack(); return; }   // slideWindowOld without depth shifting while initialising (:1806-1807)
     // slideWindowOld + removeBackShiftDepth (feature_manager.cpp:286-344)
     double Q0c[4], Q1c[4], P0c[3], P1c[3], t0[3], t1[3];
     qmul(back_Q0, ric, Q0c); qmul(Qs[0].data(), ric, Q1c);
@@ -304,11 +650,13 @@ void Estimator::slideWindow() {
       ++it;
     }
   } else {
+    const double t_second_new = Headers[Wn - 1].stamp;
     ImuBuf& dst = imu_[frame_count - 1]; const ImuBuf& src = imu_[frame_count];
     dst.dt.insert(dst.dt.end(), src.dt.begin(), src.dt.end()); dst.acc.insert(dst.acc.end(), src.acc.begin(), src.acc.end()); dst.gyr.insert(dst.gyr.end(), src.gyr.begin(), src.gyr.end());
     Headers[frame_count - 1] = Headers[frame_count]; Ps[frame_count - 1] = Ps[frame_count]; Vs[frame_count - 1] = Vs[frame_count];
     Qs[frame_count - 1] = Qs[frame_count]; Bas[frame_count - 1] = Bas[frame_count]; Bgs[frame_count - 1] = Bgs[frame_count];
     imu_[Wn] = ImuBuf();
+    if (solver_flag == INITIAL) all_image_frame.erase(t_second_new);   // :1781-1784
     removeFront(frame_count);
   }
 }
@@ -452,6 +800,8 @@ int FastVGICP::align(float* aligned, const float* guess) {
   return VILS_OK;
 }
 
+void approximate_voxel_grid_public(const float* xyzi, int n, int stride, float leaf, std::vector<float>& out) { approximate_voxel_grid(xyzi, n, stride, leaf, out); }
+
 int TransformToEnd(float* xyzi, int n, const float q[4], const float t[3], float time_factor, double min_r, double max_r, int device) {
   return vils_deskew(xyzi, n, 8, q, t, time_factor, (float)min_r, (float)max_r, device);
 }
@@ -487,6 +837,40 @@ void vh_get_info(void* p, double* out /* cost0 cost1 iters n_proj n_feat prior_n
   out[0] = e->last_summary.cost_initial; out[1] = e->last_summary.cost_final; out[2] = e->last_summary.iterations; out[3] = e->last_n_proj;
   out[4] = e->last_n_feat; out[5] = e->last_prior_n; out[6] = e->td; out[7] = e->marginalization_flag; out[8] = (double)e->feature.size();
 }
+// ---- LiDAR side of the Estimator
+int vh_process_lidar(void* p, float* xyzi, int n, int stride, double cloud_time, double time_offset) {
+  auto* e = static_cast<vils::Estimator*>(p); e->processLidar(xyzi, n, stride, cloud_time, time_offset); return e->last_status;
+}
+void vh_set_lidar_init_flag(void* p, int flag) { static_cast<vils::Estimator*>(p)->lidar_init_flag = flag != 0; }
+void vh_set_lps(void* p, const double* q, const double* t, double time) { static_cast<vils::Estimator*>(p)->setLPS(q, t, time); }
+void vh_set_lidar_point_factors(void* p, int npl, const double* pl7, const int32_t* pkf, int ned, const double* ed9, const int32_t* ekf) {
+  static_cast<vils::Estimator*>(p)->setLidarPointFactors(npl, pl7, pkf, ned, ed9, ekf);
+}
+// out: keylidar points mode n_icp_queue lidar_count lidar_count_ last_n_icp last_n_lps last_n_fixed last_n_plane last_n_edge failure_occur solver_flag
+void vh_get_lidar_info(void* p, double* out) {
+  auto* e = static_cast<vils::Estimator*>(p);
+  out[0] = e->current_lidar.keylidar; out[1] = e->current_lidar_points; out[2] = e->current_lidar.mode; out[3] = (double)e->LidarICPConstraints.size();
+  out[4] = e->lidar_count; out[5] = e->lidar_count_; out[6] = e->last_n_icp; out[7] = e->last_n_lps; out[8] = e->last_n_fixed; out[9] = e->last_n_plane;
+  out[10] = e->last_n_edge; out[11] = e->failure_occur; out[12] = e->solver_flag;
+}
+// constraint k of the ICP queue: mode ta tb tc td ti tj sqrt_info trans(16)
+int vh_get_icp(void* p, int k, double* out) {
+  auto* e = static_cast<vils::Estimator*>(p);
+  if (k < 0 || k >= (int)e->LidarICPConstraints.size()) return 1;
+  const auto& c = e->LidarICPConstraints[k];
+  out[0] = c.constraint_mode; out[1] = c.lidar_ta; out[2] = c.lidar_tb; out[3] = c.lidar_tc; out[4] = c.lidar_td; out[5] = c.lidar_ti; out[6] = c.lidar_tj; out[7] = c.lidar_sqrt_info00;
+  for (int i = 0; i < 16; i++) out[8 + i] = c.lidar_trans[i];
+  return 0;
+}
+int vh_failure_detection(void* p) { return static_cast<vils::Estimator*>(p)->failureDetection() ? 1 : 0; }
+void vh_set_solver(void* p, int mode, int iters, double mu, double max_time) {
+  auto* e = static_cast<vils::Estimator*>(p); e->solve_opts.mode = mode; e->solve_opts.max_iters = iters; e->solve_opts.mu = mu; e->solve_opts.max_solver_time = max_time;
+}
+void vh_get_header_stamps(void* p, double* out) { auto* e = static_cast<vils::Estimator*>(p); for (int i = 0; i <= e->WINDOW_SIZE; i++) out[i] = e->Headers[i].stamp; }
+void vh_voxel_filter(const float* xyzi, int n, int stride, float leaf, float* out, int* n_out) {
+  std::vector<float> o; vils::approximate_voxel_grid_public(xyzi, n, stride, leaf, o); *n_out = (int)(o.size() / 4); std::memcpy(out, o.data(), sizeof(float) * o.size());
+}
+
 void* vh_tracker_create(int rows, int cols, int max_cnt, int device) { return new vils::FeatureTracker(rows, cols, max_cnt, device); }
 void vh_tracker_destroy(void* p) { delete static_cast<vils::FeatureTracker*>(p); }
 void vh_tracker_add(void* p, const float* xy, int n) { static_cast<vils::FeatureTracker*>(p)->addPoints(xy, n); }

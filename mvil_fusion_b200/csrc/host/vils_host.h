@@ -5,8 +5,9 @@
 //   vils::TransformToEnd                                                     <- vils_estimator/src/lidar_frontend.h:287
 // ROS / Eigen / OpenCV types are replaced by plain structs (Header{stamp}, std::array, raw image pointers).  All heavy
 // arithmetic goes through libvils_b200.so (include/vils_cabi.h); there is no CPU implementation of it here.
-// Scope: the NON_LINEAR steady state of processImage (solveOdometry -> optimization -> slideWindow).  Initialisation
-// (initialStructure, estimator.cpp:618-871), SVD triangulation and failure-recovery reboot are "next" rows.
+// Scope: processIMU / processImage (INITIAL bootstrap through initialStructure, NON_LINEAR steady state with failureDetection and
+// reboot) / optimization (IMU + projection + LiDAR ICP / LPS / point factors + prior) / slideWindow / processLidar (deskew ->
+// voxel filter -> VGICP -> constraint classification).
 #pragma once
 #include <array>
 #include <cstdint>
@@ -33,6 +34,22 @@ struct FeaturePerId {                                                         //
   int endFrame() const { return start_frame + (int)feature_per_frame.size() - 1; }
 };
 
+// lidar_backend.h:5-26 / lidar_frontend.h (LidarFrame, VIOData) with Eigen types flattened
+struct LidarICPConstraint {
+  int constraint_mode = 0;                                   // 1 bad fitness, 2 VIO agrees, 3 VIO drift (constraint used), 4 zero velocity, 5 pure rotation
+  double lidar_ta = 0, lidar_tb = 0, lidar_tc = 0, lidar_td = 0, lidar_ti = 0, lidar_tj = 0;
+  double lidar_trans[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // row-major 4 x 4
+  double lidar_sqrt_info00 = 0;                              // lidar_sqrt_info(0, 0): the only entry the functor reads (lidar_backend.h:156-158)
+};
+struct LidarLPSConstraint { double LPSq[4] = {0, 0, 0, 1}; double LPSt[3] = {0, 0, 0}; double lidar_t = 0; };
+struct VIOData { double ti = 0, tj = 0, dt = 0; double Qwbi[4] = {0, 0, 0, 1}, Pwbi[3] = {0, 0, 0}, Vbi[3] = {0, 0, 0}, Qwbj[4] = {0, 0, 0, 1}, Pwbj[3] = {0, 0, 0}, Vbj[3] = {0, 0, 0}; };
+struct LidarFrame {
+  int frameID = 0; bool keylidar = false; double time = 0;   // lidarData.point_cloud.time
+  std::vector<float> cloud;                                  // voxel-filtered, x y z intensity packed
+  VIOData vioData; double last_image_t = 0, next_image_t = 0;
+  double lidar_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, lidar_T[3] = {0, 0, 0}; int mode = 0;
+};
+
 class Estimator {
  public:
   enum SolverFlag { INITIAL, NON_LINEAR };
@@ -55,6 +72,30 @@ class Estimator {
   void slideWindow();                                                                                  // estimator.cpp:1689-1814
   void triangulate();                                          // f_manager.triangulate(Ps, tic, ric) in solveOdometry (estimator.cpp:903-914)
   bool TRIANGULATE = true;
+  // estimator.cpp:122-504.  cloud: n PCL PointXYZI points (stride floats apart, 8 for PCL), deskewed IN PLACE with the NaN-ed points removed
+  // (count in current_lidar_points); cloud_time = CloudData::time; time_ = the camera-LiDAR time offset handed over by the node.
+  void processLidar(float* xyzi, int n_points, int stride_floats, double cloud_time, double time_);
+  bool failureDetection();                                     // estimator.cpp:1076-1122
+  // LPS_call / LPS_q / LPS_t / LPS_time of estimator_node.cpp:552-575: the LiDAR mapper's absolute pose, consumed by the next optimization()
+  void setLPS(const double q_xyzw[4], const double t[3], double time);
+  // Scan-to-map factors (vils_lidar_associate outputs) attached to window keyframes for the next optimization(): plane rows p(3) n(3) d,
+  // edge rows p(3) a(3) b(3), each with its keyframe index.  Cleared after the solve.
+  void setLidarPointFactors(int n_plane, const double* plane_pnd7, const int32_t* plane_kf, int n_edge, const double* edge_pab9, const int32_t* edge_kf);
+  bool initialStructure();                                     // estimator.cpp:618-871 (host SfM + visual-inertial alignment, csrc/host/vils_initial.cpp)
+
+  std::deque<LidarICPConstraint> LidarICPConstraints;          // estimator.h:150
+  std::deque<LidarLPSConstraint> LidarLPSConstraints;
+  LidarFrame current_lidar;
+  std::map<double, LidarFrame> all_lidar_frame;
+  bool lidar_init_flag = true;                                 // lidarCalibration.lidar_init_flag: true until the LiDAR extrinsic has been set
+  double RLB[9], TLB[3], TBL[3];                               // p_l = RLB p_b + TLB (estimator.cpp:449-451)
+  double LidarTimeStep = 0.1, MinDistance = 0.5, MaxDistance = 70.0, LeafSize = 0.3;   // yaml:125-130
+  bool ADD_LIDAR_ICP = true, ADD_LPS = true;                   // yaml add_lidar2lidar / add_lps
+  double SOLVER_TIME = 0.05;                                   // yaml max_solver_time
+  int lidar_count = 0, lidar_count_ = 0, current_lidar_points = 0, failure_occur = 0;
+  int last_n_icp = 0, last_n_lps = 0, last_n_fixed = 0, last_n_plane = 0, last_n_edge = 0;
+  double last_P[3] = {0, 0, 0}, last_P0[3] = {0, 0, 0}, last_Q[4] = {0, 0, 0, 1}, last_Q0[4] = {0, 0, 0, 1};
+  double initial_timestamp = 0;
 
   // ---- public state, reference names (estimator.h:67-121) ----
   int WINDOW_SIZE;
@@ -83,6 +124,9 @@ class Estimator {
   void removeBackShiftDepth();                                                               // feature_manager.cpp:286-344
   void removeFront(int frame_count_);                                                        // feature_manager.cpp:364-384
   void removeFailures();                                                                     // feature_manager.cpp:171-184
+  void removeBack();                                                                         // feature_manager.cpp:346-362
+  bool FindNearest2ID(double tl, int& id_a, int& id_b) const;                                // lidar_backend.cpp:3-36
+  bool FindWindowsID(double ta, double tb, double tc, double td, int& id_a, int& id_b, int& id_c, int& id_d) const;   // :38-97
 
   vils_config cfg_;
   vils_ba* ba_ = nullptr;
@@ -96,6 +140,16 @@ class Estimator {
   std::vector<double> prior_J_, prior_r_, prior_x0_;
   std::vector<int32_t> prior_blk_;
   int prior_n_ = 0;
+  // all_image_frame (estimator.h:118): the stamps of every image still inside / behind the window, with what initialStructure needs
+ public:
+  struct ImageFrame { double t = 0; ImageFeatures points; double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0}; bool is_key_frame = false; ImuBuf pre; };
+  std::map<double, ImageFrame> all_image_frame;
+ private:
+  double ric_cfg_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tic_cfg_[3] = {0, 0, 0}, td_cfg_ = 0;   // RIC / TIC / TD as configured (reboot)
+  ImuBuf tmp_pre_;                                             // tmp_pre_integration (estimator.cpp:104-105,524-526)
+  bool LPS_call_ = false; double LPS_q_[4] = {0, 0, 0, 1}, LPS_t_[3] = {0, 0, 0}, LPS_time_ = 0;
+  bool first_zv_ = true; double tem_zv_r_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tem_zv_t_[3] = {0, 0, 0};
+  std::vector<double> lp_plane_, lp_edge_; std::vector<int32_t> lp_plane_kf_, lp_edge_kf_;
 };
 
 // feature_tracker_/src/feature_tracker.{h,cpp}.  readImage = CLAHE (EQUALIZE) -> calcOpticalFlowPyrLK -> border check / reduceVector ->
@@ -162,6 +216,9 @@ class FastVGICP {
   std::vector<float> src_, tgt_;
   float final_[16];
 };
+
+// pcl::ApproximateVoxelGrid<PointXYZI>::filter as processLidar uses it (estimator.cpp:241-247): out = x y z intensity packed
+void approximate_voxel_grid_public(const float* xyzi, int n, int stride_floats, float leaf, std::vector<float>& out);
 
 // lidar_frontend.h:287 — in place on a PCL PointXYZI buffer (8 floats per point)
 int TransformToEnd(float* xyzi, int n_points, const float q_xyzw[4], const float t[3], float time_factor, double min_r, double max_r, int device = 0);

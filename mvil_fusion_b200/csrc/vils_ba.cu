@@ -971,6 +971,7 @@ void vils_default_config(vils_config* cfg) {
   cfg->tlb[0] = 0.2; cfg->tlb[1] = -0.005; cfg->tlb[2] = -0.1;  // yaml:48-52
   cfg->estimate_extrinsic = 1; cfg->estimate_td = 1;            // yaml:25,112
   cfg->max_kf = 10; cfg->max_feat = 150; cfg->max_proj = 1400; cfg->max_lidar = 2000; cfg->device = 0;
+  cfg->imu_noise[0] = 0.02065; cfg->imu_noise[1] = 0.00519; cfg->imu_noise[2] = 0.00667; cfg->imu_noise[3] = 0.00088056;   // yaml:81-86
 }
 
 void vils_default_solve_opts(vils_solve_opts* o) {

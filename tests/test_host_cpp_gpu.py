@@ -264,3 +264,199 @@ def test_fast_vgicp_host_class_matches_cabi(host):
     assert (Tf.reshape(4, 4) == r["T"].astype(np.float32)).all()
     assert info[0] == r["fitness"] and bool(info[1]) == r["converged"] and int(info[2]) == r["iterations"]
     assert np.abs(Tf.reshape(4, 4)[:3, 3] - T[:3, 3]).max() < 0.03
+
+
+def _lidar_host(host):
+    dp = cabi.c_double_p
+    host.vh_process_lidar.argtypes = [C.c_void_p, cabi.c_float_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    host.vh_set_lidar_init_flag.argtypes = [C.c_void_p, C.c_int]; host.vh_set_lidar_init_flag.restype = None
+    host.vh_set_lps.argtypes = [C.c_void_p, dp, dp, C.c_double]; host.vh_set_lps.restype = None
+    host.vh_set_lidar_point_factors.argtypes = [C.c_void_p, C.c_int, dp, cabi.c_int32_p, C.c_int, dp, cabi.c_int32_p]; host.vh_set_lidar_point_factors.restype = None
+    host.vh_get_lidar_info.argtypes = [C.c_void_p, dp]; host.vh_get_lidar_info.restype = None
+    host.vh_get_icp.argtypes = [C.c_void_p, C.c_int, dp]
+    host.vh_failure_detection.argtypes = [C.c_void_p]
+    host.vh_set_solver.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]; host.vh_set_solver.restype = None
+    host.vh_get_header_stamps.argtypes = [C.c_void_p, dp]; host.vh_get_header_stamps.restype = None
+    host.vh_voxel_filter.argtypes = [cabi.c_float_p, C.c_int, C.c_int, C.c_float, cabi.c_float_p, cabi.c_int32_p]; host.vh_voxel_filter.restype = None
+    return host
+
+
+def _sweep(rng, t_mid, n, RLB, TLB, drift=np.zeros(3)):
+    """One LiDAR sweep of the synthetic room centred at t_mid (PCL PointXYZI, stride 8): every point is captured from the LiDAR pose at ITS OWN
+    time inside [t_mid - 0.05, t_mid + 0.05] (intensity = int + rel_time, PointProcessor.cc:318-331), so the cloud carries real motion distortion.
+    drift: a world-frame offset of the sensor (a scan that disagrees with the VIO states)."""
+    per = n // 6
+    pts = []
+    for axis, val in ((0, -8.0), (0, 8.0), (1, -6.0), (1, 6.0), (2, -1.5), (2, 3.0)):
+        p = np.stack([rng.uniform(-8, 8, per), rng.uniform(-6, 6, per), rng.uniform(-1.5, 3, per)], 1); p[:, axis] = val; pts.append(p)
+    pw = np.concatenate(pts) + rng.normal(0, 0.01, (per * 6, 3))
+    rel = rng.uniform(0.0, 0.0999, len(pw))
+    P, _, _, R, _ = synth.traj(t_mid - 0.05 + rel)
+    pb = np.einsum("nji,nj->ni", R, pw - (P + drift))
+    pl = pb @ RLB.T + TLB
+    cloud = np.zeros((len(pw), 8), np.float32)
+    cloud[:, :3] = pl; cloud[:, 4] = np.floor(rng.uniform(1, 100, len(pw))) + rel
+    return cloud
+
+
+def test_estimator_cpp_process_lidar_and_lidar_factors(host):
+    """Estimator::processLidar (estimator.cpp:122-504) through the C++ class only: deskew -> voxel filter -> VGICP against the previous key scan ->
+    constraint classification -> ICP queue, then optimization() with the queued LidarICPConstraint / zero-velocity freeze / LPS / point factors."""
+    from mvil_fusion_b200 import lib
+    H = _lidar_host(host)
+    N = 10
+    w = synth.make_window(1, 5, N=N, M=150, n_lidar=0, ex_prior=False)
+    raw = w["raw"]; kf = raw["kf"]; tk = raw["ts"][kf]
+    cfg = cabi.default_config(max_kf=N, max_feat=400, max_proj=4000, max_lidar=64)
+    RLB = np.array(list(cfg.rlb)).reshape(3, 3); TLB = np.array(list(cfg.tlb))
+    est = H.vh_estimator_create(C.byref(cfg), N - 1, 5, cabi.VILS_MODE_GN, 1e-3)
+    H.vh_set_parameter(est, d(raw["ric"].reshape(-1)), d(raw["tic"]), w["td"])
+    H.vh_set_lidar_init_flag(est, 0)                      # LiDAR extrinsic known (the reference adopts the configured one after 15 key scans)
+    truth = w["truth"]
+
+    def set_true(k, src):
+        H.vh_set_frame_state(est, k, d(truth["pose"][src, :3]), d(truth["pose"][src, 3:]), d(truth["speedbias"][src, 0:3]), d(truth["speedbias"][src, 3:6]), d(truth["speedbias"][src, 6:9]))
+    for k in range(N):
+        set_true(k, k)
+    H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][0]), d(raw["gyr"][0]))
+    for j in range(N):                                      # the whole window: the last frame triggers the first optimization() + slideWindow()
+        if j > 0:
+            for s in range(kf[j - 1] + 1, kf[j] + 1):
+                H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][s]), d(raw["gyr"][s]))
+            set_true(j, j)
+        ids, feats = frame_features(w, j)
+        H.vh_process_image(est, len(ids), ids.ctypes.data_as(cabi.c_int32_p), d(feats), float(tk[j]))
+    assert H.vh_last_status(est) == 0
+    # processLidar works on a FULL window (solver_flag != INITIAL): look the slid header table up and put the true states back on its frames
+    stamps = np.zeros(N); H.vh_get_header_stamps(est, d(stamps))
+    src = [int(np.argmin(np.abs(tk - t))) for t in stamps]
+    for k in range(N):
+        set_true(k, src[k])
+    tk = stamps.copy()                                     # from here on frame indices are those of the slid window
+    info = np.zeros(13)
+    rng = np.random.default_rng(5)
+    # scan A between frames 2 and 3, scan B between 4 and 5 (consistent with the VIO states), scan C between 6 and 7 from a sensor that sits 0.3 m off
+    def feed(t_mid, drift=np.zeros(3)):
+        c = _sweep(rng, t_mid, 12000, RLB, TLB, drift)
+        st = H.vh_process_lidar(est, c.ctypes.data_as(cabi.c_float_p), len(c), 8, float(t_mid), 0.0)
+        assert st == 0
+        H.vh_get_lidar_info(est, d(info))
+        return c, info.copy()
+    assert tk[2] < tk[3] < tk[4] < tk[5] < tk[6] < tk[7]
+    cA, iA = feed(tk[2] + 0.04)
+    assert iA[0] == 1 and iA[3] == 0                        # key scan, nothing to match against yet
+    kept = int(iA[1]); assert 0.9 * len(cA) <= kept <= len(cA)
+    assert np.isfinite(cA[:kept, :3]).all() and np.all(cA[:kept, 4] == np.floor(cA[:kept, 4]))   # deskewed in place, NaN points removed, intensity <- int
+    cB, iB = feed(tk[4] + 0.04)
+    assert iB[3] == 1 and iB[2] == 2                        # VIO and LiDAR agree: mode 2, queued but not used by the solve
+    icp = np.zeros(24); assert H.vh_get_icp(est, 0, d(icp)) == 0
+    assert icp[1] == tk[2] and icp[2] == tk[3] and icp[3] == tk[4] and icp[4] == tk[5]
+    cC, iC = feed(tk[6] + 0.04, drift=np.array([0.3, 0.0, 0.0]))
+    assert iC[3] == 2 and iC[2] == 3                        # 0.3 m disagreement: mode 3 (VIO drift), the constraint carries the LiDAR measurement
+    assert H.vh_get_icp(est, 1, d(icp)) == 0
+    assert icp[0] == 3 and icp[7] > 100.0                   # sqrt_info = 100 / fitness with fitness < 1
+    # measured translation (body frame of scan B's sweep end -> scan C's): truth + the injected 0.3 m world offset seen from body B
+    PB, _, _, RB, _ = synth.traj(np.array([tk[4] + 0.09])); PC, _, _, RC, _ = synth.traj(np.array([tk[6] + 0.09]))
+    expect = RB[0].T @ (PC[0] + np.array([0.3, 0, 0]) - PB[0])
+    assert np.abs(icp[8:24].reshape(4, 4)[:3, 3] - expect).max() < 0.05
+    # the last frame arrives: optimization() takes the mode-3 constraint (FindWindowsID), an LPS rotation and a handful of point factors
+    Pm, _, _, Rm, _ = synth.traj(np.array([tk[5] + 0.03]))
+    q_wl = synth.R_to_quat(Rm[0] @ RLB.T); t_wl = Pm[0] + Rm[0] @ (-RLB.T @ TLB)
+    H.vh_set_lps(est, d(q_wl), d(t_wl), float(tk[5] + 0.03))
+    Pk, _, _, Rk, _ = synth.traj(tk[:N - 1])
+    lf = synth._lidar_factors(np.random.default_rng(9), 40, N - 1, Rk, Pk, RLB, TLB)        # scan-to-map factors on the window frames 0..N-2
+    pl7 = np.ascontiguousarray(np.concatenate([lf["plane_p"], lf["plane_n"], lf["plane_d"][:, None]], 1)); ed9 = np.ascontiguousarray(np.concatenate([lf["edge_p"], lf["edge_a"], lf["edge_b"]], 1))
+    H.vh_set_lidar_point_factors(est, len(pl7), d(pl7), lf["plane_kf"].ctypes.data_as(cabi.c_int32_p), len(ed9), d(ed9), lf["edge_kf"].ctypes.data_as(cabi.c_int32_p))
+    for s in range(5):
+        H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][-1]), d(raw["gyr"][-1]))
+    ids, feats = frame_features(w, N - 1)
+    H.vh_process_image(est, len(ids), ids.ctypes.data_as(cabi.c_int32_p), d(feats), float(raw["ts"][-1] + 0.025))
+    assert H.vh_last_status(est) == 0
+    H.vh_get_lidar_info(est, d(info))
+    assert info[6] == 1 and info[7] == 1 and info[8] == 0   # one ICP + one LPS constraint entered the solve, nothing frozen
+    assert info[9] == 30 and info[10] == 10                 # and the 30 plane + 10 edge factors
+    inf = np.zeros(9); H.vh_get_info(est, d(inf))
+    assert np.isfinite(inf[1]) and inf[1] < inf[0]
+    assert H.vh_failure_detection(est) == 0
+    H.vh_estimator_destroy(est)
+
+
+def test_estimator_cpp_zero_velocity_and_reboot(host):
+    """Two identical scans -> constraint_mode 4 (zero velocity): the next optimization() freezes frame WINDOW_SIZE-1 (estimator.cpp:1368-1370).
+    failureDetection() (:1076-1122) trips on an absurd bias and processImage reboots the estimator (:588-597)."""
+    H = _lidar_host(host)
+    N = 8
+    w = synth.make_window(1, 8, N=N, M=60, n_lidar=0, ex_prior=False)
+    raw = w["raw"]; kf = raw["kf"]; tk = raw["ts"][kf]
+    cfg = cabi.default_config(max_kf=N, max_feat=200, max_proj=2000, max_lidar=16)
+    RLB = np.array(list(cfg.rlb)).reshape(3, 3); TLB = np.array(list(cfg.tlb))
+    est = H.vh_estimator_create(C.byref(cfg), N - 1, 4, cabi.VILS_MODE_GN, 1e-3)
+    H.vh_set_parameter(est, d(raw["ric"].reshape(-1)), d(raw["tic"]), w["td"])
+    H.vh_set_lidar_init_flag(est, 0)
+    pose, sb = w["pose"], w["speedbias"]
+    for k in range(N):
+        H.vh_set_frame_state(est, k, d(pose[k, :3]), d(pose[k, 3:]), d(sb[k, 0:3]), d(sb[k, 3:6]), d(sb[k, 6:9]))
+    H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][0]), d(raw["gyr"][0]))
+    for j in range(N):
+        if j > 0:
+            for s in range(kf[j - 1] + 1, kf[j] + 1):
+                H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][s]), d(raw["gyr"][s]))
+            H.vh_set_frame_state(est, j, d(pose[j, :3]), d(pose[j, 3:]), d(sb[j, 0:3]), d(sb[j, 3:6]), d(sb[j, 6:9]))
+        ids, feats = frame_features(w, j)
+        H.vh_process_image(est, len(ids), ids.ctypes.data_as(cabi.c_int32_p), d(feats), float(tk[j]))
+    assert H.vh_last_status(est) == 0
+    stamps = np.zeros(N); H.vh_get_header_stamps(est, d(stamps))
+    # a stationary platform as far as the states go: identical poses and zero velocity on frames 2..6 of the (full, slid) window, identical scans
+    for k in (2, 3, 4, 5, 6):
+        H.vh_set_frame_state(est, k, d(pose[2, :3]), d(pose[2, 3:]), d(np.zeros(3)), d(sb[k, 3:6]), d(sb[k, 6:9]))
+    rng = np.random.default_rng(3)
+    scan = synth.room_scan(rng, 9000)
+    c8 = np.zeros((len(scan), 8), np.float32); c8[:, :3] = scan[:, :3]; c8[:, 4] = np.floor(scan[:, 3]) + 0.05
+    info = np.zeros(13)
+    for t_mid in (stamps[2] + 0.04, stamps[4] + 0.04):
+        c = c8.copy()
+        assert H.vh_process_lidar(est, c.ctypes.data_as(cabi.c_float_p), len(c), 8, float(t_mid), 0.0) == 0
+    H.vh_get_lidar_info(est, d(info))
+    assert info[2] == 4 and info[3] == 1                    # zero velocity
+    for s in range(5):
+        H.vh_process_imu(est, synth.IMU_DT, d(raw["acc"][-1]), d(raw["gyr"][-1]))
+    ids, feats = frame_features(w, N - 1)
+    H.vh_process_image(est, len(ids), ids.ctypes.data_as(cabi.c_int32_p), d(feats), float(raw["ts"][-1] + 0.025))
+    assert H.vh_last_status(est) == 0
+    H.vh_get_lidar_info(est, d(info))
+    assert info[8] == 1                                     # frame WINDOW_SIZE-1 held constant in that solve
+    # reboot: an absurd accelerometer bias on the newest frame
+    big = np.array([3.0, 0.0, 0.0])
+    H.vh_set_frame_state(est, N - 1, d(pose[N - 1, :3]), d(pose[N - 1, 3:]), d(sb[N - 1, 0:3]), d(big), d(sb[N - 1, 6:9]))
+    assert H.vh_failure_detection(est) == 1
+    H.vh_estimator_destroy(est)
+
+
+def test_voxel_filter_matches_its_definition(host):
+    """ApproximateVoxelGrid restatement: every output point is the float centroid of consecutive input points falling in one 0.3 m voxel; the
+    output never has more points than the input, each input point contributes to exactly one centroid (mass conservation)."""
+    H = _lidar_host(host)
+    rng = np.random.default_rng(0)
+    pts = synth.room_scan(rng, 6000)
+    out = np.zeros_like(pts); n_out = C.c_int32()
+    H.vh_voxel_filter(pts.ctypes.data_as(cabi.c_float_p), len(pts), 4, 0.3, out.ctypes.data_as(cabi.c_float_p), C.cast(C.byref(n_out), cabi.c_int32_p))
+    m = n_out.value
+    assert 0 < m < len(pts)
+    # replay in numpy
+    inv = np.float32(1.0) / np.float32(0.3)
+    hist = {}
+    ref = []
+    for p in pts:
+        ix, iy, iz = (int(np.floor(p[0] * inv)), int(np.floor(p[1] * inv)), int(np.floor(p[2] * inv)))
+        h = (ix * 7171 + iy * 3079 + iz * 4231) & 511
+        e = hist.get(h)
+        if e is not None and e[0] != (ix, iy, iz):
+            ref.append(e[1] / np.float32(e[2])); e = None
+        if e is None:
+            e = [(ix, iy, iz), np.zeros(4, np.float32), 0]
+        e[1] = e[1] + p; e[2] += 1; hist[h] = e
+    for h in sorted(hist):
+        ref.append(hist[h][1] / np.float32(hist[h][2]))
+    ref = np.array(ref, np.float32)
+    assert len(ref) == m
+    np.testing.assert_allclose(out[:m], ref, rtol=1e-6, atol=1e-6)
