@@ -49,8 +49,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"])
     # C++ host mirror of the reference's class API (Estimator / FeatureTracker), plain g++ on top of the C-ABI
-    host = os.path.join(CSRC, "host", "vils_host.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_OUT, host, "-L" + HERE, "-lvils_b200", "-Wl,-rpath,$ORIGIN"])
+    host = [os.path.join(CSRC, "host", f) for f in ("vils_host.cpp", "vils_initial.cpp")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DVILS_HOST_HAS_INITIAL", "-o", HOST_OUT] + host + ["-L" + HERE, "-lvils_b200", "-Wl,-rpath,$ORIGIN"])
     return OUT
 
 

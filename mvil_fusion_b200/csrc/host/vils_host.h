@@ -96,6 +96,9 @@ class Estimator {
   int last_n_icp = 0, last_n_lps = 0, last_n_fixed = 0, last_n_plane = 0, last_n_edge = 0;
   double last_P[3] = {0, 0, 0}, last_P0[3] = {0, 0, 0}, last_Q[4] = {0, 0, 0, 1}, last_Q0[4] = {0, 0, 0, 1};
   double initial_timestamp = 0;
+  double G_DIRECTION[3] = {0, 0, 0};                           // parameters.cpp:33: start value of the gravity direction in Estimate_vel_g_s_tic
+  int device() const { return cfg_.device; }
+  const vils_config& config() const { return cfg_; }
 
   // ---- public state, reference names (estimator.h:67-121) ----
   int WINDOW_SIZE;
@@ -130,6 +133,7 @@ class Estimator {
 
   vils_config cfg_;
   vils_ba* ba_ = nullptr;
+  vils_frontend* init_fe_ = nullptr;                         // RANSAC fundamental matrix of relativePose (created on first use)
   bool first_imu_ = false;
   double acc_0_[3] = {0, 0, 0}, gyr_0_[3] = {0, 0, 0};
   // raw IMU samples per interval (dt_buf / linear_acceleration_buf / angular_velocity_buf, estimator.h:99-101); the

@@ -289,7 +289,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   const int slot = P.slot0 + blockIdx.x;
   const Win W = decode(P, slot);
   const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
-  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  // Scratch (landmark partials, E, pair blocks, IMU products, for large windows H / Hv / tile inverses) lives in a slot owned by the SM, not
+  // by the window: one CTA is resident per SM, so n_sm slots are rewritten over and over and stay in L2 instead of streaming
+  // (windows x 0.6 MB) of write-backs to HBM.  Everything in it is rebuilt by this kernel (prep_window below).
+  unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  double* scr = P.tscratch ? P.tscratch + (size_t)smid * P.sl.total : P.scratch + (size_t)slot * P.sl.total;
   double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
   double* Hv = SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg);
   double* xs = sm + L.xs; double* xc = sm + L.xc;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
   const long long t_start = P.time_cap_ns > 0 ? global_ns() : 0;
-  if (P.do_prep) prep_window(P, W, scr, sm + L.uni);     // vils_ba_solve: no separate prep launch in the upload -> solve chain
+  if (P.do_prep || P.tscratch) prep_window(P, W, scr, sm + L.uni);     // IMU sqrt_info, prior A / b0, zero pattern of E: into the scratch slot this CTA uses
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
   { uint16_t* tb = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tb[k] = g_imu_tbl[k]; }
@@ -882,7 +886,7 @@ __global__ void eval_cons_kernel(EvalParams Q) {
 // =================================================================================================================
 // host
 // =================================================================================================================
-struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; bool on_device = false; int bytes = 0; };
+struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; bool on_device = false; bool prepped = false; int bytes = 0; };
 struct PackPool;
 
 struct vils_ba {
@@ -897,6 +901,8 @@ struct vils_ba {
   uint8_t* h_blob = nullptr; uint8_t* d_blob = nullptr;
   ScratchLayout sl{};
   double* d_scratch = nullptr;
+  double* d_tscratch = nullptr; int n_smid = 0;        // per-SM scratch of solve_kernel (n_smid slots, indexed by %smid)
+  size_t launch_smem = 0;                              // >= half the SM's shared memory: exactly one solve CTA per SM
   int64_t xstride = 0;
   double* d_xout = nullptr; double* h_xout = nullptr;
   vils_summary* d_sum = nullptr; vils_summary* h_sum = nullptr;
@@ -945,13 +951,29 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   }
   P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
   P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr; P.do_prep = 0;
+  P.tscratch = ba->d_tscratch;
   return P;
 }
 
 static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s) {
   const bool both = ba->h_in_smem && ba->hv_in_smem, tr = P.mode != VILS_MODE_GN;
-  if (both) { if (tr) solve_kernel<true, true><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); else solve_kernel<true, false><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); }
-  else { if (tr) solve_kernel<false, true><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); else solve_kernel<false, false><<<n, SOLVE_THREADS, ba->smem_bytes, s>>>(P); }
+  const size_t sm = ba->launch_smem;
+  if (both) { if (tr) solve_kernel<true, true><<<n, SOLVE_THREADS, sm, s>>>(P); else solve_kernel<true, false><<<n, SOLVE_THREADS, sm, s>>>(P); }
+  else { if (tr) solve_kernel<false, true><<<n, SOLVE_THREADS, sm, s>>>(P); else solve_kernel<false, false><<<n, SOLVE_THREADS, sm, s>>>(P); }
+}
+__global__ void nsmid_kernel(int* out) { unsigned n; asm("mov.u32 %0, %%nsmid;" : "=r"(n)); *out = (int)n; }
+// prep_kernel for the slots of [slot0, slot0 + n) whose per-window scratch (IMU sqrt_info, prior A / b0) is not up to date: the evaluate,
+// marginalization and sharded kernels read it, solve_kernel does not write it any more (it works in per-SM scratch).
+static void ensure_prepped(vils_ba* ba, int slot0, int n, cudaStream_t s) {
+  SolveParams P = make_params(ba, nullptr);
+  for (int k = slot0; k < slot0 + n;) {
+    if (ba->meta[k].prepped) { k++; continue; }
+    int e = k; while (e < slot0 + n && !ba->meta[e].prepped) e++;
+    P.slot0 = k;
+    prep_kernel<<<e - k, 256, 0, s>>>(P);
+    for (int q = k; q < e; q++) ba->meta[q].prepped = true;
+    k = e;
+  }
 }
 
 extern "C" {
@@ -1024,6 +1046,11 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_scratch, (size_t)s.total * 8 * max_windows));
+  { int* d_n = nullptr; CK(cudaMalloc(&d_n, sizeof(int))); nsmid_kernel<<<1, 1>>>(d_n); CK(cudaMemcpy(&ba->n_smid, d_n, sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(d_n); }
+  // VILS_SM_SCRATCH=1 (experiment, measured round 2: no change in DRAM traffic — the write-backs are local-memory traffic, not scratch — and 1.7 %
+  // slower because prep runs in every launch): solve_kernel uses a scratch slot per SM instead of per window
+  if (getenv("VILS_SM_SCRATCH") && atoi(getenv("VILS_SM_SCRATCH"))) CK(cudaMalloc(&ba->d_tscratch, (size_t)s.total * 8 * std::max(ba->n_smid, 1)));
+  ba->launch_smem = std::max(ba->smem_bytes, (size_t)dev_smem / 2 + 1024);   // two solve CTAs can never share an SM (and its scratch slot)
   CK(cudaMalloc(&ba->d_xout, (size_t)ba->xstride * 8 * max_windows));
   CK(cudaMallocHost(&ba->h_xout, (size_t)ba->xstride * 8 * max_windows));
   CK(cudaMalloc(&ba->d_sum, sizeof(vils_summary) * max_windows));
@@ -1064,7 +1091,7 @@ void vils_ba_destroy(vils_ba* ba) {
   if (!ba) return;
   cudaSetDevice(ba->cfg.device);
   if (ba->stream) cudaStreamSynchronize(ba->stream);
-  cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
+  cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_tscratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
   cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws); cudaFree(ba->d_shard);
   if (ba->ev0) cudaEventDestroy(ba->ev0);
   if (ba->ev1) cudaEventDestroy(ba->ev1);
@@ -1259,7 +1286,7 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
   if (o > ba->blob_stride) { m.set = false; PFAIL(VILS_ERR_CAPACITY, "vils_ba_set_window: blob overflow"); }   // cannot happen for windows inside the capacities checked above
   h->bytes = (int32_t)o;
   _mm_sfence();                                             // streaming stores visible before the copy engine is pointed at the blob
-  m.set = true; m.on_device = false; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
+  m.set = true; m.on_device = false; m.prepped = false; m.n_kf = N; m.n_feat = M; m.bytes = (int)o;
   m.n_res = 15 * w->n_imu + 2 * np + npl + 3 * ned + 3 * w->n_icp + 3 * w->n_lps + n;
   m.n_jac = (int64_t)450 * w->n_imu + (int64_t)40 * np + 6 * npl + 18 * ned + 72 * w->n_icp + 36 * w->n_lps;
   m.items = w->n_imu + np + npl + ned + w->n_icp + w->n_lps + n;
@@ -1380,7 +1407,7 @@ int vils_ba_upload(vils_ba* ba, int32_t n) {
   VILS_LAUNCH_CHECK("prep_kernel launch");
   e = cudaStreamSynchronize(ba->stream);
   if (e != cudaSuccess) return vils::fail_cuda(e, "upload sync");
-  for (int k = 0; k < n; k++) ba->meta[k].on_device = true;
+  for (int k = 0; k < n; k++) { ba->meta[k].on_device = true; ba->meta[k].prepped = true; }
   return VILS_OK;
 }
 
@@ -1543,6 +1570,7 @@ static int launch_eval(vils_ba* ba, int slot0, int n, int apply_loss) {
   const int xs_doubles = (16 * ba->cfg.max_kf + 8 + ba->cfg.max_feat + 1) & ~1, feat_ints = (ba->cfg.max_feat + 3) & ~3;
   const size_t proj_smem = (size_t)(EVP_T * EV_PLD + 14 * EVP_T + 2 * xs_doubles) * 8 + (size_t)(3 * EVP_T + 2 * feat_ints) * 4;
   static const int minb = getenv("VILS_EV_MINB") ? atoi(getenv("VILS_EV_MINB")) : 3;
+  ensure_prepped(ba, slot0, n, ba->stream);
   cudaEventRecord(ba->ev0, ba->stream);
   int launches = 0;
   // Two streams: the latency-bound IMU warps and then the persistent projection kernel on one, the streaming LiDAR / prior /
@@ -1664,6 +1692,7 @@ int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out*
   }
   MargParams q = ba->mq; q.slot = slot; q.flag = flag;
   SolveParams P = make_params(ba, nullptr);
+  ensure_prepped(ba, slot, 1, ba->stream);
   cudaMemsetAsync(ba->d_miws, 0, sizeof(int32_t) * 8, ba->stream);
   margin_kernel<<<1, SOLVE_THREADS, 16384, ba->stream>>>(P, q);
   VILS_LAUNCH_CHECK("margin_kernel launch");
@@ -1709,6 +1738,7 @@ int vils_ba_sharded_linearize(vils_ba* ba, int32_t iteration, const vils_solve_o
   if (cudaSetDevice(ba->cfg.device) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaSetDevice");
   int st = ensure_shard_buffer(ba); if (st) return st;
   SolveParams P = make_params(ba, opts);
+  ensure_prepped(ba, 0, 1, ba->stream);
   if (iteration == 0) cudaMemsetAsync(ba->d_sum, 0, sizeof(vils_summary), ba->stream);
   cudaEventRecord(ba->ev0, ba->stream);
   if (ba->h_in_smem && ba->hv_in_smem) shard_lin_kernel<true><<<1, SOLVE_THREADS, ba->smem_bytes, ba->stream>>>(P, ba->d_shard, iteration == 0, opts->mu);
@@ -1835,6 +1865,7 @@ int vils_ba_sharded_solve(vils_ba* ba, const vils_solve_opts* opts, vils_summary
   const int D = 15 * ba->meta[0].n_kf + 7, M = ba->meta[0].n_feat;
   const size_t cnt = (size_t)D * D + 2 * (size_t)D + 1;
   cudaStream_t s = ba->stream;
+  ensure_prepped(ba, 0, 1, s);
   cudaMemsetAsync(ba->d_sum, 0, sizeof(vils_summary), s);
   cudaEventRecord(ba->ev0, s);
   cudaError_t le = cudaSuccess; ncclResult_t nr = ncclSuccess;
