@@ -625,7 +625,7 @@ FeatureTracker::FeatureTracker(int rows, int cols, int max_cnt, int device) : ro
 }
 FeatureTracker::~FeatureTracker() { vils_klt_destroy(klt_); vils_frontend_destroy(fe_); }
 bool FeatureTracker::inBorder(float x, float y) const {
-  const int B = 1; const int ix = (int)std::lround(x), iy = (int)std::lround(y);   // BORDER_SIZE = 1, cvRound
+  const int B = 1; const int ix = (int)std::lrint(x), iy = (int)std::lrint(y);   // BORDER_SIZE = 1; cvRound = round half to even (lrint in the default rounding mode)
   return B <= ix && ix < cols_ - B && B <= iy && iy < rows_ - B;
 }
 void FeatureTracker::addPoints(const float* xy, int n) {
@@ -638,19 +638,20 @@ bool FeatureTracker::updateID(unsigned int i) {
 }
 void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
   prev_time = cur_time; cur_time = t;
-  std::vector<uint8_t> forw_img((size_t)rows_ * cols_);                      // compact copy (cv::Mat::step may exceed cols)
-  if (EQUALIZE) {                                                             // cv::createCLAHE(3.0, Size(8, 8))->apply (:87-93)
-    last_status = vils_clahe(fe_, img, stride, 3.0, 8, 8, forw_img.data(), cols_);
-    if (last_status != VILS_OK) return;
-  } else {
-    for (int y = 0; y < rows_; y++) std::memcpy(forw_img.data() + (size_t)y * cols_, img + (size_t)y * stride, cols_);
-  }
+  // The frame is uploaded once; CLAHE (EQUALIZE, cv::createCLAHE(3.0, Size(8, 8))->apply, :87-93), the LK pyramids and the corner detector all
+  // work on the device-resident image, and its pyramid is kept as the next call's cur_img (:160-164): no image ever comes back.
+  last_status = vils_frontend_load(fe_, img, stride, EQUALIZE ? 1 : 0, 3.0, 8, 8);
+  if (last_status != VILS_OK) return;
+  const uint8_t* forw_dev = nullptr; int32_t pitch = 0;
+  last_status = vils_frontend_current(fe_, &forw_dev, &pitch);
+  if (last_status != VILS_OK) return;
   std::vector<std::array<float, 2>> forw_pts;
-  if (has_img_ && !cur_pts.empty()) {
-    const int n = (int)cur_pts.size();
-    std::vector<std::array<float, 2>> forw(n); std::vector<uint8_t> status(n); std::vector<float> err(n);
-    last_status = vils_klt_track(klt_, cur_img_.data(), forw_img.data(), cols_, &cur_pts[0][0], n, &forw[0][0], status.data(), err.data());   // :113
-    if (last_status != VILS_OK) return;
+  const int n0 = (int)cur_pts.size();
+  std::vector<std::array<float, 2>> forw(std::max(n0, 1)); std::vector<uint8_t> status(std::max(n0, 1)); std::vector<float> err(std::max(n0, 1));
+  last_status = vils_klt_advance(klt_, forw_dev, pitch, n0 ? &cur_pts[0][0] : nullptr, n0, &forw[0][0], status.data(), err.data());   // :113
+  if (last_status != VILS_OK) return;
+  if (has_img_ && n0 > 0) {
+    const int n = n0;
     for (int i = 0; i < n; i++) if (status[i] && !inBorder(forw[i][0], forw[i][1])) status[i] = 0;        // :115-117
     prev_pts = cur_pts;
     size_t j = 0;                                                                                          // reduceVector (:21-34)
@@ -674,13 +675,12 @@ void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
     const int n_max_cnt = max_cnt_ - (int)forw_pts.size();                    // :139-151
     if (n_max_cnt > 0) {
       std::vector<float> n_pts(2 * (size_t)n_max_cnt); int32_t nn = 0;
-      last_status = vils_good_features(fe_, forw_img.data(), cols_, n_max_cnt, 0.01, (double)MIN_DIST, 1, n_pts.data(), &nn);
+      last_status = vils_good_features_resident(fe_, n_max_cnt, 0.01, (double)MIN_DIST, 1, n_pts.data(), &nn);
       if (last_status != VILS_OK) return;
       for (int k = 0; k < nn; k++) { forw_pts.push_back({n_pts[2 * k], n_pts[2 * k + 1]}); ids.push_back(-1); track_cnt.push_back(1); }   // addPoints (:71-79)
     }
   }
-  cur_pts = forw_pts;
-  cur_img_.swap(forw_img);                                                   // prev = cur, cur = forw (:160-164)
+  cur_pts = forw_pts;                                                        // prev = cur, cur = forw (:160-164): the images swapped roles on the device
   has_img_ = true;
   undistortedPoints();
 }

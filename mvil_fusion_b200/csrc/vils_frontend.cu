@@ -450,6 +450,7 @@ struct vils_frontend {
   unsigned int cand_cap = 0; int hw_radius = -1;
   bool mask_valid = false;
   float last_ms = 0;
+  const uint8_t* d_cur = nullptr;   // vils_frontend_load: the image this frame's steps work on (d_dst when equalised, d_src otherwise), resident
 };
 
 extern "C" {
@@ -500,6 +501,43 @@ static int fe_upload(vils_frontend* f, const uint8_t* img, int stride, uint8_t* 
   for (int y = 0; y < f->rows; y++) memcpy(f->h_img + (size_t)y * f->cols, img + (size_t)y * stride, f->cols);
   cudaError_t e = cudaMemcpyAsync(dst, f->h_img, (size_t)f->rows * f->cols, cudaMemcpyHostToDevice, f->st);
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "frontend upload");
+}
+
+static void clahe_launch(vils_frontend* f, double clip_limit, int tiles_x, int tiles_y);
+
+// Device-resident form of the first step of readImage (feature_tracker.cpp:87-93): upload the raw image ONCE, equalise it on the device when
+// asked (EQUALIZE), and keep the result there for vils_klt_advance / vils_good_features_resident.  Nothing comes back to the host.
+int vils_frontend_load(vils_frontend* f, const uint8_t* src, int32_t stride, int32_t equalize, double clip_limit, int32_t tiles_x, int32_t tiles_y) {
+  if (!f || !src || stride < f->cols || (equalize && (tiles_x <= 0 || tiles_y <= 0 || tiles_x * tiles_y > 256))) return vils::fail(VILS_ERR_BAD_ARG, "vils_frontend_load: bad argument");
+  cudaSetDevice(f->device);
+  int st = fe_upload(f, src, stride, f->d_src); if (st) return st;
+  cudaEventRecord(f->e0, f->st);
+  if (equalize) clahe_launch(f, clip_limit, tiles_x, tiles_y);
+  const cudaError_t le = cudaGetLastError();
+  cudaEventRecord(f->e1, f->st);
+  const cudaError_t e = cudaStreamSynchronize(f->st);          // the consumers run on other streams (the KLT handle's)
+  if (le != cudaSuccess) return vils::fail_cuda(le, "vils_frontend_load launch");
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_frontend_load");
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  f->d_cur = equalize ? f->d_dst : f->d_src;
+  return VILS_OK;
+}
+int vils_frontend_current(vils_frontend* f, const uint8_t** image_dev, int32_t* pitch_bytes) {
+  if (!f || !image_dev || !pitch_bytes || !f->d_cur) return vils::fail(VILS_ERR_BAD_ARG, "vils_frontend_current: call vils_frontend_load first");
+  *image_dev = f->d_cur; *pitch_bytes = f->cols;
+  return VILS_OK;
+}
+
+static void clahe_launch(vils_frontend* f, double clip_limit, int tiles_x, int tiles_y) {
+  const int rows = f->rows, cols = f->cols;
+  const int ext_w = cols % tiles_x == 0 ? cols : cols + (tiles_x - cols % tiles_x), ext_h = rows % tiles_y == 0 ? rows : rows + (tiles_y - rows % tiles_y);
+  const int tw = ext_w / tiles_x, th = ext_h / tiles_y, area = tw * th;
+  int clip = 0;
+  if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = std::max(clip, 1); }
+  const float lut_scale = (float)255 / area;
+  clahe_lut_kernel<<<tiles_x * tiles_y, 256, 0, f->st>>>(f->d_src, rows, cols, cols, tiles_x, tw, th, clip, lut_scale, f->d_lut);
+  dim3 B(32, 8), G((cols + 31) / 32, (rows + 7) / 8);
+  clahe_apply_kernel<<<G, B, 0, f->st>>>(f->d_src, rows, cols, cols, tiles_x, tiles_y, 1.0f / tw, 1.0f / th, f->d_lut, f->d_dst, cols);
 }
 
 int vils_clahe(vils_frontend* f, const uint8_t* src, int32_t stride, double clip_limit, int32_t tiles_x, int32_t tiles_y, uint8_t* dst, int32_t dst_stride) {
@@ -575,6 +613,8 @@ int vils_get_mask(vils_frontend* f, uint8_t* mask, int32_t stride) {
 
 // cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_distance, mask) with the defaults of the call site (:149): blockSize 3,
 // Sobel 3, min-eigenvalue score.  use_mask: 0 = no mask, 1 = the device mask left by vils_set_mask.
+static int good_features_impl(vils_frontend* f, const uint8_t* d_img, int32_t max_corners, double quality, double min_distance, int32_t use_mask, float* xy_out, int32_t* n_out);
+
 int vils_good_features(vils_frontend* f, const uint8_t* img, int32_t stride, int32_t max_corners, double quality, double min_distance, int32_t use_mask,
                        float* xy_out, int32_t* n_out) {
   if (!f || !img || stride < f->cols || !xy_out || !n_out || quality <= 0 || min_distance < 0 || (use_mask && !f->mask_valid))
@@ -583,12 +623,25 @@ int vils_good_features(vils_frontend* f, const uint8_t* img, int32_t stride, int
   *n_out = 0;
   if (max_corners == 0) return VILS_OK;
   int st = fe_upload(f, img, stride, f->d_src); if (st) return st;
+  f->d_cur = nullptr;                                          // d_src no longer holds the frame loaded by vils_frontend_load
+  return good_features_impl(f, f->d_src, max_corners, quality, min_distance, use_mask, xy_out, n_out);
+}
+// The same on the image vils_frontend_load left on the device (no upload).
+int vils_good_features_resident(vils_frontend* f, int32_t max_corners, double quality, double min_distance, int32_t use_mask, float* xy_out, int32_t* n_out) {
+  if (!f || !f->d_cur || !xy_out || !n_out || quality <= 0 || min_distance < 0 || (use_mask && !f->mask_valid))
+    return vils::fail(VILS_ERR_BAD_ARG, "vils_good_features_resident: bad argument (vils_frontend_load first)");
+  cudaSetDevice(f->device);
+  *n_out = 0;
+  if (max_corners == 0) return VILS_OK;
+  return good_features_impl(f, f->d_cur, max_corners, quality, min_distance, use_mask, xy_out, n_out);
+}
+static int good_features_impl(vils_frontend* f, const uint8_t* d_img, int32_t max_corners, double quality, double min_distance, int32_t use_mask, float* xy_out, int32_t* n_out) {
   const int rows = f->rows, cols = f->cols;
   const uint8_t* mask = use_mask ? f->d_mask : nullptr;
   cudaEventRecord(f->e0, f->st);
   cudaMemsetAsync(f->d_cnt, 0, 4 * sizeof(unsigned int), f->st);
   cudaMemsetAsync(f->d_hist, 0, 4096 * sizeof(unsigned int), f->st);
-  min_eig_kernel<<<dim3((cols + ET_X - 1) / ET_X, (rows + ET_Y - 1) / ET_Y), dim3(ET_X, ET_Y), 0, f->st>>>(f->d_src, rows, cols, cols, f->d_eig);
+  min_eig_kernel<<<dim3((cols + ET_X - 1) / ET_X, (rows + ET_Y - 1) / ET_Y), dim3(ET_X, ET_Y), 0, f->st>>>(d_img, rows, cols, cols, f->d_eig);
   masked_max_kernel<<<148 * 2, 256, 0, f->st>>>(f->d_eig, mask, rows * cols, f->d_cnt + 1);
   candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, f->st>>>(f->d_eig, mask, rows, cols, f->d_cnt + 1, (float)quality, f->d_cand, f->d_cnt,
                                                                                         f->cand_cap, f->d_hist);

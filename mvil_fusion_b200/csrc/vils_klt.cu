@@ -20,6 +20,9 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+#include <utility>
+
 #include "common.h"
 
 namespace {
@@ -186,6 +189,8 @@ struct vils_klt {
   cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
   float last_ms = 0; int n = 0;
   cudaGraphExec_t graph_exec = nullptr; bool graph_failed = false;
+  // device-resident chain (vils_klt_advance): the `next` pyramid of one call is the `prev` pyramid of the following one
+  bool has_next = false; int parity = 0; cudaGraphExec_t graph_adv[2] = {nullptr, nullptr}; bool graph_adv_failed = false;
 };
 
 static void klt_launch_pyramids(vils_klt* k) {
@@ -196,6 +201,19 @@ static void klt_launch_pyramids(vils_klt* k) {
       dim3 G((P.w[l] + B.x - 1) / B.x, (P.h[l] + B.y - 1) / B.y);
       pyrdown_kernel<<<G, B, 0, k->st>>>(P.img[l - 1], P.w[l - 1], P.h[l - 1], P.img[l], P.w[l], P.h[l]);
     }
+  }
+  for (int l = 0; l < k->levels; l++) {
+    dim3 G((k->prev.w[l] + B.x - 1) / B.x, (k->prev.h[l] + B.y - 1) / B.y);
+    scharr_kernel<<<G, B, 0, k->st>>>(k->prev.img[l], k->prev.w[l], k->prev.h[l], k->prev.der[l]);
+  }
+}
+
+// vils_klt_advance: only the NEW image's pyramid is built; the Scharr derivatives are taken on the pyramid inherited from the previous call
+static void klt_launch_advance(vils_klt* k) {
+  dim3 B(32, 8);
+  for (int l = 1; l < k->levels; l++) {
+    dim3 G((k->next.w[l] + B.x - 1) / B.x, (k->next.h[l] + B.y - 1) / B.y);
+    pyrdown_kernel<<<G, B, 0, k->st>>>(k->next.img[l - 1], k->next.w[l - 1], k->next.h[l - 1], k->next.img[l], k->next.w[l], k->next.h[l]);
   }
   for (int l = 0; l < k->levels; l++) {
     dim3 G((k->prev.w[l] + B.x - 1) / B.x, (k->prev.h[l] + B.y - 1) / B.y);
@@ -265,6 +283,7 @@ void vils_klt_destroy(vils_klt* k) {
   cudaSetDevice(k->device);
   if (k->st) cudaStreamSynchronize(k->st);
   if (k->graph_exec) cudaGraphExecDestroy(k->graph_exec);
+  for (int p = 0; p < 2; p++) if (k->graph_adv[p]) cudaGraphExecDestroy(k->graph_adv[p]);
   for (int l = 0; l < MAX_LEVELS; l++) { cudaFree(k->prev.img[l]); cudaFree(k->next.img[l]); cudaFree(k->prev.der[l]); }
   cudaFree(k->d_prev_pts); cudaFree(k->d_next_pts); cudaFree(k->d_status); cudaFree(k->d_err); cudaFreeHost(k->h_stage);
   if (k->e0) cudaEventDestroy(k->e0);
@@ -348,6 +367,58 @@ int vils_klt_track(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32_
     if (err) memcpy(err, h_err, sizeof(float) * n);
     if (status) memcpy(status, h_st, n);
   }
+  return VILS_OK;
+}
+
+// FeatureTracker::readImage keeps forw_img as next call's cur_img (feature_tracker.cpp:160-164): so does the device.  next_dev: the new
+// (equalised) image ALREADY ON THE DEVICE (vils_frontend_current), pitch_bytes apart.  The pyramid built for it by this call is next call's
+// `prev`; only one pyramid is built per frame and no image crosses PCIe here.  The first call only loads the image (n is ignored).
+int vils_klt_advance(vils_klt* k, const uint8_t* next_dev, int32_t pitch_bytes, const float* prev_xy, int32_t n, float* next_xy, uint8_t* status, float* err) {
+  if (!k || !next_dev || pitch_bytes < k->cols || n < 0 || n > k->max_pts || (n && !prev_xy)) return vils::fail(VILS_ERR_BAD_ARG, "vils_klt_advance: bad argument");
+  cudaSetDevice(k->device);
+  const bool track = k->has_next;
+  if (track) { for (int l = 0; l < k->levels; l++) std::swap(k->prev.img[l], k->next.img[l]); k->parity ^= 1; }
+  cudaMemcpy2DAsync(k->next.img[0], k->cols, next_dev, pitch_bytes, k->cols, k->rows, cudaMemcpyDeviceToDevice, k->st);
+  float* hp = reinterpret_cast<float*>(k->h_stage + ((2 * (size_t)k->rows * k->cols + 15) & ~(size_t)15));
+  const int nt = track ? n : 0;
+  if (nt) { memcpy(hp, prev_xy, sizeof(float) * 2 * nt); cudaMemcpyAsync(k->d_prev_pts, hp, sizeof(float) * 2 * nt, cudaMemcpyHostToDevice, k->st); }
+  k->n = nt;
+  cudaEventRecord(k->e0, k->st);
+  // the launch arguments alternate between two pointer sets (the pyramids swap roles every call): one captured graph per parity
+  cudaGraphExec_t& ge = k->graph_adv[k->parity];
+  if (!ge && !k->graph_adv_failed) {
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(k->st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      klt_launch_advance(k);
+      if (cudaStreamEndCapture(k->st, &g) != cudaSuccess || !g || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { ge = nullptr; k->graph_adv_failed = true; }
+      if (g) cudaGraphDestroy(g);
+    } else k->graph_adv_failed = true;
+    cudaGetLastError();
+  }
+  if (ge) cudaGraphLaunch(ge, k->st); else klt_launch_advance(k);
+  if (nt > 0) {
+    TrackParams T; T.prev = k->prev; T.next = k->next; T.prev_pts = k->d_prev_pts; T.next_pts = k->d_next_pts; T.status = k->d_status; T.err = k->d_err;
+    T.n = nt; T.levels = k->levels; T.win = k->win; T.min_eig = 1e-4f; T.max_iter = 30; T.eps2 = 0.01 * 0.01;
+    track_kernel<<<nt, TRACK_THREADS, 0, k->st>>>(T);
+  }
+  const cudaError_t le = cudaGetLastError();
+  cudaEventRecord(k->e1, k->st);
+  float* h_err = hp + 2 * (size_t)k->max_pts; uint8_t* h_st = reinterpret_cast<uint8_t*>(h_err + k->max_pts);
+  if (nt) {
+    cudaMemcpyAsync(hp, k->d_next_pts, sizeof(float) * 2 * nt, cudaMemcpyDeviceToHost, k->st);
+    cudaMemcpyAsync(h_err, k->d_err, sizeof(float) * nt, cudaMemcpyDeviceToHost, k->st);
+    cudaMemcpyAsync(h_st, k->d_status, nt, cudaMemcpyDeviceToHost, k->st);
+  }
+  const cudaError_t e = cudaStreamSynchronize(k->st);
+  if (le != cudaSuccess) return vils::fail_cuda(le, "vils_klt_advance launch");
+  if (e != cudaSuccess) return vils::fail_cuda(e, "vils_klt_advance");
+  cudaEventElapsedTime(&k->last_ms, k->e0, k->e1);
+  k->has_next = true;
+  if (nt) {
+    if (next_xy) memcpy(next_xy, hp, sizeof(float) * 2 * nt);
+    if (err) memcpy(err, h_err, sizeof(float) * nt);
+    if (status) memcpy(status, h_st, nt);
+  } else if (n && status) memset(status, 0, n);              // nothing to track against yet
   return VILS_OK;
 }
 

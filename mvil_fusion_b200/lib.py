@@ -69,6 +69,10 @@ def load():
     L.vils_klt_track_device.argtypes = [vp]
     L.vils_klt_download.argtypes = [vp, fp, up, fp]
     L.vils_klt_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_klt_advance.argtypes = [vp, vp, C.c_int32, fp, C.c_int32, fp, up, fp]
+    L.vils_frontend_load.argtypes = [vp, up, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32]
+    L.vils_frontend_current.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.vils_good_features_resident.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.c_int32, fp, ip]
     L.vils_frontend_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.vils_frontend_destroy.argtypes = [vp]
     L.vils_frontend_destroy.restype = None
@@ -352,8 +356,18 @@ class KLT:
         except Exception:
             pass
 
+    @staticmethod
+    def _rows(img):
+        """u8 image whose rows are contiguous; the row pitch may exceed the width (cv::Mat::step > cols): no copy is made for such views."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1 or img.strides[0] < img.shape[1]:
+            img = np.ascontiguousarray(img, np.uint8)
+        return img
+
     def track(self, prev, nxt, pts):
-        prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
+        prev = self._rows(prev); nxt = self._rows(nxt)
+        if prev.strides[0] != nxt.strides[0]:
+            prev = np.ascontiguousarray(prev); nxt = np.ascontiguousarray(nxt)
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
         n = pts.shape[0]
         out = np.zeros((n, 2), np.float32); status = np.zeros(n, np.uint8); err = np.zeros(n, np.float32)
@@ -361,6 +375,16 @@ class KLT:
         _check(self.L.vils_klt_track(self.h, prev.ctypes.data_as(up), nxt.ctypes.data_as(up), prev.strides[0], pts.ctypes.data_as(fp), n,
                                      out.ctypes.data_as(fp), status.ctypes.data_as(up), err.ctypes.data_as(fp)))
         return out, status, err
+
+    def advance(self, image_dev, pitch, pts):
+        """vils_klt_advance: the new frame is already on the device (Frontend.load / Frontend.current); its pyramid becomes the next call's prev."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = pts.shape[0]
+        out = np.zeros((max(n, 1), 2), np.float32); status = np.zeros(max(n, 1), np.uint8); err = np.zeros(max(n, 1), np.float32)
+        up, fp = cabi.c_uint8_p, cabi.c_float_p
+        _check(self.L.vils_klt_advance(self.h, C.c_void_p(image_dev), int(pitch), pts.ctypes.data_as(fp) if n else None, n, out.ctypes.data_as(fp),
+                                       status.ctypes.data_as(up), err.ctypes.data_as(fp)))
+        return out[:n], status[:n], err[:n]
 
     def upload(self, prev, nxt, pts):
         prev = np.ascontiguousarray(prev, np.uint8); nxt = np.ascontiguousarray(nxt, np.uint8)
@@ -488,6 +512,20 @@ class Frontend:
         img = np.ascontiguousarray(img, np.uint8); out = np.zeros_like(img)
         _check(self.L.vils_clahe(self.h, img.ctypes.data_as(cabi.c_uint8_p), img.strides[0], clip, tiles[0], tiles[1], out.ctypes.data_as(cabi.c_uint8_p), out.strides[0]))
         return out
+
+    def load(self, img, equalize=True, clip=3.0, tiles=(8, 8)):
+        """vils_frontend_load: one upload, CLAHE on the device when asked; returns (device pointer, pitch) of the resident frame."""
+        img = np.ascontiguousarray(img, np.uint8)
+        _check(self.L.vils_frontend_load(self.h, img.ctypes.data_as(cabi.c_uint8_p), img.strides[0], int(equalize), clip, tiles[0], tiles[1]))
+        p = C.c_void_p(); pitch = C.c_int32()
+        _check(self.L.vils_frontend_current(self.h, C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    def good_features_resident(self, max_corners, quality, min_distance, use_mask=False):
+        out = np.zeros((max(max_corners, 1), 2), np.float32); n = C.c_int32()
+        _check(self.L.vils_good_features_resident(self.h, max_corners, quality, min_distance, int(use_mask), out.ctypes.data_as(cabi.c_float_p),
+                                                  C.cast(C.byref(n), cabi.c_int32_p)))
+        return out[:n.value].copy()
 
     def set_mask(self, xy, track_cnt, radius):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); tc = np.ascontiguousarray(track_cnt, np.int32)

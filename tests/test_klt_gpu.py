@@ -57,6 +57,37 @@ def test_klt_border_points_and_empty():
     # strided input (cv::Mat::step > cols)
     big = np.zeros((480, 704), np.uint8); big[:, :640] = img
     big2 = np.zeros((480, 704), np.uint8); big2[:, :640] = nxt
-    out2, st2, _ = k.track(big[:, :640], big2[:, :640], pts) if False else k.track(img, nxt, pts)
-    assert np.array_equal(out2, out)
+    v1, v2 = big[:, :640], big2[:, :640]
+    assert v1.strides[0] == 704 and not v1.flags["C_CONTIGUOUS"]          # the library really sees a 704-byte row pitch
+    out2, st2, _ = k.track(v1, v2, pts)
+    assert np.array_equal(out2, out) and np.array_equal(st2, st)
     k.close()
+
+
+def test_device_resident_chain_equals_pairwise_tracking():
+    """vils_frontend_load -> vils_klt_advance (the frame never leaves the device, the pyramid of frame k is reused as `prev` for frame k + 1) gives
+    bit-identical tracks to the stateless pairwise call on the same equalised images, over a 4-frame sequence, and the resident corner detector
+    returns the same corners as the host-buffer one."""
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(11)
+    base = cv2.GaussianBlur(rng.uniform(0, 255, (480, 640)).astype(np.float32), (0, 0), 2.0)
+    base = cv2.normalize(base, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    frames = []
+    for k in range(4):
+        M = cv2.getRotationMatrix2D((320, 240), 0.4 * k, 1.0); M[:, 2] += (3.1 * k, -2.2 * k)
+        frames.append(cv2.warpAffine(base, M, (640, 480), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101))
+    f = lib.Frontend(480, 640, 512); k1 = lib.KLT(480, 640, 512, 21, 3); k2 = lib.KLT(480, 640, 512, 21, 3)
+    eq = [f.clahe(im) for im in frames]                                         # what the pairwise path sees (downloaded CLAHE output)
+    dev, pitch = f.load(frames[0], True)
+    k1.advance(dev, pitch, np.zeros((0, 2), np.float32))                       # first frame: load only
+    pts = f.good_features_resident(150, 0.01, 30.0)
+    assert np.array_equal(pts, f.good_features(eq[0], 150, 0.01, 30.0))
+    assert len(pts) > 100
+    for k in range(1, 4):
+        dev, pitch = f.load(frames[k], True)
+        out, st, err = k1.advance(dev, pitch, pts)
+        ref, st_ref, err_ref = k2.track(eq[k - 1], eq[k], pts)
+        assert np.array_equal(st, st_ref) and np.array_equal(out, ref) and np.array_equal(err, err_ref)
+        pts = out[st == 1]
+        assert len(pts) > 80
+    f.close(); k1.close(); k2.close()
