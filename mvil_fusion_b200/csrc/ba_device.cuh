@@ -65,7 +65,7 @@ struct SolveParams {
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device
-  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, rot, scc, ddc, gc, stp, craw, scl, total;
+  int xs, xc, g, dx, hd, fx, pid, gv, hdv, cinv, glam, red, linv, hv, uni, imu, tbl, rot, scc, ddc, gc, stp, craw, scl, hdr, ptab, lmst, lmft, total;
   int ntile_rows;
 };
 
@@ -83,6 +83,9 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   // raw landmark diagonal C and landmark Jacobi scale
   s.scc = take(nb * TB); s.ddc = take(nb * TB); s.gc = take(nb * TB); s.stp = take(nb * TB); s.craw = take(Mcap); s.scl = take(Mcap);
   s.red = take(64 + SOLVE_WARPS * 2);
+  // shared-memory copies of the window header and of the small index tables every phase walks (pair list, landmark CSR, landmark -> feature):
+  // dependent loads of these from global memory were the critical path of the pair-accumulate and landmark phases
+  s.hdr = take((int)((sizeof(WinHdr) + 7) / 8)); s.ptab = take(2 * (Ncap * (Ncap - 1) / 2) + 2); s.lmst = take(Mcap / 2 + 2); s.lmft = take(Mcap / 2 + 2);
   s.tbl = take(114);                                         // IMU Jacobian assembly table (450 x uint16)
   s.rot = take((Ncap + 1) * 9);                              // rotation matrices of the keyframes + ric (pair pass)
   s.linv = h_in_smem ? take(nb * TB * TB) : -1;             // large windows keep the tile inverses in the L2 scratch
@@ -113,6 +116,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct Win {   // decoded blob
   const uint8_t* base; const WinHdr* h;
   int N, M, D, Dv, Dvp, nb;
+  const int32_t* pairs_s = nullptr; const int32_t* lmst_s = nullptr; const int32_t* lmft_s = nullptr;   // shared-memory copies (stage_tables), else the blob's
+  __device__ const int32_t* pairs() const { return pairs_s ? pairs_s : i(OFF_PAIR); }
+  __device__ const int32_t* lm_start() const { return lmst_s ? lmst_s : i(OFF_LM_START); }
+  __device__ const int32_t* lm_feat() const { return lmft_s ? lmft_s : i(OFF_LM_FEAT); }
   __device__ const double* d(int which) const { return reinterpret_cast<const double*>(base + h->off[which]); }
   __device__ const int32_t* i(int which) const { return reinterpret_cast<const int32_t*>(base + h->off[which]); }
   __device__ const uint8_t* u(int which) const { return base + h->off[which]; }
@@ -122,6 +129,21 @@ __device__ __forceinline__ Win decode(const SolveParams& P, int slot) {
   Win W; W.base = P.blobs + (size_t)slot * P.blob_stride; W.h = reinterpret_cast<const WinHdr*>(W.base);
   W.N = W.h->n_kf; W.M = W.h->n_feat; W.D = 15 * W.N + 7; W.Dv = 6 * W.N + 7; W.Dvp = P.sl.Dv_pad; W.nb = (W.D + TB - 1) / TB;
   return W;
+}
+
+// Header + index tables -> shared memory; W then reads them from there.  All threads; ends with a block barrier.
+__device__ __forceinline__ void stage_tables(Win& W, const Smem& L, double* sm) {
+  int32_t* hs = reinterpret_cast<int32_t*>(sm + L.hdr); int32_t* ps = reinterpret_cast<int32_t*>(sm + L.ptab);
+  int32_t* ls = reinterpret_cast<int32_t*>(sm + L.lmst); int32_t* lf = reinterpret_cast<int32_t*>(sm + L.lmft);
+  const int32_t* hg = reinterpret_cast<const int32_t*>(W.h);
+  const int npair = W.h->n_pair, nlm = W.h->n_lm;
+  const int32_t* pg = W.i(OFF_PAIR); const int32_t* lsg = W.i(OFF_LM_START); const int32_t* lfg = W.i(OFF_LM_FEAT);
+  for (int k = threadIdx.x; k < (int)(sizeof(WinHdr) / 4); k += blockDim.x) hs[k] = hg[k];
+  for (int k = threadIdx.x; k < 4 * npair; k += blockDim.x) ps[k] = pg[k];
+  for (int k = threadIdx.x; k <= nlm; k += blockDim.x) ls[k] = lsg[k];
+  for (int k = threadIdx.x; k < nlm; k += blockDim.x) lf[k] = lfg[k];
+  __syncthreads();
+  W.h = reinterpret_cast<const WinHdr*>(hs); W.pairs_s = ps; W.lmst_s = ls; W.lmft_s = lf;
 }
 
 __device__ __forceinline__ int vis2cam(int v, int N) { return v < 6 * N ? 15 * (v / 6) + v % 6 : 15 * N + (v - 6 * N); }
@@ -147,7 +169,7 @@ __device__ double proj_cost(const SolveParams& P, const Win& W, const double* x,
 #pragma unroll
   for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
   const int i = ix[f], j = ix[np + f], rank = ix[2 * np + f];
-  const int feat = W.i(OFF_LM_FEAT)[rank];
+  const int feat = W.lm_feat()[rank];
   double r[2];
   vf::proj_eval(P.cfg, c, x + XP(i), x + XP(j), x + XE(W.N), x[XL(W.N) + feat], x[XT(W.N)], r, nullptr);
   double rho, w; vf::cauchy(P.cfg.cauchy_a, r[0] * r[0] + r[1] * r[1], rho, w);
@@ -333,8 +355,8 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int np = W.h->n_proj, npair = W.h->n_pair;
   const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
-  const int32_t* pairs = W.i(OFF_PAIR); const int32_t* perm = W.i(OFF_PAIR_PERM);
-  const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const int32_t* pairs = W.pairs(); const int32_t* perm = W.i(OFF_PAIR_PERM);
+  const int32_t* lm_feat = W.lm_feat();
   const uint8_t* dfix = W.u(OFF_FIXED);
   double* part = scr + P.sl.part; double* E = scr + P.sl.E; double* pairpart = scr + P.sl.pairpart;
   const int ra = 5 * (lane >> 3), cb = 3 * (lane & 7);
@@ -457,7 +479,7 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
 // stored scale.  With a scale the damping diagonal is clamp(C s^2, 1e-6, 1e32) / s^2 and the raw C is kept in craw.
 __device__ void landmark_reduce(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu, int jac_mode = 0, double* craw = nullptr, double* scl = nullptr) {
   const int nlm = W.h->n_lm, np = W.h->n_proj;
-  const int32_t* lm_start = W.i(OFF_LM_START); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  const int32_t* lm_start = W.lm_start(); const int32_t* ix = W.i(OFF_PROJ_IDX);
   const double* part = scr + P.sl.part; double* E = scr + P.sl.E;
   for (int rnk = threadIdx.x; rnk < nlm; rnk += blockDim.x) {
     double s[15];

@@ -220,7 +220,7 @@ __device__ void damp_and_fix(const Win& W, double* H, double* g, const double* h
 __device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, double* sm, const double* scr, const double* xin, double* xout) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* dx = sm + L.dx; const double* cinv = sm + L.cinv; const double* glam = sm + L.glam;
-  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.lm_feat();
   const int X = 16 * W.N + 8 + W.M;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
   __syncthreads();
@@ -250,7 +250,7 @@ __device__ double apply_step_dogleg(const SolveParams& P, const Win& W, const Sm
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* y = sm + L.dx; const double* stp = sm + L.stp; const double* cinv = sm + L.cinv; const double* glam = sm + L.glam;
   const double* craw = sm + L.craw; const double* scl = sm + L.scl;
-  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.i(OFF_LM_FEAT);
+  const double* E = scr + P.sl.E; const int32_t* lm_feat = W.lm_feat();
   const int X = 16 * W.N + 8 + W.M;
   double n2 = 0;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   __shared__ int chol_flag;
   __shared__ int time_flag;
   const int slot = P.slot0 + blockIdx.x;
-  const Win W = decode(P, slot);
+  Win W = decode(P, slot);
   const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
+  stage_tables(W, L, sm);
   // Scratch (landmark partials, E, pair blocks, IMU products, for large windows H / Hv / tile inverses) lives in a slot owned by the SM, not
   // by the window: one CTA is resident per SM, so n_sm slots are rewritten over and over and stay in L2 instead of streaming
   // (windows x 0.6 MB) of write-backs to HBM.  Everything in it is rebuilt by this kernel (prep_window below).
@@ -1485,6 +1486,9 @@ static int solve_pipeline(vils_ba* ba, int32_t n, const vils_window* ws, const v
     cudaStream_t s = ba->pipe[c % NS];
     size_t width = 0; for (int k = c0; k < c0 + cn; k++) width = std::max(width, (size_t)ba->meta[k].bytes);
     h2d += width * cn;
+    // pitched copy of the USED part of every blob.  (One contiguous copy of the chunk, slack included, was measured: 25 % more bytes made the
+    // pre-packed pipeline 48 % slower, 6.0 -> 8.9 ms per 592 windows: the pipeline is bound by the solve kernel and by host memory traffic, not by
+    // the PCIe rate of a single copy.)
     cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
                       cudaMemcpyHostToDevice, s);
     P.slot0 = c0; P.do_prep = 1;

@@ -11,8 +11,14 @@
 
 #include <vector>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.h"
 
+#ifndef VILS_DESKEW_TMA_DEFAULT
+#define VILS_DESKEW_TMA_DEFAULT 0
+#endif
 namespace {
 
 struct DeskewParams { float qx, qy, qz, qw, tx, ty, tz, time_factor; double min_r, max_r; };
@@ -58,6 +64,60 @@ __global__ void deskew_kernel8(float4* __restrict__ pts, int n, DeskewParams P) 
   float4 a = pts[2 * i], b = pts[2 * i + 1];
   deskew_point(P, a.x, a.y, a.z, b.x);
   pts[2 * i] = a; pts[2 * i + 1] = b;
+}
+// ---- TMA variant (sm_90+ bulk async copies, mbarrier completion): persistent CTAs stream 8 KB tiles (256 PCL points) HBM -> shared memory with
+// cp.async.bulk, de-skew them in place in shared memory and hand them back with a bulk shared -> global store.  DK_STAGES tiles are in flight per CTA,
+// so the copy engine always has loads queued while the threads compute; no thread issues a global load or store itself.
+constexpr int DK_TILE = 256, DK_STAGES = 4;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__global__ void __launch_bounds__(DK_TILE) deskew_kernel8_tma(float4* __restrict__ pts, int n, DeskewParams P) {
+  __shared__ __align__(128) float4 tile[DK_STAGES][2 * DK_TILE];
+  __shared__ __align__(8) uint64_t full[DK_STAGES];
+  const int tid = threadIdx.x, G = gridDim.x;
+  const int ntiles = (n + DK_TILE - 1) / DK_TILE;
+  if (tid == 0) { for (int s = 0; s < DK_STAGES; s++) mbar_init(&full[s], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  auto issue = [&](int it) {   // thread 0: load of this CTA's it-th tile into stage it % DK_STAGES
+    const int t = blockIdx.x + it * G;
+    if (t >= ntiles) return;
+    const int cnt = min(DK_TILE, n - t * DK_TILE); const uint32_t bytes = (uint32_t)cnt * 32u;
+    mbar_expect_tx(&full[it % DK_STAGES], bytes);
+    tma_load_1d(tile[it % DK_STAGES], pts + (size_t)2 * t * DK_TILE, bytes, &full[it % DK_STAGES]);
+  };
+  if (tid == 0) for (int it = 0; it < DK_STAGES - 1; it++) issue(it);
+  for (int it = 0;; it++) {
+    const int t = blockIdx.x + it * G;
+    if (t >= ntiles) break;
+    const int s = it % DK_STAGES;
+    if (tid == 0) {
+      // stage (it - 1) % DK_STAGES was handed to the store engine in the previous iteration: it may be refilled once that store has READ it
+      if (it >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue(it + DK_STAGES - 1);
+    }
+    mbar_wait(&full[s], (uint32_t)((it / DK_STAGES) & 1));
+    const int cnt = min(DK_TILE, n - t * DK_TILE);
+    if (tid < cnt) {
+      float4 a = tile[s][2 * tid], b = tile[s][2 * tid + 1];
+      deskew_point(P, a.x, a.y, a.z, b.x);
+      tile[s][2 * tid] = a; tile[s][2 * tid + 1] = b;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) tma_store_1d(pts + (size_t)2 * t * DK_TILE, tile[s], (uint32_t)cnt * 32u);
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __global__ void deskew_kernel_generic(float* __restrict__ pts, int n, int stride, DeskewParams P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +165,15 @@ struct LidarDev { float* d = nullptr; int n = 0, stride = 0, device = 0; cudaStr
 int run_deskew(float* d, int n, int stride, const DeskewParams& P, cudaStream_t st) {
   if (n == 0) return VILS_OK;
   const int T = 256, B = (n + T - 1) / T;
-  if (stride == 8 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) deskew_kernel8<<<B, T, 0, st>>>(reinterpret_cast<float4*>(d), n, P);
+  // VILS_DESKEW_TMA: 1 = bulk-async (TMA) tile pipeline, 0 = one point per thread with 16-byte loads / stores.  Measured on B200 (round 2,
+  // profiles/r2_deskew_tma.txt) — the default is the faster of the two at LiDAR-scan sizes.
+  static const int use_tma = getenv("VILS_DESKEW_TMA") ? atoi(getenv("VILS_DESKEW_TMA")) : VILS_DESKEW_TMA_DEFAULT;
+  if (stride == 8 && (reinterpret_cast<uintptr_t>(d) & 15) == 0 && use_tma && n >= 4 * DK_TILE) {
+    static int n_sm = 0; if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    static const int gm = getenv("VILS_DESKEW_TMA_GRID") ? atoi(getenv("VILS_DESKEW_TMA_GRID")) : 4;
+    const int tiles = (n + DK_TILE - 1) / DK_TILE, grid = std::min(tiles, n_sm * gm);
+    deskew_kernel8_tma<<<grid, DK_TILE, 0, st>>>(reinterpret_cast<float4*>(d), n, P);
+  } else if (stride == 8 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) deskew_kernel8<<<B, T, 0, st>>>(reinterpret_cast<float4*>(d), n, P);
   else deskew_kernel_generic<<<B, T, 0, st>>>(d, n, stride, P);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "deskew launch");
