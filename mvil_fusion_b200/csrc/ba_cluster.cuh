@@ -1,0 +1,399 @@
+// ba_cluster.cuh — ONE window solved by a thread-block cluster (sm_90+ / sm_100a): the latency form of the Gauss-Newton solve.
+//
+// solve_kernel gives one SM to a window, which is the right shape for hundreds of windows but leaves 147 SMs idle when the estimator
+// solves the ONE window a new frame produces (Estimator::optimization(), the drop-in case).  Here the G CTAs of a cluster (G = 2, 4 or 8
+// SMs, co-scheduled by hardware, synchronised by barrier.cluster) split every phase whose work items are independent:
+//   F  factor pass      keyframe pairs p = r, r+G, ... with their projection factors (evaluation + pair-local A^T A), IMU factors k = r, r+G, ...
+//                       (both stages), LiDAR factors of keyframes k = r, r+G, ... (6x6 blocks into a small buffer);
+//   L  landmarks        rank = r, r+G, ...: reduction of the factor partials, then the Schur SYRK over THOSE landmarks: a partial Hv per CTA;
+//   G  gather           entries t = r, r+G, ... of the visual sub-system: sum of the G partial Hv + pair blocks -> H;
+//   C  solve            CTA 0: IMU / LiDAR / ICP / LPS / prior contributions, damping, blocked Cholesky, back-substitution (the serial chain);
+//   U  update           every CTA applies dx to its own copy of the camera state (identical arithmetic), rank-strided landmarks are updated by
+//                       their owner and exchanged.
+// All exchange goes through the window's L2-resident scratch (a cluster shares nothing but L2 and DSMEM; the partial systems are a few tens of
+// KB); ordering = __threadfence + barrier.cluster.arrive.release / wait.acquire.  Results agree with solve_kernel to rounding (the partial
+// sums are associated differently), every accumulator still has exactly one owner: bit-reproducible run to run.
+#pragma once
+#include "ba_device.cuh"
+
+__device__ void warp_imu_sqrt_info(const double* cov, double* W, double* wk);   // vils_ba.cu
+
+namespace vb {
+
+constexpr int CL_MAX = 8;            // portable cluster size limit
+
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// full cluster barrier that also orders the global-memory traffic of the phase before it
+__device__ __forceinline__ void cluster_sync_all() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// prep_window split over the cluster: IMU sqrt_info factor by factor, prior A = J^T J / b0 entry-strided, zero pattern of E row-strided
+__device__ void prep_window_cluster(const SolveParams& P, const Win& W, double* scr, double* work, int r, int G) {
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const double* pre = W.d(OFF_IMU);
+  for (int k = r + G * warp; k < W.h->n_imu; k += G * nwarp) ::warp_imu_sqrt_info(pre + (size_t)k * 467 + 242, scr + P.sl.w_imu + (size_t)k * 225, work + warp * 450);
+  const int n = W.h->prior_n;
+  const double* J = W.d(OFF_PRIOR_J); const double* rl = W.d(OFF_PRIOR_R);
+  for (int e = r + G * threadIdx.x; e < n * n + n; e += G * blockDim.x) {
+    if (e < n * n) {
+      const int a = e / n, b = e % n; double s = 0;
+      for (int i = 0; i < n; i++) s = fma(J[(size_t)a * n + i], J[(size_t)b * n + i], s);
+      scr[P.sl.priorA + e] = s;
+    } else {
+      const int a = e - n * n; double s = 0;
+      for (int i = 0; i < n; i++) s = fma(J[(size_t)a * n + i], rl[i], s);
+      scr[P.sl.priorb0 + a] = s;
+    }
+  }
+  for (int64_t e = r + G * (int64_t)threadIdx.x; e < (int64_t)W.h->n_lm * P.sl.Dv_pad; e += G * blockDim.x) scr[P.sl.E + e] = 0.0;
+  if (r == 0) for (int e = threadIdx.x; e < PAIR_LD * PAIR_LD; e += blockDim.x) scr[P.sl.pairpart + (int64_t)(P.Ncap * (P.Ncap - 1) / 2) * PAIR_LD * PAIR_LD + e] = 0.0;
+  __syncthreads();
+}
+
+struct ClScratch { int64_t hvpart, gvpart, lidblk, gsc, hdsc, dxg, lamg, costp, flagg, total; };   // offsets (doubles) into a cluster's exchange area
+
+// ---- F: projection factors of the pairs owned by CTA r + IMU factors k = r (mod G) on the warps past PAIR_WARPS --------------------------
+__device__ double pair_pass_cluster(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, bool need_cost, double* imu_stage,
+                                    int imu_slots, const uint16_t* tbl, double* rot, int* own, int r, int G) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int np = W.h->n_proj, npair = W.h->n_pair;
+  const double* c0 = W.d(OFF_PROJ); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  const int32_t* pairs = W.pairs(); const int32_t* perm = W.i(OFF_PAIR_PERM);
+  const int32_t* lm_feat = W.lm_feat();
+  const uint8_t* dfix = W.u(OFF_FIXED);
+  double* part = scr + P.sl.part; double* E = scr + P.sl.E; double* pairpart = scr + P.sl.pairpart;
+  const int ra = 5 * (lane >> 3), cb = 3 * (lane & 7);
+  double cost = 0;
+  for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
+    const vm::m3 R = vm::q2R(vm::ldq((k < W.N ? x + XP(k) : x + XE(W.N)) + 3));
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) rot[9 * k + 3 * a + b] = R.m[a][b];
+  }
+  // own[0] = number of own pairs, own[1 + q] = prefix of factor counts over the own pairs (q-th own pair = pair r + q G)
+  if (threadIdx.x == 0) {
+    int nq = 0, acc = 0; own[1] = 0;
+    for (int p = r; p < npair; p += G) { acc += pairs[4 * p + 1]; nq++; own[1 + nq] = acc; }
+    own[0] = nq;
+  }
+  __syncthreads();
+  const int nq = own[0], own_np = own[1 + nq];
+  const int nimu = imu_stage ? W.h->n_imu : 0;
+  // own IMU factors: both stages by one warp each, while the other warps evaluate the first round of projection factors
+  if (warp >= PAIR_WARPS && warp - PAIR_WARPS < imu_slots) {
+    int j = 0;
+    for (int k = r; k < nimu; k += G, j++) {
+      if (j % imu_slots != warp - PAIR_WARPS) continue;
+      double* slot = imu_stage + (size_t)(j % imu_slots) * IMU_SLOT2;
+      imu_stage_R(P, W, tbl, x, k, slot);
+      cost += imu_stage_P(P, W, k, slot, scr);
+    }
+  }
+  for (int base = 0; base < own_np || base == 0; base += PAIR_CHUNK) {
+    const int cnt_round = max(0, min(PAIR_CHUNK, own_np - base));
+    const int t = threadIdx.x;
+    if (t < cnt_round) {
+      const int u = base + t;
+      int q = 0; while (own[2 + q] <= u) q++;
+      const int p = r + q * G;
+      const int f = perm[pairs[4 * p] + (u - own[1 + q])];
+      double c[14];
+#pragma unroll
+      for (int k = 0; k < 14; k++) c[k] = c0[(size_t)k * np + f];
+      const int kfi = ix[f], kfj = ix[np + f], rank = ix[2 * np + f];
+      const int feat = lm_feat[rank];
+      double* row0 = stage + (2 * t) * STAGE_LD; double* row1 = row0 + STAGE_LD;
+      double rr[2], J[40];
+      vf::proj_eval_rows(P.cfg, c, vf::ldm(rot + 9 * kfi), vf::ldm(rot + 9 * kfj), vf::ldm(rot + 9 * W.N), vm::ld3(x + XP(kfi)), vm::ld3(x + XP(kfj)), vm::ld3(x + XE(W.N)),
+                         x[XL(W.N) + feat], x[XT(W.N)], rr, J);
+      double rho, w; const double s2 = rr[0] * rr[0] + rr[1] * rr[1];
+      if (need_cost) vf::cauchy(P.cfg.cauchy_a, s2, rho, w); else { w = vf::cauchy_w(P.cfg.cauchy_a, s2); rho = s2; }
+      cost += 0.5 * rho;
+      rr[0] *= w; rr[1] *= w;
+#pragma unroll
+      for (int k = 0; k < 40; k++) J[k] *= w;
+      const bool fixed = dfix[feat] != 0;
+      const double jl0 = fixed ? 0.0 : J[18], jl1 = fixed ? 0.0 : J[38];
+#pragma unroll
+      for (int k = 0; k < 18; k++) { row0[k] = J[k]; row1[k] = J[20 + k]; }
+      row0[18] = J[19]; row0[19] = rr[0]; row1[18] = J[39]; row1[19] = rr[1];
+#pragma unroll
+      for (int k = 20; k < STAGE_LD; k++) { row0[k] = 0; row1[k] = 0; }
+      double* pt = part + (size_t)f * PART_LD;
+      pt[0] = jl0 * jl0 + jl1 * jl1;
+      pt[1] = jl0 * rr[0] + jl1 * rr[1];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        pt[2 + k] = J[k] * jl0 + J[20 + k] * jl1;
+        pt[8 + k] = J[12 + k] * jl0 + J[32 + k] * jl1;
+        E[(size_t)rank * W.Dvp + 6 * kfj + k] = J[6 + k] * jl0 + J[26 + k] * jl1;
+      }
+      pt[14] = J[19] * jl0 + J[39] * jl1;
+    }
+    __syncthreads();
+    for (int q = warp; q < nq; q += SOLVE_WARPS) {
+      const int start = own[1 + q], cnt = own[2 + q] - own[1 + q];
+      if (start >= base + cnt_round || start + cnt <= base) continue;
+      const int s0 = max(start, base), s1 = min(start + cnt, base + cnt_round);
+      double acc[5][3];
+#pragma unroll
+      for (int a = 0; a < 5; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) acc[a][b] = 0;
+      const double* sp = stage + (size_t)(2 * (s0 - base)) * STAGE_LD;
+#pragma unroll 4
+      for (int row = 0; row < 2 * (s1 - s0); row++, sp += STAGE_LD) {
+        double av[5], bv[3];
+#pragma unroll
+        for (int a = 0; a < 5; a++) av[a] = sp[ra + a];
+#pragma unroll
+        for (int b = 0; b < 3; b++) bv[b] = sp[cb + b];
+#pragma unroll
+        for (int a = 0; a < 5; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+      }
+      double* out = pairpart + (size_t)(r + q * G) * PAIR_LD * PAIR_LD;
+      const bool first = s0 == start;
+#pragma unroll
+      for (int a = 0; a < 5; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+          if (cb + b < PAIR_LD) { double* o = out + (ra + a) * PAIR_LD + cb + b; *o = first ? acc[a][b] : *o + acc[a][b]; }
+    }
+    __syncthreads();
+    if (own_np == 0) break;
+  }
+  return cost;
+}
+
+// LiDAR plane + edge factors of the keyframes k = r (mod G): [lower 6x6 (21) | g (6)] per keyframe into blk (global), no access to H
+__device__ double lidar_pass_cluster(const SolveParams& P, const Win& W, const double* x, double* blk, bool want_J, int r, int G) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npl = W.h->n_plane, ned = W.h->n_edge;
+  const double* pl = W.d(OFF_PLANE); const double* ed = W.d(OFF_EDGE);
+  const int32_t* pls = W.i(OFF_PLANE_START); const int32_t* eds = W.i(OFF_EDGE_START);
+  double cost = 0;
+  int j = 0;
+  for (int k = r; k < W.N; k += G, j++) {
+    if (j % SOLVE_WARPS != warp) continue;
+    const double* pose = x + XP(k);
+    double A[21], gg[6];
+#pragma unroll
+    for (int e = 0; e < 21; e++) A[e] = 0;
+#pragma unroll
+    for (int e = 0; e < 6; e++) gg[e] = 0;
+    if (npl) for (int f = pls[k] + lane; f < pls[k + 1]; f += 32) {
+      const vm::v3 pb = vm::mk(pl[f], pl[(size_t)npl + f], pl[(size_t)2 * npl + f]);
+      const vm::v3 n = vm::mk(pl[(size_t)3 * npl + f], pl[(size_t)4 * npl + f], pl[(size_t)5 * npl + f]);
+      double J[6];
+      double rs = vf::plane_eval(pose, pb, n, pl[(size_t)6 * npl + f], want_J ? J : nullptr);
+      double rho, w; vf::huber(P.cfg.huber_a, rs * rs, rho, w);
+      cost += 0.5 * rho;
+      if (want_J) {
+        rs *= w;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) { J[a] *= w; }
+#pragma unroll
+        for (int a = 0; a < 6; a++) { gg[a] = fma(J[a], rs, gg[a]);
+#pragma unroll
+          for (int b = 0; b <= a; b++) { A[e] = fma(J[a], J[b], A[e]); e++; } }
+      }
+    }
+    if (ned) for (int f = eds[k] + lane; f < eds[k + 1]; f += 32) {
+      const vm::v3 pb = vm::mk(ed[f], ed[(size_t)ned + f], ed[(size_t)2 * ned + f]);
+      const vm::v3 a_ = vm::mk(ed[(size_t)3 * ned + f], ed[(size_t)4 * ned + f], ed[(size_t)5 * ned + f]);
+      const vm::v3 b_ = vm::mk(ed[(size_t)6 * ned + f], ed[(size_t)7 * ned + f], ed[(size_t)8 * ned + f]);
+      double rs[3], J[18];
+      vf::edge_eval(pose, pb, a_, b_, rs, want_J ? J : nullptr);
+      double rho, w; vf::huber(P.cfg.huber_a, rs[0] * rs[0] + rs[1] * rs[1] + rs[2] * rs[2], rho, w);
+      cost += 0.5 * rho;
+      if (want_J) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double rm = rs[m] * w;
+          int e = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) { const double ja = J[m * 6 + a] * w; gg[a] = fma(ja, rm, gg[a]);
+#pragma unroll
+            for (int b = 0; b <= a; b++) { A[e] = fma(ja, J[m * 6 + b] * w, A[e]); e++; } }
+        }
+      }
+    }
+    if (want_J) {
+#pragma unroll
+      for (int e = 0; e < 21; e++) A[e] = warp_sum(A[e]);
+#pragma unroll
+      for (int e = 0; e < 6; e++) gg[e] = warp_sum(gg[e]);
+      if (lane == 0) {
+        double* o = blk + (size_t)k * 28;
+#pragma unroll
+        for (int e = 0; e < 21; e++) o[e] = A[e];
+#pragma unroll
+        for (int e = 0; e < 6; e++) o[21 + e] = gg[e];
+      }
+    }
+  }
+  return cost;
+}
+
+// CTA 0: H += the LiDAR blocks the cluster left in blk
+__device__ void lidar_add(const Win& W, double* H, double* g, double* hd, const double* blk) {
+  for (int t = threadIdx.x; t < W.N * 27; t += blockDim.x) {
+    const int k = t / 27, e = t % 27; const double v = blk[(size_t)k * 28 + e];
+    if (e < 21) {
+      int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while (a * (a + 1) / 2 > e) a--;
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      const int b = e - a * (a + 1) / 2;
+      H[tidx(15 * k + a, 15 * k + b)] += v; if (a == b) hd[15 * k + a] += v;
+    } else g[15 * k + e - 21] += v;
+  }
+}
+
+// ---- L: landmarks rank = r (mod G) ------------------------------------------------------------------------------------------------------
+__device__ void landmark_reduce_cluster(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu, int r, int G) {
+  const int nlm = W.h->n_lm;
+  const int32_t* lm_start = W.lm_start(); const int32_t* ix = W.i(OFF_PROJ_IDX);
+  const double* part = scr + P.sl.part; double* E = scr + P.sl.E;
+  for (int rnk = r + G * threadIdx.x; rnk < nlm; rnk += G * blockDim.x) {
+    double s[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) s[k] = 0;
+    const int f0 = lm_start[rnk], f1 = lm_start[rnk + 1];
+    for (int f = f0; f < f1; f++) {
+      const double* pt = part + (size_t)f * PART_LD;
+#pragma unroll
+      for (int k = 0; k < 15; k++) s[k] += pt[k];
+    }
+    const int kfi = ix[f0];
+    double* e = E + (size_t)rnk * W.Dvp;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { e[6 * kfi + k] = s[2 + k]; e[6 * W.N + k] = s[8 + k]; }
+    e[6 * W.N + 6] = s[14];
+    const double C = s[0];
+    if (C > 0.0) { cinv[rnk] = 1.0 / (C + mu * fmin(fmax(C, 1e-6), 1e32)); glam[rnk] = s[1]; }
+    else { cinv[rnk] = 0.0; glam[rnk] = 0.0; }
+  }
+}
+
+// partial Hv(lower) = -sum over OWN landmarks cinv e e^T, partial gv; written to the cluster's exchange area (global)
+__device__ void schur_syrk_cluster(const SolveParams& P, const Win& W, const double* cinv, const double* glam, double* Hv_out, double* gv_out,
+                                   double* chunk, const double* scr, int chunk_cap, int r, int G) {
+  const int Dv = W.Dv, Dvp = W.Dvp, nlm = W.h->n_lm;
+  const int n_own = nlm > r ? (nlm - r + G - 1) / G : 0;
+  const int ECH = max(1, min(chunk_cap / Dvp, max(n_own, 1)));
+  const int nt = (Dv + 2) / 3;
+  const int ntiles = nt * (nt + 1) / 2;
+  const double* E = scr + P.sl.E;
+  for (int tbase = 0; tbase < ntiles; tbase += blockDim.x) {
+    int ti = -1, tj = 0;
+    double acc[3][3], gacc[3];
+    const int t = tbase + threadIdx.x;
+    if (t < ntiles) {
+      ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while (ti * (ti + 1) / 2 > t) ti--;
+      while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+      tj = t - ti * (ti + 1) / 2;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) { gacc[a] = 0;
+#pragma unroll
+      for (int b = 0; b < 3; b++) acc[a][b] = 0; }
+    for (int j0 = 0; j0 < n_own; j0 += ECH) {
+      const int n = min(ECH, n_own - j0);
+      __syncthreads();
+      for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) { const int j = k / Dvp, c = k - j * Dvp; chunk[k] = E[(size_t)(r + G * (j0 + j)) * Dvp + c]; }
+      __syncthreads();
+      if (ti >= 0) {
+        for (int j = 0; j < n; j++) {
+          const int rnk = r + G * (j0 + j);
+          const double ci = cinv[rnk];
+          const double* e = chunk + j * Dvp;
+          double av[3], bv[3];
+#pragma unroll
+          for (int a = 0; a < 3; a++) { const int ia = 3 * ti + a; av[a] = ia < Dv ? e[ia] : 0.0; }
+#pragma unroll
+          for (int b = 0; b < 3; b++) { const int ib = 3 * tj + b; bv[b] = ib < Dv ? e[ib] * ci : 0.0; }
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+          if (tj == 0) {
+            const double gl = glam[rnk] * ci;
+#pragma unroll
+            for (int a = 0; a < 3; a++) gacc[a] = fma(av[a], gl, gacc[a]);
+          }
+        }
+      }
+    }
+    if (ti >= 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int ia = 3 * ti + a;
+        if (ia >= Dv) continue;
+#pragma unroll
+        for (int b = 0; b < 3; b++) { const int ib = 3 * tj + b; if (ib < Dv && ib <= ia) Hv_out[ia * Dvp + ib] = -acc[a][b]; }
+        if (tj == 0) gv_out[ia] = -gacc[a];
+      }
+    }
+  }
+}
+
+// ---- G: entries t = r (mod G): sum of the G partial Hv / gv + pair blocks -> H (global tiles), g and hd (global, camera-indexed) ---------
+__device__ void gather_cluster(const SolveParams& P, const Win& W, const double* hvpart, const double* gvpart, double* H, double* gsc, double* hdsc,
+                               const double* scr, const int* pid, int zblk, int r, int G) {
+  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp;
+  const double* pp = scr + P.sl.pairpart;
+  const int total = Dv * (Dv + 1) / 2 + Dv;
+  const size_t hvs = (size_t)Dvp * Dvp;
+  for (int t = r + G * threadIdx.x; t < total; t += G * blockDim.x) {
+    int a, b; bool grad = false;
+    if (t < Dv) { a = t; b = t; grad = true; }
+    else {
+      const int u = t - Dv;
+      a = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+      while (a * (a + 1) / 2 > u) a--;
+      while ((a + 1) * (a + 2) / 2 <= u) a++;
+      b = u - a * (a + 1) / 2;
+    }
+    const int p = a < 6 * N ? a / 6 : N + (a - 6 * N) / 6;
+    const int q = b < 6 * N ? b / 6 : N + (b - 6 * N) / 6;
+    const int ao = a < 6 * N ? a % 6 : (a - 6 * N) % 6, bo = b < 6 * N ? b % 6 : (b - 6 * N) % 6;
+    const int la_sh = (p == N) ? 12 + ao : 18;
+    const int lb_sh = (q == N) ? 12 + bo : 18;
+    double s0 = 0, s1 = 0, g0 = 0, g1 = 0, d0 = 0, d1 = 0;
+    if (p < N && q < N && p > q) {
+      const int pr = pid[q * N + p];
+      s0 = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (6 + ao) * PAIR_LD + bo];
+    } else if (q < N) {
+      const int la_anchor = (p < N) ? ao : la_sh, la_obs = (p < N) ? 6 + ao : la_sh;
+#pragma unroll 4
+      for (int j = 0; j < N; j++) {
+        const int pa = j > q ? pid[q * N + j] : -1, po = j < q ? pid[j * N + q] : -1;
+        const double* ba = pp + (size_t)(pa < 0 ? zblk : pa) * (PAIR_LD * PAIR_LD);
+        const double* bo2 = pp + (size_t)(po < 0 ? zblk : po) * (PAIR_LD * PAIR_LD);
+        if (grad) { g0 += ba[la_anchor * PAIR_LD + 19]; d0 += ba[la_anchor * PAIR_LD + la_anchor]; g1 += bo2[la_obs * PAIR_LD + 19]; d1 += bo2[la_obs * PAIR_LD + la_obs]; }
+        else { s0 += ba[la_anchor * PAIR_LD + bo]; s1 += bo2[la_obs * PAIR_LD + 6 + bo]; }
+      }
+    } else {
+#pragma unroll 4
+      for (int pr = 0; pr < W.h->n_pair; pr++) {
+        const double* blk = pp + (size_t)pr * (PAIR_LD * PAIR_LD);
+        if (grad) { g0 += blk[la_sh * PAIR_LD + 19]; d0 += blk[la_sh * PAIR_LD + la_sh]; }
+        else s0 += blk[la_sh * PAIR_LD + lb_sh];
+      }
+    }
+    const int ca = vis2cam(a, N), cbm = vis2cam(b, N);
+    if (grad) { double gvs = 0; for (int c = 0; c < G; c++) gvs += gvpart[(size_t)c * Dvp + a]; gsc[ca] = gvs + (g0 + g1); hdsc[ca] = d0 + d1; }
+    else { double hvsum = 0; for (int c = 0; c < G; c++) hvsum += hvpart[(size_t)c * hvs + a * Dvp + b]; H[tidx(ca, cbm)] = hvsum + (s0 + s1); }
+  }
+}
+
+}  // namespace vb

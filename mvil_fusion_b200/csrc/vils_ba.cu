@@ -15,12 +15,14 @@
 #include <thread>
 #include <vector>
 
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <immintrin.h>
 #include <nccl.h>
 
 #include "ba_device.cuh"
 #include "common.h"
+#include "ba_cluster.cuh"
 #include "margin_device.cuh"
 
 using namespace vb;
@@ -539,6 +541,166 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   }
 }
 
+// ---- latency form: one window per thread-block CLUSTER (ba_cluster.cuh) ---------------------------------------------------------------------
+// SMEM_H: the tile-packed H lives in the shared memory of CTA 0 and the other CTAs of the cluster write their share of the gather straight into it
+// through distributed shared memory (mapa / st.shared::cluster); otherwise (large windows) H sits in the window's L2 scratch.
+template <bool SMEM_H>
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolveParams P, ClScratch C, double* clbuf, int imu_slots) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int chol_flag;
+  __shared__ int own[2 + 32 * 31 / 2];
+  const int G = (int)cluster_size(), r = (int)cluster_rank();
+  const int win = blockIdx.x / G, slot = P.slot0 + win;
+  Win W = decode(P, slot);
+  const Smem L = smem_layout(P.Ncap, P.Mcap, SMEM_H ? 1 : 0, 0);   // the partial Hv always goes through the exchange area (L2)
+  stage_tables(W, L, sm);
+  double* scr = P.scratch + (size_t)slot * P.sl.total;
+  double* cx = clbuf + (size_t)slot * C.total;            // indexed by slot: chunks of one pipelined call run concurrently
+  double* hvpart = cx + C.hvpart; double* gvpart = cx + C.gvpart; double* lidblk = cx + C.lidblk; double* gsc = cx + C.gsc; double* hdsc = cx + C.hdsc;
+  double* dxg = cx + C.dxg; double* lamg = cx + C.lamg; double* costp = cx + C.costp; double* flagg = cx + C.flagg;
+  double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;        // CTA 0's copy is the one that is factored
+  double* Hdst = H;                                        // where the gather writes: CTA 0's shared memory (DSMEM) or the scratch
+  if (SMEM_H) Hdst = cooperative_groups::this_cluster().map_shared_rank(sm + L.uni, 0);
+  double* linv = SMEM_H ? sm + L.linv : scr + P.sl.linvg;
+  double* xs = sm + L.xs; double* xc = sm + L.xc;
+  int* fx = reinterpret_cast<int*>(sm + L.fx);
+  int* pid_s = reinterpret_cast<int*>(sm + L.pid);
+  const uint16_t* tb = reinterpret_cast<const uint16_t*>(sm + L.tbl);
+  const int X = 16 * W.N + 8 + W.M, Dp = W.nb * TB;
+  const double* x0 = W.d(OFF_X);
+  prep_window_cluster(P, W, scr, sm + L.uni, r, G);
+  for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
+  { const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
+  { uint16_t* tw = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tw[k] = g_imu_tbl[k]; }
+  double nf = 0;
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) { const bool f = cam_dim_fixed(P, W, d); fx[d] = f; if (f && d < W.D) nf += 1.0; }
+  if (threadIdx.x == 0) chol_flag = 0;
+  const int nfix = (int)block_sum(nf, sm + L.red);
+  for (int k = r + G * threadIdx.x; k < W.M; k += G * blockDim.x) lamg[k] = x0[XL(W.N) + k];
+  cluster_sync_all();
+
+  int status = VILS_OK, iters = 0;
+  double cost0 = 0, cost = 0;
+  const int zblk = P.Ncap * (P.Ncap - 1) / 2;
+  long long ct_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+#define CLPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - ct_; ct_ = n_; } } while (0)
+  for (int it = 0; it < P.max_iters; it++) {
+    CLPROF(11);
+    // zero this CTA's share of H / g / hd (filled by the gather after the next two barriers)
+    if (!SMEM_H) for (int e = r + G * threadIdx.x; e < tri(W.nb) * TSZ; e += G * blockDim.x) H[e] = 0.0;
+    for (int e = r + G * threadIdx.x; e < Dp; e += G * blockDim.x) { gsc[e] = 0.0; hdsc[e] = 0.0; }
+    // F: own pairs / IMU factors / LiDAR keyframes
+    double c = pair_pass_cluster(P, W, xs, sm + L.uni, scr, it == 0, sm + L.imu, imu_slots, tb, sm + L.rot, own, r, G);
+    c += lidar_pass_cluster(P, W, xs, lidblk, true, r, G);
+    if (it == 0) { c = block_sum(c, sm + L.red); if (threadIdx.x == 0) costp[r] = c; }
+    __syncthreads(); CLPROF(0);
+    cluster_sync_all();
+    CLPROF(1);
+    // L: own landmarks -> partial Schur complement
+    landmark_reduce_cluster(P, W, sm + L.cinv, sm + L.glam, scr, P.mu, r, G);
+    __syncthreads();
+    schur_syrk_cluster(P, W, sm + L.cinv, sm + L.glam, hvpart + (size_t)r * W.Dvp * W.Dvp, gvpart + (size_t)r * W.Dvp, sm + L.uni, scr, L.imu - L.uni, r, G);
+    __syncthreads();
+    if (SMEM_H && r == 0) for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;   // the staging union is free now: H of CTA 0 starts from zero
+    __syncthreads(); CLPROF(2);
+    cluster_sync_all();
+    CLPROF(3);
+    // G
+    gather_cluster(P, W, hvpart, gvpart, Hdst, gsc, hdsc, scr, pid_s, zblk, r, G);
+    __syncthreads(); CLPROF(4);
+    cluster_sync_all();
+    CLPROF(5);
+    // C: the serial chain on CTA 0
+    if (r == 0) {
+      for (int e = threadIdx.x; e < Dp; e += blockDim.x) { sm[L.g + e] = gsc[e]; sm[L.hd + e] = hdsc[e]; }
+      __syncthreads();
+      imu_add(P, W, H, sm + L.g, sm + L.hd, scr);
+      lidar_add(W, H, sm + L.g, sm + L.hd, lidblk);
+      __syncthreads();
+      double c2 = icp_lps_pass(P, W, xs, H, sm + L.g, sm + L.hd, sm + L.imu, true);
+      c2 += prior_pass(P, W, xs, H, sm + L.g, sm + L.hd, sm + L.dx, scr, true);
+      __syncthreads();
+      if (it == 0) { c2 = block_sum(c2, sm + L.red); for (int q = 0; q < G; q++) c2 += costp[q]; cost0 = c2; cost = c2; }
+      damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, P.mu);
+      if (threadIdx.x == 0) chol_flag = 0;
+      __syncthreads();
+      CLPROF(6);
+      cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+      CLPROF(7);
+      int st = VILS_OK;
+      if (chol_flag) st = VILS_ERR_CHOLESKY;
+      else if (it == 0 && !isfinite(cost0)) st = VILS_ERR_NOT_FINITE;
+      else backsub_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, sm + L.red + 32);
+      __syncthreads();
+      for (int e = threadIdx.x; e < Dp; e += blockDim.x) dxg[e] = sm[L.dx + e];
+      if (threadIdx.x == 0) flagg[0] = (double)st;
+      CLPROF(8);
+    }
+    cluster_sync_all();
+    CLPROF(9);
+    // U
+    const int st = (int)flagg[0];
+    if (st != VILS_OK) { status = st; break; }
+    for (int e = threadIdx.x; e < Dp; e += blockDim.x) sm[L.dx + e] = dxg[e];
+    for (int k = threadIdx.x; k < X; k += blockDim.x) xc[k] = xs[k];
+    __syncthreads();
+    {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const double* E = scr + P.sl.E; const int32_t* lm_feat = W.lm_feat();
+      int j = 0;
+      for (int rnk = r; rnk < W.h->n_lm; rnk += G, j++) {
+        if (j % SOLVE_WARPS != warp) continue;
+        double s = 0;
+        for (int a = lane; a < W.Dv; a += 32) s = fma(E[(size_t)rnk * W.Dvp + a], sm[L.dx + vis2cam(a, W.N)], s);
+        s = warp_sum(s);
+        if (lane == 0) { const int feat = lm_feat[rnk]; const double v = xc[XL(W.N) + feat] + -sm[L.cinv + rnk] * (sm[L.glam + rnk] + s); lamg[feat] = v; }
+      }
+      for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
+        if (k < W.N) {
+          vm::pose_plus(xc + XP(k), sm + L.dx + 15 * k);
+          for (int i = 0; i < 9; i++) xc[XS(W.N, k) + i] += sm[L.dx + 15 * k + 6 + i];
+        } else {
+          vm::pose_plus(xc + XE(W.N), sm + L.dx + 15 * W.N);
+          xc[XT(W.N)] += sm[L.dx + 15 * W.N + 6];
+        }
+      }
+    }
+    cluster_sync_all();
+    for (int k = threadIdx.x; k < W.M; k += blockDim.x) xc[XL(W.N) + k] = lamg[k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = xc[k];
+    __syncthreads();
+    CLPROF(10);
+    iters++;
+  }
+#undef CLPROF
+  // final cost, split like the factor pass
+  if (status == VILS_OK && P.max_iters > 0) {
+    double c = 0;
+    for (int f = r + G * threadIdx.x; f < W.h->n_proj; f += G * blockDim.x) c += proj_cost(P, W, xs, f);
+    c += lidar_pass_cluster(P, W, xs, lidblk, false, r, G);
+    if (r == 0) {
+      c += imu_pass(P, W, xs, nullptr, nullptr, nullptr, sm + L.imu, scr, false, false);
+      __syncthreads();
+      c += icp_lps_pass(P, W, xs, nullptr, nullptr, nullptr, sm + L.imu, false);
+      c += prior_pass(P, W, xs, nullptr, nullptr, nullptr, sm + L.g, scr, false);
+      __syncthreads();
+    }
+    c = block_sum(c, sm + L.red);
+    if (threadIdx.x == 0) costp[r] = c;
+    cluster_sync_all();
+    if (r == 0) { cost = 0; for (int q = 0; q < G; q++) cost += costp[q]; if (!isfinite(cost)) status = VILS_ERR_NOT_FINITE; }
+  }
+  if (r == 0) {
+    double* xo = P.xout + (size_t)slot * P.xout_stride;
+    for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xs[k];
+    if (threadIdx.x == 0) {
+      vils_summary s; s.status = status; s.iterations = iters; s.accepted = iters; s.reserved = 0; s.cost_initial = cost0; s.cost_final = cost;
+      P.summary[slot] = s;
+    }
+  }
+}
+
 // ---- factor-sharded mode (one window over several GPUs) ------------------------------------------------
 // shard_lin_kernel: linearise THIS rank's factors at the device-resident state, leave [H (D x D) | g | hd | cost] in `buf`
 // for the caller's all-reduce.  shard_upd_kernel: reduced buffer -> damping, Cholesky, back-substitution (identical on every
@@ -911,10 +1073,11 @@ struct vils_ba {
   double* d_er = nullptr; double* d_eJ = nullptr; int64_t er_stride = 0, eJ_stride = 0;
   std::vector<SlotMeta> meta;
   int h_in_smem = 0, hv_in_smem = 0; size_t smem_bytes = 0;
-  float last_ms = 0; int last_launches = 0; size_t last_h2d = 0, last_d2h = 0;
+  float last_ms = 0; int last_launches = 0, last_cluster = 1; size_t last_h2d = 0, last_d2h = 0;
   double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
   PackPool* pool = nullptr;                            // host packer threads (created on first use)
+  ClScratch cl{}; double* d_clbuf = nullptr; int cl_windows = 0, cl_imu_slots = 0; size_t cl_smem = 0; bool cl_smem_h = false; int cluster_pref = 0;   // latency mode (0 auto, 1 off, 2/4/8 forced)
   ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 0;   // factor-sharded mode: one rank per GPU (vils_ba_sharded_init)
   double* d_lamred = nullptr;                          // [lam * own | own] for the final inverse-depth exchange
 };
@@ -932,7 +1095,7 @@ static size_t blob_capacity(const vils_config& c) {
   return (b + 255) & ~size_t(255);
 }
 
-static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s);
+static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s, bool allow_cluster = true);
 extern "C" { static void nccl_comm_destroy(ncclComm_t c); }
 static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   SolveParams P{};
@@ -956,7 +1119,28 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   return P;
 }
 
-static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s) {
+// Cluster size for n windows: as many SMs per window as the device has to spare (8, 4 or 2), 1 = the one-CTA-per-window kernel.
+static int pick_cluster(const vils_ba* ba, const SolveParams& P, int n) {
+  if (P.slot0 + n > ba->cl_windows) return 1;               // the exchange areas cover slots [0, cl_windows)
+  static const bool prof_cluster = getenv("VILS_PROF_CLUSTER") != nullptr;
+  if (P.mode != VILS_MODE_GN || P.lin_out || (P.prof && !prof_cluster) || P.max_iters <= 0 || P.time_cap_ns > 0 || ba->cluster_pref == 1 || n > ba->cl_windows) return 1;
+  if (ba->cluster_pref >= 2) return n * ba->cluster_pref <= ba->n_sm ? std::min(ba->cluster_pref, CL_MAX) : 1;
+  for (int g = CL_MAX; g >= 2; g >>= 1) if (n * g <= ba->n_sm) return g;
+  return 1;
+}
+static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s, bool allow_cluster) {
+  const int G = allow_cluster ? pick_cluster(ba, P, n) : 1;
+  if (G > 1) {   // latency form: one thread-block cluster per window (ba_cluster.cuh)
+    cudaLaunchConfig_t cfg{}; cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(n * G); cfg.blockDim = dim3(SOLVE_THREADS); cfg.dynamicSmemBytes = ba->cl_smem; cfg.stream = s;
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (ba->cl_smem_h) cudaLaunchKernelEx(&cfg, solve_cluster_kernel<true>, P, ba->cl, ba->d_clbuf, ba->cl_imu_slots);
+    else cudaLaunchKernelEx(&cfg, solve_cluster_kernel<false>, P, ba->cl, ba->d_clbuf, ba->cl_imu_slots);
+    ba->last_cluster = G;
+    return;
+  }
+  ba->last_cluster = 1;
   const bool both = ba->h_in_smem && ba->hv_in_smem, tr = P.mode != VILS_MODE_GN;
   const size_t sm = ba->launch_smem;
   if (both) { if (tr) solve_kernel<true, true><<<n, SOLVE_THREADS, sm, s>>>(P); else solve_kernel<true, false><<<n, SOLVE_THREADS, sm, s>>>(P); }
@@ -1031,11 +1215,22 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   if ((size_t)smem_layout(N, M, ba->h_in_smem, 1).total * 8 > plan_budget) { ba->hv_in_smem = 0; }
   ba->smem_bytes = (size_t)smem_layout(N, M, ba->h_in_smem, ba->hv_in_smem).total * 8;
   if (ba->smem_bytes > budget) { delete ba; return vils::fail(VILS_ERR_CAPACITY, "vils_ba_create: window too large for shared memory plan"); }
-  s.Hg = ba->h_in_smem ? 0 : take((int64_t)tri(nb) * TSZ);
+  s.Hg = take((int64_t)tri(nb) * TSZ);                      // also used by the cluster (latency) kernel, which keeps H in L2
   s.Hvg = ba->hv_in_smem ? 0 : take((int64_t)Dvp * Dvp);
-  s.linvg = ba->h_in_smem ? 0 : take((int64_t)nb * TB * TB);
+  s.linvg = take((int64_t)nb * TB * TB);
   s.total = o;
   ba->xstride = 16 * N + 8 + M;
+  {   // exchange area of the cluster (latency) kernel: one per window that can be solved that way at a time
+    ClScratch& c = ba->cl; int64_t q = 0;
+    auto tk = [&](int64_t n) { int64_t r = q; q += (n + 1) & ~int64_t(1); return r; };
+    c.hvpart = tk((int64_t)CL_MAX * Dvp * Dvp); c.gvpart = tk((int64_t)CL_MAX * Dvp); c.lidblk = tk((int64_t)N * 28); c.gsc = tk(nb * TB); c.hdsc = tk(nb * TB);
+    c.dxg = tk(nb * TB); c.lamg = tk(std::max(M, 1)); c.costp = tk(CL_MAX); c.flagg = tk(2); c.total = q;
+    ba->cl_smem_h = (size_t)smem_layout(N, M, 1, 0).total * 8 + 4096 <= budget;     // H of CTA 0 in shared memory when it fits
+    const Smem Lc = smem_layout(N, M, ba->cl_smem_h ? 1 : 0, 0);
+    ba->cl_smem = (size_t)Lc.total * 8;
+    ba->cl_imu_slots = std::min(IMU_IDLE, (((N + 1) / 2) * 466) / IMU_SLOT2);
+    if (const char* e = getenv("VILS_CLUSTER")) ba->cluster_pref = atoi(e);
+  }
   const int64_t n_lin = (int64_t)D * D + D + 1;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, #x); } } while (0)
   CK(cudaStreamCreateWithFlags(&ba->stream, cudaStreamNonBlocking));
@@ -1053,6 +1248,9 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   if (getenv("VILS_SM_SCRATCH") && atoi(getenv("VILS_SM_SCRATCH"))) CK(cudaMalloc(&ba->d_tscratch, (size_t)s.total * 8 * std::max(ba->n_smid, 1)));
   ba->launch_smem = std::max(ba->smem_bytes, (size_t)dev_smem / 2 + 1024);   // two solve CTAs can never share an SM (and its scratch slot)
   CK(cudaMalloc(&ba->d_xout, (size_t)ba->xstride * 8 * max_windows));
+  CK(cudaDeviceGetAttribute(&ba->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+  ba->cl_windows = (ba->cl_smem + 4096 <= budget && ba->cl_imu_slots >= 1) ? std::min(max_windows, std::max(1, ba->n_sm / 2)) : 0;
+  if (ba->cl_windows) CK(cudaMalloc(&ba->d_clbuf, (size_t)ba->cl.total * 8 * ba->cl_windows));
   CK(cudaMallocHost(&ba->h_xout, (size_t)ba->xstride * 8 * max_windows));
   CK(cudaMalloc(&ba->d_sum, sizeof(vils_summary) * max_windows));
   CK(cudaMallocHost(&ba->h_sum, sizeof(vils_summary) * max_windows));
@@ -1077,6 +1275,8 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
       CK(cudaFuncSetAttribute(eval_proj_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
       CK(cudaFuncSetAttribute(eval_proj_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
       CK(cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+      CK(cudaFuncSetAttribute(solve_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));   // 2 KB of static shared memory (pair ownership table)
+      CK(cudaFuncSetAttribute(solve_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
       if (cfg->device < 64) attr_done[cfg->device] = true;
     }
   }
@@ -1092,7 +1292,7 @@ void vils_ba_destroy(vils_ba* ba) {
   if (!ba) return;
   cudaSetDevice(ba->cfg.device);
   if (ba->stream) cudaStreamSynchronize(ba->stream);
-  cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_tscratch); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
+  cudaFreeHost(ba->h_blob); cudaFree(ba->d_blob); cudaFree(ba->d_scratch); cudaFree(ba->d_tscratch); cudaFree(ba->d_clbuf); cudaFree(ba->d_xout); cudaFreeHost(ba->h_xout);
   cudaFree(ba->d_sum); cudaFreeHost(ba->h_sum); cudaFree(ba->d_lin); cudaFreeHost(ba->h_lin); cudaFree(ba->d_er); cudaFree(ba->d_eJ); cudaFree(ba->d_mws); cudaFree(ba->d_miws); cudaFree(ba->d_shard);
   if (ba->ev0) cudaEventDestroy(ba->ev0);
   if (ba->ev1) cudaEventDestroy(ba->ev1);
@@ -1431,6 +1631,14 @@ int vils_ba_solve_device(vils_ba* ba, int32_t n, const vils_solve_opts* opts) {
   if (prof) {
     long long h[24]; cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost); cudaFree(d_prof);
     static const char* names[24] = {"pair_pass", "landmark_reduce", "schur_syrk", "zero+gather", "imu", "lidar", "icp+prior+sum", "damp_fix", "cholesky", "backsub", "apply_step", "final_cost", "  chol:diag(w0)", "  chol:phaseB-wait", "  chol:panel", "  chol:phaseA", "  pair:eval(t0)", "  pair:eval-wait", "  pair:accum(w0)", "  pair:accum-wait", "  imu:loads+core", "  imu:assemble", "  imu:whiten", "  imu:JtJ+store"};
+    if (ba->last_cluster > 1) {
+      static const char* cn[12] = {"F factor pass", "  sync", "L landmarks+schur", "  sync", "G gather", "  sync", "C adds+damp", "C cholesky", "C backsub+dx", "  sync (others wait for C)", "U update+exchange", "zero H"};
+      long long t2 = 0; for (int i = 0; i < 12; i++) t2 += h[i];
+      fprintf(stderr, "[VILS_PROF] cluster of %d, CTA 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", ba->last_cluster, n, ba->last_ms);
+      for (int i = 0; i < 12; i++) fprintf(stderr, "  %-28s %10lld  %5.1f%%\n", cn[i], h[i], 100.0 * h[i] / (t2 ? t2 : 1));
+      ba->last_launches = 1;
+      return VILS_OK;
+    }
     long long tot = 0; for (int i = 0; i < 12; i++) tot += h[i];
     fprintf(stderr, "[VILS_PROF] block 0, %d windows, %.3f ms; SM cycles per phase (sum over iterations):\n", n, ba->last_ms);
     for (int i = 0; i < 24; i++) fprintf(stderr, "  %-16s %10lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
@@ -1492,7 +1700,7 @@ static int solve_pipeline(vils_ba* ba, int32_t n, const vils_window* ws, const v
     cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
                       cudaMemcpyHostToDevice, s);
     P.slot0 = c0; P.do_prep = 1;
-    launch_solve(ba, P, cn, s);
+    launch_solve(ba, P, cn, s, cn == n);               // clusters only when the whole call is one chunk (no concurrent chunk launches)
     if (le == cudaSuccess) le = cudaGetLastError();
     launches += 1;
     cudaMemcpyAsync(ba->h_xout + (size_t)c0 * ba->xstride, ba->d_xout + (size_t)c0 * ba->xstride, (size_t)ba->xstride * 8 * cn, cudaMemcpyDeviceToHost, s);
@@ -1900,6 +2108,12 @@ int vils_ba_sharded_solve(vils_ba* ba, const vils_solve_opts* opts, vils_summary
   if (summary) *summary = ba->h_sum[0];
   return ba->h_sum[0].status;
 }
+
+int vils_ba_set_cluster(vils_ba* ba, int32_t cluster_size) {
+  if (!ba || !(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8)) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_cluster: 0 (auto), 1 (off), 2, 4 or 8");
+  ba->cluster_pref = cluster_size; return VILS_OK;
+}
+int vils_ba_last_cluster(vils_ba* ba, int32_t* cluster_size) { if (!ba || !cluster_size) return VILS_ERR_BAD_ARG; *cluster_size = ba->last_cluster; return VILS_OK; }
 
 int vils_ba_last_device_ms(vils_ba* ba, float* ms) { if (!ba || !ms) return VILS_ERR_BAD_ARG; *ms = ba->last_ms; return VILS_OK; }
 int vils_ba_last_transfer_bytes(vils_ba* ba, size_t* h2d, size_t* d2h) { if (!ba) return VILS_ERR_BAD_ARG; if (h2d) *h2d = ba->last_h2d; if (d2h) *d2h = ba->last_d2h; return VILS_OK; }

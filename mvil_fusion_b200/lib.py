@@ -50,6 +50,8 @@ def load():
     L.vils_ba_linearize.argtypes = [vp, C.c_int32, dp, dp, dp]
     L.vils_ba_marginalize.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(cabi.VilsPriorOut)]
     L.vils_ba_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vils_ba_set_cluster.argtypes = [vp, C.c_int32]
+    L.vils_ba_last_cluster.argtypes = [vp, C.POINTER(C.c_int32)]
     L.vils_ba_last_launches.argtypes = [vp, C.POINTER(C.c_int32)]
     L.vils_ba_last_transfer_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.vils_ba_sharded_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -173,6 +175,16 @@ class BA:
     def put_state(self, slot, pose, sb, ex, lam, td):
         a = [np.ascontiguousarray(v, np.float64) for v in (pose, sb, ex, lam)]
         _check(self.L.vils_ba_put_state(self.h, slot, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]) if a[3].size else None, float(td)))
+
+    def set_cluster(self, size):
+        """Latency mode: 0 auto, 1 off, 2 / 4 / 8 SMs per window (vils_ba_set_cluster)."""
+        _check(self.L.vils_ba_set_cluster(self.h, int(size)))
+
+    @property
+    def last_cluster(self):
+        n = C.c_int32()
+        self.L.vils_ba_last_cluster(self.h, C.byref(n))
+        return n.value
 
     def upload(self, n):
         _check(self.L.vils_ba_upload(self.h, n))
