@@ -219,7 +219,8 @@ def other_configs(lib, device, cores, opts):
         for _ in range(6):
             h.solve_device(B4, opts); ms.append(h.last_ms)
         dev = float(np.mean(ms[2:]))
-        h.solve_device(1, opts); single = h.last_ms
+        h.set_cluster(1); h.solve_device(1, opts); h.solve_device(1, opts); single_one = h.last_ms
+        h.set_cluster(0); h.solve_device(1, opts); h.solve_device(1, opts); single = h.last_ms; single_cluster = h.last_cluster
         for _ in range(2):
             h.solve_windows(batch, opts, arr)
         t0 = time.perf_counter()
@@ -233,7 +234,8 @@ def other_configs(lib, device, cores, opts):
         cpu1 = cpu_solves_generic(ws4, cfg4, opts, 1, 2)
         ach = CFG4_BYTES_PER_SOLVE * B4 / (dev * 1e-3) / 1e9
         rec["config4"] = {"workload": "configs[3]: 20-KF window, 300 feats (3333 proj factors), 5000 LiDAR factors, 3 ICP + 3 LPS, real marginalization prior n=%d, GN x5" % int(ws4[0]["prior_n"]),
-                          "windows": B4, "device_ms": dev, "solves_per_s_device": B4 / dev * 1e3, "single_window_device_ms": single,
+                          "windows": B4, "device_ms": dev, "solves_per_s_device": B4 / dev * 1e3, "single_window_device_ms": single, "single_window_cluster_size": single_cluster,
+                          "single_window_device_ms_one_cta": single_one,
                           "e2e_ms_from_caller_arrays": e2e, "solves_per_s_e2e": B4 / e2e * 1e3, "single_window_e2e_ms": e2e_single,
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_solve": CFG4_BYTES_PER_SOLVE},
                           "cpu_baseline": {"value": cpu, "unit": UNIT, "cores": cores, "kind": "port", "single_thread_value": cpu1},
@@ -274,12 +276,12 @@ def other_configs(lib, device, cores, opts):
         # the readImage chain: raw frame uploaded once, CLAHE + ONE pyramid + LK on the device, previous pyramid reused (vils_frontend_load + vils_klt_advance)
         raw0, raw1 = (np.roll(img, 0, axis=0), nxt)
         k2 = lib.KLT(480, 640, 512, 21, 3, device=device)
-        d0, pitch = f.load(raw0, True); k2.advance(d0, pitch, np.zeros((0, 2), np.float32))
+        d0, pitch = f.load(raw0, True); k2.advance(d0, pitch, np.zeros((0, 2), np.float32), f.ready_event)
         for _ in range(3):
-            d1, pitch = f.load(raw1, True); k2.advance(d1, pitch, pts)
+            d1, pitch = f.load(raw1, True); k2.advance(d1, pitch, pts, f.ready_event)
         t0 = time.perf_counter()
         for i in range(20):
-            d1, pitch = f.load(raw1 if i % 2 == 0 else raw0, True); k2.advance(d1, pitch, pts)
+            d1, pitch = f.load(raw1 if i % 2 == 0 else raw0, True); k2.advance(d1, pitch, pts, f.ready_event)
         chain = 1e3 * (time.perf_counter() - t0) / 20
         k2.close()
         r = {"workload": "configs[2]: pyramidal LK 640x480 mono, %d corners, win 21, 3 pyramid levels above the base" % len(pts), "device_ms": dev,
@@ -407,6 +409,21 @@ def main():
     ev_ms = 0.0
     for _ in range(args.steps):
         ba.evaluate_device(B, True); ev_ms += ba.last_ms
+    # ---- single-window latency (the drop-in case: one optimization() per frame): cluster kernel (latency mode) vs one CTA
+    lat = {}
+    for mode, name in ((1, "one_cta"), (0, "cluster")):
+        ba.set_cluster(mode)
+        ms = []
+        for _ in range(8):
+            ba.solve_device(1, opts); ms.append(ba.last_ms)
+        lat[name + "_device_ms"] = float(np.mean(ms[3:])); lat[name + "_size"] = ba.last_cluster
+        for _ in range(3):
+            ba.solve_windows(batch[:1], opts, warr)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ba.solve_windows(batch[:1], opts, warr)
+        lat[name + "_e2e_ms_from_caller_arrays"] = 1e3 * (time.perf_counter() - t0) / 10
+    ba.set_cluster(0)
     sampler.stop()
     st = ba.get_state(0)
     assert st["status"] == 0, st
@@ -471,6 +488,7 @@ def main():
             "cpu_baseline": {"value": tot / T, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{tot} GN-5 solves of the same config-2 windows by oracle/ (CPU restatement) on {cores} threads",
                              "single_thread_value": v_single},
+            "latency": dict(lat, workload="ONE configs[1] window per call, GN x5; cluster = thread-block cluster per window (vils_ba_set_cluster)"),
             "clocks": sampler.summary(),
             "configs": extra,
         }

@@ -312,8 +312,8 @@ int vils_klt_download(vils_klt* k, float* next_xy, uint8_t* status, float* err);
 /* Device-resident chain (FeatureTracker keeps forw_img as the next call's cur_img, feature_tracker.cpp:160-164): next_dev is the new image
  * ALREADY ON THE DEVICE (vils_frontend_current), pitch_bytes apart.  Its pyramid, built by this call, is the next call's `prev`: one pyramid
  * per frame, no image over PCIe.  The first call only loads the image (status is zeroed). */
-int vils_klt_advance(vils_klt* k, const uint8_t* next_dev, int32_t pitch_bytes, const float* prev_xy, int32_t n, float* next_xy, uint8_t* status,
-                     float* err);
+int vils_klt_advance(vils_klt* k, const uint8_t* next_dev, int32_t pitch_bytes, void* ready_event /* cudaEvent_t of the producer or NULL */,
+                     const float* prev_xy, int32_t n, float* next_xy, uint8_t* status, float* err);
 int vils_klt_last_device_ms(vils_klt* k, float* ms);
 
 /* ---- the rest of FeatureTracker::readImage around the LK call (feature_tracker_/src/feature_tracker.cpp:81-167) ---------------
@@ -325,9 +325,11 @@ void vils_frontend_destroy(vils_frontend* f);
 int vils_clahe(vils_frontend* f, const uint8_t* src, int32_t stride, double clip_limit, int32_t tiles_x, int32_t tiles_y,
                uint8_t* dst, int32_t dst_stride);
 /* Device-resident first step of readImage (:87-93): ONE upload of the raw frame, CLAHE on the device when equalize != 0; the image the rest of
- * the frame works on stays in HBM (vils_frontend_current -> vils_klt_advance, vils_good_features_resident) and never returns to the host. */
+ * the frame works on stays in HBM (vils_frontend_current -> vils_klt_advance, vils_good_features_resident) and never returns to the host.
+ * vils_frontend_load does NOT synchronise: it records an event (returned by vils_frontend_current) that vils_klt_advance waits on in-stream, so
+ * one frame costs one host synchronisation. */
 int vils_frontend_load(vils_frontend* f, const uint8_t* src, int32_t stride, int32_t equalize, double clip_limit, int32_t tiles_x, int32_t tiles_y);
-int vils_frontend_current(vils_frontend* f, const uint8_t** image_dev, int32_t* pitch_bytes);
+int vils_frontend_current(vils_frontend* f, const uint8_t** image_dev, int32_t* pitch_bytes, void** ready_event /* may be NULL */);
 int vils_good_features_resident(vils_frontend* f, int32_t max_corners, double quality, double min_distance, int32_t use_mask, float* xy_out,
                                 int32_t* n_out);
 /* FeatureTracker::setMask (:36-69): visit points in descending track_cnt, keep a point if its pixel is still unmasked, then blank a

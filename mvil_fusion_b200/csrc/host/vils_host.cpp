@@ -642,13 +642,13 @@ void FeatureTracker::readImage(const uint8_t* img, int stride, double t) {
   // work on the device-resident image, and its pyramid is kept as the next call's cur_img (:160-164): no image ever comes back.
   last_status = vils_frontend_load(fe_, img, stride, EQUALIZE ? 1 : 0, 3.0, 8, 8);
   if (last_status != VILS_OK) return;
-  const uint8_t* forw_dev = nullptr; int32_t pitch = 0;
-  last_status = vils_frontend_current(fe_, &forw_dev, &pitch);
+  const uint8_t* forw_dev = nullptr; int32_t pitch = 0; void* ready = nullptr;
+  last_status = vils_frontend_current(fe_, &forw_dev, &pitch, &ready);
   if (last_status != VILS_OK) return;
   std::vector<std::array<float, 2>> forw_pts;
   const int n0 = (int)cur_pts.size();
   std::vector<std::array<float, 2>> forw(std::max(n0, 1)); std::vector<uint8_t> status(std::max(n0, 1)); std::vector<float> err(std::max(n0, 1));
-  last_status = vils_klt_advance(klt_, forw_dev, pitch, n0 ? &cur_pts[0][0] : nullptr, n0, &forw[0][0], status.data(), err.data());   // :113
+  last_status = vils_klt_advance(klt_, forw_dev, pitch, ready, n0 ? &cur_pts[0][0] : nullptr, n0, &forw[0][0], status.data(), err.data());   // :113
   if (last_status != VILS_OK) return;
   if (has_img_ && n0 > 0) {
     const int n = n0;

@@ -450,6 +450,7 @@ struct vils_frontend {
   unsigned int cand_cap = 0; int hw_radius = -1;
   bool mask_valid = false;
   float last_ms = 0;
+  cudaEvent_t ev_ready = nullptr;   // recorded behind the last kernel of vils_frontend_load: consumers on other streams wait on it
   const uint8_t* d_cur = nullptr;   // vils_frontend_load: the image this frame's steps work on (d_dst when equalised, d_src otherwise), resident
 };
 
@@ -489,6 +490,7 @@ void vils_frontend_destroy(vils_frontend* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   if (f->st) cudaStreamSynchronize(f->st);
+  if (f->ev_ready) cudaEventDestroy(f->ev_ready);
   cudaFree(f->d_src); cudaFree(f->d_dst); cudaFree(f->d_mask); cudaFree(f->d_lut); cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_cnt); cudaFree(f->d_hist); cudaFree(f->d_top);
   cudaFree(f->d_centers); cudaFree(f->d_hw); cudaFree(f->d_uv); cudaFree(f->d_ray); cudaFreeHost(f->h_img); cudaFreeHost(f->h_cand); cudaFreeHost(f->h_cnt);
   if (f->e0) cudaEventDestroy(f->e0);
@@ -498,6 +500,7 @@ void vils_frontend_destroy(vils_frontend* f) {
 }
 
 static int fe_upload(vils_frontend* f, const uint8_t* img, int stride, uint8_t* dst) {
+  if (f->ev_ready) cudaEventSynchronize(f->ev_ready);        // the pinned staging image may still be in flight from an unsynchronised vils_frontend_load
   for (int y = 0; y < f->rows; y++) memcpy(f->h_img + (size_t)y * f->cols, img + (size_t)y * stride, f->cols);
   cudaError_t e = cudaMemcpyAsync(dst, f->h_img, (size_t)f->rows * f->cols, cudaMemcpyHostToDevice, f->st);
   return e == cudaSuccess ? VILS_OK : vils::fail_cuda(e, "frontend upload");
@@ -515,16 +518,19 @@ int vils_frontend_load(vils_frontend* f, const uint8_t* src, int32_t stride, int
   if (equalize) clahe_launch(f, clip_limit, tiles_x, tiles_y);
   const cudaError_t le = cudaGetLastError();
   cudaEventRecord(f->e1, f->st);
-  const cudaError_t e = cudaStreamSynchronize(f->st);          // the consumers run on other streams (the KLT handle's)
+  // NOT synchronised: the consumers (the KLT handle's stream, this handle's own later calls) order themselves behind ev_ready, so the upload, the
+  // equalisation, the pyramid and the tracking of one frame run back to back with a single host synchronisation at the end of vils_klt_advance
+  if (!f->ev_ready) cudaEventCreateWithFlags(&f->ev_ready, cudaEventDisableTiming);
+  const cudaError_t e = cudaEventRecord(f->ev_ready, f->st);
   if (le != cudaSuccess) return vils::fail_cuda(le, "vils_frontend_load launch");
   if (e != cudaSuccess) return vils::fail_cuda(e, "vils_frontend_load");
-  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
   f->d_cur = equalize ? f->d_dst : f->d_src;
   return VILS_OK;
 }
-int vils_frontend_current(vils_frontend* f, const uint8_t** image_dev, int32_t* pitch_bytes) {
+int vils_frontend_current(vils_frontend* f, const uint8_t** image_dev, int32_t* pitch_bytes, void** ready_event) {
   if (!f || !image_dev || !pitch_bytes || !f->d_cur) return vils::fail(VILS_ERR_BAD_ARG, "vils_frontend_current: call vils_frontend_load first");
   *image_dev = f->d_cur; *pitch_bytes = f->cols;
+  if (ready_event) *ready_event = f->ev_ready;
   return VILS_OK;
 }
 

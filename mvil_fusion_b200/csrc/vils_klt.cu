@@ -373,11 +373,13 @@ int vils_klt_track(vils_klt* k, const uint8_t* prev, const uint8_t* next, int32_
 // FeatureTracker::readImage keeps forw_img as next call's cur_img (feature_tracker.cpp:160-164): so does the device.  next_dev: the new
 // (equalised) image ALREADY ON THE DEVICE (vils_frontend_current), pitch_bytes apart.  The pyramid built for it by this call is next call's
 // `prev`; only one pyramid is built per frame and no image crosses PCIe here.  The first call only loads the image (n is ignored).
-int vils_klt_advance(vils_klt* k, const uint8_t* next_dev, int32_t pitch_bytes, const float* prev_xy, int32_t n, float* next_xy, uint8_t* status, float* err) {
+int vils_klt_advance(vils_klt* k, const uint8_t* next_dev, int32_t pitch_bytes, void* ready_event, const float* prev_xy, int32_t n, float* next_xy, uint8_t* status,
+                     float* err) {
   if (!k || !next_dev || pitch_bytes < k->cols || n < 0 || n > k->max_pts || (n && !prev_xy)) return vils::fail(VILS_ERR_BAD_ARG, "vils_klt_advance: bad argument");
   cudaSetDevice(k->device);
   const bool track = k->has_next;
   if (track) { for (int l = 0; l < k->levels; l++) std::swap(k->prev.img[l], k->next.img[l]); k->parity ^= 1; }
+  if (ready_event) cudaStreamWaitEvent(k->st, static_cast<cudaEvent_t>(ready_event), 0);   // the producer of next_dev (vils_frontend_load) is not synchronised
   cudaMemcpy2DAsync(k->next.img[0], k->cols, next_dev, pitch_bytes, k->cols, k->rows, cudaMemcpyDeviceToDevice, k->st);
   float* hp = reinterpret_cast<float*>(k->h_stage + ((2 * (size_t)k->rows * k->cols + 15) & ~(size_t)15));
   const int nt = track ? n : 0;

@@ -71,9 +71,9 @@ def load():
     L.vils_klt_track_device.argtypes = [vp]
     L.vils_klt_download.argtypes = [vp, fp, up, fp]
     L.vils_klt_last_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
-    L.vils_klt_advance.argtypes = [vp, vp, C.c_int32, fp, C.c_int32, fp, up, fp]
+    L.vils_klt_advance.argtypes = [vp, vp, C.c_int32, vp, fp, C.c_int32, fp, up, fp]
     L.vils_frontend_load.argtypes = [vp, up, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32]
-    L.vils_frontend_current.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.vils_frontend_current.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)]
     L.vils_good_features_resident.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.c_int32, fp, ip]
     L.vils_frontend_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.vils_frontend_destroy.argtypes = [vp]
@@ -388,13 +388,13 @@ class KLT:
                                      out.ctypes.data_as(fp), status.ctypes.data_as(up), err.ctypes.data_as(fp)))
         return out, status, err
 
-    def advance(self, image_dev, pitch, pts):
+    def advance(self, image_dev, pitch, pts, ready_event=None):
         """vils_klt_advance: the new frame is already on the device (Frontend.load / Frontend.current); its pyramid becomes the next call's prev."""
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
         n = pts.shape[0]
         out = np.zeros((max(n, 1), 2), np.float32); status = np.zeros(max(n, 1), np.uint8); err = np.zeros(max(n, 1), np.float32)
         up, fp = cabi.c_uint8_p, cabi.c_float_p
-        _check(self.L.vils_klt_advance(self.h, C.c_void_p(image_dev), int(pitch), pts.ctypes.data_as(fp) if n else None, n, out.ctypes.data_as(fp),
+        _check(self.L.vils_klt_advance(self.h, C.c_void_p(image_dev), int(pitch), C.c_void_p(ready_event), pts.ctypes.data_as(fp) if n else None, n, out.ctypes.data_as(fp),
                                        status.ctypes.data_as(up), err.ctypes.data_as(fp)))
         return out[:n], status[:n], err[:n]
 
@@ -529,8 +529,9 @@ class Frontend:
         """vils_frontend_load: one upload, CLAHE on the device when asked; returns (device pointer, pitch) of the resident frame."""
         img = np.ascontiguousarray(img, np.uint8)
         _check(self.L.vils_frontend_load(self.h, img.ctypes.data_as(cabi.c_uint8_p), img.strides[0], int(equalize), clip, tiles[0], tiles[1]))
-        p = C.c_void_p(); pitch = C.c_int32()
-        _check(self.L.vils_frontend_current(self.h, C.byref(p), C.byref(pitch)))
+        p = C.c_void_p(); pitch = C.c_int32(); ev = C.c_void_p()
+        _check(self.L.vils_frontend_current(self.h, C.byref(p), C.byref(pitch), C.byref(ev)))
+        self.ready_event = ev.value
         return p.value, pitch.value
 
     def good_features_resident(self, max_corners, quality, min_distance, use_mask=False):

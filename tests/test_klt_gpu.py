@@ -79,13 +79,13 @@ def test_device_resident_chain_equals_pairwise_tracking():
     f = lib.Frontend(480, 640, 512); k1 = lib.KLT(480, 640, 512, 21, 3); k2 = lib.KLT(480, 640, 512, 21, 3)
     eq = [f.clahe(im) for im in frames]                                         # what the pairwise path sees (downloaded CLAHE output)
     dev, pitch = f.load(frames[0], True)
-    k1.advance(dev, pitch, np.zeros((0, 2), np.float32))                       # first frame: load only
+    k1.advance(dev, pitch, np.zeros((0, 2), np.float32), f.ready_event)                       # first frame: load only
     pts = f.good_features_resident(150, 0.01, 30.0)
     assert np.array_equal(pts, f.good_features(eq[0], 150, 0.01, 30.0))
     assert len(pts) > 100
     for k in range(1, 4):
         dev, pitch = f.load(frames[k], True)
-        out, st, err = k1.advance(dev, pitch, pts)
+        out, st, err = k1.advance(dev, pitch, pts, f.ready_event)
         ref, st_ref, err_ref = k2.track(eq[k - 1], eq[k], pts)
         assert np.array_equal(st, st_ref) and np.array_equal(out, ref) and np.array_equal(err, err_ref)
         pts = out[st == 1]
