@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <numeric>
@@ -1058,6 +1059,8 @@ struct vils_ba {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   static constexpr int NPIPE = 8;
   cudaStream_t pipe[NPIPE] = {};                        // vils_ba_solve: chunked upload / solve / download pipeline
+  cudaStream_t copy_stream = nullptr;                   // all uploads of the pipeline, back to back, ahead of the solves
+  std::vector<cudaEvent_t> ev_chunk;                    // "chunk c is on the device"
   int n_sm = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   size_t blob_stride = 0;
@@ -1237,9 +1240,10 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
   CK(cudaEventCreate(&ba->ev0)); CK(cudaEventCreate(&ba->ev1));
   CK(cudaStreamCreateWithFlags(&ba->stream2, cudaStreamNonBlocking));
   for (int k = 0; k < vils_ba::NPIPE; k++) CK(cudaStreamCreateWithFlags(&ba->pipe[k], cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ba->copy_stream, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ba->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaEventCreateWithFlags(&ba->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ba->ev_join, cudaEventDisableTiming));
-  CK(cudaMallocHost(&ba->h_blob, ba->blob_stride * max_windows));
+  CK(cudaHostAlloc(&ba->h_blob, ba->blob_stride * max_windows, (getenv("VILS_WC") && atoi(getenv("VILS_WC"))) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   CK(cudaMalloc(&ba->d_blob, ba->blob_stride * max_windows));
   CK(cudaMalloc(&ba->d_scratch, (size_t)s.total * 8 * max_windows));
   { int* d_n = nullptr; CK(cudaMalloc(&d_n, sizeof(int))); nsmid_kernel<<<1, 1>>>(d_n); CK(cudaMemcpy(&ba->n_smid, d_n, sizeof(int), cudaMemcpyDeviceToHost)); cudaFree(d_n); }
@@ -1300,6 +1304,8 @@ void vils_ba_destroy(vils_ba* ba) {
   if (ba->ev_join) cudaEventDestroy(ba->ev_join);
   if (ba->stream2) cudaStreamDestroy(ba->stream2);
   for (int k = 0; k < vils_ba::NPIPE; k++) if (ba->pipe[k]) cudaStreamDestroy(ba->pipe[k]);
+  if (ba->copy_stream) cudaStreamDestroy(ba->copy_stream);
+  for (cudaEvent_t v : ba->ev_chunk) cudaEventDestroy(v);
   if (ba->stream) cudaStreamDestroy(ba->stream);
   delete ba->pool;
   if (ba->comm) nccl_comm_destroy(ba->comm);
@@ -1317,6 +1323,21 @@ static const bool g_pack_nt = !(getenv("VILS_PACK_NT") && atoi(getenv("VILS_PACK
 static inline void nt_store(double* p, double v) {
   if (g_pack_nt) { long long b; std::memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long*>(p), b); }
   else *p = v;
+}
+// dst[s] = src[stride * idx[s] + c] for s < n as one sequential stream of 16-byte streaming stores fed by 4-wide AVX2 gathers (the packer is
+// bound by its ~28 k scalar load / store pairs per window, not by memory bandwidth: the sources of one window sit in the L1 / L2 cache)
+__attribute__((target("avx2"))) static void gather_stream(double* dst, const double* src, const int* idx, int n, int stride, int c) {
+  int s = 0;
+  if (!g_pack_nt) { for (; s < n; s++) dst[s] = src[(size_t)stride * idx[s] + c]; return; }
+  while (s < n && (reinterpret_cast<uintptr_t>(dst + s) & 15)) { nt_store(dst + s, src[(size_t)stride * idx[s] + c]); s++; }
+  const __m128i vstride = _mm_set1_epi32(stride), vc = _mm_set1_epi32(c);
+  for (; s + 4 <= n; s += 4) {
+    __m128i vi = _mm_loadu_si128(reinterpret_cast<const __m128i*>(idx + s));
+    vi = _mm_add_epi32(_mm_mullo_epi32(vi, vstride), vc);
+    const __m256d v = _mm256_i32gather_pd(src, vi, 8);
+    _mm_stream_pd(dst + s, _mm256_castpd256_pd128(v)); _mm_stream_pd(dst + s + 2, _mm256_extractf128_pd(v, 1));
+  }
+  for (; s < n; s++) nt_store(dst + s, src[(size_t)stride * idx[s] + c]);
 }
 struct PackScratch {
   std::vector<int> cnt, ord, rank_of, lm_start, lm_feat, pord, pairs, pair_id, plo, pls, edo, eds, pblk, pcol;
@@ -1424,7 +1445,7 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
   int32_t* pix = (int32_t*)place(OFF_PROJ_IDX, (size_t)4 * np * 4);
   {
     const int* od = S.ord.data();
-    auto field = [&](int a, const double* src, int stride, int c) { double* d = pj + (size_t)a * np; for (int s = 0; s < np; s++) nt_store(d + s, src[(size_t)stride * od[s] + c]); };
+    auto field = [&](int a, const double* src, int stride, int c) { gather_stream(pj + (size_t)a * np, src, od, np, stride, c); };
     for (int c2 = 0; c2 < 3; c2++) { field(c2, w->pts_i, 3, c2); field(3 + c2, w->pts_j, 3, c2); }
     for (int c2 = 0; c2 < 2; c2++) { field(6 + c2, w->vel_i, 2, c2); field(8 + c2, w->vel_j, 2, c2); }
     field(10, w->td_i, 1, 0); field(11, w->td_j, 1, 0); field(12, w->row_i, 1, 0); field(13, w->row_j, 1, 0);
@@ -1451,8 +1472,8 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
     for (int a = 0; a < 3; a++) nt_store(pl + (size_t)a * npl + s, pb[a]);
     plx[s] = w->plane_kf[k]; plx[npl + s] = k;
   }
-  for (int a = 0; a < 3; a++) { double* d = pl + (size_t)(3 + a) * npl; for (int s = 0; s < npl; s++) nt_store(d + s, w->plane_n[3 * (size_t)S.plo[s] + a]); }
-  { double* d = pl + (size_t)6 * npl; for (int s = 0; s < npl; s++) nt_store(d + s, w->plane_d[S.plo[s]]); }
+  for (int a = 0; a < 3; a++) gather_stream(pl + (size_t)(3 + a) * npl, w->plane_n, S.plo.data(), npl, 3, a);
+  gather_stream(pl + (size_t)6 * npl, w->plane_d, S.plo.data(), npl, 1, 0);
   int32_t* plst = (int32_t*)place(OFF_PLANE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) plst[k] = S.pls[k];
   double* ed = (double*)place(OFF_EDGE, (size_t)9 * ned * 8);
   int32_t* edx = (int32_t*)place(OFF_EDGE_IDX, (size_t)2 * ned * 4);
@@ -1462,9 +1483,8 @@ static int pack_window(vils_ba* ba, int32_t slot, const vils_window* w, PackScra
     edx[s] = w->edge_kf[k]; edx[ned + s] = k;
   }
   for (int a = 0; a < 3; a++) {
-    double* da = ed + (size_t)(3 + a) * ned; double* db = ed + (size_t)(6 + a) * ned;
-    for (int s = 0; s < ned; s++) nt_store(da + s, w->edge_a[3 * (size_t)S.edo[s] + a]);
-    for (int s = 0; s < ned; s++) nt_store(db + s, w->edge_b[3 * (size_t)S.edo[s] + a]);
+    gather_stream(ed + (size_t)(3 + a) * ned, w->edge_a, S.edo.data(), ned, 3, a);
+    gather_stream(ed + (size_t)(6 + a) * ned, w->edge_b, S.edo.data(), ned, 3, a);
   }
   int32_t* edst = (int32_t*)place(OFF_EDGE_START, (size_t)(N + 1) * 4); for (int k = 0; k <= N; k++) edst[k] = S.eds[k];
   double* ic = (double*)place(OFF_ICP, (size_t)w->n_icp * 14 * 8);
@@ -1509,7 +1529,8 @@ struct PackPool {
   std::mutex m; std::condition_variable cv;
   uint64_t generation = 0; bool stop = false;
   // current job
-  vils_ba* ba = nullptr; const vils_window* ws = nullptr; int slot0 = 0, n = 0, chunk = 1;
+  vils_ba* ba = nullptr; const vils_window* ws = nullptr; int slot0 = 0, n = 0;
+  std::vector<int> chunk_of;                               // window -> chunk (chunks may have different sizes: small ones first)
   std::atomic<int> next{0}, active{0};
   std::vector<std::atomic<int>> chunk_done;
   std::atomic<int> err_code{0}; std::string err_msg;
@@ -1524,7 +1545,7 @@ struct PackPool {
         const int st = pack_window(ba, slot0 + k, ws + k, S, e);
         if (st != VILS_OK) { std::lock_guard<std::mutex> l(m); if (err_code.load() == 0) { err_msg = e; err_code.store(st); } }
       }
-      chunk_done[k / chunk].fetch_add(1, std::memory_order_release);
+      chunk_done[chunk_of[k]].fetch_add(1, std::memory_order_release);
     }
   }
   void run() {
@@ -1535,11 +1556,14 @@ struct PackPool {
       active.fetch_sub(1, std::memory_order_release);
     }
   }
-  void begin(vils_ba* b, const vils_window* w, int s0, int cnt, int ch) {
+  // bounds: chunk c covers windows [bounds[c], bounds[c + 1])
+  void begin(vils_ba* b, const vils_window* w, int s0, int cnt, const std::vector<int>& bounds) {
     while (active.load(std::memory_order_acquire) != 0) std::this_thread::yield();      // stragglers of the previous job
     { std::lock_guard<std::mutex> l(m);
-      ba = b; ws = w; slot0 = s0; n = cnt; chunk = ch; err_code.store(0); err_msg.clear();
-      const int nc = (cnt + ch - 1) / ch;
+      ba = b; ws = w; slot0 = s0; n = cnt; err_code.store(0); err_msg.clear();
+      const int nc = (int)bounds.size() - 1;
+      chunk_of.resize(cnt);
+      for (int c = 0; c < nc; c++) for (int k = bounds[c]; k < bounds[c + 1]; k++) chunk_of[k] = c;
       if ((int)chunk_done.size() < nc) { std::vector<std::atomic<int>> v(nc); chunk_done.swap(v); }
       for (auto& c : chunk_done) c.store(0, std::memory_order_relaxed);
       next.store(0); generation++; }
@@ -1555,7 +1579,7 @@ struct PackPool {
           const int st = pack_window(ba, slot0 + k, ws + k, S, e);
           if (st != VILS_OK) { std::lock_guard<std::mutex> l(m); if (err_code.load() == 0) { err_msg = e; err_code.store(st); } }
         }
-        chunk_done[k / chunk].fetch_add(1, std::memory_order_release);
+        chunk_done[chunk_of[k]].fetch_add(1, std::memory_order_release);
       } else std::this_thread::yield();
     }
   }
@@ -1563,7 +1587,10 @@ struct PackPool {
 
 static PackPool* pack_pool(vils_ba* ba) {
   if (!ba->pool) {
+    // one rank per GPU on a node: the host cores are shared by LOCAL_WORLD_SIZE processes (torchrun exports it); oversubscribing them with a
+    // full-size pool per rank made the 8-GPU end-to-end rate collapse (round 2: 204 k solves/s with 8 x 32 threads on 32 cores)
     int T = (int)std::thread::hardware_concurrency();
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int nw = atoi(lw); if (nw > 1) T = std::max(1, T / nw); }
     if (const char* e = getenv("VILS_PACK_THREADS")) T = atoi(e);
     T = std::max(1, std::min(T, 64)) - 1;                         // the calling thread is one of the packers
     ba->pool = new PackPool(T);
@@ -1577,7 +1604,7 @@ int vils_ba_set_windows(vils_ba* ba, int32_t slot0, int32_t n, const vils_window
   static thread_local PackScratch S;
   if (n == 1) return vils_ba_set_window(ba, slot0, ws);
   PackPool* pool = pack_pool(ba);
-  pool->begin(ba, ws, slot0, n, n);
+  pool->begin(ba, ws, slot0, n, std::vector<int>{0, n});
   pool->wait_chunk(0, n, S);
   if (pool->err_code.load()) return vils::fail(pool->err_code.load(), pool->err_msg);
   return VILS_OK;
@@ -1671,21 +1698,46 @@ static int solve_pipeline(vils_ba* ba, int32_t n, const vils_window* ws, const v
   static const int chunk_env = getenv("VILS_CHUNK") ? atoi(getenv("VILS_CHUNK")) : 0;
   static const int ns_env = getenv("VILS_STREAMS") ? atoi(getenv("VILS_STREAMS")) : 0;
   const int chunk = chunk_env > 0 ? chunk_env : std::max(1, ba->n_sm / 2);
-  // enough streams that the chunks in flight can cover every SM (one CTA per window, one CTA per SM) plus one chunk being copied
-  const int NS = std::min<int>(vils_ba::NPIPE, ns_env > 0 ? ns_env : std::max(3, (ba->n_sm + chunk - 1) / chunk + 1));
+  // Uploads go back to back on their own stream, ahead of the solves (an upload queued on a solve stream would wait for the previous chunk of that
+  // stream to finish: measured, the copy engine then idles 60 % of the time and the SMs wait for data); the solve streams only need to be enough
+  // for the chunks in flight to cover every SM.
+  static const bool own_copy_stream = !(getenv("VILS_COPY_STREAM") && atoi(getenv("VILS_COPY_STREAM")) == 0);
+  const int NS = std::min<int>(vils_ba::NPIPE, ns_env > 0 ? ns_env : ws ? vils_ba::NPIPE : std::max(3, (ba->n_sm + chunk - 1) / chunk + 1));
   SolveParams P = make_params(ba, opts);
   const bool both = ba->h_in_smem && ba->hv_in_smem;
   size_t h2d = 0; int launches = 0;
   static thread_local PackScratch S;
+  // Chunk boundaries.  With in-pipeline packing the chunks repeat the pattern n_sm / 8, n_sm / 4, n_sm / 2, rest of the device: the GPU starts after
+  // ~0.1 ms of packing instead of waiting for a half-device chunk, and because one pattern covers every SM exactly once, the chunk that arrives
+  // next is as large as the one that retires next (uniform chunks after a small head leave a ragged tail: measured 6.45 vs 6.1 ms per 592 windows).
+  std::vector<int> bounds{0};
+  if (ws && n > chunk && !chunk_env) {
+    const int a = std::max(1, ba->n_sm / 8), b = std::max(1, ba->n_sm / 4), c2 = std::max(1, ba->n_sm / 2);
+    const int pat[4] = {a, b, c2, std::max(1, ba->n_sm - a - b - c2)};
+    for (int k = 0; bounds.back() < n; k++) bounds.push_back(std::min(n, bounds.back() + pat[k & 3]));
+  }
+  while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + chunk));
+  const int nchunks = (int)bounds.size() - 1;
   PackPool* pool = nullptr;
-  if (ws && n > 1) { pool = pack_pool(ba); pool->begin(ba, ws, 0, n, chunk); }
+  if (ws && n > 1) { pool = pack_pool(ba); pool->begin(ba, ws, 0, n, bounds); }
   cudaEventRecord(ba->ev_fork, ba->stream);                 // order after anything still queued on the handle's main stream
   for (int k = 0; k < NS; k++) cudaStreamWaitEvent(ba->pipe[k], ba->ev_fork, 0);
+  if (own_copy_stream) {
+    cudaStreamWaitEvent(ba->copy_stream, ba->ev_fork, 0);
+    while ((int)ba->ev_chunk.size() < nchunks) { cudaEvent_t v; if (cudaEventCreateWithFlags(&v, cudaEventDisableTiming) != cudaSuccess) return vils::fail(VILS_ERR_CUDA, "cudaEventCreate"); ba->ev_chunk.push_back(v); }
+  }
   int err = VILS_OK; std::string err_msg; cudaError_t le = cudaSuccess;
-  for (int c0 = 0, c = 0; c0 < n; c0 += chunk, c++) {
-    const int cn = std::min(chunk, n - c0);
+  static const bool trace = getenv("VILS_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  std::vector<double> t_ready, t_issued;
+  std::vector<cudaEvent_t> tev;                              // VILS_TRACE only: device timeline of every chunk (copied / solved / read back)
+  if (trace) { tev.resize(3 * nchunks + 1); for (auto& v : tev) cudaEventCreate(&v); cudaEventRecord(tev[3 * nchunks], ba->stream); }
+  for (int c = 0; c < nchunks; c++) {
+    const int c0 = bounds[c], cn = bounds[c + 1] - bounds[c];
     if (pool) {
       pool->wait_chunk(c, cn, S);
+      if (trace) t_ready.push_back(now_ms());
       if (pool->err_code.load()) { err = pool->err_code.load(); break; }
     } else if (ws) {
       err = pack_window(ba, 0, ws, S, err_msg);
@@ -1697,20 +1749,38 @@ static int solve_pipeline(vils_ba* ba, int32_t n, const vils_window* ws, const v
     // pitched copy of the USED part of every blob.  (One contiguous copy of the chunk, slack included, was measured: 25 % more bytes made the
     // pre-packed pipeline 48 % slower, 6.0 -> 8.9 ms per 592 windows: the pipeline is bound by the solve kernel and by host memory traffic, not by
     // the PCIe rate of a single copy.)
+    cudaStream_t sc = own_copy_stream ? ba->copy_stream : s;
     cudaMemcpy2DAsync(ba->d_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, ba->h_blob + (size_t)c0 * ba->blob_stride, ba->blob_stride, width, cn,
-                      cudaMemcpyHostToDevice, s);
+                      cudaMemcpyHostToDevice, sc);
+    if (trace) cudaEventRecord(tev[3 * c], sc);
+    if (own_copy_stream) { cudaEventRecord(ba->ev_chunk[c], sc); cudaStreamWaitEvent(s, ba->ev_chunk[c], 0); }
     P.slot0 = c0; P.do_prep = 1;
     launch_solve(ba, P, cn, s, cn == n);               // clusters only when the whole call is one chunk (no concurrent chunk launches)
     if (le == cudaSuccess) le = cudaGetLastError();
+    if (trace) cudaEventRecord(tev[3 * c + 1], s);
     launches += 1;
     cudaMemcpyAsync(ba->h_xout + (size_t)c0 * ba->xstride, ba->d_xout + (size_t)c0 * ba->xstride, (size_t)ba->xstride * 8 * cn, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(ba->h_sum + c0, ba->d_sum + c0, sizeof(vils_summary) * cn, cudaMemcpyDeviceToHost, s);
+    if (trace) { cudaEventRecord(tev[3 * c + 2], s); t_issued.push_back(now_ms()); }
   }
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < NS; k++) { const cudaError_t ek = cudaStreamSynchronize(ba->pipe[k]); if (e == cudaSuccess) e = ek; }
+  if (own_copy_stream) { const cudaError_t ek = cudaStreamSynchronize(ba->copy_stream); if (e == cudaSuccess) e = ek; }
+  if (trace) {
+    fprintf(stderr, "[VILS_TRACE] %s n=%d: ready/issued (ms):", who, n);
+    for (size_t k = 0; k < t_issued.size(); k++) fprintf(stderr, " %.2f/%.2f", k < t_ready.size() ? t_ready[k] : 0.0, t_issued[k]);
+    fprintf(stderr, " | all streams done %.2f\n", now_ms());
+    fprintf(stderr, "[VILS_TRACE]   device copied/solved/read back (ms after the call's fork event):");
+    for (int c = 0; c < nchunks; c++) {
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, tev[3 * nchunks], tev[3 * c]); cudaEventElapsedTime(&b, tev[3 * nchunks], tev[3 * c + 1]); cudaEventElapsedTime(&d, tev[3 * nchunks], tev[3 * c + 2]);
+      fprintf(stderr, " %.2f/%.2f/%.2f", a, b, d);
+    }
+    fprintf(stderr, "\n");
+    for (auto& v : tev) cudaEventDestroy(v);
+  }
   if (pool) {   // drain the job so that the pool is idle again (after an error the remaining windows are skipped, not packed)
-    const int nc = (n + chunk - 1) / chunk;
-    for (int c = 0; c < nc; c++) pool->wait_chunk(c, std::min(chunk, n - c * chunk), S);
+    for (int c = 0; c < nchunks; c++) pool->wait_chunk(c, bounds[c + 1] - bounds[c], S);
     if (pool->err_code.load()) { err = pool->err_code.load(); err_msg = pool->err_msg; }
   }
   if (err) return vils::fail(err, err_msg);

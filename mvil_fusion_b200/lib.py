@@ -155,8 +155,10 @@ class BA:
         return arr, keep
 
     def _note_dims(self, slot0, ws):
+        # lazily: the per-window residual / Jacobian counts are only needed by get_state / evaluate, and computing them for hundreds of windows
+        # costs more Python time than the library call itself
         for k, w in enumerate(ws):
-            self._dims[slot0 + k] = (int(w["pose"].shape[0]), int(w["inv_depth"].shape[0]), cabi.residual_count(w), cabi.jacobian_count(w))
+            self._dims[slot0 + k] = w
 
     def set_windows(self, slot0, ws, arr=None):
         """vils_ba_set_windows: pack len(ws) windows on all host threads."""
@@ -198,8 +200,15 @@ class BA:
     def solve(self, n, opts):
         _check(self.L.vils_ba_solve(self.h, n, C.byref(opts)))
 
+    def _dim(self, slot):
+        d = self._dims[slot]
+        if isinstance(d, dict):
+            d = (int(d["pose"].shape[0]), int(d["inv_depth"].shape[0]), cabi.residual_count(d), cabi.jacobian_count(d))
+            self._dims[slot] = d
+        return d
+
     def get_state(self, slot):
-        N, M, _, _ = self._dims[slot]
+        N, M, _, _ = self._dim(slot)
         pose = np.zeros((N, 7)); sb = np.zeros((N, 9)); ex = np.zeros(7); lam = np.zeros(max(M, 1)); td = C.c_double()
         s = cabi.VilsSummary()
         st = self.L.vils_ba_get_state(self.h, slot, _d(pose), _d(sb), _d(ex), _d(lam), C.byref(td), C.byref(s))
@@ -207,7 +216,7 @@ class BA:
                     accepted=s.accepted, cost_initial=s.cost_initial, cost_final=s.cost_final)
 
     def evaluate(self, slot, apply_loss=True):
-        _, _, nr, nj = self._dims[slot]
+        _, _, nr, nj = self._dim(slot)
         r = np.zeros(nr); J = np.zeros(max(nj, 1))
         _check(self.L.vils_ba_evaluate(self.h, slot, int(apply_loss), _d(r), _d(J)))
         return r, J[:nj]
@@ -216,7 +225,7 @@ class BA:
         _check(self.L.vils_ba_evaluate_device(self.h, n, int(apply_loss)))
 
     def linearize(self, slot):
-        N = self._dims[slot][0]
+        N = self._dim(slot)[0]
         D = 15 * N + 7
         S = np.zeros((D, D)); g = np.zeros(D); cost = C.c_double()
         _check(self.L.vils_ba_linearize(self.h, slot, _d(S), _d(g), C.byref(cost)))
