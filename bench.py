@@ -396,6 +396,7 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e0)
     e2e_launches = ba.last_launches
+    h2d, d2h = ba.last_transfer_bytes          # counted by the library from the copies it issued in that vils_ba_solve_windows call (all B windows)
     # the same with the blobs already packed in pinned staging (round-1 definition, kept for comparison)
     barrier()
     e0 = time.perf_counter()
@@ -453,7 +454,6 @@ def main():
         kern_ms = dev_ms / args.steps
         achieved = BYTES_PER_SOLVE * B / (kern_ms * 1e-3) / 1e9
         ev_achieved = BYTES_PER_EVAL_WINDOW * B / (ev_ms / args.steps * 1e-3) / 1e9
-        h2d, d2h = ba.last_transfer_bytes      # counted by the library from the copies it issued in the last vils_ba_solve
         # CPU baseline: the oracle ("port") on the host cores of this box, bounded sample of the same windows
         per_core = 2
         v1, dt1 = cpu_solves_per_sec(uniq[:16], cores, per_core, opts)
@@ -475,7 +475,7 @@ def main():
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "launches_per_step": e2e_launches, "from": "caller arrays (host pack inside the timed region)",
                     "prepacked_value": total / (e2e_packed_ms * 1e-3),
-                    "pipeline": "chunks of n_sm/2 windows: host pack (thread pool) | H2D | solve_kernel (prep folded in) | D2H on round-robin streams"},
+                    "pipeline": "chunks of n_sm/8, n_sm/4, n_sm/2, rest (repeating): host pack (thread pool) | H2D on a copy stream | solve_kernel (prep folded in) | D2H on round-robin streams"},
             "gpu_launches": args.steps,
             "roofline": {"kernel": "solve_kernel (fused GN loop, one CTA per window)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": SOLVE_DRAM_TRAFFIC_PER_WINDOW * B if SOLVE_DRAM_TRAFFIC_PER_WINDOW else None, "peak_source": peak_src,

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       PROF(7);
-      cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof);
+      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof);
       ok = chol_flag == 0;
       PROF(8);
       if (!ok && !TR) { status = VILS_ERR_CHOLESKY; break; }
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       CLPROF(6);
-      cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
       CLPROF(7);
       int st = VILS_OK;
       if (chol_flag) st = VILS_ERR_CHOLESKY;
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_upd_kernel(SolveParams
   damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
   __syncthreads();
   double* linv = L.linv >= 0 ? sm + L.linv : scr + P.sl.linvg;
-  cholesky_tiles(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+  cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
   int status = VILS_OK;
   if (chol_flag) status = VILS_ERR_CHOLESKY;
   else {
