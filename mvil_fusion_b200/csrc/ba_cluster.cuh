@@ -349,50 +349,57 @@ __device__ void schur_syrk_cluster(const SolveParams& P, const Win& W, const dou
 // ---- G: entries t = r (mod G): sum of the G partial Hv / gv + pair blocks -> H (global tiles), g and hd (global, camera-indexed) ---------
 __device__ void gather_cluster(const SolveParams& P, const Win& W, const double* hvpart, const double* gvpart, double* H, double* gsc, double* hdsc,
                                const double* scr, const int* pid, int zblk, int r, int G) {
-  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp;
-  const double* pp = scr + P.sl.pairpart;
-  const int total = Dv * (Dv + 1) / 2 + Dv;
+  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp, nsh = Dv - 6 * N, npair = W.h->n_pair, lane = threadIdx.x & 31;
+  const double* __restrict__ pp = scr + P.sl.pairpart;
+  const double* __restrict__ hvr = hvpart;
   const size_t hvs = (size_t)Dvp * Dvp;
-  for (int t = r + G * threadIdx.x; t < total; t += G * blockDim.x) {
-    int a, b; bool grad = false;
-    if (t < Dv) { a = t; b = t; grad = true; }
-    else {
-      const int u = t - Dv;
-      a = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
-      while (a * (a + 1) / 2 > u) a--;
-      while ((a + 1) * (a + 2) / 2 <= u) a++;
-      b = u - a * (a + 1) / 2;
+  // the four entry families of gather_visual, each entry owned by one thread (or warp) of ONE CTA of the cluster; the G partial Schur
+  // complements are summed on the way
+  for (int e = r + G * threadIdx.x; e < 21 * N + nsh * 6 * N; e += G * blockDim.x) {                       // (1)
+    const GatherTask T = gather_task1(e, N);
+    double s = gather_walk(pp, pid, N, T.q, T.off_anchor, T.off_obs, zblk);
+    for (int c = 0; c < G; c++) s += hvr[(size_t)c * hvs + T.a * Dvp + T.b];
+    H[tidx(vis2cam(T.a, N), vis2cam(T.b, N))] = s;
+  }
+  for (int e = r + G * threadIdx.x; e < 12 * N; e += G * blockDim.x) {                                     // (2)
+    const int a = e >> 1, q = a / 6, ao = a - 6 * q, which = e & 1;
+    double s = gather_walk(pp, pid, N, q, ao * PAIR_LD + (which ? ao : 19), (6 + ao) * PAIR_LD + (which ? 6 + ao : 19), zblk);
+    const int ca = vis2cam(a, N);
+    if (which) hdsc[ca] = s;
+    else { for (int c = 0; c < G; c++) s += gvpart[(size_t)c * Dvp + a]; gsc[ca] = s; }
+  }
+  {                                                                                                        // (3)
+    const int nent = N * (N - 1) / 2 * 36;
+#pragma unroll 2
+    for (int e = r + G * threadIdx.x; e < nent; e += G * blockDim.x) {
+      const int pi = e / 36, o = e - pi * 36, ao = o / 6, bo = o - ao * 6;
+      int pb, qb; gather_pair_of(pi, pb, qb);
+      const int pr = pid[qb * N + pb];
+      double v = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (6 + ao) * PAIR_LD + bo];
+      const int a = 6 * pb + ao, b = 6 * qb + bo;
+      for (int c = 0; c < G; c++) v += hvr[(size_t)c * hvs + a * Dvp + b];
+      H[tidx(vis2cam(a, N), vis2cam(b, N))] = v;
     }
-    const int p = a < 6 * N ? a / 6 : N + (a - 6 * N) / 6;
-    const int q = b < 6 * N ? b / 6 : N + (b - 6 * N) / 6;
-    const int ao = a < 6 * N ? a % 6 : (a - 6 * N) % 6, bo = b < 6 * N ? b % 6 : (b - 6 * N) % 6;
-    const int la_sh = (p == N) ? 12 + ao : 18;
-    const int lb_sh = (q == N) ? 12 + bo : 18;
-    double s0 = 0, s1 = 0, g0 = 0, g1 = 0, d0 = 0, d1 = 0;
-    if (p < N && q < N && p > q) {
-      const int pr = pid[q * N + p];
-      s0 = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (6 + ao) * PAIR_LD + bo];
-    } else if (q < N) {
-      const int la_anchor = (p < N) ? ao : la_sh, la_obs = (p < N) ? 6 + ao : la_sh;
-#pragma unroll 4
-      for (int j = 0; j < N; j++) {
-        const int pa = j > q ? pid[q * N + j] : -1, po = j < q ? pid[j * N + q] : -1;
-        const double* ba = pp + (size_t)(pa < 0 ? zblk : pa) * (PAIR_LD * PAIR_LD);
-        const double* bo2 = pp + (size_t)(po < 0 ? zblk : po) * (PAIR_LD * PAIR_LD);
-        if (grad) { g0 += ba[la_anchor * PAIR_LD + 19]; d0 += ba[la_anchor * PAIR_LD + la_anchor]; g1 += bo2[la_obs * PAIR_LD + 19]; d1 += bo2[la_obs * PAIR_LD + la_obs]; }
-        else { s0 += ba[la_anchor * PAIR_LD + bo]; s1 += bo2[la_obs * PAIR_LD + 6 + bo]; }
-      }
-    } else {
-#pragma unroll 4
-      for (int pr = 0; pr < W.h->n_pair; pr++) {
-        const double* blk = pp + (size_t)pr * (PAIR_LD * PAIR_LD);
-        if (grad) { g0 += blk[la_sh * PAIR_LD + 19]; d0 += blk[la_sh * PAIR_LD + la_sh]; }
-        else s0 += blk[la_sh * PAIR_LD + lb_sh];
-      }
+  }
+  for (int wt = r + G * (threadIdx.x >> 5); wt < nsh * (nsh + 1) / 2 + nsh; wt += G * SOLVE_WARPS) {       // (4)
+    int ia, ib; const bool grad = wt < nsh;
+    if (grad) { ia = wt; ib = wt; }
+    else { const int u = wt - nsh; ia = 0; while ((ia + 1) * (ia + 2) / 2 <= u) ia++; ib = u - ia * (ia + 1) / 2; }
+    const int la = ia < 6 ? 12 + ia : 18, lb = ib < 6 ? 12 + ib : 18;
+    const int a = 6 * N + ia, b = 6 * N + ib;
+    double s0 = 0, s1 = 0;
+    for (int pr = lane; pr < npair; pr += 32) {
+      const double* blk = pp + (size_t)pr * (PAIR_LD * PAIR_LD);
+      if (grad) { s0 += blk[la * PAIR_LD + 19]; s1 += blk[la * PAIR_LD + la]; }
+      else s0 += blk[la * PAIR_LD + lb];
     }
-    const int ca = vis2cam(a, N), cbm = vis2cam(b, N);
-    if (grad) { double gvs = 0; for (int c = 0; c < G; c++) gvs += gvpart[(size_t)c * Dvp + a]; gsc[ca] = gvs + (g0 + g1); hdsc[ca] = d0 + d1; }
-    else { double hvsum = 0; for (int c = 0; c < G; c++) hvsum += hvpart[(size_t)c * hvs + a * Dvp + b]; H[tidx(ca, cbm)] = hvsum + (s0 + s1); }
+    if (lane < G) s0 += grad ? gvpart[(size_t)lane * Dvp + a] : hvr[(size_t)lane * hvs + a * Dvp + b];
+    s0 = warp_sum(s0); if (grad) s1 = warp_sum(s1);
+    if (lane == 0) {
+      const int ca = vis2cam(a, N), cbm = vis2cam(b, N);
+      if (grad) { gsc[ca] = s0; hdsc[ca] = s1; }
+      else H[tidx(ca, cbm)] = s0;
+    }
   }
 }
 

@@ -574,55 +574,107 @@ __device__ void schur_syrk(const SolveParams& P, const Win& W, const double* cin
 }
 
 // G: Hv (Schur part) + pair blocks (direct part) -> H tiles (lower), g, hd.  One owner per entry.
-// pid: (i,j) -> pair index table in shared memory, -1 entries redirected to an all-zero block (index zblk) so the
-// accumulation loops are branch-free and their L2 loads overlap.
+// pid: (i,j) -> pair index table in shared memory, -1 entries redirected to an all-zero block (index zblk) so the accumulation loops are
+// branch-free.  Every load of a pair block is an L2 round trip, so each family of entries is written to keep many of them in flight:
+//   (1) pose block q (its own lower triangle) and the extrinsic / td rows against pose block q: one term per OTHER keyframe j (the pair (q, j)
+//       with q as the anchor if j > q, as the observer if j < q), loaded ten at a time with no branch in between;
+//   (2) the gradient / diagonal of the pose rows: the same walk, two loads per keyframe;
+//   (3) pose block p against pose block q < p: exactly one pair block, a block-wise copy;
+//   (4) extrinsic / td rows against themselves: every pair contributes, one warp per entry with the lanes over the pairs.
+// (As one task loop with a serial sum per entry the gather took 45 k cycles per linearisation of a config-2 window, the L2 latency of
+// family (1) and (4) paid term by term.)
+struct GatherTask { int a, b, q, off_anchor, off_obs; };
+
+// entry e of family (1): N x 21 in-block lower entries, then nsh x 6N entries of the shared rows
+__device__ __forceinline__ GatherTask gather_task1(int e, int N) {
+  GatherTask T;
+  if (e < 21 * N) {
+    const int blk = e / 21, w = e - blk * 21;
+    int ao = 0; while ((ao + 1) * (ao + 2) / 2 <= w) ao++;
+    const int bo = w - ao * (ao + 1) / 2;
+    T.a = 6 * blk + ao; T.b = 6 * blk + bo; T.q = blk;
+    T.off_anchor = ao * PAIR_LD + bo; T.off_obs = (6 + ao) * PAIR_LD + 6 + bo;
+  } else {
+    const int e2 = e - 21 * N, ia = e2 / (6 * N), b = e2 - ia * 6 * N, bo = b % 6, la = ia < 6 ? 12 + ia : 18;
+    T.a = 6 * N + ia; T.b = b; T.q = b / 6;
+    T.off_anchor = la * PAIR_LD + bo; T.off_obs = la * PAIR_LD + 6 + bo;
+  }
+  return T;
+}
+
+// sum over the keyframes j != q of blk(q, j)[j > q ? off_anchor : off_obs]
+__device__ __forceinline__ double gather_walk(const double* __restrict__ pp, const int* __restrict__ pid, int N, int q, int off_anchor, int off_obs, int zblk) {
+  double s = 0;
+  for (int j0 = 0; j0 < N; j0 += 10) {
+    double v[10];
+#pragma unroll
+    for (int jj = 0; jj < 10; jj++) {
+      const int j = j0 + jj;
+      const int pr = (j < N && j != q) ? (j > q ? pid[q * N + j] : pid[j * N + q]) : -1;
+      v[jj] = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (j > q ? off_anchor : off_obs)];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 10; jj++) s += v[jj];
+  }
+  return s;
+}
+
+__device__ __forceinline__ void gather_pair_of(int pi, int& pb, int& qb) {   // pi-th pose pair (pb > qb) in row-major lower-triangular order
+  pb = (int)((1.0f + sqrtf(8.0f * pi + 1.0f)) * 0.5f);
+  while (pb * (pb - 1) / 2 > pi) pb--;
+  while ((pb + 1) * pb / 2 <= pi) pb++;
+  qb = pi - pb * (pb - 1) / 2;
+}
+
 __device__ void gather_visual(const SolveParams& P, const Win& W, const double* Hv, const double* gv, double* H, double* g, double* hd,
                               const double* scr, const int* pid, int zblk) {
-  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp;
-  const double* pp = scr + P.sl.pairpart;
-  const int total = Dv * (Dv + 1) / 2 + Dv;     // lower entries + one gradient/diag task per row
-  for (int t = threadIdx.x; t < total; t += blockDim.x) {
-    int a, b; bool grad = false;
-    if (t < Dv) { a = t; b = t; grad = true; }
-    else {
-      const int u = t - Dv;
-      a = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
-      while (a * (a + 1) / 2 > u) a--;
-      while ((a + 1) * (a + 2) / 2 <= u) a++;
-      b = u - a * (a + 1) / 2;
-    }
-    const int p = a < 6 * N ? a / 6 : N + (a - 6 * N) / 6;       // block id: poses 0..N-1, ex = N, td = N+1
-    const int q = b < 6 * N ? b / 6 : N + (b - 6 * N) / 6;
-    const int ao = a < 6 * N ? a % 6 : (a - 6 * N) % 6, bo = b < 6 * N ? b % 6 : (b - 6 * N) % 6;
-    const int la_sh = (p == N) ? 12 + ao : 18;   // local row if a is ex/td
-    const int lb_sh = (q == N) ? 12 + bo : 18;
-    double s0 = 0, s1 = 0, g0 = 0, g1 = 0, d0 = 0, d1 = 0;
-    // contributions come in two families: pairs where the pose block is the ANCHOR (local offset 0) and pairs where it is
-    // the OBSERVER (local offset 6)
-    if (p < N && q < N && p > q) {                 // anchor q, observer p: exactly one pair
-      const int pr = pid[q * N + p];
-      s0 = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (6 + ao) * PAIR_LD + bo];
-    } else if (q < N) {                            // q is a pose; p == q, or p is ex/td
-      const int la_anchor = (p < N) ? ao : la_sh, la_obs = (p < N) ? 6 + ao : la_sh;
+  const int N = W.N, Dv = W.Dv, Dvp = W.Dvp, nsh = Dv - 6 * N, npair = W.h->n_pair, lane = threadIdx.x & 31;
+  const double* __restrict__ pp = scr + P.sl.pairpart;
+  // (1)
+  for (int e = threadIdx.x; e < 21 * N + nsh * 6 * N; e += blockDim.x) {
+    const GatherTask T = gather_task1(e, N);
+    const double s = gather_walk(pp, pid, N, T.q, T.off_anchor, T.off_obs, zblk);
+    H[tidx(vis2cam(T.a, N), vis2cam(T.b, N))] = Hv[T.a * Dvp + T.b] + s;
+  }
+  // (2)
+  for (int e = threadIdx.x; e < 12 * N; e += blockDim.x) {
+    const int a = e >> 1, q = a / 6, ao = a - 6 * q, which = e & 1;      // which: 0 gradient (column 19), 1 diagonal
+    const double s = gather_walk(pp, pid, N, q, ao * PAIR_LD + (which ? ao : 19), (6 + ao) * PAIR_LD + (which ? 6 + ao : 19), zblk);
+    const int ca = vis2cam(a, N);
+    if (which) hd[ca] = s; else g[ca] = gv[a] + s;
+  }
+  // (3)
+  {
+    const double* __restrict__ Hvr = Hv; double* __restrict__ Hr = H;
+    const int nent = N * (N - 1) / 2 * 36;
 #pragma unroll 4
-      for (int j = 0; j < N; j++) {
-        const int pa = j > q ? pid[q * N + j] : -1, po = j < q ? pid[j * N + q] : -1;
-        const double* ba = pp + (size_t)(pa < 0 ? zblk : pa) * (PAIR_LD * PAIR_LD);
-        const double* bo2 = pp + (size_t)(po < 0 ? zblk : po) * (PAIR_LD * PAIR_LD);
-        if (grad) { g0 += ba[la_anchor * PAIR_LD + 19]; d0 += ba[la_anchor * PAIR_LD + la_anchor]; g1 += bo2[la_obs * PAIR_LD + 19]; d1 += bo2[la_obs * PAIR_LD + la_obs]; }
-        else { s0 += ba[la_anchor * PAIR_LD + bo]; s1 += bo2[la_obs * PAIR_LD + 6 + bo]; }
-      }
-    } else {                                       // both in ex/td: every pair
-#pragma unroll 4
-      for (int pr = 0; pr < W.h->n_pair; pr++) {
-        const double* blk = pp + (size_t)pr * (PAIR_LD * PAIR_LD);
-        if (grad) { g0 += blk[la_sh * PAIR_LD + 19]; d0 += blk[la_sh * PAIR_LD + la_sh]; }
-        else s0 += blk[la_sh * PAIR_LD + lb_sh];
-      }
+    for (int e = threadIdx.x; e < nent; e += blockDim.x) {
+      const int pi = e / 36, o = e - pi * 36, ao = o / 6, bo = o - ao * 6;
+      int pb, qb; gather_pair_of(pi, pb, qb);
+      const int pr = pid[qb * N + pb];
+      const double v = pp[(size_t)(pr < 0 ? zblk : pr) * (PAIR_LD * PAIR_LD) + (6 + ao) * PAIR_LD + bo];
+      const int a = 6 * pb + ao, b = 6 * qb + bo;
+      Hr[tidx(vis2cam(a, N), vis2cam(b, N))] = Hvr[a * Dvp + b] + v;
     }
-    const int ca = vis2cam(a, N), cbm = vis2cam(b, N);
-    if (grad) { g[ca] = gv[a] + (g0 + g1); hd[ca] = d0 + d1; }
-    else H[tidx(ca, cbm)] = Hv[a * Dvp + b] + (s0 + s1);
+  }
+  // (4)
+  for (int wt = threadIdx.x >> 5; wt < nsh * (nsh + 1) / 2 + nsh; wt += SOLVE_WARPS) {
+    int ia, ib; const bool grad = wt < nsh;
+    if (grad) { ia = wt; ib = wt; }
+    else { const int u = wt - nsh; ia = 0; while ((ia + 1) * (ia + 2) / 2 <= u) ia++; ib = u - ia * (ia + 1) / 2; }
+    const int la = ia < 6 ? 12 + ia : 18, lb = ib < 6 ? 12 + ib : 18;
+    double s0 = 0, s1 = 0;
+    for (int pr = lane; pr < npair; pr += 32) {
+      const double* blk = pp + (size_t)pr * (PAIR_LD * PAIR_LD);
+      if (grad) { s0 += blk[la * PAIR_LD + 19]; s1 += blk[la * PAIR_LD + la]; }
+      else s0 += blk[la * PAIR_LD + lb];
+    }
+    s0 = warp_sum(s0); if (grad) s1 = warp_sum(s1);
+    if (lane == 0) {
+      const int a = 6 * N + ia, b = 6 * N + ib, ca = vis2cam(a, N), cbm = vis2cam(b, N);
+      if (grad) { g[ca] = gv[a] + s0; hd[ca] = s1; }
+      else H[tidx(ca, cbm)] = Hv[a * Dvp + b] + s0;
+    }
   }
 }
 
