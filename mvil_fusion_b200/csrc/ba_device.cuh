@@ -101,6 +101,15 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   return s;
 }
 
+// Clock read for the in-kernel phase profile.  BAR.SYNC blocks lazily (the warp keeps issuing independent instructions, a plain clock read
+// among them, until it needs the barrier), which booked barrier waits on the phase AFTER the barrier; a shared-memory load cannot pass the
+// barrier and the clock read is issued after it.
+__device__ __forceinline__ long long prof_clock() {
+  unsigned dummy; long long c;
+  asm volatile("ld.shared.u32 %0, [%2];\n\tmov.u64 %1, %%clock64;" : "=r"(dummy), "=l"(c) : "r"(0u) : "memory");
+  return c + (dummy & 0u);
+}
+
 // ---- tile-packed lower-triangular matrix -----------------------------------------------------------------------
 __device__ __forceinline__ int tidx(int i, int j) {  // requires i >= j
   const int bi = i >> 4, bj = j >> 4;
@@ -192,7 +201,7 @@ __device__ __forceinline__ void warp_imu_whitened(const uint16_t* tbl /* shared 
                                                   long long* prof = nullptr) {
   const int lane = threadIdx.x & 31;
   long long wt_ = prof ? clock64() : 0;
-#define WPROF(i) do { if (prof) { const long long n_ = clock64(); prof[i] += n_ - wt_; wt_ = n_; } } while (0)
+#define WPROF(i) do { if (prof) { const long long n_ = prof_clock(); prof[i] += n_ - wt_; wt_ = n_; } } while (0)
   double* J = stage; double* r = stage + 450; double* core = stage + 466; double* Wsm = core + vf::IMU_CORE_LD;
   // one coalesced pass brings everything the single-lane algebra reads from HBM/L2 into shared memory (the J area doubles
   // as the landing zone of the pre-integration record minus its covariance): one exposed latency instead of one per use
@@ -375,7 +384,7 @@ __device__ double pair_pass(const SolveParams& P, const Win& W, const double* x,
   int imu_R = 0, imu_P = 0;                      // raw stages started / product stages started (block-uniform)
   const int nimu = imu_stage ? W.h->n_imu : 0;
   long long pt_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
-#define PPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - pt_; pt_ = n_; } } while (0)
+#define PPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = prof_clock(); P.prof[i] += n_ - pt_; pt_ = n_; } } while (0)
   for (int base = 0; base < np; base += PAIR_CHUNK) {
     const int cnt_round = min(PAIR_CHUNK, np - base);
     const int t = threadIdx.x;
@@ -696,7 +705,7 @@ __device__ double imu_pass(const SolveParams& P, const Win& W, const double* x, 
     const bool mine = k < nimu && pre_all[(size_t)(k < nimu ? k : 0) * 467 + 16] <= 10.0;   // estimator.cpp:1182 skip if sum_dt > 10
     double hv[16]; int i = 0;
     long long it_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
-#define IPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - it_; it_ = n_; } } while (0)
+#define IPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = prof_clock(); P.prof[i] += n_ - it_; it_ = n_; } } while (0)
 #pragma unroll
     for (int e = 0; e < 16; e++) hv[e] = 0;
     if (mine) {
@@ -1115,7 +1124,7 @@ template <bool SH>
 __device__ bool cholesky_tiles(double* H, double* b, double* linv, double* dinv, int nb, int* flag, long long* prof = nullptr) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   long long pt = (prof && blockIdx.x == 0 && t == 0) ? clock64() : 0;
-#define CPROF(i) do { if (prof && blockIdx.x == 0 && t == 0) { const long long n_ = clock64(); prof[i] += n_ - pt; pt = n_; } } while (0)
+#define CPROF(i) do { if (prof && blockIdx.x == 0 && t == 0) { const long long n_ = prof_clock(); prof[i] += n_ - pt; pt = n_; } } while (0)
   // Schedule of one tile row kb (tools/chol_micro.cu measures it in isolation):
   //   panel    all threads: rows of the tiles below the diagonal tile (and the b row) times Lkk^-T
   //   phase A  256 threads: ONLY the next diagonal tile takes its update (one entry per thread, 16 FMAs)

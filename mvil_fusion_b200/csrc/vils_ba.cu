@@ -144,8 +144,11 @@ __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
 }
 
 // Optional phase profiling (VILS_PROF=1): thread 0 of block 0 accumulates SM cycles per phase.
+#ifndef VILS_NO_IMU_INLINE
+#define VILS_NO_IMU_INLINE 0
+#endif
 #define PROF_T0() long long prof_t = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0
-#define PROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - prof_t; prof_t = n_; } } while (0)
+#define PROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = prof_clock(); P.prof[i] += n_ - prof_t; prof_t = n_; } } while (0)
 
 // Full linearisation at state x: H (tiles, lower), g, hd and the cost (broadcast to all threads).
 __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const double* x, double* H, double* Hv,
@@ -153,7 +156,7 @@ __device__ double linearize(const SolveParams& P, const Win& W, const Smem& L, d
   double* g = sm + L.g; double* hd = sm + L.hd;
   PROF_T0();
   // IMU factors ride on the idle warps of the pair pass when their staging fits in the (still unused) Hv region
-  const bool imu_inline = P.hv_in_smem && W.h->n_imu * IMU_SLOT2 <= W.Dvp * W.Dvp + ((P.Ncap + 1) / 2) * 466;
+  const bool imu_inline = !VILS_NO_IMU_INLINE && P.hv_in_smem && W.h->n_imu * IMU_SLOT2 <= W.Dvp * W.Dvp + ((P.Ncap + 1) / 2) * 466;
   double c = pair_pass(P, W, x, sm + L.uni, scr, reinterpret_cast<const int*>(sm + L.pid), need_cost, imu_inline ? sm + L.hv : nullptr, reinterpret_cast<const uint16_t*>(sm + L.tbl), sm + L.rot);
   __syncthreads();
   PROF(0);
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
   double cost0 = 0, cost = 0;
   const int zblk = P.Ncap * (P.Ncap - 1) / 2;
   long long ct_ = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
-#define CLPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); P.prof[i] += n_ - ct_; ct_ = n_; } } while (0)
+#define CLPROF(i) do { if (P.prof && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = prof_clock(); P.prof[i] += n_ - ct_; ct_ = n_; } } while (0)
   for (int it = 0; it < P.max_iters; it++) {
     CLPROF(11);
     // zero this CTA's share of H / g / hd (filled by the gather after the next two barriers)
