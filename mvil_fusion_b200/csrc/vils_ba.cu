@@ -1055,6 +1055,7 @@ __global__ void eval_cons_kernel(EvalParams Q) {
 // =================================================================================================================
 struct SlotMeta { int n_kf = 0, n_feat = 0, n_res = 0; int64_t n_jac = 0; int items = 0; bool set = false; bool on_device = false; bool prepped = false; int bytes = 0; };
 struct PackPool;
+static void pack_pool_destroy(PackPool* p);   // defined with the pool (the type is incomplete up here: a plain delete would skip the destructor and leak the threads)
 
 struct vils_ba {
   vils_config cfg{};
@@ -1310,7 +1311,7 @@ void vils_ba_destroy(vils_ba* ba) {
   if (ba->copy_stream) cudaStreamDestroy(ba->copy_stream);
   for (cudaEvent_t v : ba->ev_chunk) cudaEventDestroy(v);
   if (ba->stream) cudaStreamDestroy(ba->stream);
-  delete ba->pool;
+  pack_pool_destroy(ba->pool);
   if (ba->comm) nccl_comm_destroy(ba->comm);
   cudaFree(ba->d_lamred);
   delete ba;
@@ -1587,6 +1588,8 @@ struct PackPool {
     }
   }
 };
+
+extern "C++" { static void pack_pool_destroy(PackPool* p) { delete p; } }
 
 static PackPool* pack_pool(vils_ba* ba) {
   if (!ba->pool) {
