@@ -309,7 +309,8 @@ __device__ void schur_syrk_cluster(const SolveParams& P, const Win& W, const dou
     for (int j0 = 0; j0 < n_own; j0 += ECH) {
       const int n = min(ECH, n_own - j0);
       __syncthreads();
-      for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) { const int j = k / Dvp, c = k - j * Dvp; chunk[k] = E[(size_t)(r + G * (j0 + j)) * Dvp + c]; }
+      for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) { const int j = k / Dvp, c = k - j * Dvp; cp_async_f64(chunk + k, E + (size_t)(r + G * (j0 + j)) * Dvp + c); }
+      cp_async_wait_all();
       __syncthreads();
       if (ti >= 0) {
         for (int j = 0; j < n; j++) {

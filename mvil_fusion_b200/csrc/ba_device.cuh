@@ -101,6 +101,13 @@ __host__ __device__ inline Smem smem_layout(int Ncap, int Mcap, int h_in_smem, i
   return s;
 }
 
+// Asynchronous global -> shared copy of one double (LDGSTS): a staging loop written as `smem[k] = gmem[k]` is one L2 round trip per element
+// and thread (the store waits for its load and the next load is issued after the store), a loop of these has every element in flight at once.
+__device__ __forceinline__ void cp_async_f64(double* dst_shared, const double* src_global) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 // Clock read for the in-kernel phase profile.  BAR.SYNC blocks lazily (the warp keeps issuing independent instructions, a plain clock read
 // among them, until it needs the barrier), which booked barrier waits on the phase AFTER the barrier; a shared-memory load cannot pass the
 // barrier and the clock read is issued after it.
@@ -546,7 +553,8 @@ __device__ void schur_syrk(const SolveParams& P, const Win& W, const double* cin
   for (int f0 = 0; f0 < nlm; f0 += ECH) {
     const int n = min(ECH, nlm - f0);
     __syncthreads();
-    for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) chunk[k] = E[(size_t)f0 * Dvp + k];
+    for (int k = threadIdx.x; k < n * Dvp; k += blockDim.x) cp_async_f64(chunk + k, E + (size_t)f0 * Dvp + k);
+    cp_async_wait_all();
     __syncthreads();
     if (ti >= 0) {
       for (int f = 0; f < n; f++) {
