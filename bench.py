@@ -40,7 +40,7 @@ BYTES_PER_LINEARISATION = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544 + (
 BYTES_PER_COST_EVAL = 906 * 124 + 9 * 2296 + 1500 * 60 + 500 * 76 + 2544
 BYTES_PER_SOLVE = 5 * BYTES_PER_LINEARISATION + BYTES_PER_COST_EVAL
 # dram__bytes_read.sum + dram__bytes_write.sum of solve_kernel per window, from the committed ncu capture
-SOLVE_DRAM_TRAFFIC_PER_WINDOW = 3347323   # (1045.36 + 936.25) MB / 592 windows, ncu --set full capture of solve_kernel (profiles/r2_ncu_solve.txt)
+SOLVE_DRAM_TRAFFIC_PER_WINDOW = 3273324   # (1026.30 + 911.50) MB / 592 windows, ncu --set full capture of solve_kernel (profiles/r2_ncu_solve_v2.txt)
 # Materialised Evaluate() traffic per window (what the CPU reference moves per linearisation; §8d first table)
 BYTES_PER_EVAL_WINDOW = 906 * 460 + 9 * 6016 + 1500 * 116 + 500 * 244 + 2544
 # Algorithmic FP64 work per linearisation (Schur SYRK 2 D^2 M = 7.4 MFLOP, Cholesky D^3/3 = 1.3 MFLOP at D = 157, M = 150;
