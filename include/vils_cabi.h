@@ -384,7 +384,9 @@ void vils_lidar_dev_free(void* handle);
  * map / scan: x y z intensity, 4 packed floats per point.  q_w_curr (x y z w), t_w_curr: current scan-to-map pose (pointAssociateToMap,
  * :170-179).  mode 0: corner points, 5-NN, line test l2 > 3 l1 -> out[i] = p(3) a(3) b(3) -  (LidarEdgeFactor::Create inputs, :626-667);
  * mode 1: surface points, 10-NN -> 5 closest intensities, plane fit + 0.2 m check -> out[i] = p(3) n(3) d - - -  (LidarPlaneNormFactor
- * inputs, :675-747).  valid[i] = 1 where the reference adds a residual block; nn_idx (may be NULL): n_scan x 5 map indices used. */
+ * inputs, :675-747).  valid[i] = 1 where the reference adds a residual block; nn_idx (may be NULL): n_scan x 5 map indices used.  The search is
+ * exact wherever the reference uses its result (5th neighbour within 1 m); for the other points (valid = 0) nn_idx holds the nearest points found
+ * in the cells around the query, 0x7fffffff where there were fewer than five. */
 int vils_lidar_associate(const float* map_xyzi, int32_t n_map, const float* scan_xyzi, int32_t n_scan, const double q_w_curr[4],
                          const double t_w_curr[3], int32_t mode, double* out /* n_scan x 10 */, uint8_t* valid, int32_t* nn_idx,
                          float* device_ms, int32_t device);
