@@ -105,6 +105,33 @@ def test_associate_matches_restatement(mode):
     assert ms > 0
 
 
+def test_associate_sparse_rim_is_still_exact():
+    """Surface points with only 6 map points within 1 m: the 10 nearest include points 1-2 m away (5 x 5 x 5 shell of the grid) or further than
+    2 m (exhaustive fallback).  The neighbour sets must still be the exact 10-NN -> 5 by intensity of the k-d tree."""
+    from mvil_fusion_b200 import lib
+    rng = np.random.default_rng(77)
+    filler = np.c_[rng.uniform(200, 260, (6000, 3)), rng.uniform(0, 100, 6000)]            # far away: makes the map large enough for the grid
+    sites, pts = [], []
+    for k in range(48):
+        c = np.array([12.0 * (k % 8), 12.0 * (k // 8), 0.37 * k])
+        sites.append(c)
+        near = c + rng.normal(0, 0.12, (6, 3))
+        r = rng.uniform(1.15, 1.8, 7) if k % 2 == 0 else rng.uniform(2.4, 3.4, 7)          # even sites: shell, odd sites: exhaustive search
+        u = rng.normal(0, 1, (7, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+        pts.append(np.c_[np.vstack([near, c + r[:, None] * u]), rng.uniform(0, 100, 13)])
+    mp = np.vstack([filler] + pts).astype(np.float32)
+    scan = np.c_[np.array(sites), rng.uniform(0, 100, len(sites))].astype(np.float32)
+    q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
+    out, valid, nn, _ = lib.lidar_associate(mp, scan, q, t, 1)
+    ro, rv, rn, cand = oracle(mp, scan, q, t, 1)
+    assert cand.all()
+    assert all(set(a) == set(b) for a, b in zip(nn, rn))
+    assert np.array_equal(valid.astype(bool), rv)
+    ok = rv
+    if ok.any():
+        assert np.abs(out[ok, 3:7] - ro[ok, 3:7]).max() <= 1e-9
+
+
 def test_associate_edge_cases():
     from mvil_fusion_b200 import lib
     q = np.array([0, 0, 0, 1.0]); t = np.zeros(3)
