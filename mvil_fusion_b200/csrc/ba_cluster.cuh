@@ -20,7 +20,9 @@ __device__ void warp_imu_sqrt_info(const double* cov, double* W, double* wk);   
 
 namespace vb {
 
-constexpr int CL_MAX = 8;            // portable cluster size limit
+constexpr int CL_MAX = 16;           // 8 is the portable cluster size limit; 16 is opt-in (cudaFuncAttributeNonPortableClusterSizeAllowed) and only
+                                     // used when the device can co-schedule such a cluster
+constexpr int CL_PORTABLE = 8;
 
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }

@@ -1084,7 +1084,8 @@ struct vils_ba {
   double* d_shard = nullptr; size_t shard_doubles = 0;
   double* d_mws = nullptr; int32_t* d_miws = nullptr; MargParams mq{}; int64_t mws_doubles = 0; int mi_ints = 0;
   PackPool* pool = nullptr;                            // host packer threads (created on first use)
-  ClScratch cl{}; double* d_clbuf = nullptr; int cl_windows = 0, cl_imu_slots = 0; size_t cl_smem = 0; bool cl_smem_h = false; int cluster_pref = 0;   // latency mode (0 auto, 1 off, 2/4/8 forced)
+  ClScratch cl{}; double* d_clbuf = nullptr; int cl_windows = 0, cl_imu_slots = 0; size_t cl_smem = 0; bool cl_smem_h = false; int cluster_pref = 0;   // latency mode (0 auto, 1 off, 2/4/8/16 forced)
+  bool cl16 = false;                                   // the device can co-schedule a cluster of 16 of these CTAs (non-portable size)
   ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 0;   // factor-sharded mode: one rank per GPU (vils_ba_sharded_init)
   double* d_lamred = nullptr;                          // [lam * own | own] for the final inverse-depth exchange
 };
@@ -1131,8 +1132,9 @@ static int pick_cluster(const vils_ba* ba, const SolveParams& P, int n) {
   if (P.slot0 + n > ba->cl_windows) return 1;               // the exchange areas cover slots [0, cl_windows)
   static const bool prof_cluster = getenv("VILS_PROF_CLUSTER") != nullptr;
   if (P.mode != VILS_MODE_GN || P.lin_out || (P.prof && !prof_cluster) || P.max_iters <= 0 || P.time_cap_ns > 0 || ba->cluster_pref == 1 || n > ba->cl_windows) return 1;
-  if (ba->cluster_pref >= 2) return n * ba->cluster_pref <= ba->n_sm ? std::min(ba->cluster_pref, CL_MAX) : 1;
-  for (int g = CL_MAX; g >= 2; g >>= 1) if (n * g <= ba->n_sm) return g;
+  const int gmax = ba->cl16 ? CL_MAX : CL_PORTABLE;
+  if (ba->cluster_pref >= 2) { const int g = std::min(ba->cluster_pref, gmax); return n * g <= ba->n_sm ? g : 1; }
+  for (int g = gmax; g >= 2; g >>= 1) if (n * g <= ba->n_sm) return g;
   return 1;
 }
 static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t s, bool allow_cluster) {
@@ -1285,10 +1287,23 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
       CK(cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
       CK(cudaFuncSetAttribute(solve_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));   // 2 KB of static shared memory (pair ownership table)
       CK(cudaFuncSetAttribute(solve_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      cudaFuncSetAttribute(solve_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);     // clusters of 16: best effort
+      cudaFuncSetAttribute(solve_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaGetLastError();
       if (cfg->device < 64) attr_done[cfg->device] = true;
     }
   }
 #undef CK
+  {   // clusters of 16 CTAs are beyond the portable limit: used only if the device says it can co-schedule one
+    cudaLaunchConfig_t qc{}; cudaLaunchAttribute at[1];
+    qc.gridDim = dim3(16); qc.blockDim = dim3(SOLVE_THREADS); qc.dynamicSmemBytes = ba->cl_smem;
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    qc.attrs = at; qc.numAttrs = 1;
+    int ncl = 0;
+    const cudaError_t qe = ba->cl_smem_h ? cudaOccupancyMaxActiveClusters(&ncl, solve_cluster_kernel<true>, &qc) : cudaOccupancyMaxActiveClusters(&ncl, solve_cluster_kernel<false>, &qc);
+    ba->cl16 = qe == cudaSuccess && ncl >= 1 && !(getenv("VILS_CLUSTER16") && atoi(getenv("VILS_CLUSTER16")) == 0);
+    cudaGetLastError();
+  }
   { uint16_t tbl[450]; vf::imu_build_table(tbl); cudaError_t e_ = cudaMemcpyToSymbol(g_imu_tbl, tbl, sizeof(tbl)); if (e_ != cudaSuccess) { vils_ba_destroy(ba); return vils::fail_cuda(e_, "imu table"); } }
   std::memset(ba->h_blob, 0, ba->blob_stride * max_windows);
   std::memset(ba->h_sum, 0, sizeof(vils_summary) * max_windows);
@@ -2186,7 +2201,7 @@ int vils_ba_sharded_solve(vils_ba* ba, const vils_solve_opts* opts, vils_summary
 }
 
 int vils_ba_set_cluster(vils_ba* ba, int32_t cluster_size) {
-  if (!ba || !(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8)) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_cluster: 0 (auto), 1 (off), 2, 4 or 8");
+  if (!ba || !(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16)) return vils::fail(VILS_ERR_BAD_ARG, "vils_ba_set_cluster: 0 (auto), 1 (off), 2, 4, 8 or 16");
   ba->cluster_pref = cluster_size; return VILS_OK;
 }
 int vils_ba_last_cluster(vils_ba* ba, int32_t* cluster_size) { if (!ba || !cluster_size) return VILS_ERR_BAD_ARG; *cluster_size = ba->last_cluster; return VILS_OK; }

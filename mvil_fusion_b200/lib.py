@@ -179,7 +179,7 @@ class BA:
         _check(self.L.vils_ba_put_state(self.h, slot, _d(a[0]), _d(a[1]), _d(a[2]), _d(a[3]) if a[3].size else None, float(td)))
 
     def set_cluster(self, size):
-        """Latency mode: 0 auto, 1 off, 2 / 4 / 8 SMs per window (vils_ba_set_cluster)."""
+        """Latency mode: 0 auto, 1 off, 2 / 4 / 8 / 16 SMs per window (vils_ba_set_cluster)."""
         _check(self.L.vils_ba_set_cluster(self.h, int(size)))
 
     @property

@@ -334,9 +334,9 @@ def test_cluster_latency_kernel_matches_single_cta_kernel(lib):
         assert ref.last_cluster == 1
         r = ref.get_state(0); o = ol.solve_window(cfg, w, opts)
         assert r["status"] == 0 and o["status"] == 0
-        for G in (2, 4, 8):
+        for G in (2, 4, 8, 16):
             h = lib.BA(cfg, 1); h.set_cluster(G); h.set_window(0, w); h.solve(1, opts)
-            assert h.last_cluster == G
+            assert h.last_cluster == G or (G == 16 and h.last_cluster == 8)      # 16 is beyond the portable cluster size: only where the device takes it
             s = h.get_state(0)
             assert s["status"] == 0 and s["iterations"] == 5
             assert helpers.rel_state_delta(s, r) <= 1e-9
@@ -346,7 +346,7 @@ def test_cluster_latency_kernel_matches_single_cta_kernel(lib):
             assert np.array_equal(s["pose"], s2["pose"]) and np.array_equal(s["inv_depth"], s2["inv_depth"])   # bit-reproducible
             h.close()
         ref.close()
-    # automatic choice: 1 window -> 8 SMs, 30 windows -> 4, 60 -> 2, 100 -> one CTA per window
+    # automatic choice: 1 window -> 16 SMs (8 where a cluster of 16 cannot be scheduled), 18 -> 8, 30 windows -> 4, 60 -> 2, 100 -> one CTA per window
     cfg = cabi.default_config()
     ws = [synth.make_window(2, 300 + k) for k in range(4)]
     h = lib.BA(cfg, 100)
@@ -354,8 +354,8 @@ def test_cluster_latency_kernel_matches_single_cta_kernel(lib):
         h.set_window(k, ws[k % 4])
     h.upload(100)
     expect = {}
-    for n, G in ((1, 8), (18, 8), (30, 4), (60, 2), (100, 1)):
-        h.solve_device(n, opts); assert h.last_cluster == G, (n, h.last_cluster)
+    for n, G in ((1, 16), (18, 8), (30, 4), (60, 2), (100, 1)):
+        h.solve_device(n, opts); assert h.last_cluster == G or (n == 1 and h.last_cluster == 8), (n, h.last_cluster)
         h.download(n); expect[n] = h.get_state(0)["pose"].copy()
     for n in (18, 30, 60, 100):
         assert np.abs(expect[n] - expect[1]).max() <= 1e-9 * np.abs(expect[1]).max()
