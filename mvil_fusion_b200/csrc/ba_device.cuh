@@ -1128,8 +1128,124 @@ __device__ __noinline__ void chol_diag_inverse(const double* Akk, const double* 
 // C: blocked Cholesky of the tile-packed lower matrix, with b (= -g) carried along as an extra row.
 // On exit: H holds L, linv[kb] the inverse of each diagonal tile, y = L^-1 b in `b`.  Returns false on breakdown.
 // =================================================================================================================
+// The same factorisation for a reduced system that does NOT fit shared memory (20-keyframe windows, D = 307: 210 tiles = 460 KB, kept in the
+// window's L2 scratch).  Run straight on global memory every operand of the trailing update was an L2 round trip (128 loads per 4x4 register
+// tile) and the pivot chain of the diagonal tile an L2 round trip per column: 45 k cycles per tile row.  Here shared memory holds what a tile
+// row re-reads: the diagonal tile being factored (two buffers: this row's and the next one's) and the panel column L(kb+1.., kb) once it is
+// computed; global memory sees every tile once per row (panel rows in, L rows out, one read-modify-write of each trailing tile).
+// stage: shared memory, (nb + 1) tiles.
+__device__ bool cholesky_tiles_staged(double* H, double* b, double* linv, double* dinv, int nb, int* flag, double* stage) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int dw = SOLVE_WARPS - 1;
+  double* dcur = stage; double* dnext = stage + TSZ; double* psm = stage + 2 * TSZ;   // psm tile j = L(kb + 1 + j, kb)
+  for (int e = t; e < 16 * TLD; e += blockDim.x) dcur[e] = H[e];
+  __syncthreads();
+  if (warp == dw) chol_diag_factor<true>(dcur, dinv, flag, lane);
+  __syncthreads();
+  for (int kb = 0; kb < nb; kb++) {
+    double* Akk_g = H + (size_t)(tri(kb) + kb) * TSZ;
+    for (int e = t; e < 16 * TLD; e += blockDim.x) Akk_g[e] = dcur[e];          // the factored diagonal tile goes back (back-substitution, dogleg)
+    // panel: rows of tiles (ib, kb), ib > kb, and the b row, times Lkk^-T (Lkk in shared memory); L rows to global memory AND to psm
+    const int nrows = (nb - kb - 1) * 16 + 1;
+    for (int rr = t; rr < nrows; rr += blockDim.x) {
+      const bool brow = rr == nrows - 1;
+      double* row = brow ? b + kb * 16 : H + (size_t)(tri(kb + 1 + rr / 16) + kb) * TSZ + (rr & 15) * TLD;
+      const double* dk = dinv + kb * 16;
+      double v[16];
+#pragma unroll
+      for (int m = 0; m < 16; m++) v[m] = row[m];
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        v[m] *= dk[m];
+#pragma unroll
+        for (int c = m + 1; c < 16; c++) v[c] = fma(-v[m], dcur[c * TLD + m], v[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; c++) row[c] = v[c];
+      if (!brow) {
+        double* ps = psm + (size_t)(rr / 16) * TSZ + (rr & 15) * TLD;
+#pragma unroll
+        for (int c = 0; c < 16; c++) ps[c] = v[c];
+      }
+    }
+    __syncthreads();
+    const int rem = nb - kb - 1;
+    if (rem == 0) break;
+    // phase A: the next diagonal tile, updated, into its shared-memory buffer
+    if (t < 256) {
+      const int i = t >> 4, j = t & 15;
+      double val = 0.0;
+      if (i >= j) {
+        const double* Li = psm + i * TLD; const double* Lj = psm + j * TLD;
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int m = 0; m < 16; m += 2) { s0 = fma(Li[m], Lj[m], s0); s1 = fma(Li[m + 1], Lj[m + 1], s1); }
+        val = H[(size_t)(tri(kb + 1) + kb + 1) * TSZ + i * TLD + j] - (s0 + s1);
+      }
+      dnext[i * TLD + j] = val;
+    }
+    __syncthreads();
+    // phase B: diagonal warp | trailing tiles and b row | inverse of this row's diagonal tile
+    if (warp == dw) {
+      chol_diag_factor<true>(dnext, dinv + (kb + 1) * 16, flag, lane);
+    } else if ((warp & 3) != (dw & 3)) {
+      const int ntile = tri(rem) - 1, ntl = ntile * 16 + rem * 16, tu = (warp - (warp >> 2)) * 32 + lane;
+      for (int it = tu; it < ntl; it += (SOLVE_WARPS - SOLVE_WARPS / 4) * 32) {
+        if (it < ntile * 16) {
+          const int tl = (it >> 4) + 1, sub = it & 15;
+          int bi = (int)((sqrtf(8.0f * tl + 1.0f) - 1.0f) * 0.5f);
+          while (bi * (bi + 1) / 2 > tl) bi--;
+          while ((bi + 1) * (bi + 2) / 2 <= tl) bi++;
+          const int bj = tl - bi * (bi + 1) / 2;
+          const double* Lik = psm + (size_t)bi * TSZ;
+          const double* Ljk = psm + (size_t)bj * TSZ;
+          double* Aij = H + (size_t)(tri(kb + 1 + bi) + kb + 1 + bj) * TSZ;
+          const int r0 = (sub >> 2) * 4, c0 = (sub & 3) * 4;
+          double acc[4][4], old[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { acc[a][c] = 0; old[a][c] = Aij[(r0 + a) * TLD + c0 + c]; }    // in flight during the products
+#pragma unroll 4
+          for (int m = 0; m < 16; m++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) av[a] = Lik[(r0 + a) * TLD + m];
+#pragma unroll
+            for (int c = 0; c < 4; c++) bv[c] = Ljk[(c0 + c) * TLD + m];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int c = 0; c < 4; c++) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+          }
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) Aij[(r0 + a) * TLD + c0 + c] = old[a][c] - acc[a][c];
+        } else {
+          const int q = it - ntile * 16, j = q >> 4, c = q & 15;
+          const double* Ljk = psm + (size_t)j * TSZ;
+          const double* yk = b + kb * 16;
+          double s0 = 0, s1 = 0;
+#pragma unroll
+          for (int m = 0; m < 16; m += 2) { s0 = fma(yk[m], Ljk[c * TLD + m], s0); s1 = fma(yk[m + 1], Ljk[c * TLD + m + 1], s1); }
+          b[(kb + 1 + j) * 16 + c] -= s0 + s1;
+        }
+      }
+    } else if (warp == (dw & 3)) {
+      chol_diag_inverse(dcur, dinv + kb * 16, linv + kb * 256);
+    }
+    __syncthreads();
+    double* sw = dcur; dcur = dnext; dnext = sw;
+  }
+  if (warp == 0) chol_diag_inverse(dcur, dinv + (nb - 1) * 16, linv + (nb - 1) * 256);
+  __syncthreads();
+  return *flag == 0;
+}
+
 template <bool SH>
-__device__ bool cholesky_tiles(double* H, double* b, double* linv, double* dinv, int nb, int* flag, long long* prof = nullptr) {
+__device__ bool cholesky_tiles(double* H, double* b, double* linv, double* dinv, int nb, int* flag, long long* prof = nullptr, double* stage = nullptr) {
+  if (!SH && stage) return cholesky_tiles_staged(H, b, linv, dinv, nb, flag, stage);   // H in the L2 scratch: operands staged in shared memory
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   long long pt = (prof && blockIdx.x == 0 && t == 0) ? clock64() : 0;
 #define CPROF(i) do { if (prof && blockIdx.x == 0 && t == 0) { const long long n_ = prof_clock(); prof[i] += n_ - pt; pt = n_; } } while (0)

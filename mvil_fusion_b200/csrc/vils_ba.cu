@@ -143,6 +143,13 @@ __device__ bool cam_dim_fixed(const SolveParams& P, const Win& W, int d) {
   return W.u(OFF_FIXED)[W.M + d / 15] != 0;       // kf_fixed
 }
 
+// Shared-memory staging area of the Cholesky of a reduced system kept in global memory: the staging union (pair-pass rows / Schur chunk, dead
+// by then), if (nb + 1) tiles fit in it.
+__device__ __forceinline__ double* chol_stage(const Smem& L, double* sm, int nb) {
+  const int have = (L.hv >= 0 ? L.hv : L.imu) - L.uni;
+  return (nb + 1) * TSZ + 16 * TLD <= have ? sm + L.uni : nullptr;
+}
+
 // Optional phase profiling (VILS_PROF=1): thread 0 of block 0 accumulates SM cycles per phase.
 #ifndef VILS_NO_IMU_INLINE
 #define VILS_NO_IMU_INLINE 0
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       PROF(7);
-      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof);
+      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof, chol_stage(L, sm, W.nb));
       ok = chol_flag == 0;
       PROF(8);
       if (!ok && !TR) { status = VILS_ERR_CHOLESKY; break; }
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       CLPROF(6);
-      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr, chol_stage(L, sm, W.nb));
       CLPROF(7);
       int st = VILS_OK;
       if (chol_flag) st = VILS_ERR_CHOLESKY;
@@ -761,7 +768,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) shard_upd_kernel(SolveParams
   damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, mu);
   __syncthreads();
   double* linv = L.linv >= 0 ? sm + L.linv : scr + P.sl.linvg;
-  cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr);
+  cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr, chol_stage(L, sm, W.nb));
   int status = VILS_OK;
   if (chol_flag) status = VILS_ERR_CHOLESKY;
   else {
