@@ -406,4 +406,135 @@ __device__ void gather_cluster(const SolveParams& P, const Win& W, const double*
   }
 }
 
+// Cholesky of a reduced system kept in GLOBAL memory (20-keyframe windows), by the whole cluster: CTA 0 runs what cholesky_tiles_staged runs
+// (write-back of the diagonal tile, panel column, next diagonal tile and its factorisation, tile inverses, b row), the trailing tiles of every
+// tile row are dealt round-robin to ALL CTAs, each with the panel column staged in its own shared memory.  Two cluster barriers per tile row
+// (panel column visible -> trailing tiles visible).  On CTA 0 alone the trailing update was 60 % of a config-4 solve on a cluster.
+// Every CTA passes its own stage ((nb + 1) tiles); b, linv, dinv, flag are CTA 0's.
+__device__ void cholesky_tiles_cluster(double* H, double* b, double* linv, double* dinv, int nb, int* flag, double* stage, const int r, const int G) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int dw = SOLVE_WARPS - 1;
+  double* dcur = stage; double* dnext = stage + TSZ; double* psm = stage + 2 * TSZ;   // psm tile j = L(kb + 1 + j, kb)
+  if (r == 0) {
+    for (int e = t; e < 16 * TLD; e += blockDim.x) dcur[e] = H[e];
+    __syncthreads();
+    if (warp == dw) chol_diag_factor<true>(dcur, dinv, flag, lane);
+    __syncthreads();
+  }
+  for (int kb = 0; kb < nb; kb++) {
+    const int rem = nb - kb - 1;
+    if (r == 0) {
+      double* Akk_g = H + (size_t)(tri(kb) + kb) * TSZ;
+      for (int e = t; e < 16 * TLD; e += blockDim.x) Akk_g[e] = dcur[e];
+      const int nrows = rem * 16 + 1;
+      for (int rr = t; rr < nrows; rr += blockDim.x) {
+        const bool brow = rr == nrows - 1;
+        double* row = brow ? b + kb * 16 : H + (size_t)(tri(kb + 1 + rr / 16) + kb) * TSZ + (rr & 15) * TLD;
+        const double* dk = dinv + kb * 16;
+        double v[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) v[m] = row[m];
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+          v[m] *= dk[m];
+#pragma unroll
+          for (int c = m + 1; c < 16; c++) v[c] = fma(-v[m], dcur[c * TLD + m], v[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) row[c] = v[c];
+        if (!brow) {
+          double* ps = psm + (size_t)(rr / 16) * TSZ + (rr & 15) * TLD;
+#pragma unroll
+          for (int c = 0; c < 16; c++) ps[c] = v[c];
+        }
+      }
+      __syncthreads();
+    }
+    if (rem == 0) break;
+    cluster_sync_all();                              // the panel column L(kb+1.., kb) is in global memory
+    if (r != 0) {
+      for (int e = t; e < rem * 16 * TLD; e += blockDim.x) {
+        const int j = e / (16 * TLD), o = e - j * 16 * TLD;
+        cp_async_f64(psm + (size_t)j * TSZ + o, H + (size_t)(tri(kb + 1 + j) + kb) * TSZ + o);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    } else {
+      // the next diagonal tile, updated, into its shared-memory buffer
+      if (t < 256) {
+        const int i = t >> 4, j = t & 15;
+        double val = 0.0;
+        if (i >= j) {
+          const double* Li = psm + i * TLD; const double* Lj = psm + j * TLD;
+          double s0 = 0, s1 = 0;
+#pragma unroll
+          for (int m = 0; m < 16; m += 2) { s0 = fma(Li[m], Lj[m], s0); s1 = fma(Li[m + 1], Lj[m + 1], s1); }
+          val = H[(size_t)(tri(kb + 1) + kb + 1) * TSZ + i * TLD + j] - (s0 + s1);
+        }
+        dnext[i * TLD + j] = val;
+      }
+      __syncthreads();
+    }
+    if (r == 0 && warp == dw) {
+      chol_diag_factor<true>(dnext, dinv + (kb + 1) * 16, flag, lane);
+    } else if (r == 0 && warp == (dw & 3)) {
+      chol_diag_inverse(dcur, dinv + kb * 16, linv + kb * 256);
+    } else if (r != 0 || (warp & 3) != (dw & 3)) {
+      // trailing tiles tl = 1 .. tri(rem) - 1 (tile 0 is the next diagonal tile): tile tl belongs to CTA tl % G; CTA 0 also takes the b row
+      const int ntile = tri(rem) - 1;
+      const int first = r == 0 ? G : r, mine = first <= ntile ? (ntile - first) / G + 1 : 0;
+      const int nb_tasks = r == 0 ? rem * 16 : 0, ntl = mine * 16 + nb_tasks;
+      const int tu = r == 0 ? (warp - (warp >> 2)) * 32 + lane : t, stride = r == 0 ? (SOLVE_WARPS - SOLVE_WARPS / 4) * 32 : SOLVE_THREADS;
+      for (int it = tu; it < ntl; it += stride) {
+        if (it < mine * 16) {
+          const int tl = first + G * (it >> 4), sub = it & 15;
+          int bi = (int)((sqrtf(8.0f * tl + 1.0f) - 1.0f) * 0.5f);
+          while (bi * (bi + 1) / 2 > tl) bi--;
+          while ((bi + 1) * (bi + 2) / 2 <= tl) bi++;
+          const int bj = tl - bi * (bi + 1) / 2;
+          const double* Lik = psm + (size_t)bi * TSZ;
+          const double* Ljk = psm + (size_t)bj * TSZ;
+          double* Aij = H + (size_t)(tri(kb + 1 + bi) + kb + 1 + bj) * TSZ;
+          const int r0 = (sub >> 2) * 4, c0 = (sub & 3) * 4;
+          double acc[4][4], old[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { acc[a][c] = 0; old[a][c] = Aij[(r0 + a) * TLD + c0 + c]; }
+#pragma unroll 4
+          for (int m = 0; m < 16; m++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) av[a] = Lik[(r0 + a) * TLD + m];
+#pragma unroll
+            for (int c = 0; c < 4; c++) bv[c] = Ljk[(c0 + c) * TLD + m];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+              for (int c = 0; c < 4; c++) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+          }
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) Aij[(r0 + a) * TLD + c0 + c] = old[a][c] - acc[a][c];
+        } else {
+          const int q = it - mine * 16, j = q >> 4, c = q & 15;
+          const double* Ljk = psm + (size_t)j * TSZ;
+          const double* yk = b + kb * 16;
+          double s0 = 0, s1 = 0;
+#pragma unroll
+          for (int m = 0; m < 16; m += 2) { s0 = fma(yk[m], Ljk[c * TLD + m], s0); s1 = fma(yk[m + 1], Ljk[c * TLD + m + 1], s1); }
+          b[(kb + 1 + j) * 16 + c] -= s0 + s1;
+        }
+      }
+    }
+    cluster_sync_all();                              // every trailing tile of this row is in global memory
+    if (r == 0) { double* sw = dcur; dcur = dnext; dnext = sw; }
+  }
+  if (r == 0) {
+    if (warp == 0) chol_diag_inverse(dcur, dinv + (nb - 1) * 16, linv + (nb - 1) * 256);
+    __syncthreads();
+  }
+}
+
 }  // namespace vb

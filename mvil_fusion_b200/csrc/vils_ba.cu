@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
     cluster_sync_all();
     CLPROF(5);
     // C: the serial chain on CTA 0
+    const bool coop_chol = !SMEM_H && chol_stage(L, sm, W.nb) != nullptr;
     if (r == 0) {
       for (int e = threadIdx.x; e < Dp; e += blockDim.x) { sm[L.g + e] = gsc[e]; sm[L.hd + e] = hdsc[e]; }
       __syncthreads();
@@ -636,7 +637,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       CLPROF(6);
-      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr, chol_stage(L, sm, W.nb));
+      if (!coop_chol) cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, nullptr, chol_stage(L, sm, W.nb));
+    }
+    if (coop_chol) {   // reduced system in global memory: the whole cluster factors it (the trailing tiles of every tile row dealt to all CTAs)
+      cluster_sync_all();                            // CTA 0's additions to H are visible to the cluster
+      cholesky_tiles_cluster(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, sm + L.uni, r, G);
+    }
+    if (r == 0) {
       CLPROF(7);
       int st = VILS_OK;
       if (chol_flag) st = VILS_ERR_CHOLESKY;
