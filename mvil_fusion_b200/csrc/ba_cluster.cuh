@@ -406,6 +406,33 @@ __device__ void gather_cluster(const SolveParams& P, const Win& W, const double*
   }
 }
 
+// H += A of the marginalization prior (n x n, n = 136 for a 20-keyframe window) on the mapped columns, for a reduced system kept in GLOBAL
+// memory: entries dealt to all CTAs, four in flight per thread (on CTA 0 alone: 48 dependent L2 read-modify-writes per thread).  The diagonal
+// also goes to the cluster's hd exchange vector.  One (a, b) of the prior maps to one entry of H: no two threads meet.
+__device__ void prior_add_H_cluster(const SolveParams& P, const Win& W, double* H, double* hdg, const double* scr, const int r, const int G) {
+  const int n = W.h->prior_n;
+  if (n == 0) return;
+  const int32_t* col = W.i(OFF_PRIOR_COL);
+  const double* A = scr + P.sl.priorA;
+  const int nn = n * n, step = G * blockDim.x;
+  for (int e0 = r * blockDim.x + threadIdx.x; e0 < nn; e0 += 4 * step) {
+    double av[4], hv[4]; int hi[4], ca[4]; bool on[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = e0 + u * step;
+      on[u] = e < nn; hi[u] = 0; ca[u] = -1; av[u] = 0; hv[u] = 0;
+      if (on[u]) {
+        const int a = e / n, b = e - a * n;
+        const int c1 = col[a], c2 = col[b];
+        on[u] = c1 >= c2;
+        if (on[u]) { hi[u] = tidx(c1, c2); av[u] = A[e]; hv[u] = H[hi[u]]; if (c1 == c2) ca[u] = c1; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (on[u]) { H[hi[u]] = hv[u] + av[u]; if (ca[u] >= 0) hdg[ca[u]] += av[u]; }
+  }
+}
+
 // Cholesky of a reduced system kept in GLOBAL memory (20-keyframe windows), by the whole cluster: CTA 0 runs what cholesky_tiles_staged runs
 // (write-back of the diagonal tile, panel column, next diagonal tile and its factorisation, tile inverses, b row), the trailing tiles of every
 // tile row are dealt round-robin to ALL CTAs, each with the panel column staged in its own shared memory.  Two cluster barriers per tile row

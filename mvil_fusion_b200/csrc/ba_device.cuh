@@ -341,18 +341,25 @@ __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g
       double pv[16];
 #pragma unroll
       for (int q = 0; q < 16; q++) { const int e = lane + 32 * q; pv[q] = e < 495 ? prod[e] : 0.0; }
+      // (H may live in global memory: its 15 entries per lane are read together, then written)
+      int hi[15]; double hv[15];
 #pragma unroll
-      for (int q = 0; q < 16; q++) {
+      for (int q = 0; q < 15; q++) {
         const int e = lane + 32 * q;
+        hi[q] = -1; hv[q] = 0.0;
         if (e < 465) {
           int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
           while (a * (a + 1) / 2 > e) a--;
           while ((a + 1) * (a + 2) / 2 <= e) a++;
           const int b = e - a * (a + 1) / 2;
-          H[tidx(base + a, base + b)] += pv[q];
+          hi[q] = tidx(base + a, base + b); hv[q] = H[hi[q]];
           if (a == b) hd[base + a] += pv[q];
-        } else if (e < 495) g[base + e - 465] += pv[q];
+        }
       }
+#pragma unroll
+      for (int q = 0; q < 15; q++) if (hi[q] >= 0) H[hi[q]] = hv[q] + pv[q];
+#pragma unroll
+      for (int q = 14; q < 16; q++) { const int e = lane + 32 * q; if (e >= 465 && e < 495) g[base + e - 465] += pv[q]; }
     }
     __syncthreads();
   }
@@ -965,7 +972,7 @@ __device__ double icp_lps_pass(const SolveParams& P, const Win& W, const double*
 // MarginalizationFactor (factor/marginalization_factor.cpp:352-400): r = r_lin + J_lin dx. A = J^T J and b0 = J^T r_lin are
 // constant across iterations and precomputed by prep_kernel, so g += b0 + A dx, H += A, cost = 1/2 |r|^2.
 __device__ double prior_pass(const SolveParams& P, const Win& W, const double* x, double* H, double* g, double* hd, double* dxp /* n doubles smem */,
-                             const double* scr, bool want_J) {
+                             const double* scr, bool want_J, bool add_H = true /* false: H += A was done by prior_add_H_cluster */) {
   const int n = W.h->prior_n;
   if (n == 0) return 0.0;
   const int nblk = W.h->prior_nblk;
@@ -981,14 +988,17 @@ __device__ double prior_pass(const SolveParams& P, const Win& W, const double* x
   }
   __syncthreads();
   double cost = 0;
+  // (operands from L2 / HBM: eight loads in flight per thread, the sums keep their order)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double r = rl[i];
+#pragma unroll 8
     for (int j = 0; j < n; j++) r = fma(Jl[(size_t)j * n + i], dxp[j], r);
     cost += 0.5 * r * r;
   }
   if (want_J) {
     for (int e = threadIdx.x; e < n * n + n; e += blockDim.x) {
       if (e < n * n) {
+        if (!add_H) continue;
         const int a = e / n, b = e % n;
         const int ca = col[a], cb2 = col[b];
         if (ca < cb2) continue;
@@ -997,7 +1007,8 @@ __device__ double prior_pass(const SolveParams& P, const Win& W, const double* x
       } else {
         const int a = e - n * n;
         double v = b0[a];
-        for (int j = 0; j < n; j++) v = fma(A[(size_t)a * n + j], dxp[j], v);
+#pragma unroll 8
+        for (int j = 0; j < n; j++) v = fma(A[(size_t)j * n + a], dxp[j], v);   // A is symmetric bit for bit (prep_window): column a read as row a, coalesced
         g[col[a]] += v;
       }
     }

@@ -623,6 +623,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
     CLPROF(5);
     // C: the serial chain on CTA 0
     const bool coop_chol = !SMEM_H && chol_stage(L, sm, W.nb) != nullptr;
+    if (!SMEM_H) {     // reduced system in global memory: the prior's n x n block is added by the whole cluster
+      prior_add_H_cluster(P, W, H, hdsc, scr, r, G);
+      cluster_sync_all();
+    }
     if (r == 0) {
       for (int e = threadIdx.x; e < Dp; e += blockDim.x) { sm[L.g + e] = gsc[e]; sm[L.hd + e] = hdsc[e]; }
       __syncthreads();
@@ -630,7 +634,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) solve_cluster_kernel(SolvePa
       lidar_add(W, H, sm + L.g, sm + L.hd, lidblk);
       __syncthreads();
       double c2 = icp_lps_pass(P, W, xs, H, sm + L.g, sm + L.hd, sm + L.imu, true);
-      c2 += prior_pass(P, W, xs, H, sm + L.g, sm + L.hd, sm + L.dx, scr, true);
+      c2 += prior_pass(P, W, xs, H, sm + L.g, sm + L.hd, sm + L.dx, scr, true, SMEM_H);
       __syncthreads();
       if (it == 0) { c2 = block_sum(c2, sm + L.red); for (int q = 0; q < G; q++) c2 += costp[q]; cost0 = c2; cost = c2; }
       damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, P.mu);
