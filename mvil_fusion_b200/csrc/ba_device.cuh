@@ -935,8 +935,9 @@ __device__ double icp_lps_pass(const SolveParams& P, const Win& W, const double*
     double rho, w; vf::cauchy(P.cfg.cauchy_a, s[0] * s[0] + s[1] * s[1] + s[2] * s[2], rho, w);
     cost += 0.5 * rho;
     for (int k = 0; k < 75; k++) s[k] *= w;
-  } else if (t < nicp + nlps) {
-    const double* c = lps + 9 * (t - nicp); double* s = stage + 76 * t;
+  } else if (t >= 32 && t - 32 < nlps) {            // the LPS constraints on the second warp: next to the ICP ones, not after them
+    const int f = nicp + t - 32;
+    const double* c = lps + 9 * (f - nicp); double* s = stage + 76 * f;
     vf::lps_eval(c, x + XP((int)c[7]), x + XP((int)c[8]), s, s + 3);
     double rho, w; vf::cauchy(P.cfg.cauchy_a, s[0] * s[0] + s[1] * s[1] + s[2] * s[2], rho, w);
     cost += 0.5 * rho;
