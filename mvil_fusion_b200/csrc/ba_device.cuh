@@ -332,8 +332,14 @@ __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nimu = W.h->n_imu;
   const int32_t* kfs = W.i(OFF_IMU_KF);
+  // Warp w owns the factors 2w, 2w + 1 (+ 2 SOLVE_WARPS ...): consecutive factors have keyframes of opposite parity, so every warp has one
+  // factor per parity phase (dealt k = w, w + 12, .. a warp got two factors of the SAME parity and half the warps none: the 19 factors of a
+  // 20-keyframe window took two serial factors per phase).
   for (int parity = 0; parity < 2; parity++) {
-    for (int k = warp; k < nimu; k += SOLVE_WARPS) {
+#pragma unroll 1
+    for (int m = 0; 2 * (warp + (m >> 1) * SOLVE_WARPS) < nimu; m++) {
+      const int k = 2 * (warp + (m >> 1) * SOLVE_WARPS) + (m & 1);
+      if (k >= nimu) continue;
       const int i = kfs[k];
       if ((i & 1) != parity) continue;
       const double* prod = scr + P.sl.imuprod + (size_t)k * IMU_PROD_LD;
@@ -341,7 +347,22 @@ __device__ void imu_add(const SolveParams& P, const Win& W, double* H, double* g
       double pv[16];
 #pragma unroll
       for (int q = 0; q < 16; q++) { const int e = lane + 32 * q; pv[q] = e < 495 ? prod[e] : 0.0; }
-      // (H may live in global memory: its 15 entries per lane are read together, then written)
+      if (P.h_in_smem) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const int e = lane + 32 * q;
+          if (e < 465) {
+            int a = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            while (a * (a + 1) / 2 > e) a--;
+            while ((a + 1) * (a + 2) / 2 <= e) a++;
+            const int b = e - a * (a + 1) / 2;
+            H[tidx(base + a, base + b)] += pv[q];
+            if (a == b) hd[base + a] += pv[q];
+          } else if (e < 495) g[base + e - 465] += pv[q];
+        }
+        continue;
+      }
+      // H in global memory: its 15 entries per lane are read together, then written (one L2 round trip, not fifteen)
       int hi[15]; double hv[15];
 #pragma unroll
       for (int q = 0; q < 15; q++) {
