@@ -425,6 +425,14 @@ def main():
             ba.solve_windows(batch[:1], opts, warr)
         lat[name + "_e2e_ms_from_caller_arrays"] = 1e3 * (time.perf_counter() - t0) / 10
     ba.set_cluster(0)
+    # what the reference's own solver options give (estimator.cpp:1400-1411: DOGLEG, max_num_iterations = NUM_ITERATIONS = 8): trust-region modes
+    # run on the one-CTA kernel
+    dl = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 8, 0.0)
+    ms = []
+    for _ in range(6):
+        ba.solve_device(1, dl); ms.append(ba.last_ms)
+    lat["dogleg8_one_cta_device_ms"] = float(np.mean(ms[2:]))
+    ba.download(1); lat["dogleg8_iterations"] = int(ba.get_state(0)["iterations"])
     sampler.stop()
     st = ba.get_state(0)
     assert st["status"] == 0, st
@@ -488,7 +496,7 @@ def main():
             "cpu_baseline": {"value": tot / T, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{tot} GN-5 solves of the same config-2 windows by oracle/ (CPU restatement) on {cores} threads",
                              "single_thread_value": v_single},
-            "latency": dict(lat, workload="ONE configs[1] window per call, GN x5; cluster = thread-block cluster per window (vils_ba_set_cluster)"),
+            "latency": dict(lat, workload="ONE configs[1] window per call, GN x5; cluster = thread-block cluster per window (vils_ba_set_cluster); dogleg8 = the reference's ceres options (DOGLEG, max 8 iterations) on the one-CTA kernel"),
             "clocks": sampler.summary(),
             "configs": extra,
         }
