@@ -237,11 +237,15 @@ __device__ void apply_step(const SolveParams& P, const Win& W, const Smem& L, do
   const int X = 16 * W.N + 8 + W.M;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
   __syncthreads();
-  for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
-    double s = 0;
-    for (int a = lane; a < W.Dv; a += 32) s = fma(E[(size_t)rnk * W.Dvp + a], dx[vis2cam(a, W.N)], s);
-    s = warp_sum(s);
-    if (lane == 0) xout[XL(W.N) + lm_feat[rnk]] += -cinv[rnk] * (glam[rnk] + s);
+  // one warp per landmark, two landmarks per trip: their E rows come from L2 and are in flight together
+  const int nlm = W.h->n_lm;
+  for (int rnk = warp; rnk < nlm; rnk += 2 * SOLVE_WARPS) {
+    const int rnk2 = rnk + SOLVE_WARPS; const bool two = rnk2 < nlm;
+    const double* e1 = E + (size_t)rnk * W.Dvp; const double* e2 = E + (size_t)(two ? rnk2 : rnk) * W.Dvp;
+    double s = 0, s2 = 0;
+    for (int a = lane; a < W.Dv; a += 32) { const double v1 = e1[a], v2 = e2[a], d = dx[vis2cam(a, W.N)]; s = fma(v1, d, s); s2 = fma(v2, d, s2); }
+    s = warp_sum(s); s2 = warp_sum(s2);
+    if (lane == 0) { xout[XL(W.N) + lm_feat[rnk]] += -cinv[rnk] * (glam[rnk] + s); if (two) xout[XL(W.N) + lm_feat[rnk2]] += -cinv[rnk2] * (glam[rnk2] + s2); }
   }
   for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
     if (k < W.N) {
