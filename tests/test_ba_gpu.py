@@ -329,6 +329,8 @@ def test_cluster_latency_kernel_matches_single_cta_kernel(lib):
     wsm = synth.make_window(config_id=9, window_idx=71, N=7, M=40, n_lidar=300, n_icp=2, n_lps=3)
     wsm["kf_fixed"] = np.array([0, 0, 0, 0, 0, 1, 0], np.uint8)
     cases.append((cabi.default_config(), wsm))
+    # 20 keyframes: the reduced system lives in global memory, the whole cluster factors it (cholesky_tiles_cluster) and adds the prior block
+    cases.append((cabi.default_config(max_kf=20, max_feat=160, max_proj=2000, max_lidar=1000), synth.make_window(4, 2, N=20, M=120, n_lidar=600, n_icp=2, n_lps=2)))
     for cfg, w in cases:
         ref = lib.BA(cfg, 1); ref.set_cluster(1); ref.set_window(0, w); ref.solve(1, opts)
         assert ref.last_cluster == 1
