@@ -56,7 +56,6 @@ __device__ void prep_window_cluster(const SolveParams& P, const Win& W, double* 
   __syncthreads();
 }
 
-struct ClScratch { int64_t hvpart, gvpart, lidblk, gsc, hdsc, dxg, lamg, costp, flagg, total; };   // offsets (doubles) into a cluster's exchange area
 
 // ---- F: projection factors of the pairs owned by CTA r + IMU factors k = r (mod G) on the warps past PAIR_WARPS --------------------------
 __device__ double pair_pass_cluster(const SolveParams& P, const Win& W, const double* x, double* stage, double* scr, bool need_cost, double* imu_stage,
@@ -260,7 +259,9 @@ __device__ void lidar_add(const Win& W, double* H, double* g, double* hd, const 
 }
 
 // ---- L: landmarks rank = r (mod G) ------------------------------------------------------------------------------------------------------
-__device__ void landmark_reduce_cluster(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu, int r, int G) {
+// jac_mode / craw / scl as landmark_reduce (dogleg: Jacobi scale of the landmark columns, fixed at the first linearisation)
+__device__ void landmark_reduce_cluster(const SolveParams& P, const Win& W, double* cinv, double* glam, double* scr, double mu, int r, int G,
+                                        int jac_mode = 0, double* craw = nullptr, double* scl = nullptr) {
   const int nlm = W.h->n_lm;
   const int32_t* lm_start = W.lm_start(); const int32_t* ix = W.i(OFF_PROJ_IDX);
   const double* part = scr + P.sl.part; double* E = scr + P.sl.E;
@@ -280,8 +281,16 @@ __device__ void landmark_reduce_cluster(const SolveParams& P, const Win& W, doub
     for (int k = 0; k < 6; k++) { e[6 * kfi + k] = s[2 + k]; e[6 * W.N + k] = s[8 + k]; }
     e[6 * W.N + 6] = s[14];
     const double C = s[0];
-    if (C > 0.0) { cinv[rnk] = 1.0 / (C + mu * fmin(fmax(C, 1e-6), 1e32)); glam[rnk] = s[1]; }
-    else { cinv[rnk] = 0.0; glam[rnk] = 0.0; }
+    if (C > 0.0) {
+      double dd = fmin(fmax(C, 1e-6), 1e32);
+      if (jac_mode) {
+        const double sj = jac_mode == 1 ? 1.0 / (1.0 + sqrt(C)) : scl[rnk];
+        if (jac_mode == 1) scl[rnk] = sj;
+        dd = fmin(fmax(C * sj * sj, 1e-6), 1e32) / (sj * sj);
+        craw[rnk] = C;
+      }
+      cinv[rnk] = 1.0 / (C + mu * dd); glam[rnk] = s[1];
+    } else { cinv[rnk] = 0.0; glam[rnk] = 0.0; if (jac_mode) craw[rnk] = 0.0; }
   }
 }
 

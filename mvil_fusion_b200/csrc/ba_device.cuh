@@ -46,6 +46,9 @@ constexpr int PAIR_LD = 20;       // pair-local block: [pose_i 6 | pose_j 6 | ex
 constexpr int ECHUNK = 32;        // landmarks per Schur chunk
 constexpr int PART_LD = 16;       // per-factor landmark partial: C, g_l, e_i(6), e_ex(6), e_td, pad
 
+// offsets (doubles) into a cluster's exchange area (latency kernels, ba_cluster.cuh)
+struct ClScratch { int64_t hvpart, gvpart, lidblk, gsc, hdsc, dxg, lamg, costp, flagg, xg, cinvg, glamg, crawg, sclg, cmd, total; };
+
 struct SolveParams {
   const uint8_t* blobs; int64_t blob_stride;
   double* scratch; ScratchLayout sl;
@@ -62,6 +65,7 @@ struct SolveParams {
   int32_t slot0;                  // first slot handled by blockIdx.x == 0
   int32_t do_prep;                // solve_kernel runs prep_window itself (vils_ba_solve's pipelined path)
   long long* prof;                // optional: per-phase SM cycle counters of block 0 (VILS_PROF=1)
+  ClScratch cl; double* clbuf; int32_t cl_imu_slots;   // cluster-assisted solves (solve_kernel<.., CL = true>): exchange area of the window's cluster
 };
 
 struct Smem {   // offsets in doubles into dynamic shared memory, computed identically on host and device

@@ -298,29 +298,123 @@ __device__ double apply_step_dogleg(const SolveParams& P, const Win& W, const Sm
 // One CTA = one window for the whole solve.  SMEM_H: the tile-packed H and the visual sub-system Hv live in shared memory
 // (windows up to ~12 keyframes); otherwise they sit in the per-window scratch (L2).  TR: the trust-region modes (Levenberg-Marquardt,
 // dogleg) are compiled into their own instantiation so that the fixed-count Gauss-Newton kernel keeps its register allocation.
-template <bool SMEM_H, bool TR>
+// ---- cluster-assisted linearisation (solve_kernel<.., CL = true>): the trust-region loop runs on CTA 0 of a thread-block cluster exactly as it
+// runs on a lone CTA; only the linearisation — factor pass, landmark reduction + partial Schur complements, gather — is dealt to all CTAs
+// (the phases of the Gauss-Newton latency kernel).  Protocol: CTA 0 publishes the state and the parameters of the linearisation in the exchange
+// area and meets the helpers at a cluster barrier; three more barriers separate the phases; the helpers then wait at the barrier of the next
+// command (another linearisation, or stop) while CTA 0 adds the serial terms, factors, and tries steps.
+struct ClPtrs { double *hvpart, *gvpart, *lidblk, *gsc, *hdsc, *costp, *xg, *cinvg, *glamg, *crawg, *sclg, *cmd; };
+__device__ __forceinline__ ClPtrs cl_ptrs(const SolveParams& P, int slot) {
+  double* cx = P.clbuf + (size_t)slot * P.cl.total;
+  ClPtrs c; c.hvpart = cx + P.cl.hvpart; c.gvpart = cx + P.cl.gvpart; c.lidblk = cx + P.cl.lidblk; c.gsc = cx + P.cl.gsc; c.hdsc = cx + P.cl.hdsc;
+  c.costp = cx + P.cl.costp; c.xg = cx + P.cl.xg; c.cinvg = cx + P.cl.cinvg; c.glamg = cx + P.cl.glamg; c.crawg = cx + P.cl.crawg; c.sclg = cx + P.cl.sclg;
+  c.cmd = cx + P.cl.cmd;
+  return c;
+}
+
+// the share of CTA r (every CTA of the cluster, CTA 0 included), from the command barrier to the barrier after the gather
+template <bool SMEM_H>
+__device__ void cluster_linearize_share(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const ClPtrs& C, const double* x,
+                                        double* H, double* Hdst, int* own, bool need_cost, double mu, int jac_mode, int r, int G) {
+  const int Dp = W.nb * TB;
+  const int* pid_s = reinterpret_cast<const int*>(sm + L.pid);
+  const uint16_t* tb = reinterpret_cast<const uint16_t*>(sm + L.tbl);
+  if (!SMEM_H) for (int e = r + G * threadIdx.x; e < tri(W.nb) * TSZ; e += G * blockDim.x) H[e] = 0.0;
+  for (int e = r + G * threadIdx.x; e < Dp; e += G * blockDim.x) { C.gsc[e] = 0.0; C.hdsc[e] = 0.0; }
+  double c = pair_pass_cluster(P, W, x, sm + L.uni, scr, need_cost, sm + L.imu, P.cl_imu_slots, tb, sm + L.rot, own, r, G);
+  c += lidar_pass_cluster(P, W, x, C.lidblk, true, r, G);
+  if (need_cost) { c = block_sum(c, sm + L.red); if (threadIdx.x == 0) C.costp[r] = c; }
+  __syncthreads();
+  cluster_sync_all();
+  landmark_reduce_cluster(P, W, sm + L.cinv, sm + L.glam, scr, mu, r, G, jac_mode, sm + L.craw, sm + L.scl);
+  __syncthreads();
+  for (int rnk = r + G * threadIdx.x; rnk < W.h->n_lm; rnk += G * blockDim.x) {      // CTA 0 needs every landmark's reduction for the step algebra
+    C.cinvg[rnk] = sm[L.cinv + rnk]; C.glamg[rnk] = sm[L.glam + rnk];
+    if (jac_mode) { C.crawg[rnk] = sm[L.craw + rnk]; C.sclg[rnk] = sm[L.scl + rnk]; }
+  }
+  schur_syrk_cluster(P, W, sm + L.cinv, sm + L.glam, C.hvpart + (size_t)r * W.Dvp * W.Dvp, C.gvpart + (size_t)r * W.Dvp, sm + L.uni, scr, L.imu - L.uni, r, G);
+  __syncthreads();
+  if (SMEM_H && r == 0) for (int e = threadIdx.x; e < tri(W.nb) * TSZ; e += blockDim.x) H[e] = 0.0;
+  __syncthreads();
+  cluster_sync_all();
+  gather_cluster(P, W, C.hvpart, C.gvpart, Hdst, C.gsc, C.hdsc, scr, pid_s, P.Ncap * (P.Ncap - 1) / 2, r, G);
+  __syncthreads();
+  cluster_sync_all();
+}
+
+// CTA 0: command + own share + the serial terms.  Leaves what linearize() leaves: H (lower tiles), g, hd, gv, cinv / glam (/ craw / scl) of every
+// landmark in shared memory, E in the scratch; returns the cost when need_cost.
+template <bool SMEM_H>
+__device__ double linearize_cluster(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const ClPtrs& C, const double* x,
+                                    double* H, int* own, double mu, bool need_cost, int jac_mode, int G) {
+  const int X = 16 * W.N + 8 + W.M, Dp = W.nb * TB;
+  for (int k = threadIdx.x; k < X; k += blockDim.x) C.xg[k] = x[k];
+  if (threadIdx.x == 0) { C.cmd[0] = 1.0; C.cmd[1] = mu; C.cmd[2] = need_cost ? 1.0 : 0.0; C.cmd[3] = (double)jac_mode; }
+  __syncthreads();
+  cluster_sync_all();                                    // command
+  cluster_linearize_share<SMEM_H>(P, W, L, sm, scr, C, x, H, H, own, need_cost, mu, jac_mode, 0, G);
+  for (int rnk = threadIdx.x; rnk < W.h->n_lm; rnk += blockDim.x) {
+    sm[L.cinv + rnk] = C.cinvg[rnk]; sm[L.glam + rnk] = C.glamg[rnk];
+    if (jac_mode) { sm[L.craw + rnk] = C.crawg[rnk]; sm[L.scl + rnk] = C.sclg[rnk]; }
+  }
+  for (int a = threadIdx.x; a < W.Dv; a += blockDim.x) { double v = 0; for (int q = 0; q < G; q++) v += C.gvpart[(size_t)q * W.Dvp + a]; sm[L.gv + a] = v; }
+  for (int e = threadIdx.x; e < Dp; e += blockDim.x) { sm[L.g + e] = C.gsc[e]; sm[L.hd + e] = C.hdsc[e]; }
+  __syncthreads();
+  imu_add(P, W, H, sm + L.g, sm + L.hd, scr);
+  lidar_add(W, H, sm + L.g, sm + L.hd, C.lidblk);
+  __syncthreads();
+  double c2 = icp_lps_pass(P, W, x, H, sm + L.g, sm + L.hd, sm + L.imu, true);
+  c2 += prior_pass(P, W, x, H, sm + L.g, sm + L.hd, sm + L.dx, scr, true);
+  __syncthreads();
+  c2 = block_sum(c2, sm + L.red);
+  if (need_cost) for (int q = 0; q < G; q++) c2 += C.costp[q];
+  return c2;
+}
+
+// helpers (CTA r > 0): serve linearisations until CTA 0 says stop
+template <bool SMEM_H>
+__device__ void cluster_helper_loop(const SolveParams& P, const Win& W, const Smem& L, double* sm, double* scr, const ClPtrs& C, double* H, double* Hdst,
+                                    int* own, int r, int G) {
+  const int X = 16 * W.N + 8 + W.M;
+  double* xs = sm + L.xs;
+  for (;;) {
+    cluster_sync_all();                                  // command
+    if (C.cmd[0] != 1.0) return;
+    const double mu = C.cmd[1]; const bool need_cost = C.cmd[2] != 0.0; const int jac_mode = (int)C.cmd[3];
+    for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = C.xg[k];
+    __syncthreads();
+    cluster_linearize_share<SMEM_H>(P, W, L, sm, scr, C, xs, H, Hdst, own, need_cost, mu, jac_mode, r, G);
+  }
+}
+
+// CL: launched as one thread-block cluster per window; the loop below runs on CTA 0, the other CTAs serve its linearisations.
+template <bool SMEM_H, bool TR, bool CL = false>
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveParams P) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int chol_flag;
   __shared__ int time_flag;
-  const int slot = P.slot0 + blockIdx.x;
+  __shared__ int own[CL ? 2 + 32 * 31 / 2 : 1];
+  const int G = CL ? (int)cluster_size() : 1, r = CL ? (int)cluster_rank() : 0;
+  const int slot = P.slot0 + (CL ? (int)blockIdx.x / G : (int)blockIdx.x);
   Win W = decode(P, slot);
-  const Smem L = smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
+  const Smem L = CL ? smem_layout(P.Ncap, P.Mcap, SMEM_H ? 1 : 0, 0) : smem_layout(P.Ncap, P.Mcap, P.h_in_smem, P.hv_in_smem);
   stage_tables(W, L, sm);
   // Scratch (landmark partials, E, pair blocks, IMU products, for large windows H / Hv / tile inverses) lives in a slot owned by the SM, not
   // by the window: one CTA is resident per SM, so n_sm slots are rewritten over and over and stay in L2 instead of streaming
   // (windows x 0.6 MB) of write-backs to HBM.  Everything in it is rebuilt by this kernel (prep_window below).
   unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  double* scr = P.tscratch ? P.tscratch + (size_t)smid * P.sl.total : P.scratch + (size_t)slot * P.sl.total;
+  double* scr = (P.tscratch && !CL) ? P.tscratch + (size_t)smid * P.sl.total : P.scratch + (size_t)slot * P.sl.total;
   double* H = SMEM_H ? sm + L.uni : scr + P.sl.Hg;
-  double* Hv = SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg);
+  double* Hv = CL ? nullptr : (SMEM_H ? sm + L.hv : (P.hv_in_smem ? sm + L.hv : scr + P.sl.Hvg));
+  ClPtrs C{}; if (CL) C = cl_ptrs(P, slot);
   double* xs = sm + L.xs; double* xc = sm + L.xc;
   double* linv = L.linv >= 0 ? sm + L.linv : scr + P.sl.linvg;   // diagonal-tile inverses: shared memory, or L2 scratch for large windows
   int* fx = reinterpret_cast<int*>(sm + L.fx);
   const int X = 16 * W.N + 8 + W.M;
   const double* x0 = W.d(OFF_X);
   const long long t_start = P.time_cap_ns > 0 ? global_ns() : 0;
-  if (P.do_prep || P.tscratch) prep_window(P, W, scr, sm + L.uni);     // IMU sqrt_info, prior A / b0, zero pattern of E: into the scratch slot this CTA uses
+  if (CL) { prep_window_cluster(P, W, scr, sm + L.uni, r, G); }
+  else if (P.do_prep || P.tscratch) prep_window(P, W, scr, sm + L.uni);     // IMU sqrt_info, prior A / b0, zero pattern of E: into the scratch slot this CTA uses
   for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = x0[k];
   { int* pid_s = reinterpret_cast<int*>(sm + L.pid); const int32_t* pid_g = W.i(OFF_PAIR_ID); for (int k = threadIdx.x; k < W.N * W.N; k += blockDim.x) pid_s[k] = pid_g[k]; }
   { uint16_t* tb = reinterpret_cast<uint16_t*>(sm + L.tbl); for (int k = threadIdx.x; k < 450; k += blockDim.x) tb[k] = g_imu_tbl[k]; }
@@ -329,6 +423,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   if (threadIdx.x == 0) { chol_flag = 0; time_flag = 0; }
   const int nfix = (int)block_sum(nf, sm + L.red);
   __syncthreads();
+  if (CL) {
+    cluster_sync_all();                                  // the prep of every CTA is in the scratch
+    if (r != 0) {
+      double* Hdst = SMEM_H ? cooperative_groups::this_cluster().map_shared_rank(sm + L.uni, 0) : H;
+      cluster_helper_loop<SMEM_H>(P, W, L, sm, scr, C, H, Hdst, own, r, G);
+      return;
+    }
+  }
 
   const bool lm = TR && P.mode == VILS_MODE_LM;
   const bool dl = TR && P.mode == VILS_MODE_DOGLEG;
@@ -350,7 +452,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
     double* bsave = sm + L.imu;   // LM: b = -g_r is overwritten by the fused forward solve; ((Ncap+1)/2)*466 doubles >= nb*16
     const bool last = !TR && (iters + 1 >= P.max_iters);
     if (!(dl && reuse)) {
-      const double c_lin = linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0);   // later costs come from cost_only()
+      const double c_lin = CL ? linearize_cluster<SMEM_H>(P, W, L, sm, scr, C, xs, H, own, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0, G)
+                              : linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0);   // later costs come from cost_only()
       if (it == 0) { cost0 = c_lin; cost = c_lin; if (TR) iters = 1; }
       if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
       if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
@@ -547,6 +650,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
   }
   if (!TR && capped) {   // a capped Gauss-Newton run reports the cost of the state it stopped at
     cost = cost_only(P, W, L, sm, scr, xs);
+  }
+  if (CL) {                                              // release the helpers
+    if (threadIdx.x == 0) C.cmd[0] = 2.0;
+    __syncthreads();
+    cluster_sync_all();
   }
   double* xo = P.xout + (size_t)slot * P.xout_stride;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xo[k] = xs[k];
@@ -1146,6 +1254,7 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
   P.Ncap = c.max_kf; P.Mcap = c.max_feat; P.h_in_smem = ba->h_in_smem; P.hv_in_smem = ba->hv_in_smem;
   P.lin_out = nullptr; P.slot0 = 0; P.prof = nullptr; P.do_prep = 0;
   P.tscratch = ba->d_tscratch;
+  P.cl = ba->cl; P.clbuf = ba->d_clbuf; P.cl_imu_slots = ba->cl_imu_slots;
   return P;
 }
 
@@ -1153,7 +1262,8 @@ static SolveParams make_params(vils_ba* ba, const vils_solve_opts* o) {
 static int pick_cluster(const vils_ba* ba, const SolveParams& P, int n) {
   if (P.slot0 + n > ba->cl_windows) return 1;               // the exchange areas cover slots [0, cl_windows)
   static const bool prof_cluster = getenv("VILS_PROF_CLUSTER") != nullptr;
-  if (P.mode != VILS_MODE_GN || P.lin_out || (P.prof && !prof_cluster) || P.max_iters <= 0 || P.time_cap_ns > 0 || ba->cluster_pref == 1 || n > ba->cl_windows) return 1;
+  if (P.lin_out || (P.prof && !prof_cluster) || P.max_iters <= 0 || ba->cluster_pref == 1 || n > ba->cl_windows) return 1;
+  if ((P.mode != VILS_MODE_GN || P.time_cap_ns > 0) && P.prof) return 1;      // the cluster phase profile belongs to the Gauss-Newton latency kernel
   const int gmax = ba->cl16 ? CL_MAX : CL_PORTABLE;
   if (ba->cluster_pref >= 2) { const int g = std::min(ba->cluster_pref, gmax); return n * g <= ba->n_sm ? g : 1; }
   for (int g = gmax; g >= 2; g >>= 1) if (n * g <= ba->n_sm) return g;
@@ -1166,7 +1276,12 @@ static void launch_solve(vils_ba* ba, const SolveParams& P, int n, cudaStream_t 
     cfg.gridDim = dim3(n * G); cfg.blockDim = dim3(SOLVE_THREADS); cfg.dynamicSmemBytes = ba->cl_smem; cfg.stream = s;
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (ba->cl_smem_h) cudaLaunchKernelEx(&cfg, solve_cluster_kernel<true>, P, ba->cl, ba->d_clbuf, ba->cl_imu_slots);
+    const bool tr = P.mode != VILS_MODE_GN;
+    if (tr || P.time_cap_ns > 0) {
+      // trust-region solves (and time-capped ones): the one-CTA loop on CTA 0 of the cluster, linearisations served by all CTAs
+      if (ba->cl_smem_h) { if (tr) cudaLaunchKernelEx(&cfg, solve_kernel<true, true, true>, P); else cudaLaunchKernelEx(&cfg, solve_kernel<true, false, true>, P); }
+      else { if (tr) cudaLaunchKernelEx(&cfg, solve_kernel<false, true, true>, P); else cudaLaunchKernelEx(&cfg, solve_kernel<false, false, true>, P); }
+    } else if (ba->cl_smem_h) cudaLaunchKernelEx(&cfg, solve_cluster_kernel<true>, P, ba->cl, ba->d_clbuf, ba->cl_imu_slots);
     else cudaLaunchKernelEx(&cfg, solve_cluster_kernel<false>, P, ba->cl, ba->d_clbuf, ba->cl_imu_slots);
     ba->last_cluster = G;
     return;
@@ -1255,7 +1370,9 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
     ClScratch& c = ba->cl; int64_t q = 0;
     auto tk = [&](int64_t n) { int64_t r = q; q += (n + 1) & ~int64_t(1); return r; };
     c.hvpart = tk((int64_t)CL_MAX * Dvp * Dvp); c.gvpart = tk((int64_t)CL_MAX * Dvp); c.lidblk = tk((int64_t)N * 28); c.gsc = tk(nb * TB); c.hdsc = tk(nb * TB);
-    c.dxg = tk(nb * TB); c.lamg = tk(std::max(M, 1)); c.costp = tk(CL_MAX); c.flagg = tk(2); c.total = q;
+    c.dxg = tk(nb * TB); c.lamg = tk(std::max(M, 1)); c.costp = tk(CL_MAX); c.flagg = tk(2);
+    c.xg = tk(16 * N + 8 + M); c.cinvg = tk(std::max(M, 1)); c.glamg = tk(std::max(M, 1)); c.crawg = tk(std::max(M, 1)); c.sclg = tk(std::max(M, 1)); c.cmd = tk(8);
+    c.total = q;
     ba->cl_smem_h = (size_t)smem_layout(N, M, 1, 0).total * 8 + 4096 <= budget;     // H of CTA 0 in shared memory when it fits
     const Smem Lc = smem_layout(N, M, ba->cl_smem_h ? 1 : 0, 0);
     ba->cl_smem = (size_t)Lc.total * 8;
@@ -1309,6 +1426,14 @@ int vils_ba_create(const vils_config* cfg, int32_t max_windows, vils_ba** out) {
       CK(cudaFuncSetAttribute(margin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
       CK(cudaFuncSetAttribute(solve_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));   // 2 KB of static shared memory (pair ownership table)
       CK(cudaFuncSetAttribute(solve_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      CK(cudaFuncSetAttribute(solve_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      CK(cudaFuncSetAttribute(solve_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      CK(cudaFuncSetAttribute(solve_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      CK(cudaFuncSetAttribute(solve_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 4096));
+      cudaFuncSetAttribute(solve_kernel<true, true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(solve_kernel<true, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(solve_kernel<false, true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(solve_kernel<false, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       cudaFuncSetAttribute(solve_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);     // clusters of 16: best effort
       cudaFuncSetAttribute(solve_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       cudaGetLastError();
