@@ -362,3 +362,35 @@ def test_cluster_latency_kernel_matches_single_cta_kernel(lib):
     for n in (18, 30, 60, 100):
         assert np.abs(expect[n] - expect[1]).max() <= 1e-9 * np.abs(expect[1]).max()
     h.close()
+
+
+def test_trust_region_solves_on_a_cluster_match_the_single_cta_kernel(lib):
+    """Dogleg (the reference's ceres options), Levenberg-Marquardt and time-capped Gauss-Newton solves of ONE window run the one-CTA loop on CTA 0
+    of a thread-block cluster with the linearisations served by all CTAs (solve_kernel<.., CL = true>): same trial / acceptance sequence, state
+    within 1e-9 of the one-CTA kernel (observed ~1e-12), for a config-2 window, a small window with ICP / LPS / fixed blocks, and a 20-keyframe
+    window whose reduced system lives in global memory."""
+    dl8 = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 8, 0.0)
+    dls = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 25, 0.0); dls.lm_initial_radius = 3.0       # rejected steps, GN point reused
+    lm = cabi.default_solve_opts(cabi.VILS_MODE_LM, 10, 0.0)
+    cap = cabi.default_solve_opts(cabi.VILS_MODE_GN, 5, 1e-8); cap.max_solver_time = 10.0
+    wsm = synth.make_window(config_id=9, window_idx=31, N=6, M=30, n_lidar=200, n_icp=1, n_lps=1)
+    wsm["kf_fixed"] = np.array([0, 0, 0, 0, 1, 0], np.uint8)
+    cases = [(cabi.default_config(), synth.make_window(2, 5), (dl8, lm, cap)), (cabi.default_config(), wsm, (dls, lm)),
+             (cabi.default_config(max_kf=20, max_feat=160, max_proj=2000, max_lidar=1000), synth.make_window(4, 2, N=20, M=120, n_lidar=600, n_icp=2, n_lps=2), (dl8,))]
+    for cfg, w, optss in cases:
+        for opts in optss:
+            ref = lib.BA(cfg, 1); ref.set_cluster(1); ref.set_window(0, w); ref.solve(1, opts); r = ref.get_state(0)
+            assert ref.last_cluster == 1 and r["status"] == 0
+            for G in (0, 4):
+                h = lib.BA(cfg, 1); h.set_cluster(G); h.set_window(0, w); h.solve(1, opts); s = h.get_state(0)
+                assert h.last_cluster > 1
+                assert s["status"] == 0 and s["iterations"] == r["iterations"] and s["accepted"] == r["accepted"]
+                assert abs(s["cost_final"] - r["cost_final"]) <= 1e-9 * r["cost_final"]
+                assert helpers.rel_state_delta(s, r) <= 1e-9
+                h.close()
+            ref.close()
+    # a 1 us cap stops the cluster-assisted loop after its first iteration too
+    tiny = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 8, 0.0); tiny.max_solver_time = 1e-6
+    h = lib.BA(cabi.default_config(), 1); h.set_window(0, synth.make_window(2, 7)); h.solve(1, tiny); s = h.get_state(0)
+    assert h.last_cluster > 1 and s["status"] == 0 and s["iterations"] <= 2
+    h.close()
