@@ -425,13 +425,16 @@ def main():
             ba.solve_windows(batch[:1], opts, warr)
         lat[name + "_e2e_ms_from_caller_arrays"] = 1e3 * (time.perf_counter() - t0) / 10
     ba.set_cluster(0)
-    # what the reference's own solver options give (estimator.cpp:1400-1411: DOGLEG, max_num_iterations = NUM_ITERATIONS = 8): trust-region modes
-    # run on the one-CTA kernel
+    # what the reference's own solver options give (estimator.cpp:1400-1411: DOGLEG, max_num_iterations = NUM_ITERATIONS = 8): on one CTA, and with the
+    # trust-region loop on CTA 0 of a cluster whose CTAs all serve the linearisations
     dl = cabi.default_solve_opts(cabi.VILS_MODE_DOGLEG, 8, 0.0)
-    ms = []
-    for _ in range(6):
-        ba.solve_device(1, dl); ms.append(ba.last_ms)
-    lat["dogleg8_one_cta_device_ms"] = float(np.mean(ms[2:]))
+    for mode, name in ((1, "dogleg8_one_cta"), (0, "dogleg8_cluster")):
+        ba.set_cluster(mode)
+        ms = []
+        for _ in range(6):
+            ba.solve_device(1, dl); ms.append(ba.last_ms)
+        lat[name + "_device_ms"] = float(np.mean(ms[2:])); lat[name + "_size"] = ba.last_cluster
+    ba.set_cluster(0)
     ba.download(1); lat["dogleg8_iterations"] = int(ba.get_state(0)["iterations"])
     sampler.stop()
     st = ba.get_state(0)

@@ -251,11 +251,13 @@ int vils_ba_linearize(vils_ba* ba, int32_t slot, double* S, double* g, double* c
 /* Marginalization (estimator.cpp:1483-1684 + marginalization_factor.cpp:110-338) of one slot at its
  * SOLVED state (or the state written by vils_ba_put_state). */
 int vils_ba_marginalize(vils_ba* ba, int32_t slot, int32_t flag, vils_prior_out* out);
-/* Latency mode.  When few windows are solved at once (the drop-in case: ONE window per optimization()), Gauss-Newton solves run as one
+/* Latency mode.  When few windows are solved at once (the drop-in case: ONE window per optimization()), solves run as one
  * thread-block CLUSTER per window — 16, 8, 4 or 2 SMs split the factor pass, the landmark Schur complement and the assembly, one CTA runs the
  * Cholesky chain — instead of one CTA per window.  cluster_size: 0 = automatic (the largest of 16 / 8 / 4 / 2 with n_windows x size <= SM
  * count; 16 exceeds the portable cluster size and is used only where the device reports that it can co-schedule such a cluster),
- * 1 = always one CTA per window, 2 / 4 / 8 / 16 = forced when it fits.  The environment variable VILS_CLUSTER sets the default. */
+ * 1 = always one CTA per window, 2 / 4 / 8 / 16 = forced when it fits.  The environment variable VILS_CLUSTER sets the default.
+ * Gauss-Newton solves use a kernel in which the update is distributed too; dogleg, Levenberg-Marquardt and time-capped solves run their
+ * trust-region loop on the first CTA of the cluster while all CTAs serve its linearisations. */
 int vils_ba_set_cluster(vils_ba* ba, int32_t cluster_size);
 int vils_ba_last_cluster(vils_ba* ba, int32_t* cluster_size);
 /* Timing of the last vils_ba_solve_device in ms (CUDA events on the handle's stream). */
