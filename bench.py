@@ -499,7 +499,7 @@ def main():
             "cpu_baseline": {"value": tot / T, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{tot} GN-5 solves of the same config-2 windows by oracle/ (CPU restatement) on {cores} threads",
                              "single_thread_value": v_single},
-            "latency": dict(lat, workload="ONE configs[1] window per call, GN x5; cluster = thread-block cluster per window (vils_ba_set_cluster); dogleg8 = the reference's ceres options (DOGLEG, max 8 iterations) on the one-CTA kernel"),
+            "latency": dict(lat, workload="ONE configs[1] window per call, GN x5; cluster = thread-block cluster per window (vils_ba_set_cluster); dogleg8 = the reference's ceres options (DOGLEG, max 8 iterations), on one CTA and on a cluster"),
             "clocks": sampler.summary(),
             "configs": extra,
         }
