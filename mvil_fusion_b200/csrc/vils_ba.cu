@@ -384,6 +384,10 @@ __device__ void cluster_helper_loop(const SolveParams& P, const Win& W, const Sm
     for (int k = threadIdx.x; k < X; k += blockDim.x) xs[k] = C.xg[k];
     __syncthreads();
     cluster_linearize_share<SMEM_H>(P, W, L, sm, scr, C, xs, H, Hdst, own, need_cost, mu, jac_mode, r, G);
+    if (!SMEM_H && chol_stage(L, sm, W.nb)) {           // a reduced system in global memory is factored by the whole cluster, if CTA 0 gets that far
+      cluster_sync_all();
+      if (C.cmd[4] == 1.0) cholesky_tiles_cluster(H, nullptr, nullptr, nullptr, W.nb, nullptr, sm + L.uni, r, G);
+    }
   }
 }
 
@@ -455,7 +459,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
       const double c_lin = CL ? linearize_cluster<SMEM_H>(P, W, L, sm, scr, C, xs, H, own, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0, G)
                               : linearize(P, W, L, sm, scr, xs, H, Hv, mu, it == 0, dl ? (scale_set ? 2 : 1) : 0);   // later costs come from cost_only()
       if (it == 0) { cost0 = c_lin; cost = c_lin; if (TR) iters = 1; }
-      if (!isfinite(c_lin)) { status = VILS_ERR_NOT_FINITE; break; }
+      const bool coop_chol = CL && !SMEM_H && chol_stage(L, sm, W.nb) != nullptr;   // the helpers wait for the verdict: factor with me, or not
+      auto chol_cmd = [&](double v) { if (threadIdx.x == 0) C.cmd[4] = v; __syncthreads(); cluster_sync_all(); };
+      if (!isfinite(c_lin)) { if (coop_chol) chol_cmd(0.0); status = VILS_ERR_NOT_FINITE; break; }
       if (P.lin_out) {   // vils_ba_linearize: one linearisation, constant blocks applied, no damping
         damp_and_fix(W, H, sm + L.g, sm + L.hd, fx, nfix, 0.0);
         __syncthreads();
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
         if (threadIdx.x == 0) P.lin_out[(size_t)D * D + D] = c_lin;
         return;
       }
-      if (P.max_iters <= 0) break;
+      if (P.max_iters <= 0) { if (coop_chol) chol_cmd(0.0); break; }
       PROF_T0();
       if (dl && !scale_set) {   // Jacobi scaling: s = 1 / (1 + |J column|), from the first linearisation only (ceres jacobi_scaling)
         for (int i = threadIdx.x; i < W.nb * TB; i += blockDim.x) sm[L.scc + i] = 1.0 / (1.0 + sqrt(fmax(sm[L.hd + i], 0.0)));
@@ -489,7 +495,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
       if (threadIdx.x == 0) chol_flag = 0;
       __syncthreads();
       PROF(7);
-      cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof, chol_stage(L, sm, W.nb));
+      if (coop_chol) { chol_cmd(1.0); cholesky_tiles_cluster(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, sm + L.uni, 0, G); }
+      else cholesky_tiles<SMEM_H>(H, sm + L.g, linv, sm + L.dx, W.nb, &chol_flag, P.prof, chol_stage(L, sm, W.nb));
       ok = chol_flag == 0;
       PROF(8);
       if (!ok && !TR) { status = VILS_ERR_CHOLESKY; break; }
