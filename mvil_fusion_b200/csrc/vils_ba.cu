@@ -272,14 +272,25 @@ __device__ double apply_step_dogleg(const SolveParams& P, const Win& W, const Sm
   double n2 = 0;
   for (int k = threadIdx.x; k < X; k += blockDim.x) xout[k] = xin[k];
   __syncthreads();
-  for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
-    double s = 0;
-    for (int q = lane; q < W.Dv; q += 32) s = fma(E[(size_t)rnk * W.Dvp + q], y[vis2cam(q, W.N)], s);
-    s = warp_sum(s);
-    if (lane == 0 && cinv[rnk] != 0.0) {
-      const double sj = scl[rnk], dd = fmin(fmax(craw[rnk] * sj * sj, 1e-6), 1e32) / (sj * sj);
-      const double st = -a * glam[rnk] / dd + b * (-cinv[rnk] * (glam[rnk] + s));
-      xout[XL(W.N) + lm_feat[rnk]] += st; n2 += st * st;
+  // one warp per landmark, two landmarks per trip (their E rows, read from L2, in flight together; same order of the sums)
+  const int nlm = W.h->n_lm;
+  for (int rnk = warp; rnk < nlm; rnk += 2 * SOLVE_WARPS) {
+    const int rnk2 = rnk + SOLVE_WARPS; const bool two = rnk2 < nlm;
+    const double* e1 = E + (size_t)rnk * W.Dvp; const double* e2 = E + (size_t)(two ? rnk2 : rnk) * W.Dvp;
+    double s = 0, s2 = 0;
+    for (int q = lane; q < W.Dv; q += 32) { const double v1 = e1[q], v2 = e2[q], yy = y[vis2cam(q, W.N)]; s = fma(v1, yy, s); s2 = fma(v2, yy, s2); }
+    s = warp_sum(s); s2 = warp_sum(s2);
+    if (lane == 0) {
+      if (cinv[rnk] != 0.0) {
+        const double sj = scl[rnk], dd = fmin(fmax(craw[rnk] * sj * sj, 1e-6), 1e32) / (sj * sj);
+        const double st = -a * glam[rnk] / dd + b * (-cinv[rnk] * (glam[rnk] + s));
+        xout[XL(W.N) + lm_feat[rnk]] += st; n2 += st * st;
+      }
+      if (two && cinv[rnk2] != 0.0) {
+        const double sj = scl[rnk2], dd = fmin(fmax(craw[rnk2] * sj * sj, 1e-6), 1e32) / (sj * sj);
+        const double st = -a * glam[rnk2] / dd + b * (-cinv[rnk2] * (glam[rnk2] + s2));
+        xout[XL(W.N) + lm_feat[rnk2]] += st; n2 += st * st;
+      }
     }
   }
   for (int k = threadIdx.x; k <= W.N; k += blockDim.x) {
@@ -527,16 +538,27 @@ __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MINB) solve_kernel(SolveP
           for (int i = j; i < W.D; i++) wj = fma(H[tidx(i, j)], sm[L.stp + i], wj);
           q += wj * wj;
         }
-        for (int rnk = warp; rnk < W.h->n_lm; rnk += SOLVE_WARPS) {
-          double tv = 0, ty = 0;
-          for (int e = lane; e < W.Dv; e += 32) { const double ev = E[(size_t)rnk * W.Dvp + e]; const int ci = vis2cam(e, W.N); tv = fma(ev, sm[L.stp + ci], tv); ty = fma(ev, sm[L.dx + ci], ty); }
-          tv = warp_sum(tv); ty = warp_sum(ty);
-          const double ci = sm[L.cinv + rnk];
-          if (lane == 0 && ci != 0.0) {
-            const double gl = sm[L.glam + rnk], C = sm[L.craw + rnk], sj = sm[L.scl + rnk], dd = fmin(fmax(C * sj * sj, 1e-6), 1e32) / (sj * sj);
-            const double yl = -ci * (gl + ty), vl = gl / dd;
-            gg += gl * vl; yy += dd * yl * yl; gy += gl * yl;
-            q += ci * tv * tv + 2.0 * tv * vl + C * vl * vl;
+        const int nlm = W.h->n_lm;
+        for (int rnk0 = warp; rnk0 < nlm; rnk0 += 2 * SOLVE_WARPS) {   // two landmarks per trip: their E rows (L2) in flight together
+          const int rnk1 = rnk0 + SOLVE_WARPS; const bool two = rnk1 < nlm;
+          const double* e0 = E + (size_t)rnk0 * W.Dvp; const double* e1 = E + (size_t)(two ? rnk1 : rnk0) * W.Dvp;
+          double tv0 = 0, ty0 = 0, tv1 = 0, ty1 = 0;
+          for (int e = lane; e < W.Dv; e += 32) {
+            const double ev0 = e0[e], ev1 = e1[e]; const int ci = vis2cam(e, W.N); const double sv = sm[L.stp + ci], dv = sm[L.dx + ci];
+            tv0 = fma(ev0, sv, tv0); ty0 = fma(ev0, dv, ty0); tv1 = fma(ev1, sv, tv1); ty1 = fma(ev1, dv, ty1);
+          }
+          tv0 = warp_sum(tv0); ty0 = warp_sum(ty0); tv1 = warp_sum(tv1); ty1 = warp_sum(ty1);
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            if (u && !two) break;
+            const int rnk = u ? rnk1 : rnk0; const double tv = u ? tv1 : tv0, ty = u ? ty1 : ty0;
+            const double ci = sm[L.cinv + rnk];
+            if (lane == 0 && ci != 0.0) {
+              const double gl = sm[L.glam + rnk], C = sm[L.craw + rnk], sj = sm[L.scl + rnk], dd = fmin(fmax(C * sj * sj, 1e-6), 1e32) / (sj * sj);
+              const double yl = -ci * (gl + ty), vl = gl / dd;
+              gg += gl * vl; yy += dd * yl * yl; gy += gl * yl;
+              q += ci * tv * tv + 2.0 * tv * vl + C * vl * vl;
+            }
           }
         }
         dl_gg = block_sum(gg, sm + L.red); dl_yy = block_sum(yy, sm + L.red); dl_gy = block_sum(gy, sm + L.red); dl_pHp = block_sum(q, sm + L.red);
